@@ -1,0 +1,288 @@
+"""bench.py -- headline benchmark of the hot path (see DESIGN.md "Measurement").
+
+  python bench.py --gpus N --steps K --warmup W            (this framework, N ranks via torchrun)
+  python bench.py --impl reference --gpus N --steps K --warmup W   (CPU restatement of the reference)
+
+One "step" = one full training step of the ETHZ-shaped workload (BASELINE.json configs[1]):
+occupancy-grid update every 8 steps, ray/AABB, ray march over the occupancy bitfield, hash
+encode, MLPs, composite, RGB+USS+ToF losses, backward, gradient allreduce (N>1), GradScaler
+unscale + Adam.  4096 rays per GPU per step (weak scaling).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RAYS_PER_GPU = 4096
+HASH_BYTES_PER_POINT = 1164          # fwd or bwd, fp32 L16 F2 (SURVEY 8(d) / BASELINE.md section 3)
+WORKLOAD = ("ETHZ-shaped synthetic scene, hash grid L=16 F=2 T=2^19 fp32 tables, 4096 rays/batch/GPU, RGB+USS+ToF "
+            "losses, VIRUS-NeRF occupancy update every 8 steps, training from the initial (all-occupied) grid")
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rays", type=int, default=RAYS_PER_GPU)
+    ap.add_argument("--cpu-rays", type=int, default=512, help="rays per step of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-autocast", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.proc, self.index = None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill(); out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------
+def run_reference(a):
+    """CPU restatement of the reference's train step on the host cores (Taichi is not
+    installable here: see oracle/oracle.cpp header).  Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    import torch
+    import oracle
+    from oracle import pipeline
+    from virus_nerf_b200 import synthetic
+    oracle.build()
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    args = synthetic.make_args(device="cpu")
+    ds = synthetic.SyntheticDataset(pool_size=1 << 16, device="cpu")
+    model = pipeline.OracleNGP(threads=cores)
+    tr = pipeline.OracleTrainer(model, lr=args.training.lr)
+    occ = pipeline.OracleOccupancyGrid(model, ds, args)
+    rng = np.random.default_rng(0)
+    n = a.cpu_rays
+    times, samples = [], []
+    for it in range(a.warmup + a.steps):
+        t0 = time.perf_counter()
+        if it % args.occ_grid.update_interval == 0:
+            occ.update()
+        data = ds(n, args.training.sampling_strategy)
+        noise = rng.random(n, dtype=np.float32)
+        _, res = tr.step(data, occ.bitfield, noise)
+        dt = time.perf_counter() - t0
+        if it >= a.warmup:
+            times.append(dt); samples.append(res["rm_samples"])
+    total = sum(times)
+    value = n * a.steps / total
+    sample = (f"{n} of the 4096 rays of each step ({a.steps} steps, grid update every 8; dense Adam over the full "
+              f"11.4M-parameter table runs every step as in the reference)")
+    line = {"impl": "reference", "metric": "train_rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": a.gpus,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * total / a.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "rays_per_step": n, "samples_per_step": float(np.mean(samples)),
+                       "reference_kind": "restated reference (Taichi ti.cpu unavailable): oracle.cpp OpenMP + torch-CPU fp32"},
+            "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from virus_nerf_b200 import _lib, synthetic
+    from virus_nerf_b200.engine import TrainEngine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- virus-nerf_b200 has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()
+    n = a.rays
+    args = synthetic.make_args(device=str(dev), batch_size=n)
+    scene = synthetic.RoomScene()
+    K, W = a.steps, a.warmup
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t)
+        return ms
+
+    def run_phase(pinned):
+        """W warm-up + K timed steps from a fresh model.  pinned=False: the ray pool is resident
+        in HBM; pinned=True: every step's batch is copied from pinned host memory inside the
+        timed region and the loss is read back to the host (end-to-end)."""
+        ds = synthetic.SyntheticDataset(scene, pool_size=1 << 18, device=str(dev), pinned=False, seed=21 + rank)
+        eng = TrainEngine(args, ds, dev, world_size=world, rank=rank, autocast=not a.no_autocast)
+        host_batches = None
+        if pinned:
+            # batches pre-assembled in pinned host memory (the reference's dataset lives on the
+            # host side of the boundary); the timed region pays the H2D copy of each batch
+            keys = ("rays_o", "rays_d", "rgb", "USS", "ToF")
+            host_batches = []
+            for _ in range(W + K):
+                b = ds(n, args.training.sampling_strategy)
+                flat = [b["rays_o"], b["rays_d"], b["rgb"], b["depth"]["USS"], b["depth"]["ToF"]]
+                host_batches.append([t.cpu().pin_memory() for t in flat])
+            loss_host = torch.zeros(1).pin_memory()
+        h2d = d2h = 0
+        samples = []
+        prof = {}
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0 = 0
+        for it in range(W + K):
+            if it == W:
+                barrier()
+                launches0 = _lib.launch_count()
+                if not pinned:
+                    _lib.profile_start(("vn_hash_encode_fwd_f32", "vn_hash_encode_bwd_f32"))
+                ev0.record()
+            if pinned:
+                hb = host_batches[it]
+                dv = [t.to(dev, non_blocking=True) for t in hb]
+                data = {"rays_o": dv[0], "rays_d": dv[1], "rgb": dv[2], "depth": {"USS": dv[3], "ToF": dv[4]}}
+                h2d = sum(t.numel() * t.element_size() for t in hb)
+            else:
+                data = ds(n, args.training.sampling_strategy)
+            loss = eng.step(data)
+            if pinned:
+                loss_host.copy_(loss.reshape(1), non_blocking=False)     # D2H read of the step's result
+                d2h = 4
+            if it >= W:
+                samples.append(eng.last_samples)
+        ev1.record()
+        barrier()
+        ms = max_over_ranks(ev0.elapsed_time(ev1))
+        if not pinned:
+            prof = _lib.profile_stop()
+        launches = _lib.launch_count() - launches0
+        samples = [int(s) for s in samples]
+        return ms, launches, samples, prof, h2d, d2h, float(loss)
+
+    clocks = ClockSampler(local)
+    clocks.start()
+    ms, launches, samples, prof, _, _, last_loss = run_phase(pinned=False)
+    clk = clocks.stop()
+    ms_e2e, _, _, _, h2d, d2h, _ = run_phase(pinned=True)
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        total_rays = n * world * K
+        value = total_rays / (ms * 1e-3)
+        # roofline of the dominant kernel: algorithmic bytes / measured kernel time (CUDA events
+        # around the launches, on the launching stream)
+        kern = {}
+        for name, calls in prof.items():
+            t_ms = sum(c[0] for c in calls); pts = sum(c[1] for c in calls)
+            if t_ms > 0:
+                kern[name] = {"ms_total": t_ms, "launches": len(calls), "points": pts,
+                              "achieved_gbs": pts * HASH_BYTES_PER_POINT / (t_ms * 1e-3) / 1e9,
+                              "share_of_step": t_ms / ms}
+        dom = max(kern, key=lambda k: kern[k]["ms_total"]) if kern else None
+        roof = None
+        if dom:
+            roof = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": kern[dom]["achieved_gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_point": HASH_BYTES_PER_POINT}
+        line = {"metric": "train_rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": K,
+                "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32 tables/encoder/composite, fp16-autocast MLP" if not a.no_autocast else "f32",
+                "data": "synthetic",
+                "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": n, "global_rays_per_step": n * world,
+                           "samples_per_step_mean": statistics.mean(samples) if samples else 0,
+                           "parallelism": f"dp{world}",
+                           "l2_policy": "inputs larger than L2: table+grad+Adam state 183 MB and per-step sample "
+                                        "buffers are streamed; a fresh ray batch every step"},
+                "roofline": roof, "kernels": kern,
+                "e2e": {"value": total_rays / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K},
+                "gpu_launches": launches, "clocks": clk, "final_loss": last_loss}
+        if world == 1 and not a.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(a)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(a):
+    """bounded sample of the same workload on the host cores through the oracle pipeline"""
+    try:
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "12",
+                              "--warmup", "2", "--cpu-rays", str(a.cpu_rays)], capture_output=True, text=True,
+                             timeout=600, env={**os.environ, "RANK": "0", "WORLD_SIZE": "1"})
+        line = json.loads(out.stdout.strip().splitlines()[-1])
+        return line["cpu_baseline"]
+    except Exception as e:   # the baseline is a reported number, never a reason to lose the bench line
+        return {"value": None, "unit": "rays/s", "cores": len(os.sched_getaffinity(0)), "kind": "port",
+                "sample": f"failed: {e!r}"}
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

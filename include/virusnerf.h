@@ -1,0 +1,206 @@
+/* virusnerf.h -- C ABI of libvirusnerf_sm100.so (hand-written sm_100a CUDA kernels).
+ *
+ * The reference (nas-git-nas/VIRUS-NeRF) has no FFI layer: its hot path is Python modules
+ * (modules/*.py) wrapping Taichi JIT kernels.  Each entry point below replaces one of those
+ * kernels / torch op sequences; the reference interface it replaces is cited as file:line
+ * (paths relative to the reference checkout).  The Python host side that mirrors the
+ * reference's module API on top of this ABI lives in virus-nerf_b200/modules/.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the parameter name starts with h_ (host);
+ *    the caller (PyTorch) owns and sizes every buffer, kernels never allocate;
+ *  - all tensors are dense row-major ("contiguous"), dtypes as in the signatures;
+ *  - work is enqueued asynchronously on `stream` (a cudaStream_t passed as void*; NULL =
+ *    the legacy default stream); no call synchronises the host;
+ *  - return value: 0 on success, a negative VN_E* code otherwise; vn_last_error() returns a
+ *    thread-local human-readable description of the last failure;
+ *  - no C++ exceptions cross this boundary.
+ */
+#ifndef VIRUSNERF_H_
+#define VIRUSNERF_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VN_ABI_VERSION 1
+#define VN_MAX_LEVELS 32
+#define VN_MAX_SAMPLES 1024 /* modules/utils.py:12 */
+
+#define VN_OK 0
+#define VN_EINVAL -1  /* bad argument (null pointer, size, alignment, unsupported config) */
+#define VN_ELAUNCH -2 /* CUDA launch / runtime failure; see vn_last_error() */
+
+/* flags for the hash-encoder kernels (tuning switches, results identical within tolerance) */
+#define VN_HASH_DEFAULT 0
+#define VN_HASH_NO_WARP_AGG 1     /* bwd: plain per-corner atomics, no warp pre-reduction */
+#define VN_HASH_LEVEL_GROUPS_1 16 /* one level per thread (grid.y = levels): level-major */
+#define VN_HASH_LEVEL_GROUPS_4 32 /* four levels per thread */
+
+const char* vn_last_error(void);
+int vn_abi_version(void);
+/* number of kernels this library has launched so far in this process */
+int64_t vn_launch_count(void);
+/* SM count / device name of the current device; proves the library talks to a GPU */
+int vn_device_info(int* sm_count, int* cc_major, int* cc_minor, char* name, int name_len);
+
+/* ---------------------------------------------------------------------------------------
+ * a1. Hash-grid level geometry -- HashEncoder.__init__, modules/hash_encoder.py:149-235 with
+ * helpers modules/utils.py:19-42.  Host-only.  `scales`/`res` are the per-level constants
+ * the Taichi kernel derives in f32 (hash_encoder.py:73-80), precomputed once here.
+ * ------------------------------------------------------------------------------------- */
+typedef struct vn_hash_levels {
+    int32_t levels;
+    int32_t begin_fast_hash_level;   /* first level that uses the xor hash */
+    int32_t offsets[VN_MAX_LEVELS];  /* entry offset of each level in the table */
+    int32_t sizes[VN_MAX_LEVELS];    /* hash_map_sizes */
+    float scales[VN_MAX_LEVELS];     /* base_res * exp(l * log_b) - 1 (f32) */
+    uint32_t res[VN_MAX_LEVELS];     /* ceil(scale) + 1 */
+    int64_t total_entries;           /* sum(sizes); hash_table has 2 * total_entries floats */
+    double log_b;
+} vn_hash_levels_t;
+
+int vn_hash_levels_init(double base_res, double max_res, int levels, int64_t max_params,
+                        vn_hash_levels_t* h_out);
+
+/* a2. hash_encoder_kernel, modules/hash_encoder.py:89-143 (feature_per_level = 2).
+ * xyz [S,3] f32 in [0,1]; table [2*total_entries] f32; out [S, 2*levels] f32. */
+int vn_hash_encode_fwd_f32(const float* xyz, const float* table, float* out, int64_t S,
+                           const vn_hash_levels_t* h_lv, int flags, void* stream);
+
+/* a3. hash_encoder_kernel.grad via _module_function.backward, hash_encoder.py:264-277.
+ * grad [2*total_entries] f32 is ACCUMULATED into (caller zeroes it). dout [S, 2*levels]. */
+int vn_hash_encode_bwd_f32(const float* xyz, const float* dout, float* grad, int64_t S,
+                           const vn_hash_levels_t* h_lv, int flags, void* stream);
+
+/* a4. half encoder, modules/hash_encoder_half.py:112-161 (fwd) and :164-213 (bwd).
+ * table_h [total_entries,2] fp16 (the per-call hash_table.to(float16) copy, :367);
+ * out_h [S, levels, 2] fp16; dout_h same shape; grad [total_entries,2] f32 (hash_grad, :300). */
+int vn_hash_encode_fwd_f16(const float* xyz, const void* table_h, void* out_h, int64_t S,
+                           const vn_hash_levels_t* h_lv, int flags, void* stream);
+int vn_hash_encode_bwd_f16(const float* xyz, const void* dout_h, float* grad, int64_t S,
+                           const vn_hash_levels_t* h_lv, int flags, void* stream);
+/* f32 master table -> fp16 copy (hash_encoder_half.py:367), n floats */
+int vn_f32_to_f16(const float* src, void* dst_h, int64_t n, void* stream);
+
+/* known-answer helper: the 8 level-local corner indices [S,levels,8] i32 and weights
+ * [S,levels,8] f32 (weights may be NULL) -- hash_encoder.py:43-71, 114-133 */
+int vn_hash_indices(const float* xyz, int64_t S, const vn_hash_levels_t* h_lv, int32_t* idx,
+                    float* w, void* stream);
+
+/* a5. ray_aabb_intersect, modules/intersection.py:8-37.  hits_t [N,2]. */
+int vn_ray_aabb(const float* rays_o, const float* rays_d, float scale, int64_t N, float* hits_t,
+                void* stream);
+
+/* a6. raymarching_train_kernel, modules/ray_march.py:9-124, split at the atomic counter:
+ *  _count: pass 1 (:29-82).  Writes counts [N] i32, then the deterministic equivalent of the
+ *          atomic counter: rays_a [N,3] i32 = (r, exclusive scan of counts in ray order, count)
+ *          and counter [2] i32 = (total samples, N).  scan_tmp: >= vn_march_scan_tmp_ints(N) i32.
+ *  _write: pass 2 (:84-124).  Re-marches and writes xyzs, dirs [*,3], deltas, ts [*] rows
+ *          rays_a[r,1] .. +count; rows >= capacity are dropped (capacity = rows allocated). */
+int64_t vn_march_scan_tmp_ints(int64_t N);
+int vn_march_train_count(const float* rays_o, const float* rays_d, const float* hits_t,
+                         const uint8_t* bitfield, const float* noise, int64_t N, int cascades,
+                         int grid_size, float scale, float exp_step_factor, int max_samples,
+                         int32_t* counts, int32_t* rays_a, int32_t* counter, int32_t* scan_tmp,
+                         void* stream);
+int vn_march_train_write(const float* rays_o, const float* rays_d, const float* hits_t,
+                         const uint8_t* bitfield, const float* noise, int64_t N, int cascades,
+                         int grid_size, float scale, float exp_step_factor, const int32_t* rays_a,
+                         int64_t capacity, float* xyzs, float* dirs, float* deltas, float* ts,
+                         void* stream);
+
+/* a7. raymarching_test_kernel, modules/ray_march.py:198-269.  alive [A] i64; slot layout
+ * n*max_samples+s; ray_indices i64, valid_mask u8 (caller zeroes), deltas/ts f32, all
+ * [A*max_samples]; counter [A] i32; hits_t [N,2] is updated in place (:258). */
+int vn_march_test(const float* rays_o, const float* rays_d, float* hits_t, const int64_t* alive,
+                  int64_t A, const uint8_t* bitfield, int cascades, int grid_size, float scale,
+                  float exp_step_factor, int max_samples, int64_t* ray_indices,
+                  uint8_t* valid_mask, float* deltas, float* ts, int32_t* counter, void* stream);
+/* the wrapper's compaction (ray_march.py:328-335) without boolean-mask host syncs:
+ * packed_info [A,2] i64 = (exclusive cumsum, count); compacted ray_indices/deltas/ts are
+ * written densely in slot order; total [1] i64 receives the number of valid samples. */
+int vn_march_test_compact(const int32_t* counter, int64_t A, int max_samples,
+                          const int64_t* ray_indices, const float* deltas, const float* ts,
+                          int64_t* packed_info, int64_t* ray_indices_out, float* deltas_out,
+                          float* ts_out, int64_t* total, int32_t* scan_tmp, void* stream);
+
+/* a8. volume_rendering_kernel, modules/volume_train.py:6-48.  rays_a [N,3] i32; sigmas,
+ * deltas, ts, ws [S]; rgbs [S,3]; outputs indexed by ray id: total_samples [N] i32,
+ * opacity, depth [N], rgb [N,3].  ws of skipped samples is written 0. */
+int vn_composite_train_fwd(const float* sigmas, const float* rgbs, const float* deltas,
+                           const float* ts, const int32_t* rays_a, int64_t N, int64_t S,
+                           float T_threshold, int32_t* total_samples, float* opacity, float* depth,
+                           float* rgb, float* ws, void* stream);
+/* a9. volume_rendering_kernel.grad, modules/volume_train.py:130-175.  dL_dws may be NULL.
+ * Writes dsigmas [S], drgbs [S,3] (every row, zeros where skipped). */
+int vn_composite_train_bwd(const float* sigmas, const float* rgbs, const float* deltas,
+                           const float* ts, const int32_t* rays_a, int64_t N, int64_t S,
+                           float T_threshold, const float* dL_dopacity, const float* dL_ddepth,
+                           const float* dL_drgb, const float* dL_dws, float* dsigmas, float* drgbs,
+                           void* stream);
+/* a10. composite_test, modules/volume_render_test.py:4-54.  pack_info [A,2] i64,
+ * alive [A] i64 (entries set to -1 when the ray is finished); opacity/depth/rgb in place. */
+int vn_composite_test(const float* sigmas, const float* rgbs, const float* deltas, const float* ts,
+                      const int64_t* pack_info, int64_t* alive, int64_t A, float T_threshold,
+                      float* opacity, float* depth, float* rgb, void* stream);
+
+/* a11. dir_encoder, modules/spherical_harmonics.py:7-42.  dirs [B,3] -> emb [B,16]. */
+int vn_sh_encode(const float* dirs, int64_t B, float* emb, void* stream);
+
+/* a15. morton3D / morton3D_invert / packbits, modules/utils.py:120-169 */
+int vn_morton3d(const int32_t* coords, int64_t n, int32_t* indices, void* stream);
+int vn_morton3d_invert(const int32_t* indices, int64_t n, int32_t* coords, void* stream);
+int vn_packbits(const float* grid, int64_t n_bytes, float threshold, uint8_t* bitfield,
+                void* stream);
+
+/* a14. OccupancyGrid, modules/occupancy_grid.py.
+ *  _calc_pos_prob: _calcPos (:293-335, with helpers/geometric_fcts.py:151-171 and _c2idx
+ *     :479-480) fused with _rayProb (:338-389) when meas != NULL.  noise [N,M,3] uniform
+ *     [0,1) or NULL.  Outputs (any may be NULL): cell_dists [N,M], cell_pos [N*M,3],
+ *     cell_idxs [N*M,3] i32, probs_occ / probs_emp [N,M].
+ *  _nerf_prob: _nerfProb (:392-408) given densities; mean/threshold computed on device
+ *     (scratch: >= 514 floats, 8-byte aligned; [512] = mean, [513] = h_thr on exit), no host
+ *     sync (the reference does torch.mean(...).item(), :402).
+ *  _bayes_update: _updateGrid (:411-430) with deterministic last-writer-wins for duplicate
+ *     cells.  winner: int32 [G^3] scratch that must be all -1 on entry and is restored.
+ *  _decay_pack: update() tail (:96-105) = optional in-place decay + cartesian2morton
+ *     (grid.py:165-170) + packbits (grid.py:205-211) in one pass. */
+int vn_occ_calc_pos_prob(const float* rays_o, const float* rays_d, const float* noise,
+                         const float* meas, int64_t N, int M, int I, int grid_size, float scale,
+                         float noise_every_m, float p_false, float std_every_m, float prob_min,
+                         float* cell_dists, float* cell_pos, int32_t* cell_idxs, float* probs_occ,
+                         float* probs_emp, void* stream);
+/* _rayProb (:338-389) on explicit distances dists [N,M] */
+int vn_occ_ray_prob(const float* meas, const float* dists, int64_t N, int M, int I, float p_false,
+                    float std_every_m, float prob_min, float* probs_occ, float* probs_emp,
+                    void* stream);
+int vn_occ_nerf_prob(const float* density, int64_t n, double thr_max, float slope, float* scratch,
+                     float* probs_occ, float* probs_emp, void* stream);
+int vn_occ_bayes_update(float* grid, int grid_size, const int32_t* cell_idxs, int64_t n,
+                        const float* probs_occ, const float* probs_emp, int32_t* winner,
+                        float* new_probs_tmp, void* stream);
+int vn_occ_decay_pack(float* grid, int grid_size, float decay, int apply_decay, float threshold,
+                      uint8_t* bitfield, void* stream);
+
+/* f1 (caller side). GradScaler.unscale_ + inf check + torch.optim.Adam(eps=1e-15) step,
+ * training/trainer.py:49-57,138-141, as one pass.  found_inf [1] f32 (device): set to 1 by
+ * vn_grad_check when a scaled gradient is non-finite; the step kernel skips the update when
+ * it is non-zero (GradScaler.step semantics).  step is the 1-based Adam step count.  When
+ * scale_dev (device, [1] f32) is non-NULL the unscale factor is 1 / scale_dev[0] (the
+ * GradScaler's device-side scale) and inv_scale is ignored. */
+int vn_grad_check(const float* g, int64_t n, float* found_inf, void* stream);
+int vn_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float inv_scale, float lr,
+                 float beta1, float beta2, float eps, int step, const float* found_inf,
+                 const float* scale_dev, void* stream);
+/* GradScaler.update() on device (torch _amp_update_scale_): scale [1] f32, growth_tracker
+ * [1] i32; found_inf is reset to 0 afterwards. */
+int vn_scaler_update(float* scale, int32_t* growth_tracker, float* found_inf, float growth_factor,
+                     float backoff_factor, int growth_interval, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIRUSNERF_H_ */

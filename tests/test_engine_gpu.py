@@ -1,0 +1,145 @@
+"""GPU end-to-end parity: the render drivers, NGP module and the train-step engine against the
+oracle pipeline (oracle/pipeline.py) with the same weights, rays, bitfield and jitter noise.
+fp32 everywhere (autocast off) so that the MLP (cuBLAS fp32 stand-in / fused kernel in fp32
+mode) is comparable at rtol 1e-4."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def N(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.fixture(scope="module")
+def setup():
+    import oracle
+    from oracle import pipeline
+    from virus_nerf_b200 import synthetic
+    from virus_nerf_b200.engine import TrainEngine
+    oracle.build()
+    args = synthetic.make_args(device=DEV, batch_size=256)
+    ds = synthetic.SyntheticDataset(pool_size=1 << 13, n_images=8, device=DEV)
+    eng = TrainEngine(args, ds, DEV, autocast=False)
+    bf = synthetic.morton_pack(ds.scene.occupancy_bitfield(128))
+    eng.model.occupancy_grid.bitfield = torch.from_numpy(bf).to(DEV)
+    om = pipeline.OracleNGP(threads=4)
+    om.load_from(eng.model)
+    return eng, om, ds, bf, args, pipeline
+
+
+def _data_cpu(data):
+    return {"rays_o": data["rays_o"].cpu(), "rays_d": data["rays_d"].cpu(), "rgb": data["rgb"].cpu(),
+            "depth": {k: v.cpu() for k, v in data["depth"].items()}}
+
+
+def test_state_dict_keys(setup):
+    eng = setup[0]
+    keys = set(eng.model.state_dict().keys())
+    assert {"pos_encoder.hash_table", "xyz_encoder.hidden_layers.0.weight", "xyz_encoder.output_layer.weight",
+            "rgb_net.hidden_layers.0.weight", "rgb_net.hidden_layers.1.weight", "rgb_net.output_layer.weight",
+            "center", "xyz_min", "xyz_max", "half_size"} <= keys
+    assert eng.model.state_dict()["pos_encoder.hash_table"].shape == (11420064,)
+    assert "pos_encoder.offsets" not in keys and "pos_encoder.hash_map_sizes" not in keys   # persistent=False
+
+
+def test_ngp_forward_matches_oracle(setup):
+    eng, om, ds, bf, args, pipeline = setup
+    x = (torch.rand(4000, 3, device=DEV) - 0.5) * 0.98
+    d = torch.randn(4000, 3, device=DEV)
+    with torch.no_grad():
+        sig, rgb = eng.model(x, d)
+        o_sig, o_rgb = om.forward(x.cpu(), d.cpu())
+    np.testing.assert_allclose(N(sig), N(o_sig), rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(N(rgb), N(o_rgb), rtol=1e-4, atol=1e-6)
+
+
+def test_render_train_and_grads_match_oracle(setup, monkeypatch):
+    eng, om, ds, bf, args, pipeline = setup
+    from virus_nerf_b200.modules import ray_march, rendering
+    data = ds(256, args.training.sampling_strategy)
+    noise = torch.rand(256, device=DEV)
+    orig = ray_march.raymarching_train
+    monkeypatch.setattr(rendering, "raymarching_train", lambda *a, **k: orig(*a, noise=noise, **k))
+    eng.flat_g.zero_()
+    loss, terms, res = eng.forward_loss(data)
+    loss.backward()
+    o_res = pipeline.render_train(om, data["rays_o"].cpu(), data["rays_d"].cpu(), bf, N(noise))
+    o_loss = pipeline.loss_fn(o_res, _data_cpu(data))
+    for p in om.parameters():
+        p.grad = None
+    o_loss.backward()
+    assert int(res["rm_samples"]) == o_res["rm_samples"]
+    np.testing.assert_array_equal(N(res["ts"]), o_res["ts"])
+    for k in ("opacity", "depth", "rgb"):
+        np.testing.assert_allclose(N(res[k]), N(o_res[k]), rtol=1e-4, atol=1e-6)
+    assert abs(float(loss) - float(o_loss)) <= 1e-4 * abs(float(o_loss))
+    g_hash = N(eng.model.pos_encoder.hash_table.grad)
+    r_hash = N(om.hash_table.grad)
+    np.testing.assert_allclose(g_hash, r_hash, rtol=1e-3, atol=1e-5 * np.abs(r_hash).max())
+    names = ["xyz_encoder.hidden_layers.0.weight", "xyz_encoder.output_layer.weight", "rgb_net.hidden_layers.0.weight",
+             "rgb_net.hidden_layers.1.weight", "rgb_net.output_layer.weight"]
+    params = dict(eng.model.named_parameters())
+    for n, w in zip(names, om.W):
+        np.testing.assert_allclose(N(params[n].grad), N(w.grad), rtol=1e-3, atol=1e-5 * float(w.grad.abs().max()))
+
+
+def test_render_test_matches_oracle(setup):
+    eng, om, ds, bf, args, pipeline = setup
+    from virus_nerf_b200.modules.rendering import render
+    from virus_nerf_b200 import synthetic
+    data = ds(300, {"pixs": "random"})
+    so, sd = synthetic.scan_rays(64, height=-0.05)
+    ro = torch.cat([data["rays_o"], torch.from_numpy(so).to(DEV)])
+    rd = torch.cat([data["rays_d"], torch.from_numpy(sd).to(DEV)])
+    # make the field opaque enough for early termination to matter
+    with torch.no_grad():
+        eng.model.xyz_encoder.output_layer.weight[0].add_(0.25)
+    om.load_from(eng.model)
+    res = render(eng.model, ro, rd, test_time=True, exp_step_factor=0.0)
+    o = pipeline.render_test(om, ro.cpu(), rd.cpu(), bf)
+    assert int(res["total_samples"]) == o["total_samples"]
+    for k in ("opacity", "depth", "rgb"):
+        np.testing.assert_allclose(N(res[k]), o[k], rtol=1e-4, atol=1e-5)
+    with torch.no_grad():
+        eng.model.xyz_encoder.output_layer.weight[0].sub_(0.25)
+    om.load_from(eng.model)
+
+
+def test_train_steps_track_oracle(setup, monkeypatch):
+    """three optimiser steps (no grid update in between): losses and parameters track the CPU
+    trainer (fp32, Adam eps 1e-15; the GPU side goes through GradScaler 2^19 + fused Adam)"""
+    eng, om, ds, bf, args, pipeline = setup
+    from virus_nerf_b200.modules import ray_march, rendering
+    om.load_from(eng.model)
+    tr = pipeline.OracleTrainer(om, lr=args.training.lr)
+    eng.step_idx = 1   # skip the occupancy update (tested separately)
+    orig = ray_march.raymarching_train
+    for it in range(3):
+        data = ds(256, args.training.sampling_strategy)
+        noise = torch.rand(256, device=DEV)
+        monkeypatch.setattr(rendering, "raymarching_train", lambda *a, **k: orig(*a, noise=noise, **k))
+        loss = float(eng.step(data))
+        o_loss, _ = tr.step(_data_cpu(data), bf, N(noise))
+        assert abs(loss - o_loss) <= 2e-3 * abs(o_loss), (it, loss, o_loss)
+    w_g = N(eng.model.rgb_net.output_layer.weight)
+    np.testing.assert_allclose(w_g, N(om.W[4]), rtol=0, atol=2e-3)
+
+
+def test_occupancy_update_runs_and_is_deterministic(setup):
+    eng, om, ds, bf, args, pipeline = setup
+    og = eng.model.occupancy_grid
+    torch.manual_seed(5); ds.gen.manual_seed(5)
+    g0 = og.occ_3d_grid.clone(); step0 = og.update_step
+    og.update(elapse_time=0.0)
+    g1, b1 = og.occ_3d_grid.clone(), og.getBitfield().clone()
+    og.occ_3d_grid.copy_(g0); og.update_step = step0
+    torch.manual_seed(5); ds.gen.manual_seed(5)
+    og.update(elapse_time=0.0)
+    assert torch.equal(og.occ_3d_grid, g1) and torch.equal(og.getBitfield(), b1)   # replicas stay bit-identical
+    assert og.getBitfield().shape == (128 ** 3 // 8,) and og.getBitfield().dtype == torch.uint8
+    assert torch.isfinite(og.occ_3d_grid).all()
+    assert not torch.equal(g0, g1)

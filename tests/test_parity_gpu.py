@@ -1,0 +1,490 @@
+"""GPU parity tests: every C-ABI kernel of libvirusnerf_sm100.so against the CPU oracle on the
+same seeded inputs.  Bars (BASELINE.json north_star): hash / Morton indices, bitfields,
+per-ray sample counts and (t, dt) sequences bit-exact; encoder and composite forward rtol
+1e-5; gradients rtol 1e-4 (+ atol scaled to the largest reference entry: float atomics
+reorder); half encoder fwd rtol 2e-3 / atol 1e-3 vs the fp16 oracle, grads rtol 1e-2."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def T(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    return t if dtype is None else t.to(dtype)
+
+
+def N(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.fixture(scope="module")
+def vn():
+    from virus_nerf_b200 import _lib
+    _lib.lib()
+    return _lib
+
+
+@pytest.fixture(scope="module")
+def scene_rays():
+    from virus_nerf_b200 import synthetic
+    sc = synthetic.RoomScene()
+    ds = synthetic.SyntheticDataset(sc, pool_size=1 << 14, n_images=16, device="cpu")
+    b = ds(3000, {"pixs": {"valid_uss": 0.4, "valid_tof": 0.4}})
+    ro, rd = b["rays_o"].numpy().copy(), b["rays_d"].numpy().copy()
+    # edge cases: axis aligned, zero components (scan rays), rays from outside, missing rays
+    so, sd = synthetic.scan_rays(64)
+    extra_o = np.array([[0, 0, 0], [0, 0, 0], [2, 2, 2], [2, 0, 0], [0.2, 0.1, 0.0], [-0.5, 0.0, 0.0]], np.float32)
+    extra_d = np.array([[1, 0, 0], [0, 0, -1], [1, 0, 0], [-1, 0, 0], [0.6, 0.8, 0.0], [1, 0, 0]], np.float32)
+    ro = np.concatenate([ro, so, extra_o]); rd = np.concatenate([rd, sd, extra_d])
+    bitfields = {
+        "carved": synthetic.morton_pack(sc.occupancy_bitfield(128)),
+        "full": np.full(128 ** 3 // 8, 255, np.uint8),
+        "empty": np.zeros(128 ** 3 // 8, np.uint8),
+        "random": np.random.default_rng(3).integers(0, 256, 128 ** 3 // 8).astype(np.uint8),
+    }
+    return ro, rd, bitfields
+
+
+def ray_coherent_points(n_rays=256, per_ray=64, seed=0):
+    """consecutive samples along rays in [0,1]^3 (what the encoder sees in training)"""
+    rng = np.random.default_rng(seed)
+    o = rng.random((n_rays, 1, 3)).astype(np.float32) * 0.6 + 0.2
+    d = rng.normal(size=(n_rays, 1, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=-1, keepdims=True)
+    t = (np.arange(per_ray, dtype=np.float32) * np.float32(np.sqrt(3) / 1024))[None, :, None]
+    return np.clip(o + d * t, 0.0, 1.0).reshape(-1, 3).astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------ a1/a2/a3
+@pytest.mark.parametrize("log2_T,max_res", [(19, 1024), (22, 1024), (19, 2048)])
+def test_hash_levels_and_indices_bit_exact(vn, oracle_mod, log2_T, max_res):
+    lv_o = oracle_mod.HashLevels(16, max_res, 16, 2 ** log2_T)
+    lv = vn.hash_levels(16, max_res, 16, 2 ** log2_T)
+    assert lv.total_entries == lv_o.total and lv.begin_fast_hash_level == lv_o.begin_fast_hash_level
+    np.testing.assert_array_equal(np.array(lv.offsets[:16]), lv_o.offsets)
+    np.testing.assert_array_equal(np.array(lv.sizes[:16]), lv_o.sizes)
+    np.testing.assert_array_equal(np.array(lv.scales[:16], np.float32), lv_o.scales)
+    np.testing.assert_array_equal(np.array(lv.res[:16], np.uint32), lv_o.res)
+    rng = np.random.default_rng(1)
+    xyz = rng.random((4096, 3)).astype(np.float32)
+    edge = np.array([[0, 0, 0], [1, 1, 1], [0.5, 0.5, 0.5], [1 - 2 ** -24] * 3, [1, 0, 0.5], [0.25, 0.75, 1.0]], np.float32)
+    xyz = np.concatenate([xyz, edge, ray_coherent_points(8, 32)])
+    S = xyz.shape[0]
+    idx = torch.zeros(S, 16, 8, dtype=torch.int32, device=DEV)
+    w = torch.zeros(S, 16, 8, dtype=torch.float32, device=DEV)
+    vn.call("vn_hash_indices", T(xyz), S, lv, idx, w)
+    idx_o, w_o = oracle_mod.hash_indices(xyz, lv_o, with_weights=True)
+    np.testing.assert_array_equal(N(idx), idx_o)
+    np.testing.assert_array_equal(N(w), w_o)
+
+
+@pytest.mark.parametrize("flags", [0, 16, 32])
+@pytest.mark.parametrize("log2_T", [19, 22])
+def test_hash_fwd_f32(vn, oracle_mod, flags, log2_T):
+    lv_o = oracle_mod.HashLevels(16, 1024, 16, 2 ** log2_T)
+    lv = vn.hash_levels(16, 1024, 16, 2 ** log2_T)
+    rng = np.random.default_rng(2)
+    table = rng.random(2 * lv_o.total, dtype=np.float32)
+    xyz = np.concatenate([rng.random((5000, 3)).astype(np.float32), ray_coherent_points(64, 48),
+                          np.array([[0, 0, 0], [1, 1, 1]], np.float32)])
+    S = xyz.shape[0]
+    out = torch.empty(S, 32, device=DEV)
+    vn.call("vn_hash_encode_fwd_f32", T(xyz), T(table), out, S, lv, flags)
+    ref = oracle_mod.hash_fwd_f32(xyz, table, lv_o)
+    np.testing.assert_allclose(N(out), ref, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("flags", [0, 1, 16, 32, 33])
+def test_hash_bwd_f32(vn, oracle_mod, flags):
+    lv_o = oracle_mod.HashLevels(16, 1024, 16, 2 ** 19)
+    lv = vn.hash_levels(16, 1024, 16, 2 ** 19)
+    rng = np.random.default_rng(4)
+    xyz = np.concatenate([rng.random((3001, 3)).astype(np.float32), ray_coherent_points(128, 64)])
+    S = xyz.shape[0]
+    dout = rng.normal(size=(S, 32)).astype(np.float32)
+    grad = torch.zeros(2 * lv_o.total, device=DEV)
+    vn.call("vn_hash_encode_bwd_f32", T(xyz), T(dout), grad, S, lv, flags)
+    ref = oracle_mod.hash_bwd_f32(xyz, dout, lv_o)
+    np.testing.assert_allclose(N(grad), ref, rtol=1e-4, atol=1e-6 * np.abs(ref).max())
+
+
+def test_hash_module_autograd(vn, oracle_mod):
+    from virus_nerf_b200.modules.hash_encoder import HashEncoder
+    enc = HashEncoder(max_params=2 ** 19, levels=16, base_res=16, max_res=1024).to(DEV)
+    assert enc.out_dim == 32 and enc.total_param_size == 11420064 and enc.begin_fast_hash_level == 6
+    xyz = torch.rand(1000, 3, device=DEV)
+    out = enc(xyz)
+    g = torch.randn_like(out)
+    out.backward(g)
+    lv_o = oracle_mod.HashLevels(16, 1024, 16, 2 ** 19)
+    np.testing.assert_allclose(N(out), oracle_mod.hash_fwd_f32(N(xyz), N(enc.hash_table), lv_o), rtol=1e-5, atol=1e-6)
+    ref = oracle_mod.hash_bwd_f32(N(xyz), N(g), lv_o)
+    np.testing.assert_allclose(N(enc.hash_table.grad), ref, rtol=1e-4, atol=1e-6 * np.abs(ref).max())
+
+
+def test_hash_empty_and_ragged(vn):
+    lv = vn.hash_levels(16, 1024, 16, 2 ** 19)
+    table = torch.rand(2 * lv.total_entries, device=DEV)
+    out = torch.empty(0, 32, device=DEV)
+    vn.call("vn_hash_encode_fwd_f32", torch.empty(0, 3, device=DEV), table, out, 0, lv, 0)
+    for S in (1, 31, 33, 257):
+        xyz = torch.rand(S, 3, device=DEV)
+        o1 = torch.empty(S, 32, device=DEV); o2 = torch.empty(S, 32, device=DEV)
+        vn.call("vn_hash_encode_fwd_f32", xyz, table, o1, S, lv, 0)
+        vn.call("vn_hash_encode_fwd_f32", xyz, table, o2, S, lv, 16)
+        assert torch.equal(o1, o2)
+
+
+# ------------------------------------------------------------------------------------ a4
+def test_hash_half(vn, oracle_mod):
+    lv_o = oracle_mod.HashLevels(16, 1024, 16, 2 ** 19)
+    lv = vn.hash_levels(16, 1024, 16, 2 ** 19)
+    rng = np.random.default_rng(5)
+    table = (rng.random((lv_o.total, 2), dtype=np.float32) * 2 - 1)
+    xyz = np.concatenate([rng.random((4000, 3)).astype(np.float32), ray_coherent_points(32, 64)])
+    S = xyz.shape[0]
+    table_h = torch.empty(lv_o.total, 2, dtype=torch.float16, device=DEV)
+    vn.call("vn_f32_to_f16", T(table), table_h, table.size)
+    np.testing.assert_array_equal(N(table_h), table.astype(np.float16))
+    out = torch.empty(S, 16, 2, dtype=torch.float16, device=DEV)
+    vn.call("vn_hash_encode_fwd_f16", T(xyz), table_h, out, S, lv, 0)
+    ref = oracle_mod.hash_fwd_f16(xyz, table.astype(np.float16), lv_o)
+    np.testing.assert_allclose(N(out).reshape(S, 32).astype(np.float32), ref.astype(np.float32), rtol=2e-3, atol=1e-3)
+    # and against the fp32 oracle on the fp16-rounded table
+    ref32 = oracle_mod.hash_fwd_f32(xyz, table.astype(np.float16).astype(np.float32).reshape(-1), lv_o)
+    np.testing.assert_allclose(N(out).reshape(S, 32).astype(np.float32), ref32, rtol=2e-3, atol=2e-3)
+    dout = rng.normal(size=(S, 16, 2)).astype(np.float16)
+    dout[::7] = 0      # zero-skip rule
+    grad = torch.zeros(lv_o.total, 2, device=DEV)
+    vn.call("vn_hash_encode_bwd_f16", T(xyz), T(dout), grad, S, lv, 0)
+    gref = oracle_mod.hash_bwd_f16(xyz, dout, lv_o)
+    np.testing.assert_allclose(N(grad), gref, rtol=1e-2, atol=1e-5 * np.abs(gref).max())
+
+
+def test_hash_half_module(vn, oracle_mod):
+    from virus_nerf_b200.modules.hash_encoder_half import HashEncoder
+    enc = HashEncoder(max_params=2 ** 19, levels=16, base_res=16, max_res=1024).to(DEV)
+    assert enc.hash_table.shape == (5710032, 2) and enc.hash_grad.shape == (5710032, 2)
+    xyz = torch.rand(500, 3, device=DEV)
+    out = enc(xyz)
+    assert out.dtype == torch.float16 and out.shape == (500, 32)
+    out.float().sum().backward()
+    assert enc.hash_table.grad is not None and torch.isfinite(enc.hash_table.grad).all()
+
+
+# ------------------------------------------------------------------------------------ a5
+def test_ray_aabb_bit_exact(vn, oracle_mod, scene_rays):
+    ro, rd, _ = scene_rays
+    for scale in (0.5, 2.0):
+        hits = torch.empty(ro.shape[0], 2, device=DEV)
+        vn.call("vn_ray_aabb", T(ro), T(rd), scale, ro.shape[0], hits)
+        np.testing.assert_array_equal(N(hits), oracle_mod.ray_aabb(ro, rd, scale))
+
+
+# ------------------------------------------------------------------------------------ a6
+@pytest.mark.parametrize("bf_name", ["carved", "full", "empty", "random"])
+@pytest.mark.parametrize("scale,esf,cascades", [(0.5, 0.0, 1), (2.0, 1 / 256, 3)])
+def test_march_train_bit_exact(vn, oracle_mod, scene_rays, bf_name, scale, esf, cascades):
+    from virus_nerf_b200.modules.ray_march import raymarching_train
+    ro, rd, bfs = scene_rays
+    bf = bfs[bf_name]
+    if cascades > 1:
+        bf = np.concatenate([bf] + [np.random.default_rng(c).integers(0, 256, bf.shape[0]).astype(np.uint8)
+                                    for c in range(1, cascades)])
+    n = ro.shape[0]
+    hits = oracle_mod.ray_aabb(ro, rd, scale)
+    noise = np.random.default_rng(7).random(n).astype(np.float32)
+    rays_a, xyzs, dirs, deltas, ts, total = raymarching_train(T(ro), T(rd), T(hits), T(bf), cascades, scale, esf, 128,
+                                                              1024, noise=T(noise))
+    o_ra, o_xyz, o_dirs, o_de, o_ts, o_total = oracle_mod.march_train(ro, rd, hits, bf, noise, cascades, scale, esf, 128)
+    assert int(total) == o_total
+    np.testing.assert_array_equal(N(rays_a), o_ra)
+    np.testing.assert_array_equal(N(ts), o_ts)
+    np.testing.assert_array_equal(N(deltas), o_de)
+    np.testing.assert_array_equal(N(xyzs), o_xyz)
+    np.testing.assert_array_equal(N(dirs), o_dirs)
+
+
+def test_march_train_max_samples_and_empty(vn, oracle_mod, scene_rays):
+    from virus_nerf_b200.modules.ray_march import raymarching_train
+    ro, rd, bfs = scene_rays
+    hits = oracle_mod.ray_aabb(ro, rd, 0.5)
+    noise = np.zeros(ro.shape[0], np.float32)
+    rays_a, *_rest, total = raymarching_train(T(ro), T(rd), T(hits), T(bfs["full"]), 1, 0.5, 0.0, 128, 17, noise=T(noise))
+    o = oracle_mod.march_train(ro, rd, hits, bfs["full"], noise, 1, 0.5, 0.0, 128, max_samples=17)
+    np.testing.assert_array_equal(N(rays_a), o[0])
+    assert N(rays_a)[:, 2].max() == 17
+    e = torch.empty(0, 3, device=DEV)
+    ra, x, d, de, ts, tot = raymarching_train(e, e, torch.empty(0, 2, device=DEV), T(bfs["full"]), 1, 0.5, 0.0, 128, 1024)
+    assert ra.shape == (0, 3) and x.shape == (0, 3) and int(tot) == 0
+
+
+# ------------------------------------------------------------------------------------ a7
+@pytest.mark.parametrize("max_samples", [1, 4, 64])
+def test_march_test_bit_exact(vn, oracle_mod, scene_rays, max_samples):
+    from virus_nerf_b200.modules.ray_march import raymarching_test
+    ro, rd, bfs = scene_rays
+    bf = bfs["carved"]
+    hits = oracle_mod.ray_aabb(ro, rd, 0.5)
+    alive = np.random.default_rng(8).permutation(ro.shape[0])[: ro.shape[0] // 2].astype(np.int64)
+    alive.sort()
+    hits_g = T(hits.copy())
+    hits_o = hits.copy()
+    for _round in range(3):      # successive rounds continue from the mutated hits_t
+        pk, ri, de, ts = raymarching_test(T(ro), T(rd), hits_g, T(alive), T(bf), 1, 0.5, 0.0, 128, max_samples)
+        o_pk, o_ri, o_de, o_ts = oracle_mod.march_test(ro, rd, hits_o, alive, bf, 1, 0.5, 0.0, 128, max_samples)
+        np.testing.assert_array_equal(N(pk), o_pk)
+        np.testing.assert_array_equal(N(ri), o_ri)
+        np.testing.assert_array_equal(N(de), o_de)
+        np.testing.assert_array_equal(N(ts), o_ts)
+        np.testing.assert_array_equal(N(hits_g), hits_o)
+
+
+# ------------------------------------------------------------------------------------ a8/a9/a10
+def _composite_inputs(oracle_mod, scene_rays, seed=9, sigma_scale=30.0):
+    ro, rd, bfs = scene_rays
+    hits = oracle_mod.ray_aabb(ro, rd, 0.5)
+    noise = np.random.default_rng(seed).random(ro.shape[0]).astype(np.float32)
+    rays_a, xyzs, dirs, deltas, ts, total = oracle_mod.march_train(ro, rd, hits, bfs["carved"], noise, 1, 0.5, 0.0, 128)
+    rng = np.random.default_rng(seed)
+    sigmas = (rng.random(total).astype(np.float32) ** 4) * sigma_scale * 20
+    rgbs = rng.random((total, 3)).astype(np.float32)
+    return rays_a, sigmas, rgbs, deltas, ts
+
+
+@pytest.mark.parametrize("sigma_scale", [1.0, 30.0, 3000.0])
+def test_composite_train_fwd_bwd(vn, oracle_mod, scene_rays, sigma_scale):
+    from virus_nerf_b200.modules.volume_train import VolumeRenderer
+    rays_a, sigmas, rgbs, deltas, ts = _composite_inputs(oracle_mod, scene_rays, sigma_scale=sigma_scale)
+    n = rays_a.shape[0]
+    sg = T(sigmas).requires_grad_(True)
+    cg = T(rgbs).requires_grad_(True)
+    vr, op, dp, rgb, ws = VolumeRenderer()(sg, cg, T(deltas), T(ts), T(rays_a), 1e-4)
+    o_total, o_op, o_dp, o_rgb, o_ws = oracle_mod.composite_train_fwd(sigmas, rgbs, deltas, ts, rays_a, 1e-4)
+    assert int(vr) == int(o_total.sum())
+    np.testing.assert_allclose(N(op), o_op, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(N(dp), o_dp, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(N(rgb), o_rgb, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(N(ws), o_ws, rtol=1e-5, atol=1e-9)
+    rng = np.random.default_rng(10)
+    dO, dD, dC = (rng.normal(size=n).astype(np.float32), rng.normal(size=n).astype(np.float32),
+                  rng.normal(size=(n, 3)).astype(np.float32))
+    dW = rng.normal(size=sigmas.shape[0]).astype(np.float32) * 0.1
+    (op * T(dO)).sum().add((dp * T(dD)).sum()).add((rgb * T(dC)).sum()).add((ws * T(dW)).sum()).backward()
+    r_ds, r_dc = oracle_mod.composite_train_bwd(sigmas, rgbs, deltas, ts, rays_a, 1e-4, dO, dD, dC, dW)
+    np.testing.assert_allclose(N(sg.grad), r_ds, rtol=1e-4, atol=1e-6 * np.abs(r_ds).max())
+    np.testing.assert_allclose(N(cg.grad), r_dc, rtol=1e-4, atol=1e-6 * np.abs(r_dc).max())
+
+
+def test_composite_closed_form(vn):
+    """constant-sigma slab: opacity = 1 - exp(-sigma L); zero-sample rays give zeros"""
+    from virus_nerf_b200.modules.volume_train import VolumeRenderer
+    ns, sigma, delta = 200, 7.0, 0.004
+    rays_a = torch.tensor([[0, 0, ns], [1, ns, 0], [2, ns, 3]], dtype=torch.int32, device=DEV)
+    S = ns + 3
+    sig = torch.full((S,), sigma, device=DEV); de = torch.full((S,), delta, device=DEV)
+    ts = torch.arange(S, device=DEV, dtype=torch.float32) * delta
+    rgbs = torch.ones(S, 3, device=DEV)
+    vr, op, dp, rgb, ws = VolumeRenderer()(sig, rgbs, de, ts, rays_a, 1e-4)
+    assert abs(float(op[0]) - (1 - np.exp(-sigma * delta * ns))) < 1e-5
+    assert float(op[1]) == 0.0 and float(dp[1]) == 0.0 and int(vr) == ns + 3
+    np.testing.assert_allclose(N(rgb[0]), N(op[0]).repeat(3), rtol=1e-6)
+
+
+def test_composite_test_kernel(vn, oracle_mod, scene_rays):
+    from virus_nerf_b200.modules.volume_render_test import composite_test
+    rays_a, sigmas, rgbs, deltas, ts = _composite_inputs(oracle_mod, scene_rays, sigma_scale=300.0)
+    n = rays_a.shape[0]
+    alive = np.arange(n, dtype=np.int64)
+    pack = np.stack([rays_a[:, 1], np.minimum(rays_a[:, 2], 8)], -1).astype(np.int64)
+    rng = np.random.default_rng(11)
+    op = (rng.random(n) * 0.5).astype(np.float32); dp = rng.random(n).astype(np.float32)
+    rgb = rng.random((n, 3)).astype(np.float32)
+    g_alive, g_op, g_dp, g_rgb = T(alive.copy()), T(op.copy()), T(dp.copy()), T(rgb.copy())
+    composite_test(T(sigmas), T(rgbs), T(deltas), T(ts), T(pack), g_alive, 1e-2, g_op, g_dp, g_rgb)
+    oracle_mod.composite_test(sigmas, rgbs, deltas, ts, pack, alive, 1e-2, op, dp, rgb)
+    np.testing.assert_array_equal(N(g_alive), alive)
+    assert (alive == -1).any() and (alive >= 0).any()
+    np.testing.assert_allclose(N(g_op), op, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(N(g_dp), dp, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(N(g_rgb), rgb, rtol=1e-5, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------ a11/a15
+def test_sh_and_morton_and_packbits(vn, oracle_mod):
+    from virus_nerf_b200.modules.spherical_harmonics import DirEncoder
+    from virus_nerf_b200.modules import utils as U
+    d = np.random.default_rng(12).random((1000, 3)).astype(np.float32)
+    np.testing.assert_allclose(N(DirEncoder()(T(d))), oracle_mod.sh_encode(d), rtol=1e-6, atol=1e-7)
+    r = np.arange(128, dtype=np.int32)
+    coords = np.stack(np.meshgrid(r, r, r, indexing="ij"), -1).reshape(-1, 3)
+    m = U.morton3D(T(coords))
+    np.testing.assert_array_equal(N(m), oracle_mod.morton3d(coords))
+    assert np.unique(N(m)).size == 128 ** 3                        # bijection
+    np.testing.assert_array_equal(N(U.morton3D_invert(m)), coords)
+    np.testing.assert_array_equal(N(U.morton3D_invert(m)), oracle_mod.morton3d_invert(N(m)))
+    g = np.random.default_rng(13).random(128 ** 3).astype(np.float32)
+    g[:16] = 0.5                                                   # strict > threshold
+    bf = torch.zeros(128 ** 3 // 8, dtype=torch.uint8, device=DEV)
+    U.packbits(T(g), 0.5, bf)
+    np.testing.assert_array_equal(N(bf), oracle_mod.packbits(g, 0.5))
+    assert N(bf)[0] == 0 and N(bf)[1] == 0
+
+
+# ------------------------------------------------------------------------------------ a14
+def _occ_grid(G=128, scale=0.5):
+    from virus_nerf_b200 import synthetic
+    from virus_nerf_b200.modules.occupancy_grid import OccupancyGrid
+    args = synthetic.make_args(device=DEV, scale=scale)
+    torch.manual_seed(0)
+    return OccupancyGrid(args, G, scene=None, dataset=None, fct_density=None), args
+
+
+@pytest.mark.parametrize("G", [32, 128])
+def test_occ_calc_pos_and_ray_prob(vn, oracle_mod, scene_rays, G):
+    ro, rd, _ = scene_rays
+    ro, rd = ro[:777], rd[:777] * np.float32(1.7)      # un-normalised directions are normalised inside
+    og, args = _occ_grid(G)
+    noise = np.random.default_rng(14).random((777, 32, 3)).astype(np.float32)
+    for nz in (None, noise):
+        dists, pos, idx = og._calcPos(T(ro), T(rd), add_noise=nz is not None, noise=None if nz is None else T(nz))
+        o_d, o_p, o_i = oracle_mod.occ_calc_pos(ro, rd, nz, 32, G, 0.5, og.nerf_pos_noise_every_m)
+        np.testing.assert_array_equal(N(dists), o_d)
+        np.testing.assert_array_equal(N(pos), o_p)
+        np.testing.assert_array_equal(N(idx), o_i)
+    meas = (np.random.default_rng(15).random(777) * 0.8 + 0.05).astype(np.float32)
+    po, pe = og._rayProb(T(meas), dists)
+    o_po, o_pe = oracle_mod.occ_ray_prob(meas, o_d, og.false_detection_prob_every_m, og.std_every_m)
+    np.testing.assert_allclose(N(po), o_po, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(N(pe), o_pe, rtol=1e-5, atol=1e-7)
+
+
+def test_occ_bayes_update_and_pack_bit_exact(vn, oracle_mod, scene_rays):
+    ro, rd, _ = scene_rays
+    og, args = _occ_grid(128)
+    grid0 = N(og.occ_3d_grid).copy()
+    _, _, idx = og._calcPos(T(ro), T(rd), add_noise=False)
+    n = idx.shape[0]
+    rng = np.random.default_rng(16)
+    po = (rng.random(n) * 0.9 + 0.05).astype(np.float32); pe = (rng.random(n) * 0.9 + 0.05).astype(np.float32)
+    og._updateGrid(idx, T(po), T(pe))
+    ref = grid0.copy()
+    oracle_mod.occ_update_grid(ref, N(idx), po, pe)
+    np.testing.assert_array_equal(N(og.occ_3d_grid), ref)            # duplicates: last index wins
+    assert (N(og._winner) == -1).all()                               # scratch restored
+    assert np.unique(N(idx), axis=0).shape[0] < n                    # the case did contain duplicates
+    # fixed point: po == pe leaves p unchanged (up to rounding of p*po/(p*po+(1-p)*po))
+    og.update_step = 0
+    og._decayAndPack(apply_decay=True)
+    bf_ref = oracle_mod.occ_decay_pack(ref, og.grid_decay, True, 0.5)
+    np.testing.assert_array_equal(N(og.occ_3d_grid), ref)
+    np.testing.assert_array_equal(N(og.getBitfield()), bf_ref)
+    # debug round trip of the reference (trainer_plot.py:73-86)
+    cart = og.morton2cartesian(og.bitfield2morton(og.getBitfield()))
+    assert torch.equal(cart, og.getBinaryCartesianGrid(0.5))
+
+
+def test_occ_nerf_prob(vn, oracle_mod):
+    og, args = _occ_grid(32)
+    rho = (np.random.default_rng(17).random(32 * 700) ** 3 * 40 + 1e-3).astype(np.float32)
+    og.fct_density = lambda x: T(rho)
+    for thr_max in (5.91, 1e9):
+        args.occ_grid.nerf_threshold_max = thr_max
+        po, pe = og._nerfProb(torch.zeros(rho.shape[0], 3, device=DEV))
+        o_po, o_pe = oracle_mod.occ_nerf_prob(rho, thr_max, args.occ_grid.nerf_threshold_slope)
+        np.testing.assert_allclose(N(po), o_po, rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(N(pe), o_pe, rtol=1e-5, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------ f1
+def test_adam_step(vn, oracle_mod):
+    n = 100003
+    rng = np.random.default_rng(18)
+    p = rng.normal(size=n).astype(np.float32); g = (rng.normal(size=n) * 2 ** 19).astype(np.float32)
+    m = np.zeros(n, np.float32); v = np.zeros(n, np.float32)
+    gp, gm, gv = T(p.copy()), T(m.copy()), T(v.copy())
+    found = torch.zeros(1, device=DEV); scale = torch.tensor([2.0 ** 19], device=DEV)
+    for step in (1, 2, 3):
+        vn.call("vn_grad_check", T(g), n, found)
+        vn.call("vn_adam_step", gp, T(g), gm, gv, n, 1.0, 5e-3, 0.9, 0.999, 1e-15, step, found, scale)
+        assert oracle_mod.adam_step(p, g, m, v, 2.0 ** -19, 5e-3, 0.9, 0.999, 1e-15, step) == 0
+    assert float(found) == 0.0
+    np.testing.assert_allclose(N(gp), p, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(N(gm), m, rtol=1e-5, atol=1e-9)
+    np.testing.assert_allclose(N(gv), v, rtol=1e-5, atol=1e-12)
+    g[77] = np.inf                                                    # GradScaler: skip + back off
+    before = N(gp).copy()
+    vn.call("vn_grad_check", T(g), n, found)
+    assert float(found) == 1.0
+    vn.call("vn_adam_step", gp, T(g), gm, gv, n, 1.0, 5e-3, 0.9, 0.999, 1e-15, 4, found, scale)
+    np.testing.assert_array_equal(N(gp), before)
+    tracker = torch.zeros(1, dtype=torch.int32, device=DEV)
+    vn.call("vn_scaler_update", scale, tracker, found, 2.0, 0.5, 2000)
+    assert float(scale) == 2.0 ** 18 and float(found) == 0.0
+
+
+# ------------------------------------------------------------------------------------ errors
+def test_error_conventions(vn):
+    lv = vn.hash_levels(16, 1024, 16, 2 ** 19)
+    with pytest.raises(RuntimeError, match="CUDA tensors"):
+        vn.call("vn_sh_encode", torch.zeros(4, 3), 4, torch.zeros(4, 16))
+    with pytest.raises(RuntimeError, match="contiguous"):
+        vn.call("vn_sh_encode", torch.zeros(3, 4, device=DEV).t(), 4, torch.zeros(4, 16, device=DEV))
+    with pytest.raises(RuntimeError, match="null pointer"):
+        vn.call("vn_hash_encode_fwd_f32", torch.zeros(4, 3, device=DEV), None, torch.zeros(4, 32, device=DEV), 4, lv, 0)
+    with pytest.raises(RuntimeError, match="power of two"):
+        vn.call("vn_occ_decay_pack", torch.zeros(100 ** 3, device=DEV), 100, 1.0, 0, 0.5,
+                torch.zeros(100 ** 3 // 8, dtype=torch.uint8, device=DEV))
+    assert vn.launch_count() > 0
+
+
+# ------------------------------------------------------------------------------------ full-size properties
+def test_full_size_properties(vn):
+    """BASELINE sizes (T=2^22 table, 2^20 points): size-independent properties instead of the
+    oracle -- linearity of the encoder in the table, adjointness <dout, enc(table)> ==
+    <scatter(dout), table>, and agreement of the three level-grouping variants."""
+    lv = vn.hash_levels(16, 1024, 16, 2 ** 22)
+    S = 1 << 20
+    g = torch.Generator(device=DEV).manual_seed(0)
+    xyz = torch.rand(S, 3, device=DEV, generator=g)
+    t1 = torch.rand(2 * lv.total_entries, device=DEV, generator=g)
+    t2 = torch.rand(2 * lv.total_entries, device=DEV, generator=g)
+    o1 = torch.empty(S, 32, device=DEV); o2 = torch.empty(S, 32, device=DEV); o12 = torch.empty(S, 32, device=DEV)
+    vn.call("vn_hash_encode_fwd_f32", xyz, t1, o1, S, lv, 0)
+    vn.call("vn_hash_encode_fwd_f32", xyz, t2, o2, S, lv, 16)
+    vn.call("vn_hash_encode_fwd_f32", xyz, t1 + t2, o12, S, lv, 32)
+    torch.testing.assert_close(o12, o1 + o2, rtol=1e-5, atol=1e-5)
+    dout = torch.randn(S, 32, device=DEV, generator=g)
+    grad = torch.zeros_like(t1)
+    vn.call("vn_hash_encode_bwd_f32", xyz, dout, grad, S, lv, 0)
+    lhs = (dout.double() * o1.double()).sum()
+    rhs = (grad.double() * t1.double()).sum()
+    assert abs(float(lhs - rhs)) <= 1e-5 * abs(float(lhs)) + 1e-2
+
+
+def test_march_properties_full_batch(vn, scene_rays):
+    """2^18 rays: counts sum to the total, per-ray ts strictly increasing, every emitted sample
+    lies in an occupied cell"""
+    from virus_nerf_b200 import synthetic
+    from virus_nerf_b200.modules.intersection import ray_aabb_intersection
+    from virus_nerf_b200.modules.ray_march import raymarching_train
+    ds = synthetic.SyntheticDataset(pool_size=1 << 18, n_images=16, device=DEV)
+    ro, rd = ds.pool["rays_o"], ds.pool["rays_d"]
+    bf = T(scene_rays[2]["carved"])
+    hits = ray_aabb_intersection(ro, rd, 0.5)
+    rays_a, xyzs, dirs, deltas, ts, total = raymarching_train(ro, rd, hits, bf, 1, 0.5, 0.0, 128, 1024)
+    ra = rays_a.long()
+    assert int(ra[:, 2].sum()) == int(total) == xyzs.shape[0]
+    assert torch.equal(ra[:, 1], torch.cumsum(ra[:, 2], 0) - ra[:, 2])
+    seg = torch.repeat_interleave(torch.arange(ra.shape[0], device=DEV), ra[:, 2])
+    same = seg[1:] == seg[:-1]
+    assert bool((ts[1:][same] > ts[:-1][same]).all())
+    cell = torch.clamp((0.5 * (xyzs / 0.5 + 1) * 128), 0, 127).to(torch.int32)
+    from virus_nerf_b200.modules.utils import morton3D
+    m = morton3D(cell).long()
+    occ = (bf[m // 8].long() >> (m % 8)) & 1
+    assert bool(occ.all())

@@ -1,0 +1,219 @@
+"""ctypes binding of libvirusnerf_sm100.so (C ABI declared in include/virusnerf.h).
+
+PyTorch is plumbing here: it owns device memory and streams; every computation on the hot
+path is a kernel of the shared library.  Loading fails loudly when the library is missing --
+there is no fallback implementation.
+"""
+import ctypes
+import os
+import subprocess
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "lib", "libvirusnerf_sm100.so")
+CSRC = os.path.join(_PKG, "csrc")
+
+VN_MAX_LEVELS = 32
+VN_HASH_NO_WARP_AGG = 1
+VN_HASH_LEVEL_GROUPS_1 = 16
+VN_HASH_LEVEL_GROUPS_4 = 32
+
+
+class HashLevels(ctypes.Structure):
+    """mirror of vn_hash_levels_t"""
+    _fields_ = [
+        ("levels", ctypes.c_int32),
+        ("begin_fast_hash_level", ctypes.c_int32),
+        ("offsets", ctypes.c_int32 * VN_MAX_LEVELS),
+        ("sizes", ctypes.c_int32 * VN_MAX_LEVELS),
+        ("scales", ctypes.c_float * VN_MAX_LEVELS),
+        ("res", ctypes.c_uint32 * VN_MAX_LEVELS),
+        ("total_entries", ctypes.c_int64),
+        ("log_b", ctypes.c_double),
+    ]
+
+
+# spec characters: p device pointer (tensor / None), l int64, i int, f float, d double,
+# h host pointer to a ctypes struct, s stream (filled in automatically)
+_SPECS = {
+    "vn_hash_levels_init": "ddilh",
+    "vn_hash_encode_fwd_f32": "ppplhis",
+    "vn_hash_encode_bwd_f32": "ppplhis",
+    "vn_hash_encode_fwd_f16": "ppplhis",
+    "vn_hash_encode_bwd_f16": "ppplhis",
+    "vn_f32_to_f16": "ppls",
+    "vn_hash_indices": "plhpps",
+    "vn_ray_aabb": "ppflps",
+    "vn_march_train_count": "pppppliiffipppps",
+    "vn_march_train_write": "ppppp" "liiff" "pl" "pppp" "s",
+    "vn_march_test": "pppp" "lp" "iiffi" "ppppp" "s",
+    "vn_march_test_compact": "plippppppppps",
+    "vn_composite_train_fwd": "ppppp" "llf" "ppppp" "s",
+    "vn_composite_train_bwd": "ppppp" "llf" "pppp" "pp" "s",
+    "vn_composite_test": "pppppplfppps",
+    "vn_sh_encode": "plps",
+    "vn_morton3d": "plps",
+    "vn_morton3d_invert": "plps",
+    "vn_packbits": "plfps",
+    "vn_occ_calc_pos_prob": "pppp" "liiif" "ffff" "ppppp" "s",
+    "vn_occ_ray_prob": "pp" "lii" "fff" "pp" "s",
+    "vn_occ_nerf_prob": "pldfppps",
+    "vn_occ_bayes_update": "piplppp" "ps",
+    "vn_occ_decay_pack": "pififps",
+    "vn_grad_check": "plps",
+    "vn_adam_step": "ppppl" "fffff" "ipps",
+    "vn_scaler_update": "pppffis",
+}
+
+_CT = {"p": ctypes.c_void_p, "l": ctypes.c_int64, "i": ctypes.c_int, "f": ctypes.c_float,
+       "d": ctypes.c_double, "h": ctypes.c_void_p, "s": ctypes.c_void_p}
+
+_lib = None
+
+
+def build(verbose=False):
+    """compile csrc/*.cu for sm_100a into lib/libvirusnerf_sm100.so (nvcc cross-compiles
+    without a GPU)"""
+    out = None if verbose else subprocess.DEVNULL
+    subprocess.check_call(["make", "-C", CSRC, "-j", str(os.cpu_count() or 4)], stdout=out)
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                f"(or `make -C {CSRC}`).  virus-nerf_b200 has no CPU / PyTorch fallback.")
+        L = ctypes.CDLL(LIB_PATH)
+        L.vn_last_error.restype = ctypes.c_char_p
+        L.vn_abi_version.restype = ctypes.c_int
+        L.vn_march_scan_tmp_ints.restype = ctypes.c_int64
+        L.vn_march_scan_tmp_ints.argtypes = [ctypes.c_int64]
+        L.vn_launch_count.restype = ctypes.c_int64
+        for name, spec in _SPECS.items():
+            fn = getattr(L, name)
+            fn.restype = ctypes.c_int
+            fn.argtypes = [_CT[c] for c in spec]
+        _lib = L
+    return _lib
+
+
+def last_error():
+    return lib().vn_last_error().decode("utf-8", "replace")
+
+
+def _ptr(t, name, pos):
+    if t is None:
+        return None
+    if isinstance(t, int):
+        return ctypes.c_void_p(t)
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: argument {pos} must be a CUDA tensor or None, got {type(t)}")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: argument {pos} is on {t.device}; virus-nerf_b200 kernels need CUDA tensors "
+                           "(there is no CPU fallback)")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name}: argument {pos} must be contiguous")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+_profile = None   # {name: [(start_event, end_event, size), ...]} while profiling
+
+
+def profile_start(names):
+    """time the given entry points with CUDA events recorded on the launching stream"""
+    global _profile
+    _profile = {n: [] for n in names}
+
+
+def profile_stop():
+    """-> {name: [(milliseconds, size), ...]}; synchronises"""
+    global _profile
+    prof, _profile = _profile, None
+    torch.cuda.synchronize()
+    return {n: [(e0.elapsed_time(e1), sz) for e0, e1, sz in calls] for n, calls in (prof or {}).items()}
+
+
+def call(name, *args):
+    """Invoke one C-ABI entry point on the current CUDA stream; raises RuntimeError with
+    vn_last_error() on a non-zero return code."""
+    L = lib()
+    spec = _SPECS[name]
+    conv = []
+    it = iter(args)
+    dev = None
+    for pos, c in enumerate(spec):
+        if c == "s":
+            conv.append(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+            continue
+        try:
+            a = next(it)
+        except StopIteration:
+            raise TypeError(f"{name}: expected {len(spec.replace('s', ''))} arguments, got {len(args)}")
+        if c == "p":
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                if dev is None:
+                    dev = a.device
+                elif a.device != dev:
+                    raise RuntimeError(f"{name}: tensors on different devices ({dev} vs {a.device})")
+            conv.append(_ptr(a, name, pos))
+        elif c == "h":
+            conv.append(ctypes.cast(ctypes.pointer(a), ctypes.c_void_p) if a is not None else None)
+        elif c == "l":
+            conv.append(ctypes.c_int64(int(a)))
+        elif c == "i":
+            conv.append(ctypes.c_int(int(a)))
+        elif c == "f":
+            conv.append(ctypes.c_float(float(a)))
+        elif c == "d":
+            conv.append(ctypes.c_double(float(a)))
+    if len(list(it)) != 0:
+        raise TypeError(f"{name}: too many arguments")
+    fn = getattr(L, name)
+    if _profile is not None and name in _profile:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*conv)
+        e1.record()
+        size = next((int(a) for a, c in zip(args, spec.replace("s", "")) if c == "l"), 0)
+        _profile[name].append((e0, e1, size))
+        if rc != 0:
+            raise RuntimeError(f"{name} failed (code {rc}): {last_error()}")
+        return
+    if dev is not None and dev.index is not None and dev.index != torch.cuda.current_device():
+        with torch.cuda.device(dev):
+            conv = [ctypes.c_void_p(torch.cuda.current_stream().cuda_stream) if c == "s" else v
+                    for c, v in zip(spec, conv)]
+            rc = fn(*conv)
+    else:
+        rc = fn(*conv)
+    if rc != 0:
+        raise RuntimeError(f"{name} failed (code {rc}): {last_error()}")
+
+
+def launch_count():
+    """kernels launched by the library so far (for bench.py's gpu_launches)"""
+    return int(lib().vn_launch_count())
+
+
+def scan_tmp_ints(n):
+    return int(lib().vn_march_scan_tmp_ints(ctypes.c_int64(int(n))))
+
+
+def hash_levels(base_res, max_res, levels, max_params):
+    """a1: host geometry (hash_encoder.py:183-208)"""
+    lv = HashLevels()
+    L = lib()
+    rc = L.vn_hash_levels_init(ctypes.c_double(base_res), ctypes.c_double(max_res), ctypes.c_int(int(levels)),
+                               ctypes.c_int64(int(max_params)), ctypes.cast(ctypes.pointer(lv), ctypes.c_void_p))
+    if rc != 0:
+        raise RuntimeError(f"vn_hash_levels_init failed (code {rc}): {last_error()}")
+    return lv
+
+
+def exported_symbols():
+    """names declared in include/virusnerf.h (used by the CPU-side ABI test)"""
+    return ["vn_last_error", "vn_abi_version", "vn_launch_count", "vn_device_info", "vn_march_scan_tmp_ints"] + list(_SPECS)

@@ -1,0 +1,100 @@
+// common.cuh -- shared host/device helpers for libvirusnerf_sm100.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/virusnerf.h"
+
+#define VN_API extern "C" __attribute__((visibility("default")))
+
+// ---- error plumbing (thread-local message, negative return codes, no exceptions) ----
+void vn_set_error(const char* fmt, ...);
+
+#define VN_REQUIRE(cond, ...)                       \
+    do {                                            \
+        if (!(cond)) {                              \
+            vn_set_error(__VA_ARGS__);              \
+            return VN_EINVAL;                       \
+        }                                           \
+    } while (0)
+
+extern unsigned long long g_vn_launches;   // kernels launched by this library (api.cu)
+
+#define VN_CHECK_LAUNCH(name)                                                        \
+    do {                                                                             \
+        ++g_vn_launches;                                                             \
+        cudaError_t e__ = cudaGetLastError();                                        \
+        if (e__ != cudaSuccess) {                                                    \
+            vn_set_error("%s: CUDA error %d (%s)", name, (int)e__, cudaGetErrorString(e__)); \
+            return VN_ELAUNCH;                                                       \
+        }                                                                            \
+    } while (0)
+
+#define VN_CUDA(call)                                                                \
+    do {                                                                             \
+        cudaError_t e__ = (call);                                                    \
+        if (e__ != cudaSuccess) {                                                    \
+            vn_set_error("%s: CUDA error %d (%s)", #call, (int)e__, cudaGetErrorString(e__)); \
+            return VN_ELAUNCH;                                                       \
+        }                                                                            \
+    } while (0)
+
+static inline bool vn_aligned(const void* p, size_t a) { return ((uintptr_t)p % a) == 0; }
+static inline unsigned vn_blocks(int64_t n, int per_block) { return (unsigned)((n + per_block - 1) / per_block); }
+int vn_sm_count();
+
+// ---- constants, modules/utils.py:12-16 ----
+#define VN_NEAR_DISTANCE 0.01f
+#define VN_SQRT3_MAX_SAMPLES ((float)(1.7320508075688772 / 1024.0))
+#define VN_SQRT3_2 ((float)(1.7320508075688772 * 2.0))
+
+// ---- device helpers.  Index-critical float expressions use __fmul_rn/__fadd_rn so nvcc
+// cannot contract them into FMAs: the oracle is defined without contraction. ----
+__device__ __forceinline__ float vn_mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float vn_add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float vn_sub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float vn_div(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float vn_clamp(float x, float lo, float hi) { return fminf(hi, fmaxf(lo, x)); }
+
+// modules/utils.py:54-57
+__device__ __forceinline__ float vn_calc_dt(float t, float esf, float dt_max) {
+    return vn_clamp(vn_mul(t, esf), VN_SQRT3_MAX_SAMPLES, dt_max);
+}
+// modules/utils.py:60-75
+__device__ __forceinline__ int vn_frexp_bit(float x) {
+    int exponent = 0;
+    if (x != 0.0f) {
+        uint32_t bits = __float_as_uint(x);
+        exponent = (int)((bits & 0x7f800000u) >> 23) - 127;
+        // frac = 1.mantissa in [1,2): "frac > 1" <=> mantissa != 0 ("frac < 0.5" never holds)
+        if ((bits & 0x7fffffu) != 0u) exponent += 1;
+    }
+    return exponent;
+}
+// modules/utils.py:95-117
+__device__ __forceinline__ uint32_t vn_expand_bits(uint32_t v) {
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+__device__ __forceinline__ uint32_t vn_morton3D(uint32_t x, uint32_t y, uint32_t z) {
+    return vn_expand_bits(x) | (vn_expand_bits(y) << 1) | (vn_expand_bits(z) << 2);
+}
+__device__ __forceinline__ uint32_t vn_morton3D_invert(uint32_t x) {
+    x = x & 0x49249249u;
+    x = (x | (x >> 2)) & 0xc30c30c3u;
+    x = (x | (x >> 4)) & 0x0f00f00fu;
+    x = (x | (x >> 8)) & 0xff0000ffu;
+    x = (x | (x >> 16)) & 0x0000ffffu;
+    return x;
+}
+// float -> u32, saturating (negative / NaN -> 0): PTX cvt.rzi.u32.f32 semantics
+__device__ __forceinline__ uint32_t vn_f2u(float x) { return __float2uint_rz(x); }
+
+__device__ __forceinline__ void vn_red_add_v2(float* addr, float a, float b) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}

@@ -1,0 +1,418 @@
+// hash_encoder.cu -- multi-resolution hash-grid encoder, forward gather + backward scatter.
+// Replaces the Taichi kernels of modules/hash_encoder.py:89-143 (+ autodiff, :264-277) and
+// modules/hash_encoder_half.py:112-213.
+//
+// Mapping: one thread = one point x LPT consecutive levels; lanes of a warp are CONSECUTIVE
+// points, i.e. consecutive samples along a ray, so at coarse levels all lanes hit the same 8
+// corners (one L1 wavefront per load) and at fine levels the level slab is L2 resident.
+// grid.y walks level groups slowest, so with LPT < levels the launch is level-major and one
+// group's slab (<= 32 MB at T=2^22) stays in the 126 MB L2 while all points stream past it.
+// Per-level constants are precomputed on the host (vn_hash_levels_init) and arrive in the
+// kernel parameter bank.
+#include "common.cuh"
+#include <math.h>
+#include <string.h>
+
+struct HashParams {
+    int levels;
+    int begin_fast;
+    int offsets[VN_MAX_LEVELS];
+    uint32_t sizes[VN_MAX_LEVELS];
+    uint32_t pow2mask[VN_MAX_LEVELS];  // size-1 when size is a power of two, else 0
+    float scales[VN_MAX_LEVELS];
+    uint32_t res[VN_MAX_LEVELS];
+};
+
+static int make_params(const vn_hash_levels_t* lv, HashParams& P) {
+    VN_REQUIRE(lv != nullptr, "hash levels: null");
+    VN_REQUIRE(lv->levels >= 1 && lv->levels <= VN_MAX_LEVELS, "hash levels: levels=%d out of [1,%d]",
+               lv->levels, VN_MAX_LEVELS);
+    P.levels = lv->levels;
+    P.begin_fast = lv->begin_fast_hash_level;
+    for (int l = 0; l < lv->levels; ++l) {
+        VN_REQUIRE(lv->sizes[l] > 0, "hash levels: size[%d] <= 0", l);
+        P.offsets[l] = lv->offsets[l];
+        P.sizes[l] = (uint32_t)lv->sizes[l];
+        uint32_t s = (uint32_t)lv->sizes[l];
+        P.pow2mask[l] = ((s & (s - 1)) == 0) ? (s - 1) : 0u;
+        P.scales[l] = lv->scales[l];
+        P.res[l] = lv->res[l];
+    }
+    return VN_OK;
+}
+
+// a1. host geometry: hash_encoder.py:183-208, utils.py:19-42 (float64) and the kernel-side
+// f32 constants of hash_encoder.py:73-80.
+VN_API int vn_hash_levels_init(double base_res, double max_res, int levels, int64_t max_params,
+                               vn_hash_levels_t* out) {
+    VN_REQUIRE(out != nullptr, "vn_hash_levels_init: null output");
+    VN_REQUIRE(levels >= 2 && levels <= VN_MAX_LEVELS, "vn_hash_levels_init: levels=%d out of [2,%d]", levels,
+               VN_MAX_LEVELS);
+    VN_REQUIRE(base_res > 0 && max_res >= base_res && max_params > 0, "vn_hash_levels_init: bad resolution/params");
+    memset(out, 0, sizeof(*out));
+    double log_b = log(max_res / base_res) / (double)(levels - 1);
+    out->levels = levels;
+    out->log_b = log_b;
+    int64_t offset = 0;
+    int begin_fast = levels;
+    for (int i = 0; i < levels; ++i) {
+        double r = ceil(base_res * exp((double)i * log_b) - 1.0) + 1.0;
+        double full = r * r * r;
+        int64_t aligned = (int64_t)((full + 7.0) / 8.0) * 8;
+        int64_t size_i = aligned < max_params ? aligned : max_params;
+        VN_REQUIRE(offset + size_i < (int64_t)1 << 30, "vn_hash_levels_init: table too large for i32 offsets");
+        out->offsets[i] = (int32_t)offset;
+        out->sizes[i] = (int32_t)size_i;
+        if (full > (double)size_i && begin_fast == levels) begin_fast = i;
+        offset += size_i;
+        float sc = (float)base_res * expf((float)i * (float)log_b) - 1.0f;
+        out->scales[i] = sc;
+        out->res[i] = (uint32_t)ceilf(sc) + 1u;
+    }
+    out->begin_fast_hash_level = begin_fast;
+    out->total_entries = offset;
+    return VN_OK;
+}
+
+// ---- per-(point, level) geometry shared by fwd / bwd / indices --------------------------
+struct Cell {
+    uint32_t g[3];
+    float f[3];
+};
+
+__device__ __forceinline__ Cell cell_of(float x, float y, float z, float scale) {
+    Cell c;
+    float p0 = vn_add(vn_mul(x, scale), 0.5f);  // hash_encoder.py:106, not contracted
+    float p1 = vn_add(vn_mul(y, scale), 0.5f);
+    float p2 = vn_add(vn_mul(z, scale), 0.5f);
+    float f0 = floorf(p0), f1 = floorf(p1), f2 = floorf(p2);
+    c.g[0] = vn_f2u(f0); c.g[1] = vn_f2u(f1); c.g[2] = vn_f2u(f2);   // :107
+    c.f[0] = vn_sub(p0, (float)c.g[0]);                                // :108
+    c.f[1] = vn_sub(p1, (float)c.g[1]);
+    c.f[2] = vn_sub(p2, (float)c.g[2]);
+    return c;
+}
+
+template <bool DENSE>
+__device__ __forceinline__ uint32_t corner_index(const Cell& c, int k, uint32_t res, uint32_t size, uint32_t mask) {
+    uint32_t c0 = c.g[0] + (k & 1), c1 = c.g[1] + ((k >> 1) & 1), c2 = c.g[2] + ((k >> 2) & 1);
+    uint32_t h;
+    if (DENSE) {
+        h = c0 + c1 * res + c2 * (res * res);      // under_hash, :53-60 (wrapping u32)
+        if (h >= size) h %= size;                  // only reachable on the x/y/z == 1 faces
+    } else {
+        h = c0 ^ (c1 * 2654435761u) ^ (c2 * 805459861u);  // fast_hash, :43-51
+        h = mask ? (h & mask) : (h % size);
+    }
+    return h;
+}
+
+__device__ __forceinline__ float corner_weight(const Cell& c, int k) {
+    // w = ((1 * wx) * wy) * wz in source order, :118-125
+    float w = (k & 1) ? c.f[0] : vn_sub(1.0f, c.f[0]);
+    w = vn_mul(w, (k & 2) ? c.f[1] : vn_sub(1.0f, c.f[1]));
+    w = vn_mul(w, (k & 4) ? c.f[2] : vn_sub(1.0f, c.f[2]));
+    return w;
+}
+
+// ---- table element access ---------------------------------------------------------------
+__device__ __forceinline__ float2 load_entry(const float2* t, uint32_t i) { return __ldg(t + i); }
+__device__ __forceinline__ float2 load_entry(const __half2* t, uint32_t i) {
+    return __half22float2(__ldg(t + i));
+}
+
+template <typename TT, bool DENSE>
+__device__ __forceinline__ void level_gather(const TT* __restrict__ tbl, const Cell& c, uint32_t res, uint32_t size,
+                                             uint32_t mask, float& a0, float& a1) {
+    float2 v[8];
+    float w[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        v[k] = load_entry(tbl, corner_index<DENSE>(c, k, res, size, mask));
+        w[k] = corner_weight(c, k);
+    }
+    if (sizeof(TT) == sizeof(float2)) {
+        a0 = 0.0f; a1 = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { a0 = fmaf(w[k], v[k].x, a0); a1 = fmaf(w[k], v[k].y, a1); }
+    } else {
+        // hash_encoder_half.py:159: local_features(f16) += f16(w * table)
+        __half h0 = __float2half_rn(0.0f), h1 = __float2half_rn(0.0f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            h0 = __hadd(h0, __float2half_rn(vn_mul(w[k], v[k].x)));
+            h1 = __hadd(h1, __float2half_rn(vn_mul(w[k], v[k].y)));
+        }
+        a0 = __half2float(h0); a1 = __half2float(h1);
+    }
+}
+
+// ---- forward ----------------------------------------------------------------------------
+template <typename TT, typename OT, int LPT>
+__global__ void __launch_bounds__(256) hash_fwd_kernel(const float* __restrict__ xyz, const TT* __restrict__ table,
+                                                       OT* __restrict__ out, int64_t S,
+                                                       const __grid_constant__ HashParams P) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S) return;
+    const int level0 = blockIdx.y * LPT;
+    const float x = __ldg(xyz + 3 * i), y = __ldg(xyz + 3 * i + 1), z = __ldg(xyz + 3 * i + 2);
+    float acc[2 * LPT];
+#pragma unroll
+    for (int l = 0; l < LPT; ++l) {
+        const int level = level0 + l;
+        if (level < P.levels) {
+            const Cell c = cell_of(x, y, z, P.scales[level]);
+            const TT* tbl = table + P.offsets[level];
+            if (level < P.begin_fast)
+                level_gather<TT, true>(tbl, c, P.res[level], P.sizes[level], 0u, acc[2 * l], acc[2 * l + 1]);
+            else
+                level_gather<TT, false>(tbl, c, P.res[level], P.sizes[level], P.pow2mask[level], acc[2 * l],
+                                        acc[2 * l + 1]);
+        } else {
+            acc[2 * l] = 0.0f; acc[2 * l + 1] = 0.0f;
+        }
+    }
+    const int W = 2 * P.levels;
+    if (sizeof(OT) == 4) {
+        float* o = (float*)out + i * W + 2 * level0;
+        if (LPT % 2 == 0 && (W % 4) == 0 && level0 + LPT <= P.levels) {
+#pragma unroll
+            for (int q = 0; q < LPT / 2; ++q)
+                ((float4*)o)[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+        } else {
+#pragma unroll
+            for (int l = 0; l < LPT; ++l)
+                if (level0 + l < P.levels) ((float2*)o)[l] = make_float2(acc[2 * l], acc[2 * l + 1]);
+        }
+    } else {
+        __half2* o = (__half2*)out + i * P.levels + level0;
+#pragma unroll
+        for (int l = 0; l < LPT; ++l)
+            if (level0 + l < P.levels) o[l] = __floats2half2_rn(acc[2 * l], acc[2 * l + 1]);
+    }
+}
+
+// ---- backward ---------------------------------------------------------------------------
+// Warp pre-reduction: lanes are consecutive samples of a ray, so lanes in the same grid cell
+// form contiguous runs.  Head flags come from cell equality with the previous lane; a
+// segmented shuffle scan leaves each run's sum in its last lane, which issues the
+// red.global.add.v2.f32.  Runs are detected per level; when (nearly) every lane is its own
+// run the scan is skipped.
+template <typename DT, bool DENSE, bool AGG, bool ZERO_SKIP>
+__device__ __forceinline__ void level_scatter(float* __restrict__ grad_level, const Cell& c, uint32_t res,
+                                              uint32_t size, uint32_t mask, float d0, float d1, bool valid) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    float v0[8], v1[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        float w = corner_weight(c, k);
+        v0[k] = valid ? vn_mul(w, d0) : 0.0f;
+        v1[k] = valid ? vn_mul(w, d1) : 0.0f;
+    }
+    bool leader = valid;
+    if (AGG) {
+        uint32_t p0 = __shfl_up_sync(full, c.g[0], 1), p1 = __shfl_up_sync(full, c.g[1], 1),
+                 p2 = __shfl_up_sync(full, c.g[2], 1);
+        int pv = __shfl_up_sync(full, (int)valid, 1);
+        bool head = (lane == 0) || !valid || !pv || p0 != c.g[0] || p1 != c.g[1] || p2 != c.g[2];
+        unsigned heads = __ballot_sync(full, head);
+        if (__popc(heads) <= 20) {  // warp-uniform: enough sharing to pay for the scan
+            int seg_start = 31 - __clz(heads & (full >> (31 - lane)));
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                bool take = (lane - off) >= seg_start;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    float a = __shfl_up_sync(full, v0[k], off), b = __shfl_up_sync(full, v1[k], off);
+                    if (take) { v0[k] += a; v1[k] += b; }
+                }
+            }
+            bool tail = (lane == 31) || ((heads >> (lane + 1)) & 1u);
+            leader = valid && tail;
+        }
+    }
+    if (leader) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (ZERO_SKIP && v0[k] == 0.0f && v1[k] == 0.0f) continue;  // hash_encoder_half.py:212
+            uint32_t idx = corner_index<DENSE>(c, k, res, size, mask);
+            vn_red_add_v2(grad_level + 2 * (size_t)idx, v0[k], v1[k]);
+        }
+    }
+}
+
+template <typename DT, int LPT, bool AGG, bool ZERO_SKIP>
+__global__ void __launch_bounds__(256) hash_bwd_kernel(const float* __restrict__ xyz, const DT* __restrict__ dout,
+                                                       float* __restrict__ grad, int64_t S,
+                                                       const __grid_constant__ HashParams P) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < S;
+    const int level0 = blockIdx.y * LPT;
+    float x = 0.f, y = 0.f, z = 0.f;
+    float d[2 * LPT];
+#pragma unroll
+    for (int l = 0; l < 2 * LPT; ++l) d[l] = 0.0f;
+    if (valid) {
+        x = __ldg(xyz + 3 * i); y = __ldg(xyz + 3 * i + 1); z = __ldg(xyz + 3 * i + 2);
+        const int W = 2 * P.levels;
+        if (sizeof(DT) == 4) {
+            const float* dp = (const float*)dout + i * W + 2 * level0;
+            if (LPT % 2 == 0 && (W % 4) == 0 && level0 + LPT <= P.levels) {
+#pragma unroll
+                for (int q = 0; q < LPT / 2; ++q) {
+                    float4 t = __ldg((const float4*)dp + q);
+                    d[4 * q] = t.x; d[4 * q + 1] = t.y; d[4 * q + 2] = t.z; d[4 * q + 3] = t.w;
+                }
+            } else {
+#pragma unroll
+                for (int l = 0; l < LPT; ++l)
+                    if (level0 + l < P.levels) { float2 t = __ldg((const float2*)dp + l); d[2 * l] = t.x; d[2 * l + 1] = t.y; }
+            }
+        } else {
+            const __half2* dp = (const __half2*)dout + i * P.levels + level0;
+#pragma unroll
+            for (int l = 0; l < LPT; ++l)
+                if (level0 + l < P.levels) { float2 t = __half22float2(__ldg(dp + l)); d[2 * l] = t.x; d[2 * l + 1] = t.y; }
+        }
+    }
+#pragma unroll
+    for (int l = 0; l < LPT; ++l) {
+        const int level = level0 + l;
+        if (level >= P.levels) break;   // warp-uniform
+        bool v = valid;
+        if (ZERO_SKIP) v = v && !(d[2 * l] == 0.0f && d[2 * l + 1] == 0.0f);  // hash_encoder_half.py:210
+        const Cell c = cell_of(x, y, z, P.scales[level]);
+        float* gl = grad + 2 * (size_t)P.offsets[level];
+        if (level < P.begin_fast)
+            level_scatter<DT, true, AGG, ZERO_SKIP>(gl, c, P.res[level], P.sizes[level], 0u, d[2 * l], d[2 * l + 1], v);
+        else
+            level_scatter<DT, false, AGG, ZERO_SKIP>(gl, c, P.res[level], P.sizes[level], P.pow2mask[level], d[2 * l],
+                                                     d[2 * l + 1], v);
+    }
+}
+
+// ---- KAT kernel -------------------------------------------------------------------------
+__global__ void hash_indices_kernel(const float* __restrict__ xyz, int64_t S, int32_t* __restrict__ idx,
+                                    float* __restrict__ w, const __grid_constant__ HashParams P) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= S * P.levels) return;
+    const int64_t i = t / P.levels;
+    const int level = (int)(t % P.levels);
+    const Cell c = cell_of(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], P.scales[level]);
+    for (int k = 0; k < 8; ++k) {
+        uint32_t h = (level < P.begin_fast) ? corner_index<true>(c, k, P.res[level], P.sizes[level], 0u)
+                                            : corner_index<false>(c, k, P.res[level], P.sizes[level], P.pow2mask[level]);
+        idx[t * 8 + k] = (int32_t)h;
+        if (w) w[t * 8 + k] = corner_weight(c, k);
+    }
+}
+
+__global__ void f32_to_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, int64_t n) {
+    int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < n) {
+        float4 v = __ldg((const float4*)(src + i));
+        ((__half2*)(dst + i))[0] = __floats2half2_rn(v.x, v.y);
+        ((__half2*)(dst + i))[1] = __floats2half2_rn(v.z, v.w);
+    } else {
+        for (; i < n; ++i) dst[i] = __float2half_rn(src[i]);
+    }
+}
+
+// ---- launchers --------------------------------------------------------------------------
+static int pick_lpt(int flags, int levels) {
+    if (flags & VN_HASH_LEVEL_GROUPS_1) return 1;
+    if (flags & VN_HASH_LEVEL_GROUPS_4) return 4;
+    (void)levels;
+    return 2;
+}
+
+template <typename TT, typename OT>
+static int launch_fwd(const float* xyz, const TT* table, OT* out, int64_t S, const vn_hash_levels_t* lv, int flags,
+                      cudaStream_t st) {
+    HashParams P;
+    int rc = make_params(lv, P);
+    if (rc) return rc;
+    if (S == 0) return VN_OK;
+    const int lpt = pick_lpt(flags, P.levels);
+    dim3 block(256), grid(vn_blocks(S, 256), (P.levels + lpt - 1) / lpt);
+    switch (lpt) {
+        case 1: hash_fwd_kernel<TT, OT, 1><<<grid, block, 0, st>>>(xyz, table, out, S, P); break;
+        case 4: hash_fwd_kernel<TT, OT, 4><<<grid, block, 0, st>>>(xyz, table, out, S, P); break;
+        default: hash_fwd_kernel<TT, OT, 2><<<grid, block, 0, st>>>(xyz, table, out, S, P); break;
+    }
+    VN_CHECK_LAUNCH("hash_fwd_kernel");
+    return VN_OK;
+}
+
+template <typename DT, bool ZERO_SKIP>
+static int launch_bwd(const float* xyz, const DT* dout, float* grad, int64_t S, const vn_hash_levels_t* lv, int flags,
+                      cudaStream_t st) {
+    HashParams P;
+    int rc = make_params(lv, P);
+    if (rc) return rc;
+    if (S == 0) return VN_OK;
+    const int lpt = pick_lpt(flags, P.levels);
+    const bool agg = !(flags & VN_HASH_NO_WARP_AGG);
+    dim3 block(256), grid(vn_blocks(S, 256), (P.levels + lpt - 1) / lpt);
+#define VN_BWD(L, A) hash_bwd_kernel<DT, L, A, ZERO_SKIP><<<grid, block, 0, st>>>(xyz, dout, grad, S, P)
+    if (agg) { switch (lpt) { case 1: VN_BWD(1, true); break; case 4: VN_BWD(4, true); break; default: VN_BWD(2, true); } }
+    else     { switch (lpt) { case 1: VN_BWD(1, false); break; case 4: VN_BWD(4, false); break; default: VN_BWD(2, false); } }
+#undef VN_BWD
+    VN_CHECK_LAUNCH("hash_bwd_kernel");
+    return VN_OK;
+}
+
+#define VN_HASH_ARGCHECK(name, a, b, c)                                                           \
+    VN_REQUIRE(S >= 0, name ": S < 0");                                                           \
+    VN_REQUIRE(S == 0 || ((a) && (b) && (c)), name ": null pointer");                             \
+    VN_REQUIRE(vn_aligned(a, 4) && vn_aligned(b, 8) && vn_aligned(c, 16), name ": misaligned buffer")
+
+VN_API int vn_hash_encode_fwd_f32(const float* xyz, const float* table, float* out, int64_t S,
+                                  const vn_hash_levels_t* lv, int flags, void* stream) {
+    VN_HASH_ARGCHECK("vn_hash_encode_fwd_f32", xyz, table, out);
+    return launch_fwd<float2, float>(xyz, (const float2*)table, out, S, lv, flags, (cudaStream_t)stream);
+}
+
+VN_API int vn_hash_encode_bwd_f32(const float* xyz, const float* dout, float* grad, int64_t S,
+                                  const vn_hash_levels_t* lv, int flags, void* stream) {
+    VN_HASH_ARGCHECK("vn_hash_encode_bwd_f32", xyz, grad, dout);
+    return launch_bwd<float, false>(xyz, dout, grad, S, lv, flags, (cudaStream_t)stream);
+}
+
+VN_API int vn_hash_encode_fwd_f16(const float* xyz, const void* table_h, void* out_h, int64_t S,
+                                  const vn_hash_levels_t* lv, int flags, void* stream) {
+    VN_REQUIRE(S >= 0, "vn_hash_encode_fwd_f16: S < 0");
+    VN_REQUIRE(S == 0 || (xyz && table_h && out_h), "vn_hash_encode_fwd_f16: null pointer");
+    VN_REQUIRE(vn_aligned(table_h, 4) && vn_aligned(out_h, 4), "vn_hash_encode_fwd_f16: misaligned buffer");
+    return launch_fwd<__half2, __half>(xyz, (const __half2*)table_h, (__half*)out_h, S, lv, flags, (cudaStream_t)stream);
+}
+
+VN_API int vn_hash_encode_bwd_f16(const float* xyz, const void* dout_h, float* grad, int64_t S,
+                                  const vn_hash_levels_t* lv, int flags, void* stream) {
+    VN_REQUIRE(S >= 0, "vn_hash_encode_bwd_f16: S < 0");
+    VN_REQUIRE(S == 0 || (xyz && dout_h && grad), "vn_hash_encode_bwd_f16: null pointer");
+    VN_REQUIRE(vn_aligned(dout_h, 4) && vn_aligned(grad, 8), "vn_hash_encode_bwd_f16: misaligned buffer");
+    return launch_bwd<__half, true>(xyz, (const __half*)dout_h, grad, S, lv, flags, (cudaStream_t)stream);
+}
+
+VN_API int vn_f32_to_f16(const float* src, void* dst_h, int64_t n, void* stream) {
+    VN_REQUIRE(n >= 0 && (n == 0 || (src && dst_h)), "vn_f32_to_f16: bad arguments");
+    VN_REQUIRE(vn_aligned(src, 16) && vn_aligned(dst_h, 8), "vn_f32_to_f16: misaligned buffer");
+    if (n == 0) return VN_OK;
+    f32_to_f16_kernel<<<vn_blocks((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(src, (__half*)dst_h, n);
+    VN_CHECK_LAUNCH("f32_to_f16_kernel");
+    return VN_OK;
+}
+
+VN_API int vn_hash_indices(const float* xyz, int64_t S, const vn_hash_levels_t* lv, int32_t* idx, float* w,
+                           void* stream) {
+    VN_REQUIRE(S >= 0 && (S == 0 || (xyz && idx)), "vn_hash_indices: bad arguments");
+    HashParams P;
+    int rc = make_params(lv, P);
+    if (rc) return rc;
+    if (S == 0) return VN_OK;
+    hash_indices_kernel<<<vn_blocks(S * P.levels, 256), 256, 0, (cudaStream_t)stream>>>(xyz, S, idx, w, P);
+    VN_CHECK_LAUNCH("hash_indices_kernel");
+    return VN_OK;
+}

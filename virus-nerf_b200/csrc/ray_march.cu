@@ -1,0 +1,385 @@
+// ray_march.cu -- ray/AABB test and occupancy-bitfield ray marching.
+// Replaces modules/intersection.py:8-37 and modules/ray_march.py:9-124, 198-269, 328-335.
+//
+// The marching arithmetic is index-critical (sample counts and (t, dt) sequences must be
+// bit-exact against the oracle), so every float expression is written with explicit
+// round-to-nearest intrinsics in the reference's source order (no FMA contraction).
+#include "common.cuh"
+
+struct MarchCfg {
+    int cascades;
+    int G;
+    uint32_t G3;
+    float scale, esf, dt_max, G_inv, Gf, Gm1;
+};
+
+static MarchCfg make_cfg(int cascades, int grid_size, float scale, float esf) {
+    MarchCfg c;
+    c.cascades = cascades;
+    c.G = grid_size;
+    c.G3 = (uint32_t)grid_size * (uint32_t)grid_size * (uint32_t)grid_size;
+    c.scale = scale;
+    c.esf = esf;
+    volatile float a = VN_SQRT3_2 * scale;   // utils.py:56-57: (SQRT3_2 * scale) / grid_size in f32
+    volatile float b = a / (float)grid_size;
+    c.dt_max = b;
+    volatile float gi = 1.0f / (float)grid_size;  // ray_march.py:38
+    c.G_inv = gi;
+    c.Gf = (float)grid_size;
+    c.Gm1 = (float)grid_size - 1.0f;
+    return c;
+}
+
+// ---- a5 ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ray_aabb_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                       float scale, int64_t N, float2* __restrict__ hits_t) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= N) return;
+    float t1 = -INFINITY, t2 = INFINITY;
+    const float half_size = vn_div(vn_sub(scale, -scale), 2.0f);     // intersection.py:17
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float o = __ldg(rays_o + 3 * r + k), d = __ldg(rays_d + 3 * r + k);
+        const float inv_d = vn_div(1.0f, d);                          // :24
+        const float tmin = vn_mul(vn_sub(vn_sub(0.0f, half_size), o), inv_d);   // :26
+        const float tmax = vn_mul(vn_sub(vn_add(0.0f, half_size), o), inv_d);   // :27
+        t1 = fmaxf(t1, fminf(tmin, tmax));                            // :29-32
+        t2 = fminf(t2, fmaxf(tmin, tmax));
+    }
+    hits_t[r] = (t2 > 0.0f) ? make_float2(fmaxf(t1, VN_NEAR_DISTANCE), t2) : make_float2(-1.0f, -1.0f);
+}
+
+VN_API int vn_ray_aabb(const float* rays_o, const float* rays_d, float scale, int64_t N, float* hits_t, void* stream) {
+    VN_REQUIRE(N >= 0 && (N == 0 || (rays_o && rays_d && hits_t)), "vn_ray_aabb: bad arguments");
+    VN_REQUIRE(vn_aligned(hits_t, 8), "vn_ray_aabb: hits_t must be 8-byte aligned");
+    if (N == 0) return VN_OK;
+    ray_aabb_kernel<<<vn_blocks(N, 256), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, scale, N, (float2*)hits_t);
+    VN_CHECK_LAUNCH("ray_aabb_kernel");
+    return VN_OK;
+}
+
+// ---- shared marching step: ray_march.py:44-75 == :232-267 ---------------------------------
+struct Ray {
+    float o[3], d[3], dinv[3];
+};
+
+__device__ __forceinline__ Ray load_ray(const float* __restrict__ rays_o, const float* __restrict__ rays_d, int64_t r) {
+    Ray ray;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        ray.o[k] = __ldg(rays_o + 3 * r + k);
+        ray.d[k] = __ldg(rays_d + 3 * r + k);
+        ray.dinv[k] = vn_div(1.0f, ray.d[k]);   // :33
+    }
+    return ray;
+}
+
+// Returns occupancy at t.  xyz/dt are the sample position and step; when the cell is empty
+// *t_next is t advanced past the cell exactly as the reference's inner loop does.
+__device__ __forceinline__ bool march_probe(const MarchCfg& c, const Ray& ray, const uint8_t* __restrict__ bitfield,
+                                            float t, float* xyz, float* dt_out, float* t_next) {
+    float mx = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        xyz[k] = vn_add(ray.o[k], vn_mul(t, ray.d[k]));                // :45
+        mx = fmaxf(mx, fabsf(xyz[k]));
+    }
+    const float dt = vn_calc_dt(t, c.esf, c.dt_max);                  // :46
+    int mip = 0;
+    if (c.cascades > 1) {                                             // utils.py:78-92
+        const int m_pos = min(c.cascades - 1, max(0, vn_frexp_bit(mx) + 1));
+        const int m_dt = min(c.cascades - 1, max(0, vn_frexp_bit(vn_mul(dt, c.Gf))));
+        mip = max(m_pos, m_dt);
+    }
+    const float mip_bound = fminf(ldexpf(1.0f, mip - 1), c.scale);    // :50
+    const float mip_bound_inv = vn_div(1.0f, mip_bound);              // :51
+    float nxyz[3];
+    uint32_t ci[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        nxyz[k] = vn_clamp(vn_mul(vn_mul(0.5f, vn_add(vn_mul(xyz[k], mip_bound_inv), 1.0f)), c.Gf), 0.0f, c.Gm1);  // :53-57
+        ci[k] = vn_f2u(nxyz[k]);
+    }
+    const uint32_t idx = (uint32_t)mip * c.G3 + vn_morton3D(ci[0], ci[1], ci[2]);   // :59
+    const bool occ = (__ldg(bitfield + (idx >> 3)) & (1u << (idx & 7u))) != 0;       // :60
+    *dt_out = dt;
+    if (!occ) {
+        float tmin = INFINITY;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float sgn = (ray.d[k] > 0.0f) ? 1.0f : ((ray.d[k] < 0.0f) ? -1.0f : 0.0f);
+            float v = vn_add(vn_add(nxyz[k], 0.5f), vn_mul(0.5f, sgn));
+            v = vn_sub(vn_mul(vn_mul(v, c.G_inv), 2.0f), 1.0f);
+            v = vn_mul(vn_sub(vn_mul(v, mip_bound), xyz[k]), ray.dinv[k]);          // :67-68
+            tmin = fminf(tmin, v);
+        }
+        const float t_target = vn_add(t, fmaxf(0.0f, tmin));                         // :70
+        float tt = vn_add(t, vn_calc_dt(t, c.esf, c.dt_max));                        // :71
+        while (tt < t_target) tt = vn_add(tt, vn_calc_dt(tt, c.esf, c.dt_max));      // :72-73
+        *t_next = tt;
+    }
+    return occ;
+}
+
+__device__ __forceinline__ float jittered_t1(const MarchCfg& c, float t1, float noise) {
+    if (t1 >= 0.0f) t1 = vn_add(t1, vn_mul(vn_calc_dt(t1, c.esf, c.dt_max), noise));   // :39-41
+    return t1;
+}
+
+// ---- a6 pass 1 --------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) march_count_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                          const float2* __restrict__ hits_t, const uint8_t* __restrict__ bitfield,
+                                                          const float* __restrict__ noise, int64_t N, const MarchCfg c,
+                                                          int max_samples, int32_t* __restrict__ counts) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= N) return;
+    const Ray ray = load_ray(rays_o, rays_d, r);
+    const float2 h = __ldg(hits_t + r);
+    float t = jittered_t1(c, h.x, __ldg(noise + r));
+    const float t2 = h.y;
+    int n = 0;
+    while (0.0f <= t && t < t2 && n < max_samples) {                 // :44
+        float xyz[3], dt, tn;
+        if (march_probe(c, ray, bitfield, t, xyz, &dt, &tn)) { t = vn_add(t, dt); ++n; }
+        else t = tn;
+    }
+    counts[r] = n;
+}
+
+// ---- exclusive scan (i32), hierarchical: 1024 elements per block ---------------------------
+__global__ void __launch_bounds__(256) scan_block_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out,
+                                                         int32_t* __restrict__ block_sums, int64_t n) {
+    __shared__ int32_t warp_sums[8];
+    const int64_t base = (int64_t)blockIdx.x * 1024 + threadIdx.x * 4;
+    int32_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = (base + k < n) ? in[base + k] : 0;
+    const int32_t tsum = v[0] + v[1] + v[2] + v[3];
+    int32_t inc = tsum;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        int32_t o = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= off) inc += o;
+    }
+    if (lane == 31) warp_sums[warp] = inc;
+    __syncthreads();
+    int32_t woff = 0;
+    for (int w = 0; w < warp; ++w) woff += warp_sums[w];
+    int32_t run = woff + inc - tsum;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (base + k < n) out[base + k] = run;
+        run += v[k];
+    }
+    if (threadIdx.x == 255 && block_sums) block_sums[blockIdx.x] = woff + inc;
+}
+
+__global__ void __launch_bounds__(256) scan_add_kernel(int32_t* __restrict__ out, const int32_t* __restrict__ block_offsets, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * 1024 + threadIdx.x * 4;
+    const int32_t off = block_offsets[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (i + k < n) out[i + k] += off;
+}
+
+static int64_t round_up4(int64_t x) { return (x + 3) / 4 * 4; }
+
+static int64_t scan_hier_ints(int64_t N) {
+    int64_t total = 0, n = N;
+    while (n > 1024) { n = (n + 1023) / 1024; total += 2 * round_up4(n); }
+    return total + 8;
+}
+
+// scratch for the count pass: N ints for the scanned starts + the scan hierarchy
+VN_API int64_t vn_march_scan_tmp_ints(int64_t N) { return round_up4(N < 0 ? 0 : N) + scan_hier_ints(N); }
+
+// out may alias in
+static int exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, int32_t* tmp, cudaStream_t st) {
+    if (n <= 0) return VN_OK;
+    const int64_t nb = (n + 1023) / 1024;
+    if (nb == 1) {
+        scan_block_kernel<<<1, 256, 0, st>>>(in, out, nullptr, n);
+        VN_CHECK_LAUNCH("scan_block_kernel");
+        return VN_OK;
+    }
+    int32_t* sums = tmp;
+    int32_t* sums_scanned = tmp + round_up4(nb);
+    scan_block_kernel<<<(unsigned)nb, 256, 0, st>>>(in, out, sums, n);
+    VN_CHECK_LAUNCH("scan_block_kernel");
+    int rc = exclusive_scan_i32(sums, sums_scanned, nb, tmp + 2 * round_up4(nb), st);
+    if (rc) return rc;
+    scan_add_kernel<<<(unsigned)nb, 256, 0, st>>>(out, sums_scanned, n);
+    VN_CHECK_LAUNCH("scan_add_kernel");
+    return VN_OK;
+}
+
+// rays_a[r] = (r, start_r, count_r); counter = (total, N): the deterministic equivalent of
+// ray_march.py:77-82 (atomic counters) in canonical ray order.
+__global__ void __launch_bounds__(256) fill_rays_a_kernel(const int32_t* __restrict__ counts,
+                                                          const int32_t* __restrict__ starts, int64_t N,
+                                                          int32_t* __restrict__ rays_a, int32_t* __restrict__ counter) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= N) return;
+    const int32_t cnt = counts[r], st = starts[r];
+    rays_a[3 * r] = (int32_t)r;
+    rays_a[3 * r + 1] = st;
+    rays_a[3 * r + 2] = cnt;
+    if (r == N - 1) { counter[0] = st + cnt; counter[1] = (int32_t)N; }
+}
+
+VN_API int vn_march_train_count(const float* rays_o, const float* rays_d, const float* hits_t, const uint8_t* bitfield,
+                                const float* noise, int64_t N, int cascades, int grid_size, float scale,
+                                float exp_step_factor, int max_samples, int32_t* counts, int32_t* rays_a,
+                                int32_t* counter, int32_t* scan_tmp, void* stream) {
+    VN_REQUIRE(N >= 0, "vn_march_train_count: N < 0");
+    VN_REQUIRE(counter != nullptr, "vn_march_train_count: null counter");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N == 0) { VN_CUDA(cudaMemsetAsync(counter, 0, 2 * sizeof(int32_t), st)); return VN_OK; }
+    VN_REQUIRE(rays_o && rays_d && hits_t && bitfield && noise && counts && rays_a && scan_tmp,
+               "vn_march_train_count: null pointer");
+    VN_REQUIRE(vn_aligned(hits_t, 8), "vn_march_train_count: hits_t must be 8-byte aligned");
+    VN_REQUIRE(cascades >= 1 && grid_size >= 1 && grid_size <= 1024 && max_samples >= 0,
+               "vn_march_train_count: bad cascades/grid_size/max_samples");
+    const MarchCfg c = make_cfg(cascades, grid_size, scale, exp_step_factor);
+    march_count_kernel<<<vn_blocks(N, 128), 128, 0, st>>>(rays_o, rays_d, (const float2*)hits_t, bitfield, noise, N, c,
+                                                          max_samples, counts);
+    VN_CHECK_LAUNCH("march_count_kernel");
+    int32_t* starts = scan_tmp;
+    int rc = exclusive_scan_i32(counts, starts, N, scan_tmp + round_up4(N), st);
+    if (rc) return rc;
+    fill_rays_a_kernel<<<vn_blocks(N, 256), 256, 0, st>>>(counts, starts, N, rays_a, counter);
+    VN_CHECK_LAUNCH("fill_rays_a_kernel");
+    return VN_OK;
+}
+
+// ---- a6 pass 2 --------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) march_write_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                          const float2* __restrict__ hits_t, const uint8_t* __restrict__ bitfield,
+                                                          const float* __restrict__ noise, int64_t N, const MarchCfg c,
+                                                          const int32_t* __restrict__ rays_a, int64_t capacity,
+                                                          float* __restrict__ xyzs, float* __restrict__ dirs,
+                                                          float* __restrict__ deltas, float* __restrict__ ts) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= N) return;
+    const int64_t start = rays_a[3 * r + 1];
+    const int n = rays_a[3 * r + 2];
+    if (n == 0) return;
+    const Ray ray = load_ray(rays_o, rays_d, r);
+    const float2 h = __ldg(hits_t + r);
+    float t = jittered_t1(c, h.x, __ldg(noise + r));
+    const float t2 = h.y;
+    int samples = 0;
+    while (t < t2 && samples < n) {                                   // :87
+        float xyz[3], dt, tn;
+        if (march_probe(c, ray, bitfield, t, xyz, &dt, &tn)) {
+            const int64_t s = start + samples;
+            if (s < capacity) {
+                xyzs[3 * s] = xyz[0]; xyzs[3 * s + 1] = xyz[1]; xyzs[3 * s + 2] = xyz[2];   // :103-105
+                dirs[3 * s] = ray.d[0]; dirs[3 * s + 1] = ray.d[1]; dirs[3 * s + 2] = ray.d[2];
+                ts[s] = t; deltas[s] = dt;                               // :109-110
+            }
+            t = vn_add(t, dt); ++samples;
+        } else t = tn;
+    }
+}
+
+VN_API int vn_march_train_write(const float* rays_o, const float* rays_d, const float* hits_t, const uint8_t* bitfield,
+                                const float* noise, int64_t N, int cascades, int grid_size, float scale,
+                                float exp_step_factor, const int32_t* rays_a, int64_t capacity, float* xyzs,
+                                float* dirs, float* deltas, float* ts, void* stream) {
+    VN_REQUIRE(N >= 0 && capacity >= 0, "vn_march_train_write: negative size");
+    if (N == 0 || capacity == 0) return VN_OK;
+    VN_REQUIRE(rays_o && rays_d && hits_t && bitfield && noise && rays_a && xyzs && dirs && deltas && ts,
+               "vn_march_train_write: null pointer");
+    VN_REQUIRE(vn_aligned(hits_t, 8), "vn_march_train_write: hits_t must be 8-byte aligned");
+    const MarchCfg c = make_cfg(cascades, grid_size, scale, exp_step_factor);
+    march_write_kernel<<<vn_blocks(N, 128), 128, 0, (cudaStream_t)stream>>>(
+        rays_o, rays_d, (const float2*)hits_t, bitfield, noise, N, c, rays_a, capacity, xyzs, dirs, deltas, ts);
+    VN_CHECK_LAUNCH("march_write_kernel");
+    return VN_OK;
+}
+
+// ---- a7 ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) march_test_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                         float2* __restrict__ hits_t, const int64_t* __restrict__ alive,
+                                                         int64_t A, const uint8_t* __restrict__ bitfield, const MarchCfg c,
+                                                         int max_samples, int64_t* __restrict__ ray_indices,
+                                                         uint8_t* __restrict__ valid_mask, float* __restrict__ deltas,
+                                                         float* __restrict__ ts, int32_t* __restrict__ counter) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= A) return;
+    const int64_t r = alive[n];
+    const Ray ray = load_ray(rays_o, rays_d, r);
+    const float2 h = hits_t[r];
+    float t = h.x;
+    const float t2 = h.y;
+    int s = 0;
+    const int64_t base = n * (int64_t)max_samples;
+    while (0.0f < t && t < t2 && s < max_samples) {                   // :231
+        float xyz[3], dt, tn;
+        if (march_probe(c, ray, bitfield, t, xyz, &dt, &tn)) {
+            const int64_t k = base + s;
+            ray_indices[k] = r; valid_mask[k] = 1; ts[k] = t; deltas[k] = dt;    // :252-256
+            t = vn_add(t, dt); ++s;
+        } else t = tn;
+    }
+    if (s > 0) hits_t[r].x = t;   // :258 stores t after every emitted sample: net effect = t after the LAST one
+    counter[n] = s;                                                    // :269
+}
+
+VN_API int vn_march_test(const float* rays_o, const float* rays_d, float* hits_t, const int64_t* alive, int64_t A,
+                         const uint8_t* bitfield, int cascades, int grid_size, float scale, float exp_step_factor,
+                         int max_samples, int64_t* ray_indices, uint8_t* valid_mask, float* deltas, float* ts,
+                         int32_t* counter, void* stream) {
+    VN_REQUIRE(A >= 0 && max_samples >= 0, "vn_march_test: negative size");
+    if (A == 0) return VN_OK;
+    VN_REQUIRE(rays_o && rays_d && hits_t && alive && bitfield && ray_indices && valid_mask && deltas && ts && counter,
+               "vn_march_test: null pointer");
+    VN_REQUIRE(vn_aligned(hits_t, 8), "vn_march_test: hits_t must be 8-byte aligned");
+    VN_REQUIRE(cascades >= 1 && grid_size >= 1 && grid_size <= 1024, "vn_march_test: bad cascades/grid_size");
+    const MarchCfg c = make_cfg(cascades, grid_size, scale, exp_step_factor);
+    march_test_kernel<<<vn_blocks(A, 128), 128, 0, (cudaStream_t)stream>>>(
+        rays_o, rays_d, (float2*)hits_t, alive, A, bitfield, c, max_samples, ray_indices, valid_mask, deltas, ts, counter);
+    VN_CHECK_LAUNCH("march_test_kernel");
+    return VN_OK;
+}
+
+// wrapper compaction, ray_march.py:328-335: packed_info = (cumsum - cnt, cnt); masked arrays
+__global__ void __launch_bounds__(256) march_compact_kernel(const int32_t* __restrict__ counter,
+                                                            const int32_t* __restrict__ starts, int64_t A, int max_samples,
+                                                            const int64_t* __restrict__ ray_indices, const float* __restrict__ deltas,
+                                                            const float* __restrict__ ts, int64_t* __restrict__ packed_info,
+                                                            int64_t* __restrict__ ray_indices_out, float* __restrict__ deltas_out,
+                                                            float* __restrict__ ts_out, int64_t* __restrict__ total) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= A) return;
+    const int cnt = counter[n];
+    const int64_t st = starts[n];
+    packed_info[2 * n] = st;
+    packed_info[2 * n + 1] = cnt;
+    const int64_t base = n * (int64_t)max_samples;
+    for (int s = 0; s < cnt; ++s) {
+        ray_indices_out[st + s] = ray_indices[base + s];
+        deltas_out[st + s] = deltas[base + s];
+        ts_out[st + s] = ts[base + s];
+    }
+    if (n == A - 1) total[0] = st + cnt;
+}
+
+VN_API int vn_march_test_compact(const int32_t* counter, int64_t A, int max_samples, const int64_t* ray_indices,
+                                 const float* deltas, const float* ts, int64_t* packed_info, int64_t* ray_indices_out,
+                                 float* deltas_out, float* ts_out, int64_t* total, int32_t* scan_tmp, void* stream) {
+    VN_REQUIRE(A >= 0 && total != nullptr, "vn_march_test_compact: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (A == 0) { VN_CUDA(cudaMemsetAsync(total, 0, sizeof(int64_t), st)); return VN_OK; }
+    VN_REQUIRE(counter && ray_indices && deltas && ts && packed_info && ray_indices_out && deltas_out && ts_out && scan_tmp,
+               "vn_march_test_compact: null pointer");
+    int32_t* starts = scan_tmp;
+    int rc = exclusive_scan_i32(counter, starts, A, scan_tmp + round_up4(A), st);
+    if (rc) return rc;
+    march_compact_kernel<<<vn_blocks(A, 256), 256, 0, st>>>(counter, starts, A, max_samples, ray_indices, deltas, ts,
+                                                            packed_info, ray_indices_out, deltas_out, ts_out, total);
+    VN_CHECK_LAUNCH("march_compact_kernel");
+    return VN_OK;
+}

@@ -35,6 +35,7 @@ def parse():
     ap.add_argument("--cpu-rays", type=int, default=512, help="rays per step of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-autocast", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end phase (profiling runs only)")
     return ap.parse_args()
 
 
@@ -226,7 +227,9 @@ def run_ours(a):
     clocks.start()
     ms, launches, samples, prof, _, _, last_loss = run_phase(pinned=False)
     clk = clocks.stop()
-    ms_e2e, _, _, _, h2d, d2h, _ = run_phase(pinned=True)
+    ms_e2e, h2d, d2h = ms, 0, 0
+    if not a.no_e2e:
+        ms_e2e, _, _, _, h2d, d2h, _ = run_phase(pinned=True)
 
     if rank == 0:
         peak, peak_src = peaks()

@@ -43,6 +43,12 @@ static const float NEAR_DISTANCE = 0.01f;
 static const float SQRT3_MAX_SAMPLES = (float)(1.7320508075688772 / 1024.0);
 static const float SQRT3_2 = (float)(1.7320508075688772 * 2.0);
 
+// exp used by the compositing kernels: correctly rounded binary32 exp (double exp, rounded
+// once).  alpha = 1 - exp(-sigma*delta) cancels catastrophically for small sigma*delta, so a
+// 1-ulp difference in expf shows up as a 6e-8 ABSOLUTE difference in every weight; fixing the
+// exp to the correctly rounded value makes oracle and kernels agree on alpha bit for bit.
+static inline float exp_cr(float x) { return (float)std::exp((double)x); }
+
 static inline int vo_threads(int threads) {
 #ifdef _OPENMP
     return threads > 1 ? threads : 1;
@@ -503,7 +509,7 @@ VO_API void vo_composite_train_fwd(const float* sigmas, const float* rgbs, const
         for (int k = 0; k < ns; ++k) {
             int64_t s = (int64_t)start + k;
             if (T > T_thr) {                                                     // :36
-                float a = 1.0f - expf(-sigmas[s] * deltas[s]);                   // :37
+                float a = 1.0f - exp_cr(-sigmas[s] * deltas[s]);                 // :37
                 float w = a * T;                                                 // :38
                 r0 += w * rgbs[3 * s]; r1 += w * rgbs[3 * s + 1]; r2 += w * rgbs[3 * s + 2];
                 dep += w * ts[s]; op += w; ws[s] = w;
@@ -536,7 +542,7 @@ VO_API void vo_composite_train_bwd(const float* sigmas, const float* rgbs, const
             int64_t s = (int64_t)start + k;
             Ts[k] = T;
             if (T > T_thr) {
-                float a = 1.0f - expf(-sigmas[s] * deltas[s]);
+                float a = 1.0f - exp_cr(-sigmas[s] * deltas[s]);
                 as[k] = a; T = T * (1.0f - a); last = k + 1;
             } else as[k] = 0.0f;
         }
@@ -573,7 +579,7 @@ VO_API void vo_composite_test(const float* sigmas, const float* rgbs, const floa
         for (int64_t s = 0; s < steps; ++s) {
             int64_t k = start + s;
             float delta = deltas[k];
-            float a = 1.0f - expf(-sigmas[k] * delta);                           // :35
+            float a = 1.0f - exp_cr(-sigmas[k] * delta);                         // :35
             float w = a * T;
             c0 += w * rgbs[3 * k]; c1 += w * rgbs[3 * k + 1]; c2 += w * rgbs[3 * k + 2];
             dep += w * ts[k]; op += w;

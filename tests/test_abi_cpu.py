@@ -1,0 +1,110 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads without a GPU, exports every
+symbol include/virusnerf.h declares, its host-only entry points work, argument errors follow
+the conventions (negative code + vn_last_error), and the Python modules refuse CPU tensors
+(there is no fallback path)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def vn():
+    from virus_nerf_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        _lib.build()
+    _lib.lib()
+    return _lib
+
+
+def _declared_symbols():
+    h = open(os.path.join(ROOT, "include", "virusnerf.h")).read()
+    h = re.sub(r"/\*.*?\*/", "", h, flags=re.S)
+    return sorted(set(re.findall(r"\b(vn_[a-z0-9_]+)\s*\(", h)))
+
+
+def test_library_exports_every_declared_symbol(vn):
+    L = vn.lib()
+    names = _declared_symbols()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/virusnerf.h but not exported"
+    assert set(vn.exported_symbols()) == set(names)          # the ctypes table covers the whole header
+    assert L.vn_abi_version() == 1
+
+
+def test_only_sm100a_code_in_the_library(vn):
+    import subprocess
+    out = subprocess.run(["cuobjdump", "--list-elf", vn.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_hash_levels_host_entry_matches_oracle(vn, oracle_mod):
+    for max_res, log2_T in ((1024, 19), (1024, 22), (2048, 19), (512, 14)):
+        lv = vn.hash_levels(16, max_res, 16, 2 ** log2_T)
+        o = oracle_mod.HashLevels(16, max_res, 16, 2 ** log2_T)
+        assert lv.total_entries == o.total and lv.begin_fast_hash_level == o.begin_fast_hash_level
+        np.testing.assert_array_equal(np.array(lv.offsets[:16]), o.offsets)
+        np.testing.assert_array_equal(np.array(lv.sizes[:16]), o.sizes)
+        np.testing.assert_array_equal(np.array(lv.scales[:16], np.float32), o.scales)
+        np.testing.assert_array_equal(np.array(lv.res[:16], np.uint32), o.res)
+        assert lv.log_b == o.log_b
+
+
+def test_error_conventions_without_gpu(vn):
+    L = vn.lib()
+    lv = vn.HashLevels()
+    rc = L.vn_hash_levels_init(ctypes.c_double(16), ctypes.c_double(1024), 1, ctypes.c_int64(2 ** 19),
+                               ctypes.cast(ctypes.pointer(lv), ctypes.c_void_p))
+    assert rc == -1 and "levels" in vn.last_error()
+    with pytest.raises(RuntimeError, match="levels"):
+        vn.hash_levels(16, 1024, 99, 2 ** 19)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        vn.call("vn_sh_encode", torch.zeros(4, 3), 4, torch.zeros(4, 16))
+    with pytest.raises(TypeError):
+        vn.call("vn_packbits")
+
+
+def test_modules_mirror_reference_api_and_refuse_cpu(vn):
+    from virus_nerf_b200.modules import (hash_encoder, hash_encoder_half, intersection, networks, occupancy_grid,
+                                         ray_march, rendering, spherical_harmonics, utils, volume_render_test,
+                                         volume_train)
+    assert rendering.MAX_SAMPLES == utils.MAX_SAMPLES == 1024 and utils.NEAR_DISTANCE == 0.01
+    enc = hash_encoder.HashEncoder(max_params=2 ** 19, levels=16, base_res=16, max_res=1024)
+    assert (enc.out_dim, enc.total_param_size, enc.begin_fast_hash_level) == (32, 11420064, 6)
+    assert list(enc.state_dict().keys()) == ["hash_table"]                      # offsets / sizes are non-persistent
+    assert 0.0 <= float(enc.hash_table.detach().min()) and float(enc.hash_table.detach().max()) <= 1.0   # U(0,1) init
+    half = hash_encoder_half.HashEncoder(max_params=2 ** 14, levels=16, base_res=16, max_res=512)
+    assert half.hash_table.dim() == 2 and set(half.state_dict().keys()) == {"hash_table", "hash_grad"}
+    assert float(half.hash_table.abs().max()) <= 1e-4
+    with pytest.raises(RuntimeError, match="CUDA"):
+        enc(torch.rand(8, 3))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        intersection.ray_aabb_intersection(torch.rand(8, 3), torch.rand(8, 3), 0.5)
+    for fn in (ray_march.raymarching_train, ray_march.raymarching_test, volume_render_test.composite_test,
+               rendering.render, utils.morton3D, utils.morton3D_invert, utils.packbits):
+        assert callable(fn)
+    assert spherical_harmonics.DirEncoder().out_dim == 16
+    assert hasattr(volume_train.VolumeRenderer(), "forward")
+    m = networks.MLP(input_dim=32, output_dim=16, net_depth=1, net_width=64, bias_enabled=False)
+    assert [tuple(p.shape) for p in m.parameters()] == [(64, 32), (16, 64)]
+    for name in ("update", "getBitfield", "_rayUpdate", "_nerfUpdate", "_calcPos", "_rayProb", "_nerfProb",
+                 "_updateGrid", "_c2idx", "_idx2c", "getOccupancyCartesianGrid", "getBinaryCartesianGrid",
+                 "bitfield2morton", "morton2cartesian", "c2oCoordinates", "cartesian2morton", "morton2bitfield"):
+        assert hasattr(occupancy_grid.OccupancyGrid, name), name
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "virus-nerf_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(import|from)\s+oracle\b", src, flags=re.M), os.path.join(dirpath, f)
+                assert "liboracle" not in src

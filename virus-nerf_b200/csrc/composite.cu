@@ -6,8 +6,11 @@
 // read-modify-writes the per-ray outputs every sample); skipped samples get ws = 0.
 #include "common.cuh"
 
+// alpha = 1 - exp(-sigma * delta), volume_train.py:37.  The exp is the correctly rounded
+// binary32 value (double exp rounded once): 1 - exp(-x) cancels for small x, so a 1-ulp expf
+// difference would be a 6e-8 absolute difference in every weight (see oracle.cpp exp_cr).
 __device__ __forceinline__ float alpha_of(float sigma, float delta) {
-    return vn_sub(1.0f, expf(vn_mul(-sigma, delta)));   // volume_train.py:37
+    return vn_sub(1.0f, (float)exp((double)vn_mul(-sigma, delta)));
 }
 
 // ---- a8 ---------------------------------------------------------------------------------

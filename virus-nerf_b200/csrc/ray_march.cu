@@ -315,6 +315,7 @@ __global__ void __launch_bounds__(128) march_test_kernel(const float* __restrict
     float t = h.x;
     const float t2 = h.y;
     int s = 0;
+    float t_last = t;
     const int64_t base = n * (int64_t)max_samples;
     while (0.0f < t && t < t2 && s < max_samples) {                   // :231
         float xyz[3], dt, tn;
@@ -322,9 +323,10 @@ __global__ void __launch_bounds__(128) march_test_kernel(const float* __restrict
             const int64_t k = base + s;
             ray_indices[k] = r; valid_mask[k] = 1; ts[k] = t; deltas[k] = dt;    // :252-256
             t = vn_add(t, dt); ++s;
+            t_last = t;                                                          // :257-258 hits_t[r,0] = t
         } else t = tn;
     }
-    if (s > 0) hits_t[r].x = t;   // :258 stores t after every emitted sample: net effect = t after the LAST one
+    if (s > 0) hits_t[r].x = t_last;   // net effect of the per-sample store: t right after the LAST emitted sample
     counter[n] = s;                                                    // :269
 }
 

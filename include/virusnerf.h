@@ -200,6 +200,11 @@ int vn_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float 
 int vn_scaler_update(float* scale, int32_t* growth_tracker, float* found_inf, float growth_factor,
                      float backoff_factor, int growth_interval, void* stream);
 
+/* tcgen05 self-test (development / CI): one 128 x N x K fp16 product through the tensor
+ * cores in the three operand modes the fused MLP uses (0 forward A*B^T, 1 dgrad A*B,
+ * 2 wgrad A^T*B); A, B fp16 row-major as stored, D [128,N] f32. */
+int vn_umma_selftest(int mode, int N, int K, const void* A, const void* B, float* D, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

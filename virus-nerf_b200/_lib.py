@@ -64,6 +64,7 @@ _SPECS = {
     "vn_grad_check": "plps",
     "vn_adam_step": "ppppl" "fffff" "ipps",
     "vn_scaler_update": "pppffis",
+    "vn_umma_selftest": "iiippps",
 }
 
 _CT = {"p": ctypes.c_void_p, "l": ctypes.c_int64, "i": ctypes.c_int, "f": ctypes.c_float,

@@ -200,6 +200,26 @@ int vn_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float 
 int vn_scaler_update(float* scale, int32_t* growth_tracker, float* found_inf, float growth_factor,
                      float backoff_factor, int growth_interval, void* stream);
 
+/* a12 (+a11 fused). NGP.density / NGP.forward dense part, modules/networks.py:134-164 and
+ * MLP.forward :271-282, with DirEncoder (spherical_harmonics.py:7-42) fused into the input
+ * stage: ONE kernel on the tcgen05 tensor cores (fp16 operands, fp32 accumulation in TMEM --
+ * the reference runs these layers as fp16 cuBLAS GEMMs under torch.autocast, trainer.py:104).
+ *   enc [S,32] hash encoding, f32 (enc_half = 0) or fp16 (enc_half = 1); dirs [S,3] raw ray
+ *   directions (normalised and mapped to (d+1)/2 inside, networks.py:160-161); W1 [64,32],
+ *   W2 [16,64], W3 [64,32], W4 [64,64], W5 [3,64] f32 in torch Linear layout [out,in].
+ * _fwd: sigmas [S] = exp(h0), rgbs [S,3] = sigmoid(...), optional h_out [S,16] (return_feat).
+ *       density_only != 0 evaluates only W1, W2 (NGP.density; dirs/W3-5/rgbs may be NULL).
+ * _bwd: recomputes the forward per tile; inputs dsigmas [S], drgbs [S,3]; writes denc [S,32]
+ *       f32 (gradient w.r.t. the encoding) and ACCUMULATES dW1..dW5 (same shapes as W, f32;
+ *       TruncExp backward clamps h0 to [-15,15], networks.py:28). */
+int vn_mlp_fwd(const void* enc, int enc_half, const float* dirs, const float* W1, const float* W2,
+               const float* W3, const float* W4, const float* W5, int64_t S, int density_only,
+               float* sigmas, float* rgbs, float* h_out, void* stream);
+int vn_mlp_bwd(const void* enc, int enc_half, const float* dirs, const float* W1, const float* W2,
+               const float* W3, const float* W4, const float* W5, int64_t S, int density_only,
+               const float* dsigmas, const float* drgbs, float* denc, float* dW1, float* dW2,
+               float* dW3, float* dW4, float* dW5, void* stream);
+
 /* tcgen05 self-test (development / CI): one 128 x N x K fp16 product through the tensor
  * cores in the three operand modes the fused MLP uses (0 forward A*B^T, 1 dgrad A*B,
  * 2 wgrad A^T*B); A, B fp16 row-major as stored, D [128,N] f32. */

@@ -1,0 +1,157 @@
+"""GPU parity of the fused tcgen05 MLP (vn_mlp_fwd / vn_mlp_bwd, SURVEY 8(a) a11 + a12).
+
+The kernel computes what the reference computes under torch.autocast(float16) on CUDA: fp16
+operands, fp32 accumulation.  Two references: (1) a torch fp32 restatement of
+networks.py:134-164 with the operands rounded to fp16 at exactly the kernel's rounding points
+(tight: rtol 2e-3 of the largest entry), and (2) the fp32 oracle (oracle.mlp_fwd, loose:
+rtol 2e-2) -- the stated fp16 tolerance of this path."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _weights(seed=0):
+    g = torch.Generator().manual_seed(seed)
+    xav = lambda o, i: ((torch.rand(o, i, generator=g) * 2 - 1) * (6.0 / (i + o)) ** 0.5)
+    return [xav(64, 32), xav(16, 64), xav(64, 32), xav(64, 64), xav(3, 64)]
+
+
+def _sh(d):
+    import oracle
+    return torch.from_numpy(oracle.sh_encode(d.numpy()))
+
+
+def ref_forward(enc, dirs, W, h16=True):
+    """fp32 math on fp16-rounded operands; returns everything needed for the backward"""
+    r = (lambda t: t.half().float()) if h16 else (lambda t: t)
+    Wr = [r(w) for w in W]
+    x0 = r(enc)
+    h1 = r(torch.relu(x0 @ Wr[0].t()))
+    h = h1 @ Wr[1].t()
+    sig = torch.exp(h[:, 0])
+    d = dirs / dirs.norm(dim=1, keepdim=True)
+    in2 = torch.cat([r(_sh((d + 1) / 2)), r(h)], 1)
+    h3 = r(torch.relu(in2 @ Wr[2].t()))
+    h4 = r(torch.relu(h3 @ Wr[3].t()))
+    rgb = torch.sigmoid(h4 @ Wr[4].t())
+    return dict(x0=x0, h1=h1, h=h, sig=sig, in2=in2, h3=h3, h4=h4, rgb=rgb, W=Wr)
+
+
+def ref_backward(f, dsig, drgb):
+    r = lambda t: t.half().float()
+    W = f["W"]
+    d5 = r(drgb * f["rgb"] * (1 - f["rgb"]))
+    dW5 = d5.t() @ f["h4"]
+    dh4 = r((d5 @ W[4]) * (f["h4"] > 0))
+    dW4 = dh4.t() @ f["h3"]
+    dh3 = r((dh4 @ W[3]) * (f["h3"] > 0))
+    dW3 = dh3.t() @ f["in2"]
+    dh = (dh3 @ W[2])[:, 16:].clone()
+    dh[:, 0] += dsig * torch.exp(f["h"][:, 0].clamp(-15, 15))
+    dh = r(dh)
+    dW2 = dh.t() @ f["h1"]
+    dh1 = r((dh @ W[1]) * (f["h1"] > 0))
+    dW1 = dh1.t() @ f["x0"]
+    denc = dh1 @ W[0]
+    return denc, [dW1, dW2, dW3, dW4, dW5]
+
+
+def close(a, b, rtol, what):
+    a, b = a.detach().cpu().float(), b.detach().cpu().float()
+    tol = rtol * float(b.abs().max()) + 1e-12
+    err = float((a - b).abs().max())
+    assert err <= tol, f"{what}: max err {err:.4g} > {tol:.4g} (ref max {float(b.abs().max()):.4g})"
+
+
+@pytest.mark.parametrize("S", [1, 100, 128, 129, 1000, 40000])
+def test_fused_mlp_forward_backward(S):
+    from virus_nerf_b200 import _lib
+    import oracle
+    torch.manual_seed(S)
+    W = _weights(S)
+    enc = torch.rand(S, 32)
+    dirs = torch.randn(S, 3)
+    Wg = [w.to(DEV).contiguous() for w in W]
+    sig = torch.empty(S, device=DEV); rgb = torch.empty(S, 3, device=DEV); h = torch.empty(S, 16, device=DEV)
+    _lib.call("vn_mlp_fwd", enc.to(DEV), 0, dirs.to(DEV), *Wg, S, 0, sig, rgb, h)
+    f = ref_forward(enc, dirs, W)
+    close(sig, f["sig"], 2e-3, "sigma")
+    close(rgb, f["rgb"], 2e-3, "rgb")
+    close(h, f["h"], 2e-3, "h")
+    o_sig, o_rgb = oracle.mlp_fwd(enc.numpy(), dirs.numpy(), *[w.numpy() for w in W])
+    close(sig, torch.from_numpy(o_sig), 2e-2, "sigma vs fp32 oracle")
+    close(rgb, torch.from_numpy(o_rgb), 2e-2, "rgb vs fp32 oracle")
+    # density-only variant
+    sig2 = torch.empty(S, device=DEV)
+    _lib.call("vn_mlp_fwd", enc.to(DEV), 0, None, Wg[0], Wg[1], None, None, None, S, 1, sig2, None, None)
+    close(sig2, f["sig"], 2e-3, "sigma (density only)")
+    # backward
+    dsig = torch.randn(S) * 4; drgb = torch.randn(S, 3) * 4
+    denc = torch.empty(S, 32, device=DEV)
+    dW = [torch.zeros_like(w) for w in Wg]
+    _lib.call("vn_mlp_bwd", enc.to(DEV), 0, dirs.to(DEV), *Wg, S, 0, dsig.to(DEV), drgb.to(DEV), denc, *dW)
+    r_denc, r_dW = ref_backward(f, dsig, drgb)
+    close(denc, r_denc, 3e-3, "denc")
+    for i in range(5):
+        close(dW[i], r_dW[i], 3e-3, f"dW{i + 1}")
+    # and against fp32 autograd (loose)
+    Wt = [w.clone().requires_grad_(True) for w in W]
+    e32 = enc.clone().requires_grad_(True)
+    f32 = ref_forward(e32, dirs, Wt, h16=False)
+    ((f32["sig"] * dsig).sum() + (f32["rgb"] * drgb).sum()).backward()
+    close(denc, e32.grad, 3e-2, "denc vs fp32 autograd")
+    for i in range(5):
+        close(dW[i], Wt[i].grad, 3e-2, f"dW{i + 1} vs fp32 autograd")
+
+
+def test_fused_mlp_half_input_and_accumulation():
+    from virus_nerf_b200 import _lib
+    S = 3000
+    torch.manual_seed(1)
+    W = _weights(1)
+    Wg = [w.to(DEV).contiguous() for w in W]
+    enc = torch.rand(S, 32)
+    dirs = torch.randn(S, 3)
+    s32 = torch.empty(S, device=DEV); c32 = torch.empty(S, 3, device=DEV)
+    s16 = torch.empty(S, device=DEV); c16 = torch.empty(S, 3, device=DEV)
+    _lib.call("vn_mlp_fwd", enc.half().float().to(DEV), 0, dirs.to(DEV), *Wg, S, 0, s32, c32, None)
+    _lib.call("vn_mlp_fwd", enc.half().to(DEV), 1, dirs.to(DEV), *Wg, S, 0, s16, c16, None)
+    assert torch.equal(s32, s16) and torch.equal(c32, c16)
+    # dW is accumulated into (engine: straight into the flat gradient buffer)
+    dW = [torch.ones_like(w) for w in Wg]
+    denc = torch.empty(S, 32, device=DEV)
+    z = torch.zeros(S, device=DEV); z3 = torch.zeros(S, 3, device=DEV)
+    _lib.call("vn_mlp_bwd", enc.to(DEV), 0, dirs.to(DEV), *Wg, S, 0, z, z3, denc, *dW)
+    for w in dW:
+        assert torch.equal(w, torch.ones_like(w))
+    assert float(denc.abs().max()) == 0.0
+
+
+def test_ngp_module_uses_fused_kernel():
+    from virus_nerf_b200 import _lib, synthetic
+    from virus_nerf_b200.modules.networks import NGP
+    args = synthetic.make_args(device=DEV)
+    torch.manual_seed(0)
+    m = NGP(scale=0.5, max_res=1024, args=args, dataset=None).to(DEV)
+    assert m.fused_mlp
+    x = (torch.rand(5000, 3, device=DEV) - 0.5) * 0.98
+    d = torch.randn(5000, 3, device=DEV)
+    n0 = _lib.launch_count()
+    with torch.autocast(device_type="cuda", dtype=torch.float16):
+        sig, rgb = m(x, d)
+        (sig.sum() + rgb.sum()).backward()
+    assert _lib.launch_count() - n0 == 4          # hash fwd, mlp fwd, mlp bwd, hash bwd
+    m.fused_mlp = False
+    with torch.no_grad():
+        sig2, rgb2 = m(x, d)
+    close(sig, sig2, 2e-2, "module sigma fused vs fp32 torch")
+    close(rgb, rgb2, 2e-2, "module rgb fused vs fp32 torch")
+    for p in m.parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all()
+    m.fused_mlp = True
+    with torch.no_grad():
+        s_d = m.density(x)
+    close(s_d, sig, 1e-6, "density() == forward() sigma")

@@ -65,6 +65,8 @@ _SPECS = {
     "vn_adam_step": "ppppl" "fffff" "ipps",
     "vn_scaler_update": "pppffis",
     "vn_umma_selftest": "iiippps",
+    "vn_mlp_fwd": "pip" "ppppp" "li" "ppp" "s",
+    "vn_mlp_bwd": "pip" "ppppp" "li" "pp" "p" "ppppp" "s",
 }
 
 _CT = {"p": ctypes.c_void_p, "l": ctypes.c_int64, "i": ctypes.c_int, "f": ctypes.c_float,

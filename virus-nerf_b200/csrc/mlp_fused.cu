@@ -66,3 +66,436 @@ VN_API int vn_umma_selftest(int mode, int N, int K, const void* A, const void* B
     VN_CHECK_LAUNCH("umma_selftest_kernel");
     return VN_OK;
 }
+
+// =========================================================================================
+// Fused NGP MLPs.  One CTA = 128 threads = one tile of 128 samples; thread t owns sample row
+// t = TMEM lane t.  Per layer: the activation tile (fp16, chunk-major, see umma.cuh) is the A
+// operand, the weight matrix (fp16, chunk-major, resident in shared memory for the whole
+// kernel) the B operand, the fp32 accumulator lives in TMEM; the epilogue (ReLU / exp /
+// sigmoid / SH concat) reads its own row with tcgen05.ld and writes the next layer's operand.
+//
+//   enc[32] -W1-> relu[64] -W2-> h[16]; sigma = exp(h0)          networks.py:142-145
+//   [SH16((d/|d|+1)/2) | h16] -W3-> relu[64] -W4-> relu[64] -W5-> sigmoid[3]   networks.py:160-162
+//
+// Backward (same kernel, BWD = true) recomputes the forward per tile, then chains the five
+// dgrad products (weights read as MN-major operands) and accumulates the five weight
+// gradients in TMEM across all tiles of the CTA (activations / gradients read as MN-major
+// operands, M = 64), flushing them with one atomicAdd pass at the end.
+// =========================================================================================
+namespace {
+
+constexpr int TILE = 128;
+// shared-memory operand buffers (bytes)
+constexpr int SZ_X0 = TILE * 32 * 2, SZ_H = TILE * 64 * 2, SZ_16 = TILE * 16 * 2;
+constexpr int OFF_X0 = 0;
+constexpr int OFF_H1 = OFF_X0 + SZ_X0;
+constexpr int OFF_IN2 = OFF_H1 + SZ_H;       // 32 cols: [SH16 | h16]
+constexpr int OFF_H3 = OFF_IN2 + SZ_X0;
+constexpr int OFF_H4 = OFF_H3 + SZ_H;
+constexpr int OFF_W1 = OFF_H4 + SZ_H;        // [64 x 32]
+constexpr int OFF_W2 = OFF_W1 + 64 * 32 * 2; // [16 x 64]
+constexpr int OFF_W3 = OFF_W2 + 16 * 64 * 2; // [64 x 32]
+constexpr int OFF_W4 = OFF_W3 + 64 * 32 * 2; // [64 x 64]
+constexpr int OFF_W5 = OFF_W4 + 64 * 64 * 2; // [16 x 64], rows 3..15 zero
+constexpr int SMEM_FWD = OFF_W5 + 16 * 64 * 2;
+constexpr int OFF_D5 = SMEM_FWD;             // [128 x 16] d(out5)
+constexpr int OFF_DH = OFF_D5 + SZ_16;       // [128 x 16] d(h)
+constexpr int OFF_G = OFF_DH + SZ_16;        // [128 x 64] dH4 / dH3 / dH1 (reused)
+constexpr int SMEM_BWD = OFF_G + SZ_H;
+// TMEM columns
+constexpr int TC_TMP = 0;                    // 64-column scratch accumulator
+constexpr int TC_DW1 = 64, TC_DW3 = 96, TC_DW4 = 128, TC_DW2T = 192, TC_DW5T = 208;   // wgrad accumulators
+constexpr int TMEM_FWD = 64, TMEM_BWD = 256;
+
+struct MlpArgs {
+    const float* enc;      // [S,32] f32 (or fp16 when enc_half)
+    const float* dirs;     // [S,3]
+    const float* W[5];     // torch Linear layout [out,in] f32
+    float* sigmas;         // [S]
+    float* rgbs;           // [S,3]
+    float* h_out;          // [S,16] or null: the density net's feature vector (return_feat)
+    const float* dsigmas;  // [S]     (BWD)
+    const float* drgbs;    // [S,3]   (BWD)
+    float* denc;           // [S,32]  (BWD)
+    float* dW[5];          // accumulated (BWD)
+    int64_t S;
+    int enc_half;
+    int density_only;
+};
+
+__device__ __forceinline__ void load_weight(uint8_t* smem, int off, const float* __restrict__ W, int R, int C, int R_valid,
+                                            int tid) {
+    // [R x C] chunk-major fp16; rows >= R_valid are zero padding
+    for (int i = tid; i < R * C; i += TILE) {
+        const int r = i / C, c = i % C;
+        const float v = (r < R_valid) ? __ldg(W + (size_t)r * C + c) : 0.0f;
+        *reinterpret_cast<__half*>(smem + off + (c / 8) * R * 16 + r * 16 + (c % 8) * 2) = __float2half_rn(v);
+    }
+}
+
+// this thread's row of a 128-row operand buffer: 8 fp16 of column chunk c
+__device__ __forceinline__ uint4 ld_chunk(const uint8_t* smem, int off, int r, int c) {
+    return *reinterpret_cast<const uint4*>(smem + off + c * TILE * 16 + r * 16);
+}
+__device__ __forceinline__ void st_row8(uint8_t* smem, int off, int r, int c, const float* v8) {
+    umma::st_chunk(reinterpret_cast<__half*>(smem + off), TILE, r, c, v8);
+}
+
+__device__ __forceinline__ void sh16_half(float x, float y, float z, float* e) {
+    // spherical_harmonics.py:16-42
+    const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
+    e[0] = 0.28209479177387814f;
+    e[1] = -0.48860251190291987f * y;
+    e[2] = 0.48860251190291987f * z;
+    e[3] = -0.48860251190291987f * x;
+    e[4] = 1.0925484305920792f * xy;
+    e[5] = -1.0925484305920792f * yz;
+    e[6] = 0.94617469575755997f * z2 - 0.31539156525251999f;
+    e[7] = -1.0925484305920792f * xz;
+    e[8] = 0.54627421529603959f * x2 - 0.54627421529603959f * y2;
+    e[9] = 0.59004358992664352f * y * (-3.0f * x2 + y2);
+    e[10] = 2.8906114426405538f * xy * z;
+    e[11] = 0.45704579946446572f * y * (1.0f - 5.0f * z2);
+    e[12] = 0.3731763325901154f * z * (5.0f * z2 - 3.0f);
+    e[13] = 0.45704579946446572f * x * (1.0f - 5.0f * z2);
+    e[14] = 1.4453057213202769f * z * (x2 - y2);
+    e[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
+}
+
+struct Pipe {
+    uint64_t* bar;
+    uint32_t phase;
+    uint32_t tm;      // TMEM base
+    uint32_t lane;    // (warp * 32) << 16
+};
+
+// all threads: operands written -> visible to the tensor core; then thread 0 may issue
+__device__ __forceinline__ void publish() {
+    umma::fence_async_smem();
+    umma::fence_before_sync();
+    __syncthreads();
+}
+__device__ __forceinline__ void wait_mma(Pipe& p) {
+    umma::mbar_wait(p.bar, p.phase);
+    p.phase ^= 1u;
+    umma::fence_after_sync();
+}
+// read N (multiple of 16) accumulator columns of this thread's row
+template <int N>
+__device__ __forceinline__ void read_acc(const Pipe& p, int col, float* v) {
+#pragma unroll
+    for (int c = 0; c < N; c += 16) umma::tmem_ld16(p.tm + p.lane + (uint32_t)(col + c), v + c);
+    umma::tmem_ld_wait();
+}
+
+// forward: D[128,N] = A[128,K] * W[N,K]^T
+__device__ __forceinline__ void mma_fwd(uint32_t sbase, int offA, int offW, int N, int K, uint32_t tm_col) {
+    const uint32_t idesc = umma::instr_desc_f16(128, N, 0, 0);
+    for (int k = 0; k < K / 16; ++k)
+        umma::mma_f16(tm_col, umma::desc_kmajor(sbase + offA, TILE, k), umma::desc_kmajor(sbase + offW, N, k), idesc, k > 0);
+}
+// dgrad: D[128,N=in] = dY[128,K=out] * W[out,in]      (W stored [Wrows x N], read MN-major)
+__device__ __forceinline__ void mma_dgrad(uint32_t sbase, int offdY, int offW, int Wrows, int N, int K, uint32_t tm_col) {
+    const uint32_t idesc = umma::instr_desc_f16(128, N, 0, 1);
+    for (int k = 0; k < K / 16; ++k)
+        umma::mma_f16(tm_col, umma::desc_kmajor(sbase + offdY, TILE, k), umma::desc_mnmajor(sbase + offW, Wrows, k), idesc, k > 0);
+}
+// wgrad: D[64,N] (+)= P[128 samples, 64]^T * Q[128 samples, N]   (both read MN-major, K = 128 samples)
+__device__ __forceinline__ void mma_wgrad(uint32_t sbase, int offP, int offQ, int N, uint32_t tm_col, bool first_tile) {
+    const uint32_t idesc = umma::instr_desc_f16(64, N, 1, 1);
+    for (int k = 0; k < TILE / 16; ++k)
+        umma::mma_f16(tm_col, umma::desc_mnmajor(sbase + offP, TILE, k), umma::desc_mnmajor(sbase + offQ, TILE, k), idesc,
+                      !(first_tile && k == 0));
+}
+
+__device__ __forceinline__ void relu_store(uint8_t* smem, int off, int r, const float* v, int ncols) {
+    for (int c = 0; c < ncols / 8; ++c) {
+        float t[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[j] = fmaxf(v[8 * c + j], 0.0f);
+        st_row8(smem, off, r, c, t);
+    }
+}
+// g * (act > 0) -> fp16 operand buffer
+__device__ __forceinline__ void mask_store(uint8_t* smem, int off_dst, int off_act, int r, const float* g) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const uint4 a = ld_chunk(smem, off_act, r, c);
+        const __half2* h = reinterpret_cast<const __half2*>(&a);
+        float t[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = __half22float2(h[j]);
+            t[2 * j] = f.x > 0.0f ? g[8 * c + 2 * j] : 0.0f;
+            t[2 * j + 1] = f.y > 0.0f ? g[8 * c + 2 * j + 1] : 0.0f;
+        }
+        st_row8(smem, off_dst, r, c, t);
+    }
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(TILE) mlp_kernel(const MlpArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t sbase = umma::smem_u32(smem);
+
+    load_weight(smem, OFF_W1, a.W[0], 64, 32, 64, tid);
+    load_weight(smem, OFF_W2, a.W[1], 16, 64, 16, tid);
+    load_weight(smem, OFF_W3, a.W[2], 64, 32, 64, tid);
+    load_weight(smem, OFF_W4, a.W[3], 64, 64, 64, tid);
+    load_weight(smem, OFF_W5, a.W[4], 16, 64, 3, tid);
+    if (warp == 0) umma::tmem_alloc(&tmem_base, BWD ? TMEM_BWD : TMEM_FWD);
+    if (tid == 0) { umma::mbar_init(&bar, 1); umma::mbar_fence_init(); }
+    publish();
+    umma::fence_after_sync();
+    Pipe p{&bar, 0u, tmem_base, (uint32_t)(warp * 32) << 16};
+    const uint32_t tmp = p.tm + TC_TMP;
+
+    const int64_t n_tiles = (a.S + TILE - 1) / TILE;
+    bool first_tile = true;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, first_tile = false) {
+        const int64_t s = tile * TILE + tid;
+        const bool valid = s < a.S;
+        // ---- stage inputs: enc row -> X0, SH(dir) -> IN2[:, 0:16] -------------------------
+        {
+            float v[32];
+            if (valid) {
+                if (a.enc_half) {
+                    const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(a.enc) + s * 32);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint4 u = __ldg(src + q);
+                        const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); v[8 * q + 2 * j] = f.x; v[8 * q + 2 * j + 1] = f.y; }
+                    }
+                } else {
+                    const float4* src = reinterpret_cast<const float4*>(a.enc + s * 32);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) { const float4 f = __ldg(src + q); v[4 * q] = f.x; v[4 * q + 1] = f.y; v[4 * q + 2] = f.z; v[4 * q + 3] = f.w; }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0.0f;
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) st_row8(smem, OFF_X0, tid, c, v + 8 * c);
+            if (!a.density_only) {
+                float dx = 1.0f, dy = 0.0f, dz = 0.0f;
+                if (valid) { dx = __ldg(a.dirs + 3 * s); dy = __ldg(a.dirs + 3 * s + 1); dz = __ldg(a.dirs + 3 * s + 2); }
+                const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);          // networks.py:160
+                float e[16];
+                sh16_half((dx / nrm + 1.0f) * 0.5f, (dy / nrm + 1.0f) * 0.5f, (dz / nrm + 1.0f) * 0.5f, e);   // :161
+                st_row8(smem, OFF_IN2, tid, 0, e);
+                st_row8(smem, OFF_IN2, tid, 1, e + 8);
+            }
+        }
+        publish();
+        // ---- L1: 32 -> 64, ReLU -----------------------------------------------------------
+        if (tid == 0) { umma::fence_after_sync(); mma_fwd(sbase, OFF_X0, OFF_W1, 64, 32, tmp); umma::commit(&bar); }
+        wait_mma(p);
+        float acc[64];
+        read_acc<64>(p, TC_TMP, acc);
+        relu_store(smem, OFF_H1, tid, acc, 64);
+        publish();
+        // ---- L2: 64 -> 16; sigma = exp(h0) ------------------------------------------------
+        if (tid == 0) { umma::fence_after_sync(); mma_fwd(sbase, OFF_H1, OFF_W2, 16, 64, tmp); umma::commit(&bar); }
+        wait_mma(p);
+        read_acc<16>(p, TC_TMP, acc);
+        const float h0 = acc[0];
+        if (!BWD && valid) {
+            a.sigmas[s] = expf(h0);                                            // TruncExp fwd, networks.py:23
+            if (a.h_out) {
+                float4* hd = reinterpret_cast<float4*>(a.h_out + s * 16);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) hd[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+            }
+        }
+        float rgb[3] = {0.f, 0.f, 0.f};
+        if (!a.density_only) {
+            st_row8(smem, OFF_IN2, tid, 2, acc);
+            st_row8(smem, OFF_IN2, tid, 3, acc + 8);
+            publish();
+            // ---- L3: [SH | h] 32 -> 64, ReLU ---------------------------------------------
+            if (tid == 0) { umma::fence_after_sync(); mma_fwd(sbase, OFF_IN2, OFF_W3, 64, 32, tmp); umma::commit(&bar); }
+            wait_mma(p);
+            read_acc<64>(p, TC_TMP, acc);
+            relu_store(smem, OFF_H3, tid, acc, 64);
+            publish();
+            // ---- L4: 64 -> 64, ReLU ------------------------------------------------------
+            if (tid == 0) { umma::fence_after_sync(); mma_fwd(sbase, OFF_H3, OFF_W4, 64, 64, tmp); umma::commit(&bar); }
+            wait_mma(p);
+            read_acc<64>(p, TC_TMP, acc);
+            relu_store(smem, OFF_H4, tid, acc, 64);
+            publish();
+            // ---- L5: 64 -> 3 (padded to 16), sigmoid -------------------------------------
+            if (tid == 0) { umma::fence_after_sync(); mma_fwd(sbase, OFF_H4, OFF_W5, 16, 64, tmp); umma::commit(&bar); }
+            wait_mma(p);
+            read_acc<16>(p, TC_TMP, acc);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) rgb[c] = 1.0f / (1.0f + expf(-acc[c]));
+            if (!BWD && valid) { a.rgbs[3 * s] = rgb[0]; a.rgbs[3 * s + 1] = rgb[1]; a.rgbs[3 * s + 2] = rgb[2]; }
+        }
+        if (!BWD) { umma::fence_before_sync(); continue; }
+
+        // =============================== backward =========================================
+        float dh_sigma = 0.0f;
+        if (valid) dh_sigma = __ldg(a.dsigmas + s) * expf(fminf(fmaxf(h0, -15.0f), 15.0f));   // TruncExp bwd, networks.py:28
+        if (!a.density_only) {
+            // d(out5) = drgb * rgb * (1 - rgb)
+            float d5[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) d5[j] = 0.0f;
+            if (valid) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) d5[c] = __ldg(a.drgbs + 3 * s + c) * rgb[c] * (1.0f - rgb[c]);
+            }
+            st_row8(smem, OFF_D5, tid, 0, d5);
+            st_row8(smem, OFF_D5, tid, 1, d5 + 8);
+            publish();
+            if (tid == 0) {
+                umma::fence_after_sync();
+                mma_dgrad(sbase, OFF_D5, OFF_W5, 16, 64, 16, tmp);                       // dH4raw = d5 * W5
+                mma_wgrad(sbase, OFF_H4, OFF_D5, 16, p.tm + TC_DW5T, first_tile);        // dW5^T += H4^T d5
+                umma::commit(&bar);
+            }
+            wait_mma(p);
+            read_acc<64>(p, TC_TMP, acc);
+            mask_store(smem, OFF_G, OFF_H4, tid, acc);                                   // dH4
+            publish();
+            if (tid == 0) {
+                umma::fence_after_sync();
+                mma_dgrad(sbase, OFF_G, OFF_W4, 64, 64, 64, tmp);                        // dH3raw = dH4 * W4
+                mma_wgrad(sbase, OFF_G, OFF_H3, 64, p.tm + TC_DW4, first_tile);          // dW4 += dH4^T H3
+                umma::commit(&bar);
+            }
+            wait_mma(p);
+            read_acc<64>(p, TC_TMP, acc);
+            mask_store(smem, OFF_G, OFF_H3, tid, acc);                                   // dH3 (dH4 no longer needed)
+            publish();
+            if (tid == 0) {
+                umma::fence_after_sync();
+                mma_dgrad(sbase, OFF_G, OFF_W3, 64, 32, 64, tmp);                        // dIN2raw = dH3 * W3
+                mma_wgrad(sbase, OFF_G, OFF_IN2, 32, p.tm + TC_DW3, first_tile);         // dW3 += dH3^T [SH|h]
+                umma::commit(&bar);
+            }
+            wait_mma(p);
+            read_acc<32>(p, TC_TMP, acc);                                                // cols 16..31 = d(h)
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] = 0.0f;
+        }
+        {
+            float dh[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) dh[j] = valid ? acc[16 + j] : 0.0f;
+            dh[0] += dh_sigma;
+            st_row8(smem, OFF_DH, tid, 0, dh);
+            st_row8(smem, OFF_DH, tid, 1, dh + 8);
+        }
+        publish();
+        if (tid == 0) {
+            umma::fence_after_sync();
+            mma_dgrad(sbase, OFF_DH, OFF_W2, 16, 64, 16, tmp);                           // dH1raw = dh * W2
+            mma_wgrad(sbase, OFF_H1, OFF_DH, 16, p.tm + TC_DW2T, first_tile);            // dW2^T += H1^T dh
+            umma::commit(&bar);
+        }
+        wait_mma(p);
+        read_acc<64>(p, TC_TMP, acc);
+        mask_store(smem, OFF_G, OFF_H1, tid, acc);                                       // dH1
+        publish();
+        if (tid == 0) {
+            umma::fence_after_sync();
+            mma_dgrad(sbase, OFF_G, OFF_W1, 64, 32, 64, tmp);                            // d(enc) = dH1 * W1
+            mma_wgrad(sbase, OFF_G, OFF_X0, 32, p.tm + TC_DW1, first_tile);              // dW1 += dH1^T enc
+            umma::commit(&bar);
+        }
+        wait_mma(p);
+        read_acc<32>(p, TC_TMP, acc);
+        if (valid) {
+            float4* dst = reinterpret_cast<float4*>(a.denc + s * 32);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) dst[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+        }
+        umma::fence_before_sync();
+    }
+
+    if (BWD && !first_tile) {
+        // flush the weight-gradient accumulators: M = 64 layout -> row 16*warp + lane (lane < 16)
+        __syncthreads();
+        umma::fence_after_sync();
+        const int row = 16 * warp + lane;
+        float v[64];
+        // dW1 [64 out x 32 in]
+        read_acc<32>(p, TC_DW1, v);
+        if (lane < 16) for (int j = 0; j < 32; ++j) atomicAdd(a.dW[0] + row * 32 + j, v[j]);
+        // dW2^T [64 in x 16 out] -> dW2 [16 x 64]
+        read_acc<16>(p, TC_DW2T, v);
+        if (lane < 16) for (int j = 0; j < 16; ++j) atomicAdd(a.dW[1] + j * 64 + row, v[j]);
+        if (!a.density_only) {
+            read_acc<32>(p, TC_DW3, v);
+            if (lane < 16) for (int j = 0; j < 32; ++j) atomicAdd(a.dW[2] + row * 32 + j, v[j]);
+            read_acc<64>(p, TC_DW4, v);
+            if (lane < 16) for (int j = 0; j < 64; ++j) atomicAdd(a.dW[3] + row * 64 + j, v[j]);
+            read_acc<16>(p, TC_DW5T, v);
+            if (lane < 16) for (int j = 0; j < 3; ++j) atomicAdd(a.dW[4] + j * 64 + row, v[j]);
+        }
+        umma::fence_before_sync();
+    }
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(p.tm, BWD ? TMEM_BWD : TMEM_FWD);
+}
+
+int launch_mlp(bool bwd, const MlpArgs& a, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        VN_CUDA(cudaFuncSetAttribute(mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD));
+        VN_CUDA(cudaFuncSetAttribute(mlp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD));
+        attr_set = true;
+    }
+    const int64_t n_tiles = (a.S + TILE - 1) / TILE;
+    const int per_sm = bwd ? 2 : 2;
+    int64_t grid = (int64_t)vn_sm_count() * per_sm;
+    if (grid > n_tiles) grid = n_tiles;
+    if (bwd) mlp_kernel<true><<<(unsigned)grid, TILE, SMEM_BWD, st>>>(a);
+    else     mlp_kernel<false><<<(unsigned)grid, TILE, SMEM_FWD, st>>>(a);
+    VN_CHECK_LAUNCH(bwd ? "mlp_kernel<bwd>" : "mlp_kernel<fwd>");
+    return VN_OK;
+}
+
+}  // namespace
+
+VN_API int vn_mlp_fwd(const void* enc, int enc_half, const float* dirs, const float* W1, const float* W2, const float* W3,
+                      const float* W4, const float* W5, int64_t S, int density_only, float* sigmas, float* rgbs,
+                      float* h_out, void* stream) {
+    VN_REQUIRE(S >= 0, "vn_mlp_fwd: S < 0");
+    if (S == 0) return VN_OK;
+    VN_REQUIRE(enc && W1 && W2 && sigmas, "vn_mlp_fwd: null pointer");
+    VN_REQUIRE(density_only || (dirs && W3 && W4 && W5 && rgbs), "vn_mlp_fwd: null colour-network pointer");
+    VN_REQUIRE(vn_aligned(enc, 16), "vn_mlp_fwd: enc must be 16-byte aligned");
+    MlpArgs a{};
+    a.enc = (const float*)enc; a.enc_half = enc_half; a.dirs = dirs;
+    a.W[0] = W1; a.W[1] = W2; a.W[2] = density_only ? W1 : W3; a.W[3] = density_only ? W1 : W4; a.W[4] = density_only ? W1 : W5;
+    a.sigmas = sigmas; a.rgbs = rgbs; a.h_out = h_out; a.S = S; a.density_only = density_only;
+    return launch_mlp(false, a, (cudaStream_t)stream);
+}
+
+VN_API int vn_mlp_bwd(const void* enc, int enc_half, const float* dirs, const float* W1, const float* W2, const float* W3,
+                      const float* W4, const float* W5, int64_t S, int density_only, const float* dsigmas,
+                      const float* drgbs, float* denc, float* dW1, float* dW2, float* dW3, float* dW4, float* dW5,
+                      void* stream) {
+    VN_REQUIRE(S >= 0, "vn_mlp_bwd: S < 0");
+    if (S == 0) return VN_OK;
+    VN_REQUIRE(enc && W1 && W2 && dsigmas && denc && dW1 && dW2, "vn_mlp_bwd: null pointer");
+    VN_REQUIRE(density_only || (dirs && W3 && W4 && W5 && drgbs && dW3 && dW4 && dW5), "vn_mlp_bwd: null colour-network pointer");
+    VN_REQUIRE(vn_aligned(enc, 16) && vn_aligned(denc, 16), "vn_mlp_bwd: enc/denc must be 16-byte aligned");
+    MlpArgs a{};
+    a.enc = (const float*)enc; a.enc_half = enc_half; a.dirs = dirs;
+    a.W[0] = W1; a.W[1] = W2; a.W[2] = density_only ? W1 : W3; a.W[3] = density_only ? W1 : W4; a.W[4] = density_only ? W1 : W5;
+    a.dsigmas = dsigmas; a.drgbs = drgbs; a.denc = denc;
+    a.dW[0] = dW1; a.dW[1] = dW2; a.dW[2] = dW3; a.dW[3] = dW4; a.dW[4] = dW5;
+    a.S = S; a.density_only = density_only;
+    return launch_mlp(true, a, (cudaStream_t)stream);
+}

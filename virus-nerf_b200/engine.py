@@ -76,6 +76,7 @@ class TrainEngine:
         self.model = NGP(scale=args.model.scale, pos_encoder_type='hash', levels=args.model.hash_levels,
                          max_res=max_res, log2_T=log2_T, half_opt=half_opt, args=args, dataset=dataset)
         self.model.to(self.device)
+        self.model.fused_mlp = self.model.fused_mlp and autocast   # fp32 mode (tests): torch.nn.Linear fp32
         self.loss_fn = Loss(args)
         self.step_idx = 0
         self.grid_update_interval = args.occ_grid.update_interval

@@ -9,8 +9,67 @@ import numpy as np
 import torch
 from torch import nn
 
+from .. import _lib
 from .spherical_harmonics import DirEncoder
 from .volume_train import VolumeRenderer
+
+
+class _FusedMLP(torch.autograd.Function):
+    """density net + SH + colour net as one tcgen05 kernel (vn_mlp_fwd / vn_mlp_bwd):
+    networks.py:142-145 and :160-162.  fp16 operands / fp32 accumulation, i.e. what the
+    reference computes under torch.autocast(float16) on CUDA (trainer.py:104)."""
+
+    @staticmethod
+    def forward(ctx, enc, dirs, W1, W2, W3, W4, W5):
+        S = enc.shape[0]
+        sig = torch.empty(S, dtype=torch.float32, device=enc.device)
+        rgb = torch.empty(S, 3, dtype=torch.float32, device=enc.device)
+        half = 1 if enc.dtype == torch.float16 else 0
+        Ws = [w.detach().float().contiguous() for w in (W1, W2, W3, W4, W5)]
+        _lib.call("vn_mlp_fwd", enc, half, dirs, *Ws, S, 0, sig, rgb, None)
+        ctx.save_for_backward(enc, dirs, *Ws)
+        ctx.half = half
+        return sig, rgb
+
+    @staticmethod
+    def backward(ctx, dsig, drgb):
+        enc, dirs, *Ws = ctx.saved_tensors
+        S = enc.shape[0]
+        denc = torch.empty(S, 32, dtype=torch.float32, device=enc.device)
+        dWs = [torch.zeros_like(w) for w in Ws]
+        dsig = torch.zeros(S, device=enc.device) if dsig is None else dsig.contiguous().float()
+        drgb = torch.zeros(S, 3, device=enc.device) if drgb is None else drgb.contiguous().float()
+        _lib.call("vn_mlp_bwd", enc, ctx.half, dirs, *Ws, S, 0, dsig, drgb, denc, *dWs)
+        return (denc.to(enc.dtype), None, *dWs)
+
+
+class _FusedDensity(torch.autograd.Function):
+    """density net only (NGP.density): vn_mlp_fwd / vn_mlp_bwd with density_only = 1"""
+
+    @staticmethod
+    def forward(ctx, enc, W1, W2, want_h):
+        S = enc.shape[0]
+        sig = torch.empty(S, dtype=torch.float32, device=enc.device)
+        h = torch.empty(S, 16, dtype=torch.float32, device=enc.device) if want_h else None
+        half = 1 if enc.dtype == torch.float16 else 0
+        W1c, W2c = W1.detach().float().contiguous(), W2.detach().float().contiguous()
+        _lib.call("vn_mlp_fwd", enc, half, None, W1c, W2c, None, None, None, S, 1, sig, None, h)
+        ctx.save_for_backward(enc, W1c, W2c)
+        ctx.half = half
+        if want_h:
+            ctx.mark_non_differentiable(h)
+            return sig, h
+        return sig
+
+    @staticmethod
+    def backward(ctx, dsig, *_):
+        enc, W1, W2 = ctx.saved_tensors
+        S = enc.shape[0]
+        denc = torch.empty(S, 32, dtype=torch.float32, device=enc.device)
+        dW1, dW2 = torch.zeros_like(W1), torch.zeros_like(W2)
+        _lib.call("vn_mlp_bwd", enc, ctx.half, None, W1, W2, None, None, None, S, 1, dsig.contiguous().float(), None,
+                  denc, dW1, dW2, None, None, None)
+        return denc.to(enc.dtype), dW1, dW2, None
 
 
 class TruncExp(torch.autograd.Function):
@@ -106,6 +165,10 @@ class NGP(nn.Module):
         self.cascades = max(1 + int(np.ceil(np.log2(2 * scale))), 1)   # :65
         self.grid_size = 128                                            # :66
         self.half_opt = half_opt
+        # fused tcgen05 MLP (fp16 operands, as the reference under autocast on CUDA).  Set to False
+        # to run the layers as fp32 torch.nn.Linear (the reference's CUDA-less behaviour; used by
+        # the fp32 parity tests).
+        self.fused_mlp = (xyz_net_width, xyz_net_depth, xyz_net_out_dim, rgb_net_depth, rgb_net_width) == (64, 1, 16, 2, 64)
 
         if pos_encoder_type == 'hash':
             if half_opt:
@@ -139,14 +202,27 @@ class NGP(nn.Module):
         """networks.py:134-148"""
         x = (x - self.xyz_min) / (self.xyz_max - self.xyz_min)
         embedding = self.pos_encoder(x)
+        if self._use_fused(embedding):
+            return _FusedDensity.apply(embedding.contiguous(), self.xyz_encoder.hidden_layers[0].weight,
+                                       self.xyz_encoder.output_layer.weight, return_feat)
         h = self.xyz_encoder(embedding)
         sigmas = TruncExp.apply(h[:, 0])
         if return_feat:
             return sigmas, h
         return sigmas
 
+    def _use_fused(self, t):
+        return self.fused_mlp and t.is_cuda and self.pos_encoder.out_dim == 32
+
     def forward(self, x, d):
         """networks.py:150-164"""
+        if self._use_fused(x):
+            xn = (x - self.xyz_min) / (self.xyz_max - self.xyz_min)
+            embedding = self.pos_encoder(xn)
+            return _FusedMLP.apply(embedding.contiguous(), d.contiguous().float(),
+                                   self.xyz_encoder.hidden_layers[0].weight, self.xyz_encoder.output_layer.weight,
+                                   self.rgb_net.hidden_layers[0].weight, self.rgb_net.hidden_layers[1].weight,
+                                   self.rgb_net.output_layer.weight)
         sigmas, h = self.density(x, return_feat=True)
         d = d / torch.norm(d, dim=1, keepdim=True)
         d = self.dir_encoder((d + 1) / 2)

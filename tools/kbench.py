@@ -99,6 +99,19 @@ def main():
                     ms = timeit(lambda: _lib.call("vn_hash_encode_bwd_f16", x, douth, grad, S, lv, 0))
                     rec("hash_bwd_f16", ms, state=state, S=S, log2_T=log2_T, flags=0, gbs=round(S * 1100 / ms / 1e6, 1))
                     del table, grad
+    if "mlp" in which or "hash" in which:
+        g = torch.Generator().manual_seed(0)
+        xav = lambda o, i: ((torch.rand(o, i, generator=g) * 2 - 1) * (6.0 / (i + o)) ** 0.5).to(DEV)
+        W = [xav(64, 32), xav(16, 64), xav(64, 32), xav(64, 64), xav(3, 64)]
+        for S in (69710, 1 << 20):
+            enc = torch.rand(S, 32, device=DEV); dirs = torch.randn(S, 3, device=DEV)
+            sig = torch.empty(S, device=DEV); rgb = torch.empty(S, 3, device=DEV)
+            ms = timeit(lambda: _lib.call("vn_mlp_fwd", enc, 0, dirs, *W, S, 0, sig, rgb, None))
+            rec("mlp_fwd", ms, S=S, tflops=round(S * 18816 / ms / 1e9, 2), gbs=round(S * 156 / ms / 1e6, 1))
+            dsig = torch.randn(S, device=DEV); drgb = torch.randn(S, 3, device=DEV)
+            denc = torch.empty(S, 32, device=DEV); dW = [torch.zeros_like(w) for w in W]
+            ms = timeit(lambda: _lib.call("vn_mlp_bwd", enc, 0, dirs, *W, S, 0, dsig, drgb, denc, *dW))
+            rec("mlp_bwd", ms, S=S, tflops=round(S * 56448 / ms / 1e9, 2), gbs=round(S * 284 / ms / 1e6, 1))
     if "adam" in which:
         n = 11429472
         p, g, m, v = (torch.randn(n, device=DEV) for _ in range(4))

@@ -2,7 +2,7 @@
 // Replaces modules/volume_train.py:6-48 (+ Taichi autodiff, :130-175) and
 // modules/volume_render_test.py:4-54.
 //
-// Transmittance lives in a register (the reference round-trips a global T[] scratch and
+// Transmittance lives in registers (the reference round-trips a global T[] scratch and
 // read-modify-writes the per-ray outputs every sample); skipped samples get ws = 0.
 #include "common.cuh"
 
@@ -14,39 +14,81 @@ __device__ __forceinline__ float alpha_of(float sigma, float delta) {
 }
 
 // ---- a8 ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) composite_fwd_kernel(const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+// One WARP per ray.  Lanes take 32 consecutive samples (coalesced loads), alpha is computed
+// per lane, the transmittance in front of each sample is an exclusive product scan over the
+// warp (shuffles) times the running transmittance of the previous chunks.  T is monotone
+// non-increasing, so "T > threshold" (volume_train.py:36) selects a prefix of the ray: the
+// chunk loop stops at the first chunk whose first sample fails the test.
+#define VN_FULL 0xffffffffu
+
+__device__ __forceinline__ float warp_excl_prod(float v, int lane, float* total) {
+    float inc = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const float o = __shfl_up_sync(VN_FULL, inc, off);
+        if (lane >= off) inc *= o;
+    }
+    *total = __shfl_sync(VN_FULL, inc, 31);
+    const float ex = __shfl_up_sync(VN_FULL, inc, 1);
+    return lane == 0 ? 1.0f : ex;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(VN_FULL, v, off);
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(VN_FULL, v, off);
+    return v;
+}
+
+__global__ void __launch_bounds__(256) composite_fwd_kernel(const float* __restrict__ sigmas, const float* __restrict__ rgbs,
                                                             const float* __restrict__ deltas, const float* __restrict__ ts,
                                                             const int32_t* __restrict__ rays_a, int64_t N, int64_t S,
                                                             float T_thr, int32_t* __restrict__ total_samples,
                                                             float* __restrict__ opacity, float* __restrict__ depth,
                                                             float* __restrict__ rgb, float* __restrict__ ws) {
-    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (n >= N) return;
     const int ray = rays_a[3 * n];
     const int64_t start = rays_a[3 * n + 1];
     int ns = rays_a[3 * n + 2];
     if (start + ns > S) ns = (int)max((int64_t)0, S - start);
     float r0 = 0.f, r1 = 0.f, r2 = 0.f, dep = 0.f, op = 0.f, T = 1.0f;
-    int cnt = 0;
-    for (int k = 0; k < ns; ++k) {
+    int cnt = 0, k0 = 0;
+    for (; k0 < ns; k0 += 32) {
+        if (!(T > T_thr)) break;                                    // warp-uniform
+        const int k = k0 + lane;
+        const bool in = k < ns;
         const int64_t s = start + k;
-        if (T > T_thr) {                                            // :36
-            const float a = alpha_of(__ldg(sigmas + s), __ldg(deltas + s));
-            const float w = vn_mul(a, T);                           // :38
-            r0 = vn_add(r0, vn_mul(w, __ldg(rgbs + 3 * s)));
-            r1 = vn_add(r1, vn_mul(w, __ldg(rgbs + 3 * s + 1)));
-            r2 = vn_add(r2, vn_mul(w, __ldg(rgbs + 3 * s + 2)));
-            dep = vn_add(dep, vn_mul(w, __ldg(ts + s)));
-            op = vn_add(op, w);
-            ws[s] = w;
-            T = vn_mul(T, vn_sub(1.0f, a));                         // :47
-            ++cnt;
-        } else {
-            ws[s] = 0.0f;
+        float a = 0.0f, c0 = 0.f, c1 = 0.f, c2 = 0.f, tm = 0.f;
+        if (in) {
+            a = alpha_of(__ldg(sigmas + s), __ldg(deltas + s));     // :37
+            c0 = __ldg(rgbs + 3 * s); c1 = __ldg(rgbs + 3 * s + 1); c2 = __ldg(rgbs + 3 * s + 2);
+            tm = __ldg(ts + s);
         }
+        float chunk_prod;
+        const float Tj = T * warp_excl_prod(1.0f - a, lane, &chunk_prod);   // transmittance in front of sample k
+        const bool use = in && (Tj > T_thr);                        // :36
+        const float w = use ? a * Tj : 0.0f;                        // :38
+        if (in) ws[s] = w;
+        r0 += w * c0; r1 += w * c1; r2 += w * c2; dep += w * tm; op += w;
+        const unsigned m = __ballot_sync(VN_FULL, use);
+        cnt += __popc(m);
+        // transmittance after the last USED sample of this chunk (prefix property)
+        const int last = 31 - __clz(m | 1u);
+        const float Tafter = __shfl_sync(VN_FULL, Tj * (1.0f - a), last);
+        T = (m == 0u) ? T : Tafter;
+        if (m != __ballot_sync(VN_FULL, in)) { k0 += 32; break; }   // threshold hit inside this chunk
     }
-    rgb[3 * ray] = r0; rgb[3 * ray + 1] = r1; rgb[3 * ray + 2] = r2;
-    depth[ray] = dep; opacity[ray] = op; total_samples[ray] = cnt;
+    for (int k = k0 + lane; k < ns; k += 32) ws[start + k] = 0.0f;  // skipped tail
+    r0 = warp_sum(r0); r1 = warp_sum(r1); r2 = warp_sum(r2); dep = warp_sum(dep); op = warp_sum(op);
+    if (lane == 0) {
+        rgb[3 * ray] = r0; rgb[3 * ray + 1] = r1; rgb[3 * ray + 2] = r2;
+        depth[ray] = dep; opacity[ray] = op; total_samples[ray] = cnt;
+    }
 }
 
 VN_API int vn_composite_train_fwd(const float* sigmas, const float* rgbs, const float* deltas, const float* ts,
@@ -57,9 +99,9 @@ VN_API int vn_composite_train_fwd(const float* sigmas, const float* rgbs, const 
     if (N == 0) return VN_OK;
     VN_REQUIRE(rays_a && total_samples && opacity && depth && rgb, "vn_composite_train_fwd: null pointer");
     VN_REQUIRE(S == 0 || (sigmas && rgbs && deltas && ts && ws), "vn_composite_train_fwd: null sample pointer");
-    composite_fwd_kernel<<<vn_blocks(N, 128), 128, 0, (cudaStream_t)stream>>>(sigmas, rgbs, deltas, ts, rays_a, N, S,
-                                                                            T_threshold, total_samples, opacity,
-                                                                            depth, rgb, ws);
+    composite_fwd_kernel<<<vn_blocks(N * 32, 256), 256, 0, (cudaStream_t)stream>>>(sigmas, rgbs, deltas, ts, rays_a, N, S,
+                                                                                 T_threshold, total_samples, opacity,
+                                                                                 depth, rgb, ws);
     VN_CHECK_LAUNCH("composite_fwd_kernel");
     return VN_OK;
 }
@@ -67,16 +109,18 @@ VN_API int vn_composite_train_fwd(const float* sigmas, const float* rgbs, const 
 // ---- a9 ---------------------------------------------------------------------------------
 // With G_s = dL/drgb.c_s + dL/ddepth t_s + dL/dopacity + dL/dws_s and R = sum_j G_j w_j:
 //   dL/dsigma_s = delta_s * (G_s T_{s+1} - sum_{j>s} G_j w_j),   dL/dc_s = w_s dL/drgb.
-// Sweep 1 accumulates R, sweep 2 walks front to back with the running prefix (both in double:
-// the suffix R - prefix cancels heavily for the last samples of a ray).
-__global__ void __launch_bounds__(128) composite_bwd_kernel(const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+// One warp per ray, two sweeps over the ray: sweep 1 accumulates R, sweep 2 forms the suffix
+// as R - (inclusive prefix); R and the prefix are kept in double because the suffix cancels
+// heavily for the last samples of a ray.
+__global__ void __launch_bounds__(256) composite_bwd_kernel(const float* __restrict__ sigmas, const float* __restrict__ rgbs,
                                                             const float* __restrict__ deltas, const float* __restrict__ ts,
                                                             const int32_t* __restrict__ rays_a, int64_t N, int64_t S,
                                                             float T_thr, const float* __restrict__ dL_dopacity,
                                                             const float* __restrict__ dL_ddepth, const float* __restrict__ dL_drgb,
                                                             const float* __restrict__ dL_dws, float* __restrict__ dsigmas,
                                                             float* __restrict__ drgbs) {
-    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (n >= N) return;
     const int ray = rays_a[3 * n];
     const int64_t start = rays_a[3 * n + 1];
@@ -84,38 +128,72 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(const float* __restr
     if (start + ns > S) ns = (int)max((int64_t)0, S - start);
     const float g0 = __ldg(dL_drgb + 3 * ray), g1 = __ldg(dL_drgb + 3 * ray + 1), g2 = __ldg(dL_drgb + 3 * ray + 2);
     const float gd = __ldg(dL_ddepth + ray), go = __ldg(dL_dopacity + ray);
-    double R = 0.0;
+    // ---- sweep 1: R = sum G_j w_j over the used prefix
+    double Rl = 0.0;
     float T = 1.0f;
-    int last = 0;
-    for (int k = 0; k < ns; ++k) {
-        const int64_t s = start + k;
+    for (int k0 = 0; k0 < ns; k0 += 32) {
         if (!(T > T_thr)) break;
-        const float a = alpha_of(__ldg(sigmas + s), __ldg(deltas + s));
-        const float w = vn_mul(a, T);
-        float G = g0 * __ldg(rgbs + 3 * s) + g1 * __ldg(rgbs + 3 * s + 1) + g2 * __ldg(rgbs + 3 * s + 2) +
-                  gd * __ldg(ts + s) + go;
-        if (dL_dws) G += __ldg(dL_dws + s);
-        R += (double)G * (double)w;
-        T = vn_mul(T, vn_sub(1.0f, a));
-        last = k + 1;
+        const int k = k0 + lane;
+        const bool in = k < ns;
+        const int64_t s = start + k;
+        float a = 0.0f, G = 0.0f;
+        if (in) {
+            a = alpha_of(__ldg(sigmas + s), __ldg(deltas + s));
+            G = g0 * __ldg(rgbs + 3 * s) + g1 * __ldg(rgbs + 3 * s + 1) + g2 * __ldg(rgbs + 3 * s + 2) + gd * __ldg(ts + s) + go;
+            if (dL_dws) G += __ldg(dL_dws + s);
+        }
+        float chunk_prod;
+        const float Tj = T * warp_excl_prod(1.0f - a, lane, &chunk_prod);
+        const bool use = in && (Tj > T_thr);
+        if (use) Rl += (double)G * (double)(a * Tj);
+        const unsigned m = __ballot_sync(VN_FULL, use);
+        const int last = 31 - __clz(m | 1u);
+        const float Tafter = __shfl_sync(VN_FULL, Tj * (1.0f - a), last);
+        T = (m == 0u) ? T : Tafter;
+        if (m != __ballot_sync(VN_FULL, in)) break;
     }
+    const double R = warp_sum_d(Rl);
+    // ---- sweep 2
     T = 1.0f;
     double prefix = 0.0;
-    for (int k = 0; k < last; ++k) {
+    int k0 = 0;
+    for (; k0 < ns; k0 += 32) {
+        if (!(T > T_thr)) break;
+        const int k = k0 + lane;
+        const bool in = k < ns;
         const int64_t s = start + k;
-        const float delta = __ldg(deltas + s);
-        const float a = alpha_of(__ldg(sigmas + s), delta);
-        const float w = vn_mul(a, T);
-        float G = g0 * __ldg(rgbs + 3 * s) + g1 * __ldg(rgbs + 3 * s + 1) + g2 * __ldg(rgbs + 3 * s + 2) +
-                  gd * __ldg(ts + s) + go;
-        if (dL_dws) G += __ldg(dL_dws + s);
-        prefix += (double)G * (double)w;
-        const float Tn = vn_mul(T, vn_sub(1.0f, a));
-        dsigmas[s] = (float)((double)delta * ((double)G * (double)Tn - (R - prefix)));
-        drgbs[3 * s] = w * g0; drgbs[3 * s + 1] = w * g1; drgbs[3 * s + 2] = w * g2;
-        T = Tn;
+        float a = 0.0f, G = 0.0f, delta = 0.0f;
+        if (in) {
+            delta = __ldg(deltas + s);
+            a = alpha_of(__ldg(sigmas + s), delta);
+            G = g0 * __ldg(rgbs + 3 * s) + g1 * __ldg(rgbs + 3 * s + 1) + g2 * __ldg(rgbs + 3 * s + 2) + gd * __ldg(ts + s) + go;
+            if (dL_dws) G += __ldg(dL_dws + s);
+        }
+        float chunk_prod;
+        const float Tj = T * warp_excl_prod(1.0f - a, lane, &chunk_prod);
+        const bool use = in && (Tj > T_thr);
+        const float w = use ? a * Tj : 0.0f;
+        // inclusive prefix of G*w inside the chunk (double)
+        double inc = (double)G * (double)w;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const double o = __shfl_up_sync(VN_FULL, inc, off);
+            if (lane >= off) inc += o;
+        }
+        const double pre = prefix + inc;
+        prefix += __shfl_sync(VN_FULL, inc, 31);
+        if (in) {
+            const float Tn = Tj * (1.0f - a);
+            dsigmas[s] = use ? (float)((double)delta * ((double)G * (double)Tn - (R - pre))) : 0.0f;
+            drgbs[3 * s] = w * g0; drgbs[3 * s + 1] = w * g1; drgbs[3 * s + 2] = w * g2;
+        }
+        const unsigned m = __ballot_sync(VN_FULL, use);
+        const int last = 31 - __clz(m | 1u);
+        const float Tafter = __shfl_sync(VN_FULL, Tj * (1.0f - a), last);
+        T = (m == 0u) ? T : Tafter;
+        if (m != __ballot_sync(VN_FULL, in)) { k0 += 32; break; }
     }
-    for (int k = last; k < ns; ++k) {
+    for (int k = k0 + lane; k < ns; k += 32) {
         const int64_t s = start + k;
         dsigmas[s] = 0.0f;
         drgbs[3 * s] = 0.0f; drgbs[3 * s + 1] = 0.0f; drgbs[3 * s + 2] = 0.0f;
@@ -130,7 +208,7 @@ VN_API int vn_composite_train_bwd(const float* sigmas, const float* rgbs, const 
     if (N == 0 || S == 0) return VN_OK;
     VN_REQUIRE(sigmas && rgbs && deltas && ts && rays_a && dL_dopacity && dL_ddepth && dL_drgb && dsigmas && drgbs,
                "vn_composite_train_bwd: null pointer");
-    composite_bwd_kernel<<<vn_blocks(N, 128), 128, 0, (cudaStream_t)stream>>>(
+    composite_bwd_kernel<<<vn_blocks(N * 32, 256), 256, 0, (cudaStream_t)stream>>>(
         sigmas, rgbs, deltas, ts, rays_a, N, S, T_threshold, dL_dopacity, dL_ddepth, dL_drgb, dL_dws, dsigmas, drgbs);
     VN_CHECK_LAUNCH("composite_bwd_kernel");
     return VN_OK;

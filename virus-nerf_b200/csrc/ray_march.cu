@@ -126,25 +126,185 @@ __device__ __forceinline__ float jittered_t1(const MarchCfg& c, float t1, float 
     return t1;
 }
 
-// ---- a6 pass 1 --------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) march_count_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
-                                                          const float2* __restrict__ hits_t, const uint8_t* __restrict__ bitfield,
-                                                          const float* __restrict__ noise, int64_t N, const MarchCfg c,
-                                                          int max_samples, int32_t* __restrict__ counts) {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// ---- a6: warp-cooperative marcher (both passes) --------------------------------------------
+// The sample positions of a ray form a FIXED lattice t_{k+1} = fl(t_k + dt(t_k)) that does not
+// depend on the occupancy (both branches of the reference advance t by calc_dt(t)); occupancy
+// only decides which lattice points are emitted and which are skipped without being looked
+// at (t < t_target).  One warp marches one ray: every lane regenerates the next 32 lattice
+// points with the reference's sequential float adds (bit-identical t), probes "its" point in
+// parallel (one bitfield latency per 32 points instead of 32), and the emit / skip chain is
+// then resolved with ballots.  Points that turn out to be skipped were probed speculatively;
+// that costs bandwidth, not correctness.
+__device__ __forceinline__ float lattice32(const MarchCfg& c, float t0, int lane, float* t_after) {
+    float t = t0, mine = t0;
+    if (c.esf == 0.0f) {
+        const float dt = vn_calc_dt(0.0f, 0.0f, c.dt_max);      // constant step
+#pragma unroll
+        for (int k = 0; k < 32; ++k) { if (k == lane) mine = t; t = vn_add(t, dt); }
+    } else {
+#pragma unroll 4
+        for (int k = 0; k < 32; ++k) { if (k == lane) mine = t; t = vn_add(t, vn_calc_dt(t, c.esf, c.dt_max)); }
+    }
+    *t_after = t;
+    return mine;
+}
+
+// occupancy at lattice point t and, when empty, the reference's skip target (ray_march.py:67-70)
+__device__ __forceinline__ bool probe_point(const MarchCfg& c, const Ray& ray, const uint8_t* __restrict__ bitfield, float t,
+                                            float* xyz, float* dt_out, float* t_target) {
+    float mx = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { xyz[k] = vn_add(ray.o[k], vn_mul(t, ray.d[k])); mx = fmaxf(mx, fabsf(xyz[k])); }   // :45
+    const float dt = vn_calc_dt(t, c.esf, c.dt_max);
+    int mip = 0;
+    if (c.cascades > 1) {
+        const int m_pos = min(c.cascades - 1, max(0, vn_frexp_bit(mx) + 1));
+        const int m_dt = min(c.cascades - 1, max(0, vn_frexp_bit(vn_mul(dt, c.Gf))));
+        mip = max(m_pos, m_dt);
+    }
+    const float mip_bound = fminf(ldexpf(1.0f, mip - 1), c.scale);
+    const float mip_bound_inv = vn_div(1.0f, mip_bound);
+    float nxyz[3];
+    uint32_t ci[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        nxyz[k] = vn_clamp(vn_mul(vn_mul(0.5f, vn_add(vn_mul(xyz[k], mip_bound_inv), 1.0f)), c.Gf), 0.0f, c.Gm1);
+        ci[k] = vn_f2u(nxyz[k]);
+    }
+    const uint32_t idx = (uint32_t)mip * c.G3 + vn_morton3D(ci[0], ci[1], ci[2]);
+    const bool occ = (__ldg(bitfield + (idx >> 3)) & (1u << (idx & 7u))) != 0;
+    *dt_out = dt;
+    float tmin = INFINITY;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float sgn = (ray.d[k] > 0.0f) ? 1.0f : ((ray.d[k] < 0.0f) ? -1.0f : 0.0f);
+        float v = vn_add(vn_add(nxyz[k], 0.5f), vn_mul(0.5f, sgn));
+        v = vn_sub(vn_mul(vn_mul(v, c.G_inv), 2.0f), 1.0f);
+        v = vn_mul(vn_sub(vn_mul(v, mip_bound), xyz[k]), ray.dinv[k]);
+        tmin = fminf(tmin, v);
+    }
+    *t_target = vn_add(t, fmaxf(0.0f, tmin));
+    return occ;
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(256) march_warp_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                         const float2* __restrict__ hits_t, const uint8_t* __restrict__ bitfield,
+                                                         const float* __restrict__ noise, int64_t N, const MarchCfg c,
+                                                         int max_samples, int32_t* __restrict__ counts,
+                                                         const int32_t* __restrict__ rays_a, int64_t capacity,
+                                                         float* __restrict__ xyzs, float* __restrict__ dirs,
+                                                         float* __restrict__ deltas, float* __restrict__ ts) {
+    const unsigned full = 0xffffffffu;
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (r >= N) return;
+    int n_max = max_samples;
+    int64_t start = 0;
+    if (WRITE) {
+        start = rays_a[3 * r + 1];
+        n_max = rays_a[3 * r + 2];
+        if (n_max == 0) return;
+    }
     const Ray ray = load_ray(rays_o, rays_d, r);
     const float2 h = __ldg(hits_t + r);
     float t = jittered_t1(c, h.x, __ldg(noise + r));
     const float t2 = h.y;
     int n = 0;
-    while (0.0f <= t && t < t2 && n < max_samples) {                 // :44
-        float xyz[3], dt, tn;
-        if (march_probe(c, ray, bitfield, t, xyz, &dt, &tn)) { t = vn_add(t, dt); ++n; }
-        else t = tn;
+    bool pending = false;
+    float pending_target = 0.0f;
+    while (0.0f <= t && t < t2 && n < n_max) {                       // ray_march.py:44 (warp-uniform)
+        float t_after;
+        const float ti = lattice32(c, t, lane, &t_after);
+        const bool inr = ti < t2;
+        float xyz[3] = {0.f, 0.f, 0.f}, dt = 0.0f, ttar = 0.0f;
+        bool occ = false;
+        if (inr) occ = probe_point(c, ray, bitfield, ti, xyz, &dt, &ttar);
+        const unsigned inmask = __ballot_sync(full, inr);
+        const unsigned occmask = __ballot_sync(full, inr && occ);
+        int cur = 0;
+        unsigned emit = 0u;
+        bool done = false;
+        if (pending) {                                               // skip started in the previous chunk
+            const unsigned ge = __ballot_sync(full, ti >= pending_target);
+            if (ge == 0u) cur = 32; else { cur = __ffs(ge) - 1; pending = false; }
+        }
+        while (cur < 32) {
+            if (!((inmask >> cur) & 1u)) { done = true; break; }     // t >= t2
+            const int room = n_max - n - __popc(emit);
+            if (room <= 0) { done = true; break; }                   // N_samples == max_samples
+            if ((occmask >> cur) & 1u) {
+                const unsigned run = occmask >> cur;
+                int len = (~run == 0u) ? 32 : (__ffs(~run) - 1);     // consecutive occupied points
+                len = min(len, room);
+                const unsigned bits = (len >= 32) ? full : ((1u << len) - 1u);
+                emit |= bits << cur;
+                cur += len;
+            } else {
+                const float tt = __shfl_sync(full, ttar, cur);
+                unsigned ge = __ballot_sync(full, ti >= tt);
+                ge &= (cur >= 31) ? 0u : (full << (cur + 1));        // at least one step (:71)
+                if (ge == 0u) { pending = true; pending_target = tt; cur = 32; }
+                else cur = __ffs(ge) - 1;
+            }
+        }
+        if (WRITE) {
+            if ((emit >> lane) & 1u) {
+                const int64_t s = start + n + __popc(emit & ((1u << lane) - 1u));
+                if (s < capacity) {
+                    xyzs[3 * s] = xyz[0]; xyzs[3 * s + 1] = xyz[1]; xyzs[3 * s + 2] = xyz[2];
+                    dirs[3 * s] = ray.d[0]; dirs[3 * s + 1] = ray.d[1]; dirs[3 * s + 2] = ray.d[2];
+                    ts[s] = ti; deltas[s] = dt;
+                }
+            }
+        }
+        n += __popc(emit);
+        if (done) break;
+        t = t_after;
     }
-    counts[r] = n;
+    if (!WRITE && lane == 0) counts[r] = n;
 }
+
+// thread-per-ray variant of both passes: preferable when there are enough rays to fill the
+// machine and most lattice points are skipped (carved scenes), because skipped points are
+// never probed.  Bit-identical results; the launcher picks by ray count.
+template <bool WRITE>
+__global__ void __launch_bounds__(128) march_thread_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                           const float2* __restrict__ hits_t, const uint8_t* __restrict__ bitfield,
+                                                           const float* __restrict__ noise, int64_t N, const MarchCfg c,
+                                                           int max_samples, int32_t* __restrict__ counts,
+                                                           const int32_t* __restrict__ rays_a, int64_t capacity,
+                                                           float* __restrict__ xyzs, float* __restrict__ dirs,
+                                                           float* __restrict__ deltas, float* __restrict__ ts) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= N) return;
+    int n_max = max_samples;
+    int64_t start = 0;
+    if (WRITE) { start = rays_a[3 * r + 1]; n_max = rays_a[3 * r + 2]; if (n_max == 0) return; }
+    const Ray ray = load_ray(rays_o, rays_d, r);
+    const float2 h = __ldg(hits_t + r);
+    float t = jittered_t1(c, h.x, __ldg(noise + r));
+    const float t2 = h.y;
+    int n = 0;
+    while (0.0f <= t && t < t2 && n < n_max) {                       // :44 / :87
+        float xyz[3], dt, tn;
+        if (march_probe(c, ray, bitfield, t, xyz, &dt, &tn)) {
+            if (WRITE) {
+                const int64_t s = start + n;
+                if (s < capacity) {
+                    xyzs[3 * s] = xyz[0]; xyzs[3 * s + 1] = xyz[1]; xyzs[3 * s + 2] = xyz[2];
+                    dirs[3 * s] = ray.d[0]; dirs[3 * s + 1] = ray.d[1]; dirs[3 * s + 2] = ray.d[2];
+                    ts[s] = t; deltas[s] = dt;
+                }
+            }
+            t = vn_add(t, dt); ++n;
+        } else t = tn;
+    }
+    if (!WRITE) counts[r] = n;
+}
+
+// rays at or above this count use the thread-per-ray marcher
+static const int64_t kWarpMarchMaxRays = 16384;
 
 // ---- exclusive scan (i32), hierarchical: 1024 elements per block ---------------------------
 __global__ void __launch_bounds__(256) scan_block_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out,
@@ -242,9 +402,15 @@ VN_API int vn_march_train_count(const float* rays_o, const float* rays_d, const 
     VN_REQUIRE(cascades >= 1 && grid_size >= 1 && grid_size <= 1024 && max_samples >= 0,
                "vn_march_train_count: bad cascades/grid_size/max_samples");
     const MarchCfg c = make_cfg(cascades, grid_size, scale, exp_step_factor);
-    march_count_kernel<<<vn_blocks(N, 128), 128, 0, st>>>(rays_o, rays_d, (const float2*)hits_t, bitfield, noise, N, c,
-                                                          max_samples, counts);
-    VN_CHECK_LAUNCH("march_count_kernel");
+    if (N < kWarpMarchMaxRays)
+        march_warp_kernel<false><<<vn_blocks(N * 32, 256), 256, 0, st>>>(rays_o, rays_d, (const float2*)hits_t, bitfield,
+                                                                         noise, N, c, max_samples, counts, nullptr, 0,
+                                                                         nullptr, nullptr, nullptr, nullptr);
+    else
+        march_thread_kernel<false><<<vn_blocks(N, 128), 128, 0, st>>>(rays_o, rays_d, (const float2*)hits_t, bitfield, noise,
+                                                                      N, c, max_samples, counts, nullptr, 0, nullptr,
+                                                                      nullptr, nullptr, nullptr);
+    VN_CHECK_LAUNCH("march kernel <count>");
     int32_t* starts = scan_tmp;
     int rc = exclusive_scan_i32(counts, starts, N, scan_tmp + round_up4(N), st);
     if (rc) return rc;
@@ -253,37 +419,7 @@ VN_API int vn_march_train_count(const float* rays_o, const float* rays_d, const 
     return VN_OK;
 }
 
-// ---- a6 pass 2 --------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) march_write_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
-                                                          const float2* __restrict__ hits_t, const uint8_t* __restrict__ bitfield,
-                                                          const float* __restrict__ noise, int64_t N, const MarchCfg c,
-                                                          const int32_t* __restrict__ rays_a, int64_t capacity,
-                                                          float* __restrict__ xyzs, float* __restrict__ dirs,
-                                                          float* __restrict__ deltas, float* __restrict__ ts) {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= N) return;
-    const int64_t start = rays_a[3 * r + 1];
-    const int n = rays_a[3 * r + 2];
-    if (n == 0) return;
-    const Ray ray = load_ray(rays_o, rays_d, r);
-    const float2 h = __ldg(hits_t + r);
-    float t = jittered_t1(c, h.x, __ldg(noise + r));
-    const float t2 = h.y;
-    int samples = 0;
-    while (t < t2 && samples < n) {                                   // :87
-        float xyz[3], dt, tn;
-        if (march_probe(c, ray, bitfield, t, xyz, &dt, &tn)) {
-            const int64_t s = start + samples;
-            if (s < capacity) {
-                xyzs[3 * s] = xyz[0]; xyzs[3 * s + 1] = xyz[1]; xyzs[3 * s + 2] = xyz[2];   // :103-105
-                dirs[3 * s] = ray.d[0]; dirs[3 * s + 1] = ray.d[1]; dirs[3 * s + 2] = ray.d[2];
-                ts[s] = t; deltas[s] = dt;                               // :109-110
-            }
-            t = vn_add(t, dt); ++samples;
-        } else t = tn;
-    }
-}
-
+// ---- a6 pass 2: march_warp_kernel<true> -----------------------------------------------------
 VN_API int vn_march_train_write(const float* rays_o, const float* rays_d, const float* hits_t, const uint8_t* bitfield,
                                 const float* noise, int64_t N, int cascades, int grid_size, float scale,
                                 float exp_step_factor, const int32_t* rays_a, int64_t capacity, float* xyzs,
@@ -294,9 +430,13 @@ VN_API int vn_march_train_write(const float* rays_o, const float* rays_d, const 
                "vn_march_train_write: null pointer");
     VN_REQUIRE(vn_aligned(hits_t, 8), "vn_march_train_write: hits_t must be 8-byte aligned");
     const MarchCfg c = make_cfg(cascades, grid_size, scale, exp_step_factor);
-    march_write_kernel<<<vn_blocks(N, 128), 128, 0, (cudaStream_t)stream>>>(
-        rays_o, rays_d, (const float2*)hits_t, bitfield, noise, N, c, rays_a, capacity, xyzs, dirs, deltas, ts);
-    VN_CHECK_LAUNCH("march_write_kernel");
+    if (N < kWarpMarchMaxRays)
+        march_warp_kernel<true><<<vn_blocks(N * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+            rays_o, rays_d, (const float2*)hits_t, bitfield, noise, N, c, 0, nullptr, rays_a, capacity, xyzs, dirs, deltas, ts);
+    else
+        march_thread_kernel<true><<<vn_blocks(N, 128), 128, 0, (cudaStream_t)stream>>>(
+            rays_o, rays_d, (const float2*)hits_t, bitfield, noise, N, c, 0, nullptr, rays_a, capacity, xyzs, dirs, deltas, ts);
+    VN_CHECK_LAUNCH("march kernel <write>");
     return VN_OK;
 }
 

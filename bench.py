@@ -35,6 +35,7 @@ def parse():
     ap.add_argument("--cpu-rays", type=int, default=512, help="rays per step of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-autocast", action="store_true")
+    ap.add_argument("--autograd-step", action="store_true", help="use the torch-autograd step instead of the fused step")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end phase (profiling runs only)")
     return ap.parse_args()
 
@@ -208,7 +209,7 @@ def run_ours(a):
                 h2d = sum(t.numel() * t.element_size() for t in hb)
             else:
                 data = ds(n, args.training.sampling_strategy)
-            loss = eng.step(data)
+            loss = eng.step_fast(data) if not a.autograd_step else eng.step(data)
             if pinned:
                 loss_host.copy_(loss.reshape(1), non_blocking=False)     # D2H read of the step's result
                 d2h = 4

@@ -99,7 +99,9 @@ int vn_ray_aabb(const float* rays_o, const float* rays_d, float scale, int64_t N
  *          atomic counter: rays_a [N,3] i32 = (r, exclusive scan of counts in ray order, count)
  *          and counter [2] i32 = (total samples, N).  scan_tmp: >= vn_march_scan_tmp_ints(N) i32.
  *  _write: pass 2 (:84-124).  Re-marches and writes xyzs, dirs [*,3], deltas, ts [*] rows
- *          rays_a[r,1] .. +count; rows >= capacity are dropped (capacity = rows allocated). */
+ *          rays_a[r,1] .. +count; rows >= capacity are dropped (capacity = rows allocated).
+ *          xyzs_unit (may be NULL): the same positions mapped to the unit cube,
+ *          (x - xyz_min) / (xyz_max - xyz_min) of NGP.density (networks.py:142). */
 int64_t vn_march_scan_tmp_ints(int64_t N);
 int vn_march_train_count(const float* rays_o, const float* rays_d, const float* hits_t,
                          const uint8_t* bitfield, const float* noise, int64_t N, int cascades,
@@ -110,7 +112,7 @@ int vn_march_train_write(const float* rays_o, const float* rays_d, const float* 
                          const uint8_t* bitfield, const float* noise, int64_t N, int cascades,
                          int grid_size, float scale, float exp_step_factor, const int32_t* rays_a,
                          int64_t capacity, float* xyzs, float* dirs, float* deltas, float* ts,
-                         void* stream);
+                         float* xyzs_unit, void* stream);
 
 /* a7. raymarching_test_kernel, modules/ray_march.py:198-269.  alive [A] i64; slot layout
  * n*max_samples+s; ray_indices i64, valid_mask u8 (caller zeroes), deltas/ts f32, all
@@ -184,6 +186,24 @@ int vn_occ_bayes_update(float* grid, int grid_size, const int32_t* cell_idxs, in
                         float* new_probs_tmp, void* stream);
 int vn_occ_decay_pack(float* grid, int grid_size, float decay, int apply_decay, float threshold,
                       uint8_t* bitfield, void* stream);
+
+/* f2 (caller side). training/loss.py:34-198 as two kernels around the (optional) allreduce of
+ * the valid counts.  Per-ray inputs: rgb [N,3] (composite output, before background), opacity,
+ * depth [N]; targets gt_rgb [N,3], uss / tof / rgbd [N] (NaN = no measurement; any may be NULL).
+ *  _fwd: accumulates sums[4] / counts[4] (order: colour, USS, ToF, RGBD) -- caller zeroes both.
+ *        pred = rgb + bg * (1 - opacity) (rendering.py:219-226); USS counts only rays with
+ *        depth < uss - uss_tol (loss.py:186-194).
+ *  _bwd: with the (global) counts, writes the loss-scaled gradient seeds dL/drgb [N,3],
+ *        dL/ddepth [N], dL/dopacity [N] and loss_out[0] = sum_k weights[k] * sums[k]/counts[k]
+ *        (this rank's share of the global loss).  scale_dev = GradScaler scale [1] (device). */
+int vn_loss_fwd(const float* rgb, const float* opacity, const float* depth, const float* gt_rgb,
+                const float* uss, const float* tof, const float* rgbd, int64_t N, float bg,
+                float uss_tol, float* sums, float* counts, void* stream);
+int vn_loss_bwd(const float* rgb, const float* opacity, const float* depth, const float* gt_rgb,
+                const float* uss, const float* tof, const float* rgbd, int64_t N, float bg,
+                float uss_tol, const float* sums, const float* counts, float w_color, float w_uss,
+                float w_tof, float w_rgbd, const float* scale_dev, float* dL_drgb, float* dL_ddepth,
+                float* dL_dopacity, float* loss_out, void* stream);
 
 /* f1 (caller side). GradScaler.unscale_ + inf check + torch.optim.Adam(eps=1e-15) step,
  * training/trainer.py:49-57,138-141, as one pass.  found_inf [1] f32 (device): set to 1 by

@@ -143,3 +143,31 @@ def test_occupancy_update_runs_and_is_deterministic(setup):
     assert og.getBitfield().shape == (128 ** 3 // 8,) and og.getBitfield().dtype == torch.uint8
     assert torch.isfinite(og.occ_3d_grid).all()
     assert not torch.equal(g0, g1)
+
+
+def test_fast_step_matches_autograd_step(monkeypatch):
+    """the hand-chained C-ABI step (engine.step_fast) and the autograd step through the drop-in
+    modules produce the same loss, gradients and parameter update (same rays, same jitter)"""
+    from virus_nerf_b200 import synthetic
+    from virus_nerf_b200.engine import TrainEngine
+    from virus_nerf_b200.modules import ray_march, rendering
+    args = synthetic.make_args(device=DEV, batch_size=512)
+    ds = synthetic.SyntheticDataset(pool_size=1 << 13, n_images=8, device=DEV)
+    e1 = TrainEngine(args, ds, DEV)
+    e2 = TrainEngine(args, ds, DEV)
+    assert torch.equal(e1.flat_p, e2.flat_p)
+    e1.step_idx = e2.step_idx = 1                       # no occupancy update (it draws random numbers)
+    bf = torch.from_numpy(synthetic.morton_pack(ds.scene.occupancy_bitfield(128))).to(DEV)
+    e1.model.occupancy_grid.bitfield = bf; e2.model.occupancy_grid.bitfield = bf
+    orig = ray_march.raymarching_train
+    for it in range(2):
+        data = ds(512, args.training.sampling_strategy)
+        noise = torch.rand(512, device=DEV)
+        monkeypatch.setattr(rendering, "raymarching_train", lambda *a, **k: orig(*a, noise=noise, **k))
+        l1 = float(e1.step(data))
+        l2 = float(e2.step_fast(data, noise=noise))
+        assert abs(l1 - l2) <= 1e-5 * abs(l1), (l1, l2)
+        g1, g2 = e1.flat_g, e2.flat_g
+        assert float((g1 - g2).norm() / g1.norm()) < 1e-4
+        assert float((e1.flat_p - e2.flat_p).abs().max()) < 1e-4
+    assert int(e1.last_samples) == int(e2.last_samples) > 0

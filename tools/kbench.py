@@ -63,7 +63,7 @@ def main():
                                               counts, rays_a, counter, tmp))
                 rec("march_count", ms, state=state, rays=n_rays, samples=S)
                 ms = timeit(lambda: _lib.call("vn_march_train_write", ro, rd, hits, bf, noise, n_rays, 1, 128, 0.5, 0.0, rays_a,
-                                              S, xyzs, dirs, deltas, ts))
+                                              S, xyzs, dirs, deltas, ts, None))
                 rec("march_write", ms, state=state, rays=n_rays, samples=S, gbs=round(S * 32 / ms / 1e6, 1))
             if "composite" in which:
                 sig = torch.rand(S, device=DEV) * 20; rgbs = torch.rand(S, 3, device=DEV)

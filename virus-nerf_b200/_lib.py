@@ -46,7 +46,7 @@ _SPECS = {
     "vn_hash_indices": "plhpps",
     "vn_ray_aabb": "ppflps",
     "vn_march_train_count": "pppppliiffipppps",
-    "vn_march_train_write": "ppppp" "liiff" "pl" "pppp" "s",
+    "vn_march_train_write": "ppppp" "liiff" "pl" "ppppp" "s",
     "vn_march_test": "pppp" "lp" "iiffi" "ppppp" "s",
     "vn_march_test_compact": "plippppppppps",
     "vn_composite_train_fwd": "ppppp" "llf" "ppppp" "s",
@@ -61,6 +61,8 @@ _SPECS = {
     "vn_occ_nerf_prob": "pldfppps",
     "vn_occ_bayes_update": "piplppp" "ps",
     "vn_occ_decay_pack": "pififps",
+    "vn_loss_fwd": "ppppppp" "lff" "pp" "s",
+    "vn_loss_bwd": "ppppppp" "lff" "pp" "ffff" "p" "pppp" "s",
     "vn_grad_check": "plps",
     "vn_adam_step": "ppppl" "fffff" "ipps",
     "vn_scaler_update": "pppffis",

@@ -92,3 +92,108 @@ VN_API int vn_scaler_update(float* scale, int32_t* growth_tracker, float* found_
     VN_CHECK_LAUNCH("scaler_update_kernel");
     return VN_OK;
 }
+
+// ---- f2: training/loss.py as two kernels --------------------------------------------------
+struct RayLoss { float dc[3]; float e_uss, e_tof, e_rgbd; bool v_uss, v_tof, v_rgbd; };
+
+__device__ __forceinline__ RayLoss ray_loss(const float* __restrict__ rgb, const float* __restrict__ opacity,
+                                            const float* __restrict__ depth, const float* __restrict__ gt_rgb,
+                                            const float* __restrict__ uss, const float* __restrict__ tof,
+                                            const float* __restrict__ rgbd, int64_t n, float bg, float uss_tol) {
+    RayLoss r;
+    const float op = __ldg(opacity + n), d = __ldg(depth + n);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) r.dc[c] = (__ldg(rgb + 3 * n + c) + bg * (1.0f - op)) - __ldg(gt_rgb + 3 * n + c);   // rendering.py:225
+    r.v_uss = r.v_tof = r.v_rgbd = false;
+    r.e_uss = r.e_tof = r.e_rgbd = 0.0f;
+    if (uss) { const float m = __ldg(uss + n); r.v_uss = !isnan(m) && (d < m - uss_tol); if (r.v_uss) r.e_uss = d - m; }   // loss.py:186-194
+    if (tof) { const float m = __ldg(tof + n); r.v_tof = !isnan(m); if (r.v_tof) r.e_tof = d - m; }                        // loss.py:140-141
+    if (rgbd) { const float m = __ldg(rgbd + n); r.v_rgbd = !isnan(m); if (r.v_rgbd) r.e_rgbd = d - m; }                   // loss.py:118-119
+    return r;
+}
+
+__global__ void __launch_bounds__(256) loss_fwd_kernel(const float* __restrict__ rgb, const float* __restrict__ opacity,
+                                                       const float* __restrict__ depth, const float* __restrict__ gt_rgb,
+                                                       const float* __restrict__ uss, const float* __restrict__ tof,
+                                                       const float* __restrict__ rgbd, int64_t N, float bg, float uss_tol,
+                                                       float* __restrict__ sums, float* __restrict__ counts) {
+    __shared__ float sm[8][8];
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // sums[4], counts[4]
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
+        const RayLoss r = ray_loss(rgb, opacity, depth, gt_rgb, uss, tof, rgbd, n, bg, uss_tol);
+        v[0] += r.dc[0] * r.dc[0] + r.dc[1] * r.dc[1] + r.dc[2] * r.dc[2]; v[4] += 3.0f;
+        v[1] += r.e_uss * r.e_uss; v[5] += r.v_uss ? 1.0f : 0.0f;
+        v[2] += r.e_tof * r.e_tof; v[6] += r.v_tof ? 1.0f : 0.0f;
+        v[3] += r.e_rgbd * r.e_rgbd; v[7] += r.v_rgbd ? 1.0f : 0.0f;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], off);
+        if (lane == 0) sm[warp][k] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        float t = 0.0f;
+        for (int w = 0; w < 8; ++w) t += sm[w][threadIdx.x];
+        if (t != 0.0f) atomicAdd((threadIdx.x < 4 ? sums : counts) + (threadIdx.x & 3), t);
+    }
+}
+
+__global__ void __launch_bounds__(256) loss_bwd_kernel(const float* __restrict__ rgb, const float* __restrict__ opacity,
+                                                       const float* __restrict__ depth, const float* __restrict__ gt_rgb,
+                                                       const float* __restrict__ uss, const float* __restrict__ tof,
+                                                       const float* __restrict__ rgbd, int64_t N, float bg, float uss_tol,
+                                                       const float* __restrict__ sums, const float* __restrict__ counts,
+                                                       float w_color, float w_uss, float w_tof, float w_rgbd,
+                                                       const float* __restrict__ scale_dev, float* __restrict__ dL_drgb,
+                                                       float* __restrict__ dL_ddepth, float* __restrict__ dL_dopacity,
+                                                       float* __restrict__ loss_out) {
+    const float scale = scale_dev ? *scale_dev : 1.0f;
+    const float c0 = counts[0], c1 = counts[1], c2 = counts[2], c3 = counts[3];
+    // d(mean)/dx = 2 x / count; empty masks contribute nothing (loss.py:140-141, 186-190)
+    const float k_color = c0 > 0.f ? scale * w_color * 2.0f / c0 : 0.f;
+    const float k_uss = c1 > 0.f ? scale * w_uss * 2.0f / c1 : 0.f;
+    const float k_tof = c2 > 0.f ? scale * w_tof * 2.0f / c2 : 0.f;
+    const float k_rgbd = c3 > 0.f ? scale * w_rgbd * 2.0f / c3 : 0.f;
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n == 0 && loss_out)
+        loss_out[0] = (c0 > 0.f ? w_color * sums[0] / c0 : 0.f) + (c1 > 0.f ? w_uss * sums[1] / c1 : 0.f) +
+                      (c2 > 0.f ? w_tof * sums[2] / c2 : 0.f) + (c3 > 0.f ? w_rgbd * sums[3] / c3 : 0.f);
+    if (n >= N) return;
+    const RayLoss r = ray_loss(rgb, opacity, depth, gt_rgb, uss, tof, rgbd, n, bg, uss_tol);
+    float go = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { const float g = k_color * r.dc[c]; dL_drgb[3 * n + c] = g; go -= bg * g; }
+    dL_dopacity[n] = go;
+    dL_ddepth[n] = k_uss * r.e_uss + k_tof * r.e_tof + k_rgbd * r.e_rgbd;
+}
+
+VN_API int vn_loss_fwd(const float* rgb, const float* opacity, const float* depth, const float* gt_rgb, const float* uss,
+                       const float* tof, const float* rgbd, int64_t N, float bg, float uss_tol, float* sums, float* counts,
+                       void* stream) {
+    VN_REQUIRE(N >= 0 && sums && counts, "vn_loss_fwd: bad arguments");
+    if (N == 0) return VN_OK;
+    VN_REQUIRE(rgb && opacity && depth && gt_rgb, "vn_loss_fwd: null pointer");
+    int64_t blocks = (N + 255) / 256;
+    if (blocks > 2 * vn_sm_count()) blocks = 2 * vn_sm_count();
+    loss_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(rgb, opacity, depth, gt_rgb, uss, tof, rgbd, N, bg,
+                                                                      uss_tol, sums, counts);
+    VN_CHECK_LAUNCH("loss_fwd_kernel");
+    return VN_OK;
+}
+
+VN_API int vn_loss_bwd(const float* rgb, const float* opacity, const float* depth, const float* gt_rgb, const float* uss,
+                       const float* tof, const float* rgbd, int64_t N, float bg, float uss_tol, const float* sums,
+                       const float* counts, float w_color, float w_uss, float w_tof, float w_rgbd, const float* scale_dev,
+                       float* dL_drgb, float* dL_ddepth, float* dL_dopacity, float* loss_out, void* stream) {
+    VN_REQUIRE(N >= 0 && sums && counts, "vn_loss_bwd: bad arguments");
+    if (N == 0) return VN_OK;
+    VN_REQUIRE(rgb && opacity && depth && gt_rgb && dL_drgb && dL_ddepth && dL_dopacity, "vn_loss_bwd: null pointer");
+    loss_bwd_kernel<<<vn_blocks(N, 256), 256, 0, (cudaStream_t)stream>>>(rgb, opacity, depth, gt_rgb, uss, tof, rgbd, N, bg,
+                                                                       uss_tol, sums, counts, w_color, w_uss, w_tof, w_rgbd,
+                                                                       scale_dev, dL_drgb, dL_ddepth, dL_dopacity, loss_out);
+    VN_CHECK_LAUNCH("loss_bwd_kernel");
+    return VN_OK;
+}

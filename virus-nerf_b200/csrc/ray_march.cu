@@ -121,6 +121,14 @@ __device__ __forceinline__ bool march_probe(const MarchCfg& c, const Ray& ray, c
     return occ;
 }
 
+// NGP.density's input normalisation (networks.py:142): (x - xyz_min) / (xyz_max - xyz_min)
+// with xyz_min = -scale, xyz_max = +scale, same IEEE operations as the torch expression
+__device__ __forceinline__ void write_unit(const MarchCfg& c, float* dst, const float* xyz) {
+    const float den = vn_sub(c.scale, -c.scale);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) dst[k] = vn_div(vn_sub(xyz[k], -c.scale), den);
+}
+
 __device__ __forceinline__ float jittered_t1(const MarchCfg& c, float t1, float noise) {
     if (t1 >= 0.0f) t1 = vn_add(t1, vn_mul(vn_calc_dt(t1, c.esf, c.dt_max), noise));   // :39-41
     return t1;
@@ -194,7 +202,8 @@ __global__ void __launch_bounds__(256) march_warp_kernel(const float* __restrict
                                                          int max_samples, int32_t* __restrict__ counts,
                                                          const int32_t* __restrict__ rays_a, int64_t capacity,
                                                          float* __restrict__ xyzs, float* __restrict__ dirs,
-                                                         float* __restrict__ deltas, float* __restrict__ ts) {
+                                                         float* __restrict__ deltas, float* __restrict__ ts,
+                                                         float* __restrict__ xyzs_unit) {
     const unsigned full = 0xffffffffu;
     const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -255,6 +264,7 @@ __global__ void __launch_bounds__(256) march_warp_kernel(const float* __restrict
                     xyzs[3 * s] = xyz[0]; xyzs[3 * s + 1] = xyz[1]; xyzs[3 * s + 2] = xyz[2];
                     dirs[3 * s] = ray.d[0]; dirs[3 * s + 1] = ray.d[1]; dirs[3 * s + 2] = ray.d[2];
                     ts[s] = ti; deltas[s] = dt;
+                    if (xyzs_unit) write_unit(c, xyzs_unit + 3 * s, xyz);
                 }
             }
         }
@@ -275,7 +285,8 @@ __global__ void __launch_bounds__(128) march_thread_kernel(const float* __restri
                                                            int max_samples, int32_t* __restrict__ counts,
                                                            const int32_t* __restrict__ rays_a, int64_t capacity,
                                                            float* __restrict__ xyzs, float* __restrict__ dirs,
-                                                           float* __restrict__ deltas, float* __restrict__ ts) {
+                                                           float* __restrict__ deltas, float* __restrict__ ts,
+                                                           float* __restrict__ xyzs_unit) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= N) return;
     int n_max = max_samples;
@@ -295,6 +306,7 @@ __global__ void __launch_bounds__(128) march_thread_kernel(const float* __restri
                     xyzs[3 * s] = xyz[0]; xyzs[3 * s + 1] = xyz[1]; xyzs[3 * s + 2] = xyz[2];
                     dirs[3 * s] = ray.d[0]; dirs[3 * s + 1] = ray.d[1]; dirs[3 * s + 2] = ray.d[2];
                     ts[s] = t; deltas[s] = dt;
+                    if (xyzs_unit) write_unit(c, xyzs_unit + 3 * s, xyz);
                 }
             }
             t = vn_add(t, dt); ++n;
@@ -405,11 +417,11 @@ VN_API int vn_march_train_count(const float* rays_o, const float* rays_d, const 
     if (N < kWarpMarchMaxRays)
         march_warp_kernel<false><<<vn_blocks(N * 32, 256), 256, 0, st>>>(rays_o, rays_d, (const float2*)hits_t, bitfield,
                                                                          noise, N, c, max_samples, counts, nullptr, 0,
-                                                                         nullptr, nullptr, nullptr, nullptr);
+                                                                         nullptr, nullptr, nullptr, nullptr, nullptr);
     else
         march_thread_kernel<false><<<vn_blocks(N, 128), 128, 0, st>>>(rays_o, rays_d, (const float2*)hits_t, bitfield, noise,
                                                                       N, c, max_samples, counts, nullptr, 0, nullptr,
-                                                                      nullptr, nullptr, nullptr);
+                                                                      nullptr, nullptr, nullptr, nullptr);
     VN_CHECK_LAUNCH("march kernel <count>");
     int32_t* starts = scan_tmp;
     int rc = exclusive_scan_i32(counts, starts, N, scan_tmp + round_up4(N), st);
@@ -423,7 +435,7 @@ VN_API int vn_march_train_count(const float* rays_o, const float* rays_d, const 
 VN_API int vn_march_train_write(const float* rays_o, const float* rays_d, const float* hits_t, const uint8_t* bitfield,
                                 const float* noise, int64_t N, int cascades, int grid_size, float scale,
                                 float exp_step_factor, const int32_t* rays_a, int64_t capacity, float* xyzs,
-                                float* dirs, float* deltas, float* ts, void* stream) {
+                                float* dirs, float* deltas, float* ts, float* xyzs_unit, void* stream) {
     VN_REQUIRE(N >= 0 && capacity >= 0, "vn_march_train_write: negative size");
     if (N == 0 || capacity == 0) return VN_OK;
     VN_REQUIRE(rays_o && rays_d && hits_t && bitfield && noise && rays_a && xyzs && dirs && deltas && ts,
@@ -432,10 +444,10 @@ VN_API int vn_march_train_write(const float* rays_o, const float* rays_d, const 
     const MarchCfg c = make_cfg(cascades, grid_size, scale, exp_step_factor);
     if (N < kWarpMarchMaxRays)
         march_warp_kernel<true><<<vn_blocks(N * 32, 256), 256, 0, (cudaStream_t)stream>>>(
-            rays_o, rays_d, (const float2*)hits_t, bitfield, noise, N, c, 0, nullptr, rays_a, capacity, xyzs, dirs, deltas, ts);
+            rays_o, rays_d, (const float2*)hits_t, bitfield, noise, N, c, 0, nullptr, rays_a, capacity, xyzs, dirs, deltas, ts, xyzs_unit);
     else
         march_thread_kernel<true><<<vn_blocks(N, 128), 128, 0, (cudaStream_t)stream>>>(
-            rays_o, rays_d, (const float2*)hits_t, bitfield, noise, N, c, 0, nullptr, rays_a, capacity, xyzs, dirs, deltas, ts);
+            rays_o, rays_d, (const float2*)hits_t, bitfield, noise, N, c, 0, nullptr, rays_a, capacity, xyzs, dirs, deltas, ts, xyzs_unit);
     VN_CHECK_LAUNCH("march kernel <write>");
     return VN_OK;
 }

@@ -64,6 +64,25 @@ class Loss:
         return (per_term * ws).sum(), per_term.detach()
 
 
+class _Workspace:
+    """persistent per-step sample buffers (grown geometrically, never shrunk): the fast step
+    never touches the caching allocator in steady state"""
+
+    def __init__(self, device):
+        self.device = device
+        self.bufs = {}
+
+    def get(self, name, rows, cols=None, dtype=torch.float32):
+        key = (name, cols, dtype)
+        t = self.bufs.get(key)
+        if t is None or t.shape[0] < rows:
+            cap = max(int(rows * 1.25) + 1024, 4096)
+            shape = (cap,) if cols is None else (cap, cols)
+            t = torch.empty(shape, dtype=dtype, device=self.device)
+            self.bufs[key] = t
+        return t[:rows]
+
+
 class TrainEngine:
     def __init__(self, args, dataset, device, world_size=1, rank=0, log2_T=19, max_res=1024, half_opt=False,
                  autocast=True, seed=21, grad_scale=2.0 ** 19):
@@ -108,6 +127,16 @@ class TrainEngine:
         self.found_inf = torch.zeros(1, device=self.device)
         self.adam_step = 0
         self.last_samples = 0
+        # fast-path state
+        self._ws = _Workspace(self.device)
+        self._counter = torch.zeros(2, dtype=torch.int32, device=self.device)
+        self._loss_acc = torch.zeros(8, device=self.device)
+        self._loss_out = torch.zeros(1, device=self.device)
+        names = ["xyz_encoder.hidden_layers.0.weight", "xyz_encoder.output_layer.weight", "rgb_net.hidden_layers.0.weight",
+                 "rgb_net.hidden_layers.1.weight", "rgb_net.output_layer.weight"]
+        pd = dict(self.model.named_parameters())
+        self._mlp_w = [pd[n].data for n in names]           # views into flat_p
+        self._mlp_g = [pd[n].grad for n in names]           # views into flat_g
 
     # ------------------------------------------------------------------------------------
     def occupancy_update(self, elapse_time=0.0):
@@ -133,6 +162,75 @@ class TrainEngine:
         self.step_idx += 1
         self.last_samples = results['rm_samples']
         return loss.detach()
+
+    # ------------------------------------------------------------------------------------
+    def step_fast(self, data, elapse_time=0.0, noise=None):
+        """The same train step as step(), hand-chained through the C ABI: no autograd graph, no
+        torch element-wise glue, persistent workspace.  ~20 kernel launches per step:
+        aabb, march count (+scan), march write (also emits unit-cube positions), hash fwd, fused
+        MLP fwd, composite fwd, loss fwd, [allreduce counts], loss bwd (gradient seeds),
+        composite bwd, fused MLP bwd (dW straight into the flat gradient), hash bwd (ditto),
+        [allreduce flat gradient], grad check, Adam, scaler update."""
+        m, a, dev = self.model, self.args, self.device
+        if self.step_idx % self.grid_update_interval == 0:
+            self.occupancy_update(elapse_time)
+        ws = self._ws
+        call = _lib.call
+        rays_o, rays_d = data['rays_o'].contiguous(), data['rays_d'].contiguous()
+        N = rays_o.shape[0]
+        scale, esf = float(m.scale), float(a.exp_step_factor)
+        enc = m.pos_encoder
+        bitfield = m.occupancy_grid.getBitfield()
+        self.flat_g.zero_()
+        hits = ws.get("hits", N, 2)
+        call("vn_ray_aabb", rays_o, rays_d, scale, N, hits)
+        if noise is None:
+            noise = torch.rand(N, device=dev)                             # ray_march.py:139
+        counts = ws.get("counts", N, None, torch.int32)
+        rays_a = ws.get("rays_a", N, 3, torch.int32)
+        scan_tmp = ws.get("scan_tmp", _lib.scan_tmp_ints(N), None, torch.int32)
+        call("vn_march_train_count", rays_o, rays_d, hits, bitfield, noise, N, m.cascades, m.grid_size, scale, esf,
+             1024, counts, rays_a, self._counter, scan_tmp)
+        S = int(self._counter[0].item())                                  # the one host sync of the step
+        self.last_samples = S
+        xyzs = ws.get("xyzs", S, 3); dirs = ws.get("dirs", S, 3); unit = ws.get("unit", S, 3)
+        deltas = ws.get("deltas", S); ts = ws.get("ts", S)
+        call("vn_march_train_write", rays_o, rays_d, hits, bitfield, noise, N, m.cascades, m.grid_size, scale, esf,
+             rays_a, S, xyzs, dirs, deltas, ts, unit)
+        encoded = ws.get("enc", S, 32)
+        call("vn_hash_encode_fwd_f32", unit, enc.hash_table, encoded, S, enc._levels, enc.kernel_flags)
+        W = self._mlp_w
+        sig = ws.get("sig", S); rgbs = ws.get("rgbs", S, 3)
+        call("vn_mlp_fwd", encoded, 0, dirs, *W, S, 0, sig, rgbs, None)
+        vr = ws.get("vr", N, None, torch.int32)
+        op = ws.get("op", N); dp = ws.get("dp", N); rgb = ws.get("rgb", N, 3); w_s = ws.get("ws", S)
+        call("vn_composite_train_fwd", sig, rgbs, deltas, ts, rays_a, N, S, 1e-4, vr, op, dp, rgb, w_s)
+        # ---- loss + gradient seeds (training/loss.py) -------------------------------------
+        t = a.training
+        depth = data['depth']
+        uss = depth.get('USS') if 'USS' in t.sensors else None
+        tof = depth.get('ToF') if 'ToF' in t.sensors else None
+        rgbd = depth.get('RGBD') if 'RGBD' in t.sensors else None
+        bg = 1.0 if esf == 0 else 0.0                                     # rendering.py:219-224
+        self._loss_acc.zero_()
+        sums, cnts = self._loss_acc[:4], self._loss_acc[4:]
+        call("vn_loss_fwd", rgb, op, dp, data['rgb'], uss, tof, rgbd, N, bg, self.loss_fn.uss_depth_tol, sums, cnts)
+        if self.world_size > 1:
+            dist.all_reduce(cnts)                                         # global normalisers
+        d_rgb = ws.get("d_rgb", N, 3); d_dp = ws.get("d_dp", N); d_op = ws.get("d_op", N)
+        call("vn_loss_bwd", rgb, op, dp, data['rgb'], uss, tof, rgbd, N, bg, self.loss_fn.uss_depth_tol, sums, cnts,
+             t.color_loss_w, t.uss_loss_w, t.tof_loss_w, t.rgbd_loss_w, self.scale, d_rgb, d_dp, d_op, self._loss_out)
+        # ---- backward chain ----------------------------------------------------------------
+        d_sig = ws.get("d_sig", S); d_rgbs = ws.get("d_rgbs", S, 3)
+        call("vn_composite_train_bwd", sig, rgbs, deltas, ts, rays_a, N, S, 1e-4, d_op, d_dp, d_rgb, None, d_sig, d_rgbs)
+        d_enc = ws.get("d_enc", S, 32)
+        call("vn_mlp_bwd", encoded, 0, dirs, *W, S, 0, d_sig, d_rgbs, d_enc, *self._mlp_g)
+        call("vn_hash_encode_bwd_f32", unit, d_enc, enc.hash_table.grad, S, enc._levels, enc.kernel_flags)
+        if self.world_size > 1:
+            dist.all_reduce(self.flat_g)
+        self.optimizer_step()
+        self.step_idx += 1
+        return self._loss_out[0]
 
     def optimizer_step(self):
         """grad_scaler.step(optimizer); grad_scaler.update() (trainer.py:140-141), fused"""

@@ -34,7 +34,7 @@ def raymarching_train(rays_o, rays_d, hits_t, density_bitfield, cascades, scale,
     deltas = torch.empty(total, device=dev, dtype=torch_type)
     ts = torch.empty(total, device=dev, dtype=torch_type)
     _lib.call("vn_march_train_write", rays_o, rays_d, hits_t, density_bitfield, noise, N, int(cascades),
-              int(grid_size), float(scale), float(exp_step_factor), rays_a, total, xyzs, dirs, deltas, ts)
+              int(grid_size), float(scale), float(exp_step_factor), rays_a, total, xyzs, dirs, deltas, ts, None)
     return rays_a, xyzs, dirs, deltas, ts, total_samples
 
 

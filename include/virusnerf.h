@@ -36,8 +36,12 @@ extern "C" {
 /* flags for the hash-encoder kernels (tuning switches, results identical within tolerance) */
 #define VN_HASH_DEFAULT 0
 #define VN_HASH_NO_WARP_AGG 1     /* bwd: plain per-corner atomics, no warp pre-reduction */
-#define VN_HASH_LEVEL_GROUPS_1 16 /* one level per thread (grid.y = levels): level-major */
-#define VN_HASH_LEVEL_GROUPS_4 32 /* four levels per thread */
+#define VN_HASH_LEVEL_GROUPS_1 16  /* one level per thread (grid.y = levels): level-major */
+#define VN_HASH_LEVEL_GROUPS_4 32  /* four levels per thread */
+#define VN_HASH_LEVEL_GROUPS_8 64  /* eight levels per thread */
+#define VN_HASH_LEVEL_GROUPS_16 128 /* all (<= 16) levels per thread: every row touched once */
+#define VN_HASH_LEVEL_GROUPS_2 256 /* two levels per thread */
+/* default (no GROUPS flag): 4 (backward: 2 when the table exceeds the L2, > 96 MB) */
 
 const char* vn_last_error(void);
 int vn_abi_version(void);

@@ -82,7 +82,7 @@ def test_hash_levels_and_indices_bit_exact(vn, oracle_mod, log2_T, max_res):
     np.testing.assert_array_equal(N(w), w_o)
 
 
-@pytest.mark.parametrize("flags", [0, 16, 32])
+@pytest.mark.parametrize("flags", [0, 16, 32, 64, 128, 256])
 @pytest.mark.parametrize("log2_T", [19, 22])
 def test_hash_fwd_f32(vn, oracle_mod, flags, log2_T):
     lv_o = oracle_mod.HashLevels(16, 1024, 16, 2 ** log2_T)
@@ -98,7 +98,7 @@ def test_hash_fwd_f32(vn, oracle_mod, flags, log2_T):
     np.testing.assert_allclose(N(out), ref, rtol=1e-5, atol=1e-6)
 
 
-@pytest.mark.parametrize("flags", [0, 1, 16, 32, 33])
+@pytest.mark.parametrize("flags", [0, 1, 16, 32, 33, 64, 128, 129, 256])
 def test_hash_bwd_f32(vn, oracle_mod, flags):
     lv_o = oracle_mod.HashLevels(16, 1024, 16, 2 ** 19)
     lv = vn.hash_levels(16, 1024, 16, 2 ** 19)

@@ -85,10 +85,10 @@ def main():
                     o = torch.empty(S, 32, device=DEV)
                     dout = torch.randn(S, 32, device=DEV)
                     grad = torch.zeros(2 * lv.total_entries, device=DEV)
-                    for flags in (0, 16, 32):
+                    for flags in (0, 256):
                         ms = timeit(lambda: _lib.call("vn_hash_encode_fwd_f32", x, table, o, S, lv, flags))
                         rec("hash_fwd_f32", ms, state=state, S=S, log2_T=log2_T, flags=flags, gbs=round(S * 1164 / ms / 1e6, 1))
-                    for flags in (0, 1, 16, 17, 32, 33):
+                    for flags in (0, 256, 32):
                         ms = timeit(lambda: _lib.call("vn_hash_encode_bwd_f32", x, dout, grad, S, lv, flags))
                         rec("hash_bwd_f32", ms, state=state, S=S, log2_T=log2_T, flags=flags, gbs=round(S * 1164 / ms / 1e6, 1))
                     table_h = table.half().view(-1, 2)

@@ -18,6 +18,9 @@ VN_MAX_LEVELS = 32
 VN_HASH_NO_WARP_AGG = 1
 VN_HASH_LEVEL_GROUPS_1 = 16
 VN_HASH_LEVEL_GROUPS_4 = 32
+VN_HASH_LEVEL_GROUPS_8 = 64
+VN_HASH_LEVEL_GROUPS_16 = 128
+VN_HASH_LEVEL_GROUPS_2 = 256
 
 
 class HashLevels(ctypes.Structure):

@@ -198,6 +198,41 @@ __global__ void __launch_bounds__(256) hash_fwd_kernel(const float* __restrict__
 // segmented shuffle scan leaves each run's sum in its last lane, which issues the
 // red.global.add.v2.f32.  Runs are detected per level; when (nearly) every lane is its own
 // run the scan is skipped.
+// All 32 lanes contribute to the same 8 corners: reduce 8 float2 values across the warp by
+// recursive halving (each step a lane keeps half of its values and adds its partner's copy of
+// that half): 4 + 2 + 1 float2 exchanges, then two plain butterfly steps.  18 shuffles instead
+// of 80, and the 8 corner sums end up in 8 different lanes (lane & 3 == 0), which then issue
+// the 8 atomics in parallel.
+__device__ __forceinline__ void warp_reduce8_distribute(float* v0, float* v1, int lane, float* r0, float* r1) {
+    const unsigned full = 0xffffffffu;
+    float a0[4], a1[4];
+    const bool hi16 = lane & 16;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float s0 = hi16 ? v0[j] : v0[j + 4], s1 = hi16 ? v1[j] : v1[j + 4];
+        const float k0 = hi16 ? v0[j + 4] : v0[j], k1 = hi16 ? v1[j + 4] : v1[j];
+        a0[j] = k0 + __shfl_xor_sync(full, s0, 16);
+        a1[j] = k1 + __shfl_xor_sync(full, s1, 16);
+    }
+    float b0[2], b1[2];
+    const bool hi8 = lane & 8;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const float s0 = hi8 ? a0[j] : a0[j + 2], s1 = hi8 ? a1[j] : a1[j + 2];
+        const float k0 = hi8 ? a0[j + 2] : a0[j], k1 = hi8 ? a1[j + 2] : a1[j];
+        b0[j] = k0 + __shfl_xor_sync(full, s0, 8);
+        b1[j] = k1 + __shfl_xor_sync(full, s1, 8);
+    }
+    const bool hi4 = lane & 4;
+    float c0 = (hi4 ? b0[1] : b0[0]) + __shfl_xor_sync(full, hi4 ? b0[0] : b0[1], 4);
+    float c1 = (hi4 ? b1[1] : b1[0]) + __shfl_xor_sync(full, hi4 ? b1[0] : b1[1], 4);
+    c0 += __shfl_xor_sync(full, c0, 2); c1 += __shfl_xor_sync(full, c1, 2);
+    c0 += __shfl_xor_sync(full, c0, 1); c1 += __shfl_xor_sync(full, c1, 1);
+    *r0 = c0; *r1 = c1;   // corner index held by this lane: ((lane>>4)&1)*4 + ((lane>>3)&1)*2 + ((lane>>2)&1)
+}
+
+constexpr int kScanMaxHeads = 24;
+
 template <typename DT, bool DENSE, bool AGG, bool ZERO_SKIP>
 __device__ __forceinline__ void level_scatter(float* __restrict__ grad_level, const Cell& c, uint32_t res,
                                               uint32_t size, uint32_t mask, float d0, float d1, bool valid) {
@@ -217,10 +252,23 @@ __device__ __forceinline__ void level_scatter(float* __restrict__ grad_level, co
         int pv = __shfl_up_sync(full, (int)valid, 1);
         bool head = (lane == 0) || !valid || !pv || p0 != c.g[0] || p1 != c.g[1] || p2 != c.g[2];
         unsigned heads = __ballot_sync(full, head);
-        if (__popc(heads) <= 20) {  // warp-uniform: enough sharing to pay for the scan
+        if (heads == 1u) {          // the whole warp sits in one cell (coarse levels)
+            float r0, r1;
+            warp_reduce8_distribute(v0, v1, lane, &r0, &r1);
+            if ((lane & 3) == 0 && !(ZERO_SKIP && r0 == 0.0f && r1 == 0.0f)) {
+                const int k = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+                const uint32_t idx = corner_index<DENSE>(c, k, res, size, mask);
+                vn_red_add_v2(grad_level + 2 * (size_t)idx, r0, r1);
+            }
+            return;
+        }
+        if (__popc(heads) <= kScanMaxHeads) {  // warp-uniform: enough sharing to pay for the scan
             int seg_start = 31 - __clz(heads & (full >> (31 - lane)));
+            // longest run in the warp bounds the number of scan steps that can do anything
+            const int max_run = __reduce_max_sync(full, lane - seg_start + 1);
 #pragma unroll
             for (int off = 1; off < 32; off <<= 1) {
+                if (off >= max_run) break;
                 bool take = (lane - off) >= seg_start;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
@@ -320,11 +368,19 @@ __global__ void f32_to_f16_kernel(const float* __restrict__ src, __half* __restr
 }
 
 // ---- launchers --------------------------------------------------------------------------
-static int pick_lpt(int flags, int levels) {
+// levels per thread.  Measured on B200 (tools/kbench.py, profiles/r1_kbench.md): 4 levels per
+// thread is the best forward at both table sizes and the best backward while the table is L2
+// resident; the backward prefers 2 when it is not (T = 2^22).  8 / 16 levels per thread touch
+// every output row only once (less DRAM traffic) but lose more to occupancy than they gain.
+static int pick_lpt(int flags, const vn_hash_levels_t* lv, size_t entry_bytes, bool backward) {
     if (flags & VN_HASH_LEVEL_GROUPS_1) return 1;
+    if (flags & VN_HASH_LEVEL_GROUPS_2) return 2;
     if (flags & VN_HASH_LEVEL_GROUPS_4) return 4;
-    (void)levels;
-    return 2;
+    if (flags & VN_HASH_LEVEL_GROUPS_8) return 8;
+    if (flags & VN_HASH_LEVEL_GROUPS_16) return 16;
+    const size_t table_bytes = (size_t)lv->total_entries * entry_bytes;
+    if (backward && table_bytes > ((size_t)96 << 20)) return 2;
+    return 4;
 }
 
 template <typename TT, typename OT>
@@ -334,12 +390,14 @@ static int launch_fwd(const float* xyz, const TT* table, OT* out, int64_t S, con
     int rc = make_params(lv, P);
     if (rc) return rc;
     if (S == 0) return VN_OK;
-    const int lpt = pick_lpt(flags, P.levels);
+    const int lpt = pick_lpt(flags, lv, sizeof(TT), false);
     dim3 block(256), grid(vn_blocks(S, 256), (P.levels + lpt - 1) / lpt);
     switch (lpt) {
         case 1: hash_fwd_kernel<TT, OT, 1><<<grid, block, 0, st>>>(xyz, table, out, S, P); break;
+        case 2: hash_fwd_kernel<TT, OT, 2><<<grid, block, 0, st>>>(xyz, table, out, S, P); break;
         case 4: hash_fwd_kernel<TT, OT, 4><<<grid, block, 0, st>>>(xyz, table, out, S, P); break;
-        default: hash_fwd_kernel<TT, OT, 2><<<grid, block, 0, st>>>(xyz, table, out, S, P); break;
+        case 8: hash_fwd_kernel<TT, OT, 8><<<grid, block, 0, st>>>(xyz, table, out, S, P); break;
+        default: hash_fwd_kernel<TT, OT, 16><<<grid, block, 0, st>>>(xyz, table, out, S, P); break;
     }
     VN_CHECK_LAUNCH("hash_fwd_kernel");
     return VN_OK;
@@ -352,12 +410,17 @@ static int launch_bwd(const float* xyz, const DT* dout, float* grad, int64_t S, 
     int rc = make_params(lv, P);
     if (rc) return rc;
     if (S == 0) return VN_OK;
-    const int lpt = pick_lpt(flags, P.levels);
+    const int lpt = pick_lpt(flags, lv, 8, true);
     const bool agg = !(flags & VN_HASH_NO_WARP_AGG);
     dim3 block(256), grid(vn_blocks(S, 256), (P.levels + lpt - 1) / lpt);
 #define VN_BWD(L, A) hash_bwd_kernel<DT, L, A, ZERO_SKIP><<<grid, block, 0, st>>>(xyz, dout, grad, S, P)
-    if (agg) { switch (lpt) { case 1: VN_BWD(1, true); break; case 4: VN_BWD(4, true); break; default: VN_BWD(2, true); } }
-    else     { switch (lpt) { case 1: VN_BWD(1, false); break; case 4: VN_BWD(4, false); break; default: VN_BWD(2, false); } }
+    if (agg) {
+        switch (lpt) { case 1: VN_BWD(1, true); break; case 2: VN_BWD(2, true); break; case 4: VN_BWD(4, true); break;
+                       case 8: VN_BWD(8, true); break; default: VN_BWD(16, true); }
+    } else {
+        switch (lpt) { case 1: VN_BWD(1, false); break; case 2: VN_BWD(2, false); break; case 4: VN_BWD(4, false); break;
+                       case 8: VN_BWD(8, false); break; default: VN_BWD(16, false); }
+    }
 #undef VN_BWD
     VN_CHECK_LAUNCH("hash_bwd_kernel");
     return VN_OK;

@@ -177,7 +177,8 @@ def run_ours(a):
         """W warm-up + K timed steps from a fresh model.  pinned=False: the ray pool is resident
         in HBM; pinned=True: every step's batch is copied from pinned host memory inside the
         timed region and the loss is read back to the host (end-to-end)."""
-        ds = synthetic.SyntheticDataset(scene, pool_size=1 << 18, device=str(dev), pinned=False, seed=21 + rank)
+        ds = synthetic.SyntheticDataset(scene, pool_size=1 << 18, device=str(dev), pinned=False, seed=21)
+        ds.gen.manual_seed(1000 + rank)           # same pool on every rank, different training batches
         eng = TrainEngine(args, ds, dev, world_size=world, rank=rank, autocast=not a.no_autocast)
         host_batches = None
         if pinned:
@@ -222,15 +223,21 @@ def run_ours(a):
             prof = _lib.profile_stop()
         launches = _lib.launch_count() - launches0
         samples = [int(s) for s in samples]
-        return ms, launches, samples, prof, h2d, d2h, float(loss)
+        same = True
+        if world > 1:
+            c = eng.replica_checksum()
+            lo, hi = c.clone(), c.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            same = bool((lo == hi).all())
+        return ms, launches, samples, prof, h2d, d2h, float(loss), same
 
     clocks = ClockSampler(local)
     clocks.start()
-    ms, launches, samples, prof, _, _, last_loss = run_phase(pinned=False)
+    ms, launches, samples, prof, _, _, last_loss, replicas_same = run_phase(pinned=False)
     clk = clocks.stop()
     ms_e2e, h2d, d2h = ms, 0, 0
     if not a.no_e2e:
-        ms_e2e, _, _, _, h2d, d2h, _ = run_phase(pinned=True)
+        ms_e2e, _, _, _, h2d, d2h, _, _ = run_phase(pinned=True)
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -263,7 +270,8 @@ def run_ours(a):
                 "roofline": roof, "kernels": kern,
                 "e2e": {"value": total_rays / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K},
-                "gpu_launches": launches, "clocks": clk, "final_loss": last_loss}
+                "gpu_launches": launches, "clocks": clk, "final_loss": last_loss,
+                "replicas_bit_identical": replicas_same}
         if world == 1 and not a.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(a)
         print(json.dumps(line), flush=True)

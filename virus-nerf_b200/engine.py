@@ -95,6 +95,11 @@ class TrainEngine:
         self.model = NGP(scale=args.model.scale, pos_encoder_type='hash', levels=args.model.hash_levels,
                          max_res=max_res, log2_T=log2_T, half_opt=half_opt, args=args, dataset=dataset)
         self.model.to(self.device)
+        # the occupancy update is REPLICATED: every rank runs the same update from the same
+        # ray pool with an identically seeded sampler, so the grids stay bit-identical without
+        # any broadcast; the training sampler may differ per rank.
+        if hasattr(dataset, "clone_with_seed"):
+            self.model.occupancy_grid.dataset = dataset.clone_with_seed(seed)
         self.model.fused_mlp = self.model.fused_mlp and autocast   # fp32 mode (tests): torch.nn.Linear fp32
         self.loss_fn = Loss(args)
         self.step_idx = 0
@@ -231,6 +236,12 @@ class TrainEngine:
         self.optimizer_step()
         self.step_idx += 1
         return self._loss_out[0]
+
+    def replica_checksum(self):
+        """(bitfield, parameter) checksums used to verify that DP replicas are bit-identical"""
+        bf = self.model.occupancy_grid.getBitfield().to(torch.int64)
+        w = torch.arange(1, bf.numel() + 1, device=bf.device, dtype=torch.int64)
+        return torch.stack([(bf * w).sum(), self.flat_p.view(torch.int32).to(torch.int64).sum()])
 
     def optimizer_step(self):
         """grad_scaler.step(optimizer); grad_scaler.update() (trainer.py:140-141), fused"""

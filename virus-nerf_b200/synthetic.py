@@ -209,6 +209,14 @@ class SyntheticDataset:
     def __len__(self):
         return self.n_images
 
+    def clone_with_seed(self, seed):
+        """same ray pool, independent sampler state (shallow copy)"""
+        import copy
+        c = copy.copy(self)
+        c.gen = torch.Generator(device=self.gen.device)
+        c.gen.manual_seed(seed)
+        return c
+
     def sample_indices(self, batch_size, sampling_strategy):
         pixs = sampling_strategy.get("pixs", "random") if sampling_strategy else "random"
         dev = self.gen.device

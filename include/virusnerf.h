@@ -79,6 +79,12 @@ int vn_hash_encode_fwd_f32(const float* xyz, const float* table, float* out, int
 int vn_hash_encode_bwd_f32(const float* xyz, const float* dout, float* grad, int64_t S,
                            const vn_hash_levels_t* h_lv, int flags, void* stream);
 
+/* the same restricted to levels [level_begin, level_end): lets a data-parallel caller start
+ * the allreduce of a finished level slab while the remaining levels are still scattering */
+int vn_hash_encode_bwd_f32_levels(const float* xyz, const float* dout, float* grad, int64_t S,
+                                  const vn_hash_levels_t* h_lv, int flags, int level_begin,
+                                  int level_end, void* stream);
+
 /* a4. half encoder, modules/hash_encoder_half.py:112-161 (fwd) and :164-213 (bwd).
  * table_h [total_entries,2] fp16 (the per-call hash_table.to(float16) copy, :367);
  * out_h [S, levels, 2] fp16; dout_h same shape; grad [total_entries,2] f32 (hash_grad, :300). */

@@ -112,6 +112,25 @@ def test_hash_bwd_f32(vn, oracle_mod, flags):
     np.testing.assert_allclose(N(grad), ref, rtol=1e-4, atol=1e-6 * np.abs(ref).max())
 
 
+def test_hash_bwd_level_ranges(vn, oracle_mod):
+    """the per-level-group launches used for the overlapped DP allreduce add up to the full backward"""
+    lv_o = oracle_mod.HashLevels(16, 1024, 16, 2 ** 19)
+    lv = vn.hash_levels(16, 1024, 16, 2 ** 19)
+    xyz = ray_coherent_points(64, 64)
+    S = xyz.shape[0]
+    dout = np.random.default_rng(6).normal(size=(S, 32)).astype(np.float32)
+    grad = torch.zeros(2 * lv_o.total, device=DEV)
+    for lb, le in ((12, 16), (8, 12), (4, 8), (0, 4)):
+        vn.call("vn_hash_encode_bwd_f32_levels", T(xyz), T(dout), grad, S, lv, 0, lb, le)
+        part = N(grad)
+        lo, hi = 2 * lv_o.offsets[lb], 2 * (lv_o.offsets[le] if le < 16 else lv_o.total)
+        assert np.abs(part[lo:hi]).max() > 0
+    ref = oracle_mod.hash_bwd_f32(xyz, dout, lv_o)
+    np.testing.assert_allclose(N(grad), ref, rtol=1e-4, atol=1e-6 * np.abs(ref).max())
+    with pytest.raises(RuntimeError, match="level range"):
+        vn.call("vn_hash_encode_bwd_f32_levels", T(xyz), T(dout), grad, S, lv, 0, 8, 4)
+
+
 def test_hash_module_autograd(vn, oracle_mod):
     from virus_nerf_b200.modules.hash_encoder import HashEncoder
     enc = HashEncoder(max_params=2 ** 19, levels=16, base_res=16, max_res=1024).to(DEV)

@@ -43,6 +43,7 @@ _SPECS = {
     "vn_hash_levels_init": "ddilh",
     "vn_hash_encode_fwd_f32": "ppplhis",
     "vn_hash_encode_bwd_f32": "ppplhis",
+    "vn_hash_encode_bwd_f32_levels": "ppplhiiis",
     "vn_hash_encode_fwd_f16": "ppplhis",
     "vn_hash_encode_bwd_f16": "ppplhis",
     "vn_f32_to_f16": "ppls",

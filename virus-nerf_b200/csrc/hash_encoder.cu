@@ -14,7 +14,9 @@
 #include <string.h>
 
 struct HashParams {
-    int levels;
+    int levels;        // launches cover levels [level_begin, levels)
+    int level_begin;
+    int level_end;
     int begin_fast;
     int offsets[VN_MAX_LEVELS];
     uint32_t sizes[VN_MAX_LEVELS];
@@ -28,6 +30,8 @@ static int make_params(const vn_hash_levels_t* lv, HashParams& P) {
     VN_REQUIRE(lv->levels >= 1 && lv->levels <= VN_MAX_LEVELS, "hash levels: levels=%d out of [1,%d]",
                lv->levels, VN_MAX_LEVELS);
     P.levels = lv->levels;
+    P.level_begin = 0;
+    P.level_end = lv->levels;
     P.begin_fast = lv->begin_fast_hash_level;
     for (int l = 0; l < lv->levels; ++l) {
         VN_REQUIRE(lv->sizes[l] > 0, "hash levels: size[%d] <= 0", l);
@@ -296,7 +300,7 @@ __global__ void __launch_bounds__(256) hash_bwd_kernel(const float* __restrict__
                                                        const __grid_constant__ HashParams P) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < S;
-    const int level0 = blockIdx.y * LPT;
+    const int level0 = P.level_begin + blockIdx.y * LPT;
     float x = 0.f, y = 0.f, z = 0.f;
     float d[2 * LPT];
 #pragma unroll
@@ -306,7 +310,7 @@ __global__ void __launch_bounds__(256) hash_bwd_kernel(const float* __restrict__
         const int W = 2 * P.levels;
         if (sizeof(DT) == 4) {
             const float* dp = (const float*)dout + i * W + 2 * level0;
-            if (LPT % 2 == 0 && (W % 4) == 0 && level0 + LPT <= P.levels) {
+            if (LPT % 2 == 0 && (W % 4) == 0 && level0 + LPT <= P.level_end) {
 #pragma unroll
                 for (int q = 0; q < LPT / 2; ++q) {
                     float4 t = __ldg((const float4*)dp + q);
@@ -315,19 +319,19 @@ __global__ void __launch_bounds__(256) hash_bwd_kernel(const float* __restrict__
             } else {
 #pragma unroll
                 for (int l = 0; l < LPT; ++l)
-                    if (level0 + l < P.levels) { float2 t = __ldg((const float2*)dp + l); d[2 * l] = t.x; d[2 * l + 1] = t.y; }
+                    if (level0 + l < P.level_end) { float2 t = __ldg((const float2*)dp + l); d[2 * l] = t.x; d[2 * l + 1] = t.y; }
             }
         } else {
             const __half2* dp = (const __half2*)dout + i * P.levels + level0;
 #pragma unroll
             for (int l = 0; l < LPT; ++l)
-                if (level0 + l < P.levels) { float2 t = __half22float2(__ldg(dp + l)); d[2 * l] = t.x; d[2 * l + 1] = t.y; }
+                if (level0 + l < P.level_end) { float2 t = __half22float2(__ldg(dp + l)); d[2 * l] = t.x; d[2 * l + 1] = t.y; }
         }
     }
 #pragma unroll
     for (int l = 0; l < LPT; ++l) {
         const int level = level0 + l;
-        if (level >= P.levels) break;   // warp-uniform
+        if (level >= P.level_end) break;   // warp-uniform
         bool v = valid;
         if (ZERO_SKIP) v = v && !(d[2 * l] == 0.0f && d[2 * l + 1] == 0.0f);  // hash_encoder_half.py:210
         const Cell c = cell_of(x, y, z, P.scales[level]);
@@ -405,14 +409,19 @@ static int launch_fwd(const float* xyz, const TT* table, OT* out, int64_t S, con
 
 template <typename DT, bool ZERO_SKIP>
 static int launch_bwd(const float* xyz, const DT* dout, float* grad, int64_t S, const vn_hash_levels_t* lv, int flags,
-                      cudaStream_t st) {
+                      cudaStream_t st, int level_begin = 0, int level_end = -1) {
     HashParams P;
     int rc = make_params(lv, P);
     if (rc) return rc;
-    if (S == 0) return VN_OK;
+    if (level_end < 0) level_end = P.levels;
+    VN_REQUIRE(level_begin >= 0 && level_begin <= level_end && level_end <= P.levels, "hash bwd: bad level range [%d,%d)",
+               level_begin, level_end);
+    P.level_begin = level_begin;
+    P.level_end = level_end;
+    if (S == 0 || level_begin == level_end) return VN_OK;
     const int lpt = pick_lpt(flags, lv, 8, true);
     const bool agg = !(flags & VN_HASH_NO_WARP_AGG);
-    dim3 block(256), grid(vn_blocks(S, 256), (P.levels + lpt - 1) / lpt);
+    dim3 block(256), grid(vn_blocks(S, 256), (level_end - level_begin + lpt - 1) / lpt);
 #define VN_BWD(L, A) hash_bwd_kernel<DT, L, A, ZERO_SKIP><<<grid, block, 0, st>>>(xyz, dout, grad, S, P)
     if (agg) {
         switch (lpt) { case 1: VN_BWD(1, true); break; case 2: VN_BWD(2, true); break; case 4: VN_BWD(4, true); break;
@@ -441,6 +450,13 @@ VN_API int vn_hash_encode_bwd_f32(const float* xyz, const float* dout, float* gr
                                   const vn_hash_levels_t* lv, int flags, void* stream) {
     VN_HASH_ARGCHECK("vn_hash_encode_bwd_f32", xyz, grad, dout);
     return launch_bwd<float, false>(xyz, dout, grad, S, lv, flags, (cudaStream_t)stream);
+}
+
+VN_API int vn_hash_encode_bwd_f32_levels(const float* xyz, const float* dout, float* grad, int64_t S,
+                                         const vn_hash_levels_t* lv, int flags, int level_begin, int level_end,
+                                         void* stream) {
+    VN_HASH_ARGCHECK("vn_hash_encode_bwd_f32_levels", xyz, grad, dout);
+    return launch_bwd<float, false>(xyz, dout, grad, S, lv, flags, (cudaStream_t)stream, level_begin, level_end);
 }
 
 VN_API int vn_hash_encode_fwd_f16(const float* xyz, const void* table_h, void* out_h, int64_t S,

@@ -142,6 +142,10 @@ class TrainEngine:
         pd = dict(self.model.named_parameters())
         self._mlp_w = [pd[n].data for n in names]           # views into flat_p
         self._mlp_g = [pd[n].grad for n in names]           # views into flat_g
+        self._comm_stream = torch.cuda.Stream(device=self.device) if world_size > 1 else None
+        self._hash_slice_idx = [i for i, p in enumerate(params) if p is enc.hash_table][0]
+        L = enc.hash_level
+        self._level_groups = [(max(L - 4 * (g + 1), 0), L - 4 * g) for g in range((L + 3) // 4)]   # finest first
 
     # ------------------------------------------------------------------------------------
     def occupancy_update(self, elapse_time=0.0):
@@ -230,12 +234,42 @@ class TrainEngine:
         call("vn_composite_train_bwd", sig, rgbs, deltas, ts, rays_a, N, S, 1e-4, d_op, d_dp, d_rgb, None, d_sig, d_rgbs)
         d_enc = ws.get("d_enc", S, 32)
         call("vn_mlp_bwd", encoded, 0, dirs, *W, S, 0, d_sig, d_rgbs, d_enc, *self._mlp_g)
-        call("vn_hash_encode_bwd_f32", unit, d_enc, enc.hash_table.grad, S, enc._levels, enc.kernel_flags)
         if self.world_size > 1:
-            dist.all_reduce(self.flat_g)
+            self._bwd_hash_overlapped(unit, d_enc, S)
+        else:
+            call("vn_hash_encode_bwd_f32", unit, d_enc, enc.hash_table.grad, S, enc._levels, enc.kernel_flags)
         self.optimizer_step()
         self.step_idx += 1
         return self._loss_out[0]
+
+    def _bwd_hash_overlapped(self, unit, d_enc, S):
+        """DP: the hash backward is issued per level group (finest first); each finished slab of
+        the flat gradient is allreduced on a side stream while the next group scatters.  The MLP
+        gradients (already complete) go first.  The main stream joins before the optimiser."""
+        enc = self.model.pos_encoder
+        main = torch.cuda.current_stream()
+        comm = self._comm_stream
+        works = []
+
+        def reduce_slab(lo, hi):
+            ev = torch.cuda.Event()
+            ev.record(main)
+            comm.wait_event(ev)
+            with torch.cuda.stream(comm):
+                works.append(dist.all_reduce(self.flat_g[lo:hi], async_op=True))
+
+        h0, hn = self.slices[self._hash_slice_idx]
+        reduce_slab(h0 + hn, self.n_params)              # everything after the table: MLP weights
+        if h0 > 0:
+            reduce_slab(0, h0)
+        L = enc.hash_level
+        offs = [int(o) for o in enc.offsets.tolist()] + [int(enc._levels.total_entries)]
+        for lb, le in self._level_groups:
+            _lib.call("vn_hash_encode_bwd_f32_levels", unit, d_enc, enc.hash_table.grad, S, enc._levels,
+                      enc.kernel_flags, lb, le)
+            reduce_slab(h0 + 2 * offs[lb], h0 + 2 * offs[le])
+        for w in works:
+            w.wait()                                        # main stream waits for the collectives
 
     def replica_checksum(self):
         """(bitfield, parameter) checksums used to verify that DP replicas are bit-identical"""

@@ -186,7 +186,7 @@ def run_ours(a):
             # host side of the boundary); the timed region pays the H2D copy of each batch
             keys = ("rays_o", "rays_d", "rgb", "USS", "ToF")
             host_batches = []
-            for _ in range(W + K):
+            for _ in range(W + K + 1):
                 b = ds(n, args.training.sampling_strategy)
                 flat = [b["rays_o"], b["rays_d"], b["rgb"], b["depth"]["USS"], b["depth"]["ToF"]]
                 host_batches.append([t.cpu().pin_memory() for t in flat])
@@ -196,6 +196,14 @@ def run_ours(a):
         prof = {}
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         launches0 = 0
+        def get_batch(it):
+            if pinned:
+                hb = host_batches[it]
+                dv = [t.to(dev, non_blocking=True) for t in hb]
+                return {"rays_o": dv[0], "rays_d": dv[1], "rgb": dv[2], "depth": {"USS": dv[3], "ToF": dv[4]}}
+            return ds(n, args.training.sampling_strategy)
+
+        data = get_batch(0)
         for it in range(W + K):
             if it == W:
                 barrier()
@@ -203,16 +211,19 @@ def run_ours(a):
                 if not pinned:
                     _lib.profile_start(("vn_hash_encode_fwd_f32", "vn_hash_encode_bwd_f32"))
                 ev0.record()
+            # the next batch is fetched (H2D copy in the e2e phase) before this step is enqueued so that
+            # the engine can pipeline its front half; every batch is copied exactly once, inside the
+            # timed region for all timed steps but the first (whose copy replaces the last step's)
+            nxt = get_batch(it + 1) if (pinned or it + 1 < W + K) else None
             if pinned:
-                hb = host_batches[it]
-                dv = [t.to(dev, non_blocking=True) for t in hb]
-                data = {"rays_o": dv[0], "rays_d": dv[1], "rgb": dv[2], "depth": {"USS": dv[3], "ToF": dv[4]}}
-                h2d = sum(t.numel() * t.element_size() for t in hb)
+                h2d = sum(t.numel() * t.element_size() for t in host_batches[it])
+            if a.autograd_step:
+                loss = eng.step(data)
             else:
-                data = ds(n, args.training.sampling_strategy)
-            loss = eng.step_fast(data) if not a.autograd_step else eng.step(data)
+                loss = eng.step_fast(data, next_data=nxt)
+            data = nxt
             if pinned:
-                loss_host.copy_(loss.reshape(1), non_blocking=False)     # D2H read of the step's result
+                loss_host.copy_(loss.reshape(1), non_blocking=True)      # D2H read of the step's result (pinned, in stream)
                 d2h = 4
             if it >= W:
                 samples.append(eng.last_samples)

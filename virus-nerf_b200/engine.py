@@ -135,6 +135,9 @@ class TrainEngine:
         # fast-path state
         self._ws = _Workspace(self.device)
         self._counter = torch.zeros(2, dtype=torch.int32, device=self.device)
+        self._counter_host = torch.zeros(2, dtype=torch.int32).pin_memory() if self.device.type == "cuda" else None
+        self._ticket = None
+        self._prep_step = 0
         self._loss_acc = torch.zeros(8, device=self.device)
         self._loss_out = torch.zeros(1, device=self.device)
         names = ["xyz_encoder.hidden_layers.0.weight", "xyz_encoder.output_layer.weight", "rgb_net.hidden_layers.0.weight",
@@ -162,6 +165,7 @@ class TrainEngine:
         """one full train step: (grid update) -> render -> loss -> backward -> allreduce -> Adam"""
         if self.step_idx % self.grid_update_interval == 0:              # trainer.py:106-117
             self.occupancy_update(elapse_time)
+        self._prep_step = self.step_idx + 1
         self.flat_g.zero_()                                             # optimizer.zero_grad()
         loss, terms, results = self.forward_loss(data)
         (loss * self.scale).sum().backward()                            # grad_scaler.scale(loss).backward()
@@ -173,35 +177,57 @@ class TrainEngine:
         return loss.detach()
 
     # ------------------------------------------------------------------------------------
-    def step_fast(self, data, elapse_time=0.0, noise=None):
-        """The same train step as step(), hand-chained through the C ABI: no autograd graph, no
-        torch element-wise glue, persistent workspace.  ~20 kernel launches per step:
-        aabb, march count (+scan), march write (also emits unit-cube positions), hash fwd, fused
-        MLP fwd, composite fwd, loss fwd, [allreduce counts], loss bwd (gradient seeds),
-        composite bwd, fused MLP bwd (dW straight into the flat gradient), hash bwd (ditto),
-        [allreduce flat gradient], grad check, Adam, scaler update."""
+    def prepare(self, data, elapse_time=0.0, noise=None):
+        """front half of a step, independent of the gradients in flight: (occupancy update if
+        due) -> ray/AABB -> march count + scan -> async read-back of the sample total into
+        pinned memory.  step_fast() enqueues it for the NEXT batch while the current step's
+        backward / allreduce is still running, so the one host sync of a step never stalls."""
         m, a, dev = self.model, self.args, self.device
-        if self.step_idx % self.grid_update_interval == 0:
+        if self._prep_step % self.grid_update_interval == 0:
             self.occupancy_update(elapse_time)
-        ws = self._ws
-        call = _lib.call
+        self._prep_step += 1
+        ws, call = self._ws, _lib.call
         rays_o, rays_d = data['rays_o'].contiguous(), data['rays_d'].contiguous()
         N = rays_o.shape[0]
         scale, esf = float(m.scale), float(a.exp_step_factor)
-        enc = m.pos_encoder
         bitfield = m.occupancy_grid.getBitfield()
-        self.flat_g.zero_()
         hits = ws.get("hits", N, 2)
         call("vn_ray_aabb", rays_o, rays_d, scale, N, hits)
         if noise is None:
-            noise = torch.rand(N, device=dev)                             # ray_march.py:139
+            noise = ws.get("noise", N)
+            noise.uniform_()                                                # ray_march.py:139
         counts = ws.get("counts", N, None, torch.int32)
         rays_a = ws.get("rays_a", N, 3, torch.int32)
         scan_tmp = ws.get("scan_tmp", _lib.scan_tmp_ints(N), None, torch.int32)
         call("vn_march_train_count", rays_o, rays_d, hits, bitfield, noise, N, m.cascades, m.grid_size, scale, esf,
              1024, counts, rays_a, self._counter, scan_tmp)
-        S = int(self._counter[0].item())                                  # the one host sync of the step
+        self._counter_host.copy_(self._counter, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return {"data": data, "rays_o": rays_o, "rays_d": rays_d, "hits": hits, "noise": noise, "rays_a": rays_a,
+                "bitfield": bitfield, "event": ev, "N": N}
+
+    def step_fast(self, data, elapse_time=0.0, noise=None, next_data=None):
+        """The same train step as step(), hand-chained through the C ABI: no autograd graph, no
+        torch element-wise glue, persistent workspace, ~20 kernel launches:
+        [prepare: aabb, march count + scan], march write (also emits unit-cube positions), hash
+        fwd, fused MLP fwd, composite fwd, loss fwd, [allreduce counts], loss bwd (gradient
+        seeds), composite bwd, fused MLP bwd (dW straight into the flat gradient), hash bwd
+        (ditto), [allreduce flat gradient || prepare(next_data)], grad check, Adam, scaler update.
+        Pass next_data to software-pipeline the front half of the next step."""
+        m, a, dev = self.model, self.args, self.device
+        tk = self._ticket if (self._ticket is not None and self._ticket["data"] is data) else \
+            self.prepare(data, elapse_time, noise)
+        self._ticket = None
+        ws, call = self._ws, _lib.call
+        rays_o, rays_d, hits, noise, rays_a, bitfield, N = (tk["rays_o"], tk["rays_d"], tk["hits"], tk["noise"],
+                                                            tk["rays_a"], tk["bitfield"], tk["N"])
+        scale, esf = float(m.scale), float(a.exp_step_factor)
+        enc = m.pos_encoder
+        tk["event"].synchronize()                                         # the one host sync of the step
+        S = int(self._counter_host[0])
         self.last_samples = S
+        self.flat_g.zero_()
         xyzs = ws.get("xyzs", S, 3); dirs = ws.get("dirs", S, 3); unit = ws.get("unit", S, 3)
         deltas = ws.get("deltas", S); ts = ws.get("ts", S)
         call("vn_march_train_write", rays_o, rays_d, hits, bitfield, noise, N, m.cascades, m.grid_size, scale, esf,
@@ -234,12 +260,22 @@ class TrainEngine:
         call("vn_composite_train_bwd", sig, rgbs, deltas, ts, rays_a, N, S, 1e-4, d_op, d_dp, d_rgb, None, d_sig, d_rgbs)
         d_enc = ws.get("d_enc", S, 32)
         call("vn_mlp_bwd", encoded, 0, dirs, *W, S, 0, d_sig, d_rgbs, d_enc, *self._mlp_g)
-        if self.world_size > 1:
-            self._bwd_hash_overlapped(unit, d_enc, S)
-        else:
-            call("vn_hash_encode_bwd_f32", unit, d_enc, enc.hash_table.grad, S, enc._levels, enc.kernel_flags)
-        self.optimizer_step()
+        call("vn_hash_encode_bwd_f32", unit, d_enc, enc.hash_table.grad, S, enc._levels, enc.kernel_flags)
         self.step_idx += 1
+        work = None
+        if self.world_size > 1:
+            ev = torch.cuda.Event(); ev.record()
+            self._comm_stream.wait_event(ev)
+            with torch.cuda.stream(self._comm_stream):
+                work = dist.all_reduce(self.flat_g, async_op=True)        # overlaps prepare(next) below
+        update_due = self._prep_step % self.grid_update_interval == 0     # next front half needs the new weights
+        if next_data is not None and not update_due:
+            self._ticket = self.prepare(next_data, elapse_time)
+        if work is not None:
+            work.wait()
+        self.optimizer_step()
+        if next_data is not None and update_due:
+            self._ticket = self.prepare(next_data, elapse_time)
         return self._loss_out[0]
 
     def _bwd_hash_overlapped(self, unit, d_enc, S):

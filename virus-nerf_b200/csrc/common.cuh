@@ -95,6 +95,9 @@ __device__ __forceinline__ uint32_t vn_morton3D_invert(uint32_t x) {
 // float -> u32, saturating (negative / NaN -> 0): PTX cvt.rzi.u32.f32 semantics
 __device__ __forceinline__ uint32_t vn_f2u(float x) { return __float2uint_rz(x); }
 
+__device__ __forceinline__ void vn_red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 __device__ __forceinline__ void vn_red_add_v2(float* addr, float a, float b) {
     asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
 }

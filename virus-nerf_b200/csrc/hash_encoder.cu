@@ -285,11 +285,23 @@ __device__ __forceinline__ void level_scatter(float* __restrict__ grad_level, co
         }
     }
     if (leader) {
+        // the x / x+1 corners of a cell are neighbouring table entries whenever their indices
+        // differ only in bit 0 (dense levels: x + ... with an even index; hashed levels: the x
+        // prime is 1, so an even x gives h and h^1): one 16-byte red.v4 instead of two red.v2
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            if (ZERO_SKIP && v0[k] == 0.0f && v1[k] == 0.0f) continue;  // hash_encoder_half.py:212
-            uint32_t idx = corner_index<DENSE>(c, k, res, size, mask);
-            vn_red_add_v2(grad_level + 2 * (size_t)idx, v0[k], v1[k]);
+        for (int k = 0; k < 8; k += 2) {
+            const uint32_t i0 = corner_index<DENSE>(c, k, res, size, mask);
+            const uint32_t i1 = corner_index<DENSE>(c, k + 1, res, size, mask);
+            if ((i0 ^ i1) == 1u) {
+                const bool lo0 = (i0 & 1u) == 0u;
+                vn_red_add_v4(grad_level + 2 * (size_t)(i0 & ~1u), lo0 ? v0[k] : v0[k + 1], lo0 ? v1[k] : v1[k + 1],
+                              lo0 ? v0[k + 1] : v0[k], lo0 ? v1[k + 1] : v1[k]);
+            } else {
+                if (!(ZERO_SKIP && v0[k] == 0.0f && v1[k] == 0.0f))       // hash_encoder_half.py:212
+                    vn_red_add_v2(grad_level + 2 * (size_t)i0, v0[k], v1[k]);
+                if (!(ZERO_SKIP && v0[k + 1] == 0.0f && v1[k + 1] == 0.0f))
+                    vn_red_add_v2(grad_level + 2 * (size_t)i1, v0[k + 1], v1[k + 1]);
+            }
         }
     }
 }

@@ -97,11 +97,23 @@ constexpr int OFF_W2 = OFF_W1 + 64 * 32 * 2; // [16 x 64]
 constexpr int OFF_W3 = OFF_W2 + 16 * 64 * 2; // [64 x 32]
 constexpr int OFF_W4 = OFF_W3 + 64 * 32 * 2; // [64 x 64]
 constexpr int OFF_W5 = OFF_W4 + 64 * 64 * 2; // [16 x 64], rows 3..15 zero
-constexpr int SMEM_FWD = OFF_W5 + 16 * 64 * 2;
-constexpr int OFF_D5 = SMEM_FWD;             // [128 x 16] d(out5)
+constexpr int SMEM_FULL = OFF_W5 + 16 * 64 * 2;
+constexpr int OFF_D5 = SMEM_FULL;            // [128 x 16] d(out5)
 constexpr int OFF_DH = OFF_D5 + SZ_16;       // [128 x 16] d(h)
 constexpr int OFF_G = OFF_DH + SZ_16;        // [128 x 64] dH4 / dH3 / dH1 (reused)
 constexpr int SMEM_BWD = OFF_G + SZ_H;
+// forward-only kernel: H1 / H3 / H4 are never live together -> one buffer, 52 KB, 4 CTAs per SM
+constexpr int FOFF_X0 = 0, FOFF_H = FOFF_X0 + SZ_X0, FOFF_IN2 = FOFF_H + SZ_H, FOFF_W1 = FOFF_IN2 + SZ_X0;
+constexpr int FOFF_W2 = FOFF_W1 + 64 * 32 * 2, FOFF_W3 = FOFF_W2 + 16 * 64 * 2, FOFF_W4 = FOFF_W3 + 64 * 32 * 2;
+constexpr int FOFF_W5 = FOFF_W4 + 64 * 64 * 2;
+constexpr int SMEM_FWD = FOFF_W5 + 16 * 64 * 2;
+
+template <bool BWD> struct Lay {
+    static constexpr int X0 = BWD ? OFF_X0 : FOFF_X0, H1 = BWD ? OFF_H1 : FOFF_H, IN2 = BWD ? OFF_IN2 : FOFF_IN2;
+    static constexpr int H3 = BWD ? OFF_H3 : FOFF_H, H4 = BWD ? OFF_H4 : FOFF_H;
+    static constexpr int W1 = BWD ? OFF_W1 : FOFF_W1, W2 = BWD ? OFF_W2 : FOFF_W2, W3 = BWD ? OFF_W3 : FOFF_W3;
+    static constexpr int W4 = BWD ? OFF_W4 : FOFF_W4, W5 = BWD ? OFF_W5 : FOFF_W5;
+};
 // TMEM columns
 constexpr int TC_TMP = 0;                    // 64-column scratch accumulator
 constexpr int TC_DW1 = 64, TC_DW3 = 96, TC_DW4 = 128, TC_DW2T = 192, TC_DW5T = 208;   // wgrad accumulators
@@ -125,11 +137,18 @@ struct MlpArgs {
 
 __device__ __forceinline__ void load_weight(uint8_t* smem, int off, const float* __restrict__ W, int R, int C, int R_valid,
                                             int tid) {
-    // [R x C] chunk-major fp16; rows >= R_valid are zero padding
-    for (int i = tid; i < R * C; i += TILE) {
-        const int r = i / C, c = i % C;
-        const float v = (r < R_valid) ? __ldg(W + (size_t)r * C + c) : 0.0f;
-        *reinterpret_cast<__half*>(smem + off + (c / 8) * R * 16 + r * 16 + (c % 8) * 2) = __float2half_rn(v);
+    // [R x C] f32 row-major -> chunk-major fp16; one 16-byte chunk (8 columns of one row) per
+    // thread and iteration: two LDG.128, one STS.128.  Rows >= R_valid are zero padding.
+    const int chunks_per_row = C / 8;
+    for (int i = tid; i < R * chunks_per_row; i += TILE) {
+        const int r = i / chunks_per_row, c = i % chunks_per_row;
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (r < R_valid) {
+            const float4* src = reinterpret_cast<const float4*>(W + (size_t)r * C + 8 * c);
+            const float4 lo = __ldg(src), hi = __ldg(src + 1);
+            v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+        }
+        umma::st_chunk(reinterpret_cast<__half*>(smem + off), R, r, c, v);
     }
 }
 
@@ -235,17 +254,18 @@ __device__ __forceinline__ void mask_store(uint8_t* smem, int off_dst, int off_a
 
 template <bool BWD>
 __global__ void __launch_bounds__(TILE) mlp_kernel(const MlpArgs a) {
+    using L = Lay<BWD>;
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_base;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t sbase = umma::smem_u32(smem);
 
-    load_weight(smem, OFF_W1, a.W[0], 64, 32, 64, tid);
-    load_weight(smem, OFF_W2, a.W[1], 16, 64, 16, tid);
-    load_weight(smem, OFF_W3, a.W[2], 64, 32, 64, tid);
-    load_weight(smem, OFF_W4, a.W[3], 64, 64, 64, tid);
-    load_weight(smem, OFF_W5, a.W[4], 16, 64, 3, tid);
+    load_weight(smem, L::W1, a.W[0], 64, 32, 64, tid);
+    load_weight(smem, L::W2, a.W[1], 16, 64, 16, tid);
+    load_weight(smem, L::W3, a.W[2], 64, 32, 64, tid);
+    load_weight(smem, L::W4, a.W[3], 64, 64, 64, tid);
+    load_weight(smem, L::W5, a.W[4], 16, 64, 3, tid);
     if (warp == 0) umma::tmem_alloc(&tmem_base, BWD ? TMEM_BWD : TMEM_FWD);
     if (tid == 0) { umma::mbar_init(&bar, 1); umma::mbar_fence_init(); }
     publish();
@@ -254,54 +274,76 @@ __global__ void __launch_bounds__(TILE) mlp_kernel(const MlpArgs a) {
     const uint32_t tmp = p.tm + TC_TMP;
 
     const int64_t n_tiles = (a.S + TILE - 1) / TILE;
+    // software prefetch: the NEXT tile's enc row / direction (and, for the backward, its output
+    // gradients) are loaded into registers while the current tile runs through the layer chain
+    struct Staged { float4 e[8]; float d[3]; float dsig; float drgb[3]; };
+    auto fetch = [&](int64_t tile, Staged& st) {
+        const int64_t s = tile * TILE + tid;
+        const bool valid = tile < n_tiles && s < a.S;
+        if (valid) {
+            if (a.enc_half) {
+                const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(a.enc) + s * 32);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint4 u = __ldg(src + q);
+                    const __half2* h = reinterpret_cast<const __half2*>(&u);
+                    const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]), f2 = __half22float2(h[2]), f3 = __half22float2(h[3]);
+                    st.e[2 * q] = make_float4(f0.x, f0.y, f1.x, f1.y);
+                    st.e[2 * q + 1] = make_float4(f2.x, f2.y, f3.x, f3.y);
+                }
+            } else {
+                const float4* src = reinterpret_cast<const float4*>(a.enc + s * 32);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) st.e[q] = __ldg(src + q);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) st.e[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        st.d[0] = 1.0f; st.d[1] = 0.0f; st.d[2] = 0.0f;
+        if (valid && !a.density_only) { st.d[0] = __ldg(a.dirs + 3 * s); st.d[1] = __ldg(a.dirs + 3 * s + 1); st.d[2] = __ldg(a.dirs + 3 * s + 2); }
+        st.dsig = 0.0f; st.drgb[0] = st.drgb[1] = st.drgb[2] = 0.0f;
+        if (BWD && valid) {
+            st.dsig = __ldg(a.dsigmas + s);
+            if (!a.density_only) { st.drgb[0] = __ldg(a.drgbs + 3 * s); st.drgb[1] = __ldg(a.drgbs + 3 * s + 1); st.drgb[2] = __ldg(a.drgbs + 3 * s + 2); }
+        }
+    };
+    Staged cur;
+    fetch(blockIdx.x, cur);
     bool first_tile = true;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, first_tile = false) {
         const int64_t s = tile * TILE + tid;
         const bool valid = s < a.S;
         // ---- stage inputs: enc row -> X0, SH(dir) -> IN2[:, 0:16] -------------------------
         {
-            float v[32];
-            if (valid) {
-                if (a.enc_half) {
-                    const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(a.enc) + s * 32);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const uint4 u = __ldg(src + q);
-                        const __half2* h = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); v[8 * q + 2 * j] = f.x; v[8 * q + 2 * j + 1] = f.y; }
-                    }
-                } else {
-                    const float4* src = reinterpret_cast<const float4*>(a.enc + s * 32);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) { const float4 f = __ldg(src + q); v[4 * q] = f.x; v[4 * q + 1] = f.y; v[4 * q + 2] = f.z; v[4 * q + 3] = f.w; }
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = 0.0f;
+            for (int c = 0; c < 4; ++c) {
+                const float v[8] = {cur.e[2 * c].x, cur.e[2 * c].y, cur.e[2 * c].z, cur.e[2 * c].w,
+                                    cur.e[2 * c + 1].x, cur.e[2 * c + 1].y, cur.e[2 * c + 1].z, cur.e[2 * c + 1].w};
+                st_row8(smem, L::X0, tid, c, v);
             }
-#pragma unroll
-            for (int c = 0; c < 4; ++c) st_row8(smem, OFF_X0, tid, c, v + 8 * c);
             if (!a.density_only) {
-                float dx = 1.0f, dy = 0.0f, dz = 0.0f;
-                if (valid) { dx = __ldg(a.dirs + 3 * s); dy = __ldg(a.dirs + 3 * s + 1); dz = __ldg(a.dirs + 3 * s + 2); }
+                const float dx = cur.d[0], dy = cur.d[1], dz = cur.d[2];
                 const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);          // networks.py:160
                 float e[16];
                 sh16_half((dx / nrm + 1.0f) * 0.5f, (dy / nrm + 1.0f) * 0.5f, (dz / nrm + 1.0f) * 0.5f, e);   // :161
-                st_row8(smem, OFF_IN2, tid, 0, e);
-                st_row8(smem, OFF_IN2, tid, 1, e + 8);
+                st_row8(smem, L::IN2, tid, 0, e);
+                st_row8(smem, L::IN2, tid, 1, e + 8);
             }
         }
+        const float my_dsig = cur.dsig;
+        const float my_drgb[3] = {cur.drgb[0], cur.drgb[1], cur.drgb[2]};
+        fetch(tile + gridDim.x, cur);                                         // prefetch the next tile
         publish();
         // ---- L1: 32 -> 64, ReLU -----------------------------------------------------------
-        if (tid == 0) { umma::fence_after_sync(); mma_fwd(sbase, OFF_X0, OFF_W1, 64, 32, tmp); umma::commit(&bar); }
+        if (tid == 0) { umma::fence_after_sync(); mma_fwd(sbase, L::X0, L::W1, 64, 32, tmp); umma::commit(&bar); }
         wait_mma(p);
         float acc[64];
         read_acc<64>(p, TC_TMP, acc);
-        relu_store(smem, OFF_H1, tid, acc, 64);
+        relu_store(smem, L::H1, tid, acc, 64);
         publish();
         // ---- L2: 64 -> 16; sigma = exp(h0) ------------------------------------------------
-        if (tid == 0) { umma::fence_after_sync(); mma_fwd(sbase, OFF_H1, OFF_W2, 16, 64, tmp); umma::commit(&bar); }
+        if (tid == 0) { umma::fence_after_sync(); mma_fwd(sbase, L::H1, L::W2, 16, 64, tmp); umma::commit(&bar); }
         wait_mma(p);
         read_acc<16>(p, TC_TMP, acc);
         const float h0 = acc[0];
@@ -315,23 +357,23 @@ __global__ void __launch_bounds__(TILE) mlp_kernel(const MlpArgs a) {
         }
         float rgb[3] = {0.f, 0.f, 0.f};
         if (!a.density_only) {
-            st_row8(smem, OFF_IN2, tid, 2, acc);
-            st_row8(smem, OFF_IN2, tid, 3, acc + 8);
+            st_row8(smem, L::IN2, tid, 2, acc);
+            st_row8(smem, L::IN2, tid, 3, acc + 8);
             publish();
             // ---- L3: [SH | h] 32 -> 64, ReLU ---------------------------------------------
-            if (tid == 0) { umma::fence_after_sync(); mma_fwd(sbase, OFF_IN2, OFF_W3, 64, 32, tmp); umma::commit(&bar); }
+            if (tid == 0) { umma::fence_after_sync(); mma_fwd(sbase, L::IN2, L::W3, 64, 32, tmp); umma::commit(&bar); }
             wait_mma(p);
             read_acc<64>(p, TC_TMP, acc);
-            relu_store(smem, OFF_H3, tid, acc, 64);
+            relu_store(smem, L::H3, tid, acc, 64);
             publish();
             // ---- L4: 64 -> 64, ReLU ------------------------------------------------------
-            if (tid == 0) { umma::fence_after_sync(); mma_fwd(sbase, OFF_H3, OFF_W4, 64, 64, tmp); umma::commit(&bar); }
+            if (tid == 0) { umma::fence_after_sync(); mma_fwd(sbase, L::H3, L::W4, 64, 64, tmp); umma::commit(&bar); }
             wait_mma(p);
             read_acc<64>(p, TC_TMP, acc);
-            relu_store(smem, OFF_H4, tid, acc, 64);
+            relu_store(smem, L::H4, tid, acc, 64);
             publish();
             // ---- L5: 64 -> 3 (padded to 16), sigmoid -------------------------------------
-            if (tid == 0) { umma::fence_after_sync(); mma_fwd(sbase, OFF_H4, OFF_W5, 16, 64, tmp); umma::commit(&bar); }
+            if (tid == 0) { umma::fence_after_sync(); mma_fwd(sbase, L::H4, L::W5, 16, 64, tmp); umma::commit(&bar); }
             wait_mma(p);
             read_acc<16>(p, TC_TMP, acc);
 #pragma unroll
@@ -342,7 +384,7 @@ __global__ void __launch_bounds__(TILE) mlp_kernel(const MlpArgs a) {
 
         // =============================== backward =========================================
         float dh_sigma = 0.0f;
-        if (valid) dh_sigma = __ldg(a.dsigmas + s) * expf(fminf(fmaxf(h0, -15.0f), 15.0f));   // TruncExp bwd, networks.py:28
+        if (valid) dh_sigma = my_dsig * expf(fminf(fmaxf(h0, -15.0f), 15.0f));   // TruncExp bwd, networks.py:28
         if (!a.density_only) {
             // d(out5) = drgb * rgb * (1 - rgb)
             float d5[16];
@@ -350,35 +392,35 @@ __global__ void __launch_bounds__(TILE) mlp_kernel(const MlpArgs a) {
             for (int j = 0; j < 16; ++j) d5[j] = 0.0f;
             if (valid) {
 #pragma unroll
-                for (int c = 0; c < 3; ++c) d5[c] = __ldg(a.drgbs + 3 * s + c) * rgb[c] * (1.0f - rgb[c]);
+                for (int c = 0; c < 3; ++c) d5[c] = my_drgb[c] * rgb[c] * (1.0f - rgb[c]);
             }
             st_row8(smem, OFF_D5, tid, 0, d5);
             st_row8(smem, OFF_D5, tid, 1, d5 + 8);
             publish();
             if (tid == 0) {
                 umma::fence_after_sync();
-                mma_dgrad(sbase, OFF_D5, OFF_W5, 16, 64, 16, tmp);                       // dH4raw = d5 * W5
-                mma_wgrad(sbase, OFF_H4, OFF_D5, 16, p.tm + TC_DW5T, first_tile);        // dW5^T += H4^T d5
+                mma_dgrad(sbase, OFF_D5, L::W5, 16, 64, 16, tmp);                       // dH4raw = d5 * W5
+                mma_wgrad(sbase, L::H4, OFF_D5, 16, p.tm + TC_DW5T, first_tile);        // dW5^T += H4^T d5
                 umma::commit(&bar);
             }
             wait_mma(p);
             read_acc<64>(p, TC_TMP, acc);
-            mask_store(smem, OFF_G, OFF_H4, tid, acc);                                   // dH4
+            mask_store(smem, OFF_G, L::H4, tid, acc);                                   // dH4
             publish();
             if (tid == 0) {
                 umma::fence_after_sync();
-                mma_dgrad(sbase, OFF_G, OFF_W4, 64, 64, 64, tmp);                        // dH3raw = dH4 * W4
-                mma_wgrad(sbase, OFF_G, OFF_H3, 64, p.tm + TC_DW4, first_tile);          // dW4 += dH4^T H3
+                mma_dgrad(sbase, OFF_G, L::W4, 64, 64, 64, tmp);                        // dH3raw = dH4 * W4
+                mma_wgrad(sbase, OFF_G, L::H3, 64, p.tm + TC_DW4, first_tile);          // dW4 += dH4^T H3
                 umma::commit(&bar);
             }
             wait_mma(p);
             read_acc<64>(p, TC_TMP, acc);
-            mask_store(smem, OFF_G, OFF_H3, tid, acc);                                   // dH3 (dH4 no longer needed)
+            mask_store(smem, OFF_G, L::H3, tid, acc);                                   // dH3 (dH4 no longer needed)
             publish();
             if (tid == 0) {
                 umma::fence_after_sync();
-                mma_dgrad(sbase, OFF_G, OFF_W3, 64, 32, 64, tmp);                        // dIN2raw = dH3 * W3
-                mma_wgrad(sbase, OFF_G, OFF_IN2, 32, p.tm + TC_DW3, first_tile);         // dW3 += dH3^T [SH|h]
+                mma_dgrad(sbase, OFF_G, L::W3, 64, 32, 64, tmp);                        // dIN2raw = dH3 * W3
+                mma_wgrad(sbase, OFF_G, L::IN2, 32, p.tm + TC_DW3, first_tile);         // dW3 += dH3^T [SH|h]
                 umma::commit(&bar);
             }
             wait_mma(p);
@@ -398,18 +440,18 @@ __global__ void __launch_bounds__(TILE) mlp_kernel(const MlpArgs a) {
         publish();
         if (tid == 0) {
             umma::fence_after_sync();
-            mma_dgrad(sbase, OFF_DH, OFF_W2, 16, 64, 16, tmp);                           // dH1raw = dh * W2
-            mma_wgrad(sbase, OFF_H1, OFF_DH, 16, p.tm + TC_DW2T, first_tile);            // dW2^T += H1^T dh
+            mma_dgrad(sbase, OFF_DH, L::W2, 16, 64, 16, tmp);                           // dH1raw = dh * W2
+            mma_wgrad(sbase, L::H1, OFF_DH, 16, p.tm + TC_DW2T, first_tile);            // dW2^T += H1^T dh
             umma::commit(&bar);
         }
         wait_mma(p);
         read_acc<64>(p, TC_TMP, acc);
-        mask_store(smem, OFF_G, OFF_H1, tid, acc);                                       // dH1
+        mask_store(smem, OFF_G, L::H1, tid, acc);                                       // dH1
         publish();
         if (tid == 0) {
             umma::fence_after_sync();
-            mma_dgrad(sbase, OFF_G, OFF_W1, 64, 32, 64, tmp);                            // d(enc) = dH1 * W1
-            mma_wgrad(sbase, OFF_G, OFF_X0, 32, p.tm + TC_DW1, first_tile);              // dW1 += dH1^T enc
+            mma_dgrad(sbase, OFF_G, L::W1, 64, 32, 64, tmp);                            // d(enc) = dH1 * W1
+            mma_wgrad(sbase, OFF_G, L::X0, 32, p.tm + TC_DW1, first_tile);              // dW1 += dH1^T enc
             umma::commit(&bar);
         }
         wait_mma(p);
@@ -456,7 +498,7 @@ int launch_mlp(bool bwd, const MlpArgs& a, cudaStream_t st) {
         attr_set = true;
     }
     const int64_t n_tiles = (a.S + TILE - 1) / TILE;
-    const int per_sm = bwd ? 2 : 2;
+    const int per_sm = bwd ? 2 : 4;
     int64_t grid = (int64_t)vn_sm_count() * per_sm;
     if (grid > n_tiles) grid = n_tiles;
     if (bwd) mlp_kernel<true><<<(unsigned)grid, TILE, SMEM_BWD, st>>>(a);
@@ -475,6 +517,8 @@ VN_API int vn_mlp_fwd(const void* enc, int enc_half, const float* dirs, const fl
     VN_REQUIRE(enc && W1 && W2 && sigmas, "vn_mlp_fwd: null pointer");
     VN_REQUIRE(density_only || (dirs && W3 && W4 && W5 && rgbs), "vn_mlp_fwd: null colour-network pointer");
     VN_REQUIRE(vn_aligned(enc, 16), "vn_mlp_fwd: enc must be 16-byte aligned");
+    VN_REQUIRE(vn_aligned(W1, 16) && vn_aligned(W2, 16) && vn_aligned(W3, 16) && vn_aligned(W4, 16) && vn_aligned(W5, 16),
+               "vn_mlp_fwd: weight matrices must be 16-byte aligned");
     MlpArgs a{};
     a.enc = (const float*)enc; a.enc_half = enc_half; a.dirs = dirs;
     a.W[0] = W1; a.W[1] = W2; a.W[2] = density_only ? W1 : W3; a.W[3] = density_only ? W1 : W4; a.W[4] = density_only ? W1 : W5;
@@ -491,6 +535,8 @@ VN_API int vn_mlp_bwd(const void* enc, int enc_half, const float* dirs, const fl
     VN_REQUIRE(enc && W1 && W2 && dsigmas && denc && dW1 && dW2, "vn_mlp_bwd: null pointer");
     VN_REQUIRE(density_only || (dirs && W3 && W4 && W5 && drgbs && dW3 && dW4 && dW5), "vn_mlp_bwd: null colour-network pointer");
     VN_REQUIRE(vn_aligned(enc, 16) && vn_aligned(denc, 16), "vn_mlp_bwd: enc/denc must be 16-byte aligned");
+    VN_REQUIRE(vn_aligned(W1, 16) && vn_aligned(W2, 16) && vn_aligned(W3, 16) && vn_aligned(W4, 16) && vn_aligned(W5, 16),
+               "vn_mlp_bwd: weight matrices must be 16-byte aligned");
     MlpArgs a{};
     a.enc = (const float*)enc; a.enc_half = enc_half; a.dirs = dirs;
     a.W[0] = W1; a.W[1] = W2; a.W[2] = density_only ? W1 : W3; a.W[3] = density_only ? W1 : W4; a.W[4] = density_only ? W1 : W5;

@@ -47,6 +47,14 @@ const char* vn_last_error(void);
 int vn_abi_version(void);
 /* number of kernels this library has launched so far in this process */
 int64_t vn_launch_count(void);
+/* in-stream kernel timing: while enabled, the launchers of the major kernels bracket their
+ * launch with CUDA events on the launching stream; _get synchronises on record i and returns
+ * (kernel id, problem size = samples / rays / params, milliseconds).  ids: 0 hash fwd, 1 hash
+ * bwd, 2 MLP fwd, 3 MLP bwd, 4 march count, 5 march write, 6 composite fwd, 7 composite bwd,
+ * 8 Adam. */
+int vn_profile_enable(int on);
+int vn_profile_count(void);
+int vn_profile_get(int i, int* h_kernel_id, int64_t* h_size, float* h_ms);
 /* SM count / device name of the current device; proves the library talks to a GPU */
 int vn_device_info(int* sm_count, int* cc_major, int* cc_minor, char* name, int name_len);
 
@@ -249,6 +257,45 @@ int vn_mlp_bwd(const void* enc, int enc_half, const float* dirs, const float* W1
                const float* W3, const float* W4, const float* W5, int64_t S, int density_only,
                const float* dsigmas, const float* drgbs, float* denc, float* dW1, float* dW2,
                float* dW3, float* dW4, float* dW5, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Native step runner (caller side): the body of Trainer.train()'s loop
+ * (training/trainer.py:104-141) as TWO host calls that enqueue every kernel of a step on
+ * `stream` with plain C++ launch overhead instead of one Python -> ctypes round trip per
+ * kernel.  All buffers are caller-owned device memory; `S` is the sample total read back from
+ * counter[0] after _prepare.
+ *  _prepare: vn_ray_aabb + vn_march_train_count (no dependence on gradients in flight).
+ *  _run    : cudaMemsetAsync(grad, loss accumulators) + march write + hash fwd + fused MLP fwd +
+ *            composite fwd + loss fwd + loss bwd + composite bwd + fused MLP bwd + hash bwd,
+ *            and, when do_optim != 0, grad check + Adam + scaler update.  A data-parallel
+ *            caller passes do_optim = 0, allreduces `flat_g` (and, between two _run calls split
+ *            at the loss, the counts) and then calls vn_train_step_optim. */
+typedef struct vn_step {
+    /* rays (N) */
+    int64_t N;
+    const float *rays_o, *rays_d, *noise, *gt_rgb, *uss, *tof, *rgbd; /* targets may be NULL */
+    float *hits_t; int32_t *counts, *rays_a, *counter, *scan_tmp;
+    const uint8_t* bitfield;
+    int32_t cascades, grid_size, max_samples; float scale, exp_step_factor, T_threshold, bg, uss_tol;
+    /* samples (capacity >= S rows) */
+    float *xyzs, *dirs, *unit, *deltas, *ts, *enc, *sigmas, *rgbs, *ws, *d_sigmas, *d_rgbs, *d_enc;
+    /* per ray outputs / seeds */
+    int32_t* vr_samples; float *opacity, *depth, *rgb, *d_rgb, *d_depth, *d_opacity;
+    /* model: flat parameter / gradient / Adam buffers and the slices inside them */
+    float *flat_p, *flat_g, *flat_m, *flat_v; int64_t n_params;
+    int64_t table_off, w_off[5];          /* offsets (floats) of the hash table and W1..W5 */
+    vn_hash_levels_t levels; int32_t hash_flags;
+    /* loss + optimiser state */
+    float *loss_acc /* [8]: sums[4], counts[4] */, *loss_out /* [1] */;
+    float w_color, w_uss, w_tof, w_rgbd;
+    float *scale_dev, *found_inf; int32_t* growth_tracker;
+    float lr, beta1, beta2, eps; int32_t adam_step;
+} vn_step_t;
+
+int vn_train_step_prepare(const vn_step_t* h_step, void* stream);
+/* phase: 0 = whole forward+backward, 1 = up to and including loss fwd, 2 = from loss bwd on */
+int vn_train_step_run(const vn_step_t* h_step, int64_t S, int phase, int do_optim, void* stream);
+int vn_train_step_optim(const vn_step_t* h_step, void* stream);
 
 /* tcgen05 self-test (development / CI): one 128 x N x K fp16 product through the tensor
  * cores in the three operand modes the fused MLP uses (0 forward A*B^T, 1 dgrad A*B,

@@ -37,6 +37,38 @@ class HashLevels(ctypes.Structure):
     ]
 
 
+_P, _F, _I32, _I64 = ctypes.c_void_p, ctypes.c_float, ctypes.c_int32, ctypes.c_int64
+
+
+class Step(ctypes.Structure):
+    """mirror of vn_step_t (include/virusnerf.h): every buffer of one train step"""
+    _fields_ = (
+        [("N", _I64)] +
+        [(n, _P) for n in ("rays_o", "rays_d", "noise", "gt_rgb", "uss", "tof", "rgbd")] +
+        [(n, _P) for n in ("hits_t", "counts", "rays_a", "counter", "scan_tmp", "bitfield")] +
+        [("cascades", _I32), ("grid_size", _I32), ("max_samples", _I32), ("scale", _F), ("exp_step_factor", _F),
+         ("T_threshold", _F), ("bg", _F), ("uss_tol", _F)] +
+        [(n, _P) for n in ("xyzs", "dirs", "unit", "deltas", "ts", "enc", "sigmas", "rgbs", "ws", "d_sigmas", "d_rgbs",
+                           "d_enc")] +
+        [(n, _P) for n in ("vr_samples", "opacity", "depth", "rgb", "d_rgb", "d_depth", "d_opacity")] +
+        [(n, _P) for n in ("flat_p", "flat_g", "flat_m", "flat_v")] + [("n_params", _I64)] +
+        [("table_off", _I64), ("w_off", _I64 * 5)] +
+        [("levels", HashLevels), ("hash_flags", _I32)] +
+        [("loss_acc", _P), ("loss_out", _P)] +
+        [("w_color", _F), ("w_uss", _F), ("w_tof", _F), ("w_rgbd", _F)] +
+        [("scale_dev", _P), ("found_inf", _P), ("growth_tracker", _P)] +
+        [("lr", _F), ("beta1", _F), ("beta2", _F), ("eps", _F), ("adam_step", _I32)])
+
+    def set_ptrs(self, **tensors):
+        for k, t in tensors.items():
+            if t is None:
+                setattr(self, k, None)
+                continue
+            if not (t.is_cuda and t.is_contiguous()):
+                raise RuntimeError(f"vn_step_t.{k}: needs a contiguous CUDA tensor")
+            setattr(self, k, t.data_ptr())
+
+
 # spec characters: p device pointer (tensor / None), l int64, i int, f float, d double,
 # h host pointer to a ctypes struct, s stream (filled in automatically)
 _SPECS = {
@@ -71,6 +103,9 @@ _SPECS = {
     "vn_adam_step": "ppppl" "fffff" "ipps",
     "vn_scaler_update": "pppffis",
     "vn_umma_selftest": "iiippps",
+    "vn_train_step_prepare": "hs",
+    "vn_train_step_run": "hliis",
+    "vn_train_step_optim": "hs",
     "vn_mlp_fwd": "pip" "ppppp" "li" "ppp" "s",
     "vn_mlp_bwd": "pip" "ppppp" "li" "pp" "p" "ppppp" "s",
 }
@@ -129,21 +164,26 @@ def _ptr(t, name, pos):
     return ctypes.c_void_p(t.data_ptr())
 
 
-_profile = None   # {name: [(start_event, end_event, size), ...]} while profiling
+KERNEL_NAMES = ["hash_encode_fwd", "hash_encode_bwd", "mlp_fwd", "mlp_bwd", "march_count", "march_write",
+                "composite_fwd", "composite_bwd", "adam"]
 
 
-def profile_start(names):
-    """time the given entry points with CUDA events recorded on the launching stream"""
-    global _profile
-    _profile = {n: [] for n in names}
+def profile_start():
+    """bracket every major kernel launch with CUDA events on the launching stream (vn_profile_*)"""
+    lib().vn_profile_enable(1)
 
 
 def profile_stop():
-    """-> {name: [(milliseconds, size), ...]}; synchronises"""
-    global _profile
-    prof, _profile = _profile, None
-    torch.cuda.synchronize()
-    return {n: [(e0.elapsed_time(e1), sz) for e0, e1, sz in calls] for n, calls in (prof or {}).items()}
+    """-> {kernel name: [(milliseconds, problem size), ...]}; synchronises"""
+    L = lib()
+    L.vn_profile_enable(0)
+    out = {}
+    kid, size, ms = ctypes.c_int(0), ctypes.c_int64(0), ctypes.c_float(0)
+    for i in range(L.vn_profile_count()):
+        if L.vn_profile_get(i, ctypes.byref(kid), ctypes.byref(size), ctypes.byref(ms)) != 0:
+            raise RuntimeError(last_error())
+        out.setdefault(KERNEL_NAMES[kid.value], []).append((ms.value, size.value))
+    return out
 
 
 def call(name, *args):
@@ -182,16 +222,6 @@ def call(name, *args):
     if len(list(it)) != 0:
         raise TypeError(f"{name}: too many arguments")
     fn = getattr(L, name)
-    if _profile is not None and name in _profile:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        rc = fn(*conv)
-        e1.record()
-        size = next((int(a) for a, c in zip(args, spec.replace("s", "")) if c == "l"), 0)
-        _profile[name].append((e0, e1, size))
-        if rc != 0:
-            raise RuntimeError(f"{name} failed (code {rc}): {last_error()}")
-        return
     if dev is not None and dev.index is not None and dev.index != torch.cuda.current_device():
         with torch.cuda.device(dev):
             conv = [ctypes.c_void_p(torch.cuda.current_stream().cuda_stream) if c == "s" else v
@@ -225,4 +255,4 @@ def hash_levels(base_res, max_res, levels, max_params):
 
 def exported_symbols():
     """names declared in include/virusnerf.h (used by the CPU-side ABI test)"""
-    return ["vn_last_error", "vn_abi_version", "vn_launch_count", "vn_device_info", "vn_march_scan_tmp_ints"] + list(_SPECS)
+    return ["vn_last_error", "vn_abi_version", "vn_launch_count", "vn_profile_enable", "vn_profile_count", "vn_profile_get", "vn_device_info", "vn_march_scan_tmp_ints"] + list(_SPECS)

@@ -39,3 +39,35 @@ VN_API int vn_device_info(int* sm_count, int* cc_major, int* cc_minor, char* nam
     if (name && name_len > 0) { strncpy(name, prop.name, (size_t)name_len - 1); name[name_len - 1] = 0; }
     return VN_OK;
 }
+
+// ---- in-stream kernel timing -----------------------------------------------------------------
+bool g_vn_profiling = false;
+namespace {
+struct ProfRec { int id; int64_t size; cudaEvent_t e0, e1; };
+const int kMaxRecs = 8192;
+ProfRec g_recs[kMaxRecs];
+int g_nrecs = 0, g_nevents = 0;
+}
+
+void vn_prof_begin(int kernel_id, int64_t size, cudaStream_t st) {
+    if (g_nrecs >= kMaxRecs) { g_vn_profiling = false; return; }
+    ProfRec& r = g_recs[g_nrecs];
+    if (g_nrecs >= g_nevents) { cudaEventCreate(&r.e0); cudaEventCreate(&r.e1); ++g_nevents; }
+    r.id = kernel_id; r.size = size;
+    cudaEventRecord(r.e0, st);
+}
+void vn_prof_end(cudaStream_t st) {
+    if (g_nrecs >= kMaxRecs) return;
+    cudaEventRecord(g_recs[g_nrecs].e1, st);
+    ++g_nrecs;
+}
+
+VN_API int vn_profile_enable(int on) { g_vn_profiling = on != 0; if (on) g_nrecs = 0; return VN_OK; }
+VN_API int vn_profile_count(void) { return g_nrecs; }
+VN_API int vn_profile_get(int i, int* kernel_id, int64_t* size, float* ms) {
+    VN_REQUIRE(i >= 0 && i < g_nrecs && kernel_id && size && ms, "vn_profile_get: bad index");
+    VN_CUDA(cudaEventSynchronize(g_recs[i].e1));
+    VN_CUDA(cudaEventElapsedTime(ms, g_recs[i].e0, g_recs[i].e1));
+    *kernel_id = g_recs[i].id; *size = g_recs[i].size;
+    return VN_OK;
+}

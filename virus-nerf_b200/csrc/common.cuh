@@ -41,6 +41,18 @@ extern unsigned long long g_vn_launches;   // kernels launched by this library (
         }                                                                            \
     } while (0)
 
+// ---- optional in-stream kernel timing (CUDA events around a launch; see vn_profile_*) ----
+enum { VN_K_HASH_FWD = 0, VN_K_HASH_BWD, VN_K_MLP_FWD, VN_K_MLP_BWD, VN_K_MARCH_COUNT, VN_K_MARCH_WRITE, VN_K_COMP_FWD,
+       VN_K_COMP_BWD, VN_K_ADAM, VN_K_COUNT };
+extern bool g_vn_profiling;
+void vn_prof_begin(int kernel_id, int64_t size, cudaStream_t st);
+void vn_prof_end(cudaStream_t st);
+struct VnProfScope {
+    cudaStream_t st; bool on;
+    VnProfScope(int id, int64_t size, cudaStream_t s) : st(s), on(g_vn_profiling) { if (on) vn_prof_begin(id, size, st); }
+    ~VnProfScope() { if (on) vn_prof_end(st); }
+};
+
 static inline bool vn_aligned(const void* p, size_t a) { return ((uintptr_t)p % a) == 0; }
 static inline unsigned vn_blocks(int64_t n, int per_block) { return (unsigned)((n + per_block - 1) / per_block); }
 int vn_sm_count();

@@ -99,6 +99,7 @@ VN_API int vn_composite_train_fwd(const float* sigmas, const float* rgbs, const 
     if (N == 0) return VN_OK;
     VN_REQUIRE(rays_a && total_samples && opacity && depth && rgb, "vn_composite_train_fwd: null pointer");
     VN_REQUIRE(S == 0 || (sigmas && rgbs && deltas && ts && ws), "vn_composite_train_fwd: null sample pointer");
+    VnProfScope prof(VN_K_COMP_FWD, S, (cudaStream_t)stream);
     composite_fwd_kernel<<<vn_blocks(N * 32, 256), 256, 0, (cudaStream_t)stream>>>(sigmas, rgbs, deltas, ts, rays_a, N, S,
                                                                                  T_threshold, total_samples, opacity,
                                                                                  depth, rgb, ws);
@@ -208,6 +209,7 @@ VN_API int vn_composite_train_bwd(const float* sigmas, const float* rgbs, const 
     if (N == 0 || S == 0) return VN_OK;
     VN_REQUIRE(sigmas && rgbs && deltas && ts && rays_a && dL_dopacity && dL_ddepth && dL_drgb && dsigmas && drgbs,
                "vn_composite_train_bwd: null pointer");
+    VnProfScope prof(VN_K_COMP_BWD, S, (cudaStream_t)stream);
     composite_bwd_kernel<<<vn_blocks(N * 32, 256), 256, 0, (cudaStream_t)stream>>>(
         sigmas, rgbs, deltas, ts, rays_a, N, S, T_threshold, dL_dopacity, dL_ddepth, dL_drgb, dL_dws, dsigmas, drgbs);
     VN_CHECK_LAUNCH("composite_bwd_kernel");

@@ -406,6 +406,7 @@ static int launch_fwd(const float* xyz, const TT* table, OT* out, int64_t S, con
     int rc = make_params(lv, P);
     if (rc) return rc;
     if (S == 0) return VN_OK;
+    VnProfScope prof(VN_K_HASH_FWD, S, st);
     const int lpt = pick_lpt(flags, lv, sizeof(TT), false);
     dim3 block(256), grid(vn_blocks(S, 256), (P.levels + lpt - 1) / lpt);
     switch (lpt) {
@@ -431,6 +432,7 @@ static int launch_bwd(const float* xyz, const DT* dout, float* grad, int64_t S, 
     P.level_begin = level_begin;
     P.level_end = level_end;
     if (S == 0 || level_begin == level_end) return VN_OK;
+    VnProfScope prof(VN_K_HASH_BWD, S, st);
     const int lpt = pick_lpt(flags, lv, 8, true);
     const bool agg = !(flags & VN_HASH_NO_WARP_AGG);
     dim3 block(256), grid(vn_blocks(S, 256), (level_end - level_begin + lpt - 1) / lpt);

@@ -497,6 +497,7 @@ int launch_mlp(bool bwd, const MlpArgs& a, cudaStream_t st) {
         VN_CUDA(cudaFuncSetAttribute(mlp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD));
         attr_set = true;
     }
+    VnProfScope prof(bwd ? VN_K_MLP_BWD : VN_K_MLP_FWD, a.S, st);
     const int64_t n_tiles = (a.S + TILE - 1) / TILE;
     const int per_sm = bwd ? 2 : 4;
     int64_t grid = (int64_t)vn_sm_count() * per_sm;

@@ -70,6 +70,7 @@ VN_API int vn_adam_step(float* p, const float* g, float* m, float* v, int64_t n,
     c.omb1 = 1.0f - beta1; c.omb2 = 1.0f - beta2; c.eps = eps;
     c.step_size = (float)((double)lr / bc1);
     c.bc2_sqrt = (float)sqrt(bc2);
+    VnProfScope prof(VN_K_ADAM, n, (cudaStream_t)stream);
     adam_kernel<<<vn_blocks((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, c, found_inf, scale_dev);
     VN_CHECK_LAUNCH("adam_kernel");
     return VN_OK;

@@ -414,6 +414,7 @@ VN_API int vn_march_train_count(const float* rays_o, const float* rays_d, const 
     VN_REQUIRE(cascades >= 1 && grid_size >= 1 && grid_size <= 1024 && max_samples >= 0,
                "vn_march_train_count: bad cascades/grid_size/max_samples");
     const MarchCfg c = make_cfg(cascades, grid_size, scale, exp_step_factor);
+    VnProfScope prof(VN_K_MARCH_COUNT, N, st);
     if (N < kWarpMarchMaxRays)
         march_warp_kernel<false><<<vn_blocks(N * 32, 256), 256, 0, st>>>(rays_o, rays_d, (const float2*)hits_t, bitfield,
                                                                          noise, N, c, max_samples, counts, nullptr, 0,
@@ -442,6 +443,7 @@ VN_API int vn_march_train_write(const float* rays_o, const float* rays_d, const 
                "vn_march_train_write: null pointer");
     VN_REQUIRE(vn_aligned(hits_t, 8), "vn_march_train_write: hits_t must be 8-byte aligned");
     const MarchCfg c = make_cfg(cascades, grid_size, scale, exp_step_factor);
+    VnProfScope prof(VN_K_MARCH_WRITE, capacity, (cudaStream_t)stream);
     if (N < kWarpMarchMaxRays)
         march_warp_kernel<true><<<vn_blocks(N * 32, 256), 256, 0, (cudaStream_t)stream>>>(
             rays_o, rays_d, (const float2*)hits_t, bitfield, noise, N, c, 0, nullptr, rays_a, capacity, xyzs, dirs, deltas, ts, xyzs_unit);

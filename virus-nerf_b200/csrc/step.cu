@@ -1,0 +1,60 @@
+// step.cu -- native step runner: enqueues every kernel of one train step from C++ (see
+// include/virusnerf.h "Native step runner").  Pure orchestration over the other entry points.
+#include "common.cuh"
+
+#define VN_TRY(call) do { int rc__ = (call); if (rc__ != VN_OK) return rc__; } while (0)
+
+VN_API int vn_train_step_prepare(const vn_step_t* s, void* stream) {
+    VN_REQUIRE(s != nullptr, "vn_train_step_prepare: null step");
+    VN_TRY(vn_ray_aabb(s->rays_o, s->rays_d, s->scale, s->N, s->hits_t, stream));
+    VN_TRY(vn_march_train_count(s->rays_o, s->rays_d, s->hits_t, s->bitfield, s->noise, s->N, s->cascades, s->grid_size,
+                                s->scale, s->exp_step_factor, s->max_samples, s->counts, s->rays_a, s->counter,
+                                s->scan_tmp, stream));
+    return VN_OK;
+}
+
+VN_API int vn_train_step_optim(const vn_step_t* s, void* stream) {
+    VN_REQUIRE(s != nullptr, "vn_train_step_optim: null step");
+    VN_TRY(vn_grad_check(s->flat_g, s->n_params, s->found_inf, stream));
+    VN_TRY(vn_adam_step(s->flat_p, s->flat_g, s->flat_m, s->flat_v, s->n_params, 1.0f, s->lr, s->beta1, s->beta2, s->eps,
+                        s->adam_step, s->found_inf, s->scale_dev, stream));
+    VN_TRY(vn_scaler_update(s->scale_dev, s->growth_tracker, s->found_inf, 2.0f, 0.5f, 2000, stream));
+    return VN_OK;
+}
+
+VN_API int vn_train_step_run(const vn_step_t* s, int64_t S, int phase, int do_optim, void* stream) {
+    VN_REQUIRE(s != nullptr && S >= 0 && phase >= 0 && phase <= 2, "vn_train_step_run: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    const float* W[5];
+    float* dW[5];
+    for (int i = 0; i < 5; ++i) { W[i] = s->flat_p + s->w_off[i]; dW[i] = s->flat_g + s->w_off[i]; }
+    const float* table = s->flat_p + s->table_off;
+    float* table_grad = s->flat_g + s->table_off;
+    float* sums = s->loss_acc;
+    float* cnts = s->loss_acc + 4;
+    if (phase == 0 || phase == 1) {
+        VN_CUDA(cudaMemsetAsync(s->flat_g, 0, sizeof(float) * (size_t)s->n_params, st));
+        VN_CUDA(cudaMemsetAsync(s->loss_acc, 0, sizeof(float) * 8, st));
+        VN_TRY(vn_march_train_write(s->rays_o, s->rays_d, s->hits_t, s->bitfield, s->noise, s->N, s->cascades, s->grid_size,
+                                    s->scale, s->exp_step_factor, s->rays_a, S, s->xyzs, s->dirs, s->deltas, s->ts, s->unit,
+                                    stream));
+        VN_TRY(vn_hash_encode_fwd_f32(s->unit, table, s->enc, S, &s->levels, s->hash_flags, stream));
+        VN_TRY(vn_mlp_fwd(s->enc, 0, s->dirs, W[0], W[1], W[2], W[3], W[4], S, 0, s->sigmas, s->rgbs, nullptr, stream));
+        VN_TRY(vn_composite_train_fwd(s->sigmas, s->rgbs, s->deltas, s->ts, s->rays_a, s->N, S, s->T_threshold, s->vr_samples,
+                                      s->opacity, s->depth, s->rgb, s->ws, stream));
+        VN_TRY(vn_loss_fwd(s->rgb, s->opacity, s->depth, s->gt_rgb, s->uss, s->tof, s->rgbd, s->N, s->bg, s->uss_tol, sums,
+                           cnts, stream));
+    }
+    if (phase == 0 || phase == 2) {
+        VN_TRY(vn_loss_bwd(s->rgb, s->opacity, s->depth, s->gt_rgb, s->uss, s->tof, s->rgbd, s->N, s->bg, s->uss_tol, sums,
+                           cnts, s->w_color, s->w_uss, s->w_tof, s->w_rgbd, s->scale_dev, s->d_rgb, s->d_depth, s->d_opacity,
+                           s->loss_out, stream));
+        VN_TRY(vn_composite_train_bwd(s->sigmas, s->rgbs, s->deltas, s->ts, s->rays_a, s->N, S, s->T_threshold, s->d_opacity,
+                                      s->d_depth, s->d_rgb, nullptr, s->d_sigmas, s->d_rgbs, stream));
+        VN_TRY(vn_mlp_bwd(s->enc, 0, s->dirs, W[0], W[1], W[2], W[3], W[4], S, 0, s->d_sigmas, s->d_rgbs, s->d_enc, dW[0], dW[1],
+                          dW[2], dW[3], dW[4], stream));
+        VN_TRY(vn_hash_encode_bwd_f32(s->unit, s->d_enc, table_grad, S, &s->levels, s->hash_flags, stream));
+        if (do_optim) VN_TRY(vn_train_step_optim(s, stream));
+    }
+    return VN_OK;
+}

@@ -147,8 +147,7 @@ class TrainEngine:
         self._mlp_g = [pd[n].grad for n in names]           # views into flat_g
         self._comm_stream = torch.cuda.Stream(device=self.device) if world_size > 1 else None
         self._hash_slice_idx = [i for i, p in enumerate(params) if p is enc.hash_table][0]
-        L = enc.hash_level
-        self._level_groups = [(max(L - 4 * (g + 1), 0), L - 4 * g) for g in range((L + 3) // 4)]   # finest first
+        self._structs = [self._new_step_struct(), self._new_step_struct()] if self.device.type == "cuda" else None
 
     # ------------------------------------------------------------------------------------
     def occupancy_update(self, elapse_time=0.0):
@@ -177,135 +176,111 @@ class TrainEngine:
         return loss.detach()
 
     # ------------------------------------------------------------------------------------
+    def _new_step_struct(self):
+        """vn_step_t with everything that does not change from step to step"""
+        m, a = self.model, self.args
+        enc = m.pos_encoder
+        st = _lib.Step()
+        st.cascades, st.grid_size, st.max_samples = m.cascades, m.grid_size, 1024
+        st.scale, st.exp_step_factor, st.T_threshold = float(m.scale), float(a.exp_step_factor), 1e-4
+        st.bg = 1.0 if a.exp_step_factor == 0 else 0.0                   # rendering.py:219-224
+        st.uss_tol = float(self.loss_fn.uss_depth_tol)
+        st.set_ptrs(flat_p=self.flat_p, flat_g=self.flat_g, flat_m=self.flat_m, flat_v=self.flat_v,
+                    loss_acc=self._loss_acc, loss_out=self._loss_out, scale_dev=self.scale, found_inf=self.found_inf,
+                    growth_tracker=self.growth_tracker, counter=self._counter)
+        st.n_params = self.n_params
+        esz = self.flat_p.element_size()
+        st.table_off = (enc.hash_table.data_ptr() - self.flat_p.data_ptr()) // esz
+        for i, w in enumerate(self._mlp_w):
+            st.w_off[i] = (w.data_ptr() - self.flat_p.data_ptr()) // esz
+        st.levels = enc._levels
+        st.hash_flags = enc.kernel_flags
+        t = a.training
+        st.w_color, st.w_uss, st.w_tof, st.w_rgbd = t.color_loss_w, t.uss_loss_w, t.tof_loss_w, t.rgbd_loss_w
+        st.lr, st.beta1, st.beta2, st.eps = self.lr, self.betas[0], self.betas[1], self.eps
+        return st
+
     def prepare(self, data, elapse_time=0.0, noise=None):
         """front half of a step, independent of the gradients in flight: (occupancy update if
-        due) -> ray/AABB -> march count + scan -> async read-back of the sample total into
-        pinned memory.  step_fast() enqueues it for the NEXT batch while the current step's
-        backward / allreduce is still running, so the one host sync of a step never stalls."""
-        m, a, dev = self.model, self.args, self.device
+        due) -> ray/AABB -> march count + scan (vn_train_step_prepare) -> async read-back of the
+        sample total into pinned memory.  step_fast() enqueues it for the NEXT batch while the
+        current step's backward / allreduce is still running, so the one host sync of a step
+        never stalls."""
+        m = self.model
         if self._prep_step % self.grid_update_interval == 0:
             self.occupancy_update(elapse_time)
         self._prep_step += 1
-        ws, call = self._ws, _lib.call
+        ws = self._ws
         rays_o, rays_d = data['rays_o'].contiguous(), data['rays_d'].contiguous()
         N = rays_o.shape[0]
-        scale, esf = float(m.scale), float(a.exp_step_factor)
-        bitfield = m.occupancy_grid.getBitfield()
-        hits = ws.get("hits", N, 2)
-        call("vn_ray_aabb", rays_o, rays_d, scale, N, hits)
         if noise is None:
             noise = ws.get("noise", N)
             noise.uniform_()                                                # ray_march.py:139
-        counts = ws.get("counts", N, None, torch.int32)
-        rays_a = ws.get("rays_a", N, 3, torch.int32)
-        scan_tmp = ws.get("scan_tmp", _lib.scan_tmp_ints(N), None, torch.int32)
-        call("vn_march_train_count", rays_o, rays_d, hits, bitfield, noise, N, m.cascades, m.grid_size, scale, esf,
-             1024, counts, rays_a, self._counter, scan_tmp)
+        st = self._structs[self._prep_step & 1]
+        t = self.args.training
+        depth = data['depth']
+        st.N = N
+        st.set_ptrs(rays_o=rays_o, rays_d=rays_d, noise=noise.contiguous(), gt_rgb=data['rgb'].contiguous(),
+                    uss=depth.get('USS') if 'USS' in t.sensors else None,
+                    tof=depth.get('ToF') if 'ToF' in t.sensors else None,
+                    rgbd=depth.get('RGBD') if 'RGBD' in t.sensors else None,
+                    hits_t=ws.get("hits", N, 2), counts=ws.get("counts", N, None, torch.int32),
+                    rays_a=ws.get("rays_a", N, 3, torch.int32),
+                    scan_tmp=ws.get("scan_tmp", _lib.scan_tmp_ints(N), None, torch.int32),
+                    bitfield=m.occupancy_grid.getBitfield(),
+                    vr_samples=ws.get("vr", N, None, torch.int32), opacity=ws.get("op", N), depth=ws.get("dp", N),
+                    rgb=ws.get("rgb", N, 3), d_rgb=ws.get("d_rgb", N, 3), d_depth=ws.get("d_dp", N),
+                    d_opacity=ws.get("d_op", N))
+        _lib.call("vn_train_step_prepare", st)
         self._counter_host.copy_(self._counter, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
-        return {"data": data, "rays_o": rays_o, "rays_d": rays_d, "hits": hits, "noise": noise, "rays_a": rays_a,
-                "bitfield": bitfield, "event": ev, "N": N}
+        return {"data": data, "struct": st, "event": ev, "keep": (rays_o, rays_d, noise)}
 
     def step_fast(self, data, elapse_time=0.0, noise=None, next_data=None):
-        """The same train step as step(), hand-chained through the C ABI: no autograd graph, no
-        torch element-wise glue, persistent workspace, ~20 kernel launches:
-        [prepare: aabb, march count + scan], march write (also emits unit-cube positions), hash
-        fwd, fused MLP fwd, composite fwd, loss fwd, [allreduce counts], loss bwd (gradient
-        seeds), composite bwd, fused MLP bwd (dW straight into the flat gradient), hash bwd
-        (ditto), [allreduce flat gradient || prepare(next_data)], grad check, Adam, scaler update.
-        Pass next_data to software-pipeline the front half of the next step."""
-        m, a, dev = self.model, self.args, self.device
+        """The same train step as step(), enqueued by the native step runner (csrc/step.cu): no
+        autograd graph, no torch glue, persistent workspace, three host calls per step:
+        [prepare: aabb, march count + scan] -> host reads S -> [run: march write (also emits
+        unit-cube positions), hash fwd, fused MLP fwd, composite fwd, loss fwd, (allreduce
+        counts), loss bwd (gradient seeds), composite bwd, fused MLP bwd (dW straight into the
+        flat gradient), hash bwd (ditto)] -> (allreduce flat gradient || prepare(next_data)) ->
+        [optim: grad check, Adam, scaler update].  Pass next_data to software-pipeline the front
+        half of the next step."""
         tk = self._ticket if (self._ticket is not None and self._ticket["data"] is data) else \
             self.prepare(data, elapse_time, noise)
         self._ticket = None
-        ws, call = self._ws, _lib.call
-        rays_o, rays_d, hits, noise, rays_a, bitfield, N = (tk["rays_o"], tk["rays_d"], tk["hits"], tk["noise"],
-                                                            tk["rays_a"], tk["bitfield"], tk["N"])
-        scale, esf = float(m.scale), float(a.exp_step_factor)
-        enc = m.pos_encoder
+        st, ws = tk["struct"], self._ws
         tk["event"].synchronize()                                         # the one host sync of the step
         S = int(self._counter_host[0])
         self.last_samples = S
-        self.flat_g.zero_()
-        xyzs = ws.get("xyzs", S, 3); dirs = ws.get("dirs", S, 3); unit = ws.get("unit", S, 3)
-        deltas = ws.get("deltas", S); ts = ws.get("ts", S)
-        call("vn_march_train_write", rays_o, rays_d, hits, bitfield, noise, N, m.cascades, m.grid_size, scale, esf,
-             rays_a, S, xyzs, dirs, deltas, ts, unit)
-        encoded = ws.get("enc", S, 32)
-        call("vn_hash_encode_fwd_f32", unit, enc.hash_table, encoded, S, enc._levels, enc.kernel_flags)
-        W = self._mlp_w
-        sig = ws.get("sig", S); rgbs = ws.get("rgbs", S, 3)
-        call("vn_mlp_fwd", encoded, 0, dirs, *W, S, 0, sig, rgbs, None)
-        vr = ws.get("vr", N, None, torch.int32)
-        op = ws.get("op", N); dp = ws.get("dp", N); rgb = ws.get("rgb", N, 3); w_s = ws.get("ws", S)
-        call("vn_composite_train_fwd", sig, rgbs, deltas, ts, rays_a, N, S, 1e-4, vr, op, dp, rgb, w_s)
-        # ---- loss + gradient seeds (training/loss.py) -------------------------------------
-        t = a.training
-        depth = data['depth']
-        uss = depth.get('USS') if 'USS' in t.sensors else None
-        tof = depth.get('ToF') if 'ToF' in t.sensors else None
-        rgbd = depth.get('RGBD') if 'RGBD' in t.sensors else None
-        bg = 1.0 if esf == 0 else 0.0                                     # rendering.py:219-224
-        self._loss_acc.zero_()
-        sums, cnts = self._loss_acc[:4], self._loss_acc[4:]
-        call("vn_loss_fwd", rgb, op, dp, data['rgb'], uss, tof, rgbd, N, bg, self.loss_fn.uss_depth_tol, sums, cnts)
-        if self.world_size > 1:
-            dist.all_reduce(cnts)                                         # global normalisers
-        d_rgb = ws.get("d_rgb", N, 3); d_dp = ws.get("d_dp", N); d_op = ws.get("d_op", N)
-        call("vn_loss_bwd", rgb, op, dp, data['rgb'], uss, tof, rgbd, N, bg, self.loss_fn.uss_depth_tol, sums, cnts,
-             t.color_loss_w, t.uss_loss_w, t.tof_loss_w, t.rgbd_loss_w, self.scale, d_rgb, d_dp, d_op, self._loss_out)
-        # ---- backward chain ----------------------------------------------------------------
-        d_sig = ws.get("d_sig", S); d_rgbs = ws.get("d_rgbs", S, 3)
-        call("vn_composite_train_bwd", sig, rgbs, deltas, ts, rays_a, N, S, 1e-4, d_op, d_dp, d_rgb, None, d_sig, d_rgbs)
-        d_enc = ws.get("d_enc", S, 32)
-        call("vn_mlp_bwd", encoded, 0, dirs, *W, S, 0, d_sig, d_rgbs, d_enc, *self._mlp_g)
-        call("vn_hash_encode_bwd_f32", unit, d_enc, enc.hash_table.grad, S, enc._levels, enc.kernel_flags)
+        st.set_ptrs(xyzs=ws.get("xyzs", S, 3), dirs=ws.get("dirs", S, 3), unit=ws.get("unit", S, 3),
+                    deltas=ws.get("deltas", S), ts=ws.get("ts", S), enc=ws.get("enc", S, 32), sigmas=ws.get("sig", S),
+                    rgbs=ws.get("rgbs", S, 3), ws=ws.get("ws", S), d_sigmas=ws.get("d_sig", S),
+                    d_rgbs=ws.get("d_rgbs", S, 3), d_enc=ws.get("d_enc", S, 32))
+        self.adam_step += 1
+        st.adam_step = self.adam_step
         self.step_idx += 1
-        work = None
-        if self.world_size > 1:
-            ev = torch.cuda.Event(); ev.record()
-            self._comm_stream.wait_event(ev)
-            with torch.cuda.stream(self._comm_stream):
-                work = dist.all_reduce(self.flat_g, async_op=True)        # overlaps prepare(next) below
         update_due = self._prep_step % self.grid_update_interval == 0     # next front half needs the new weights
+        if self.world_size == 1:
+            _lib.call("vn_train_step_run", st, S, 0, 1)
+            if next_data is not None:
+                self._ticket = self.prepare(next_data, elapse_time)
+            return self._loss_out[0]
+        # ---- data parallel ----------------------------------------------------------------
+        _lib.call("vn_train_step_run", st, S, 1, 0)
+        dist.all_reduce(self._loss_acc[4:])                               # global normalisers
+        _lib.call("vn_train_step_run", st, S, 2, 0)
+        ev = torch.cuda.Event(); ev.record()
+        self._comm_stream.wait_event(ev)
+        with torch.cuda.stream(self._comm_stream):
+            work = dist.all_reduce(self.flat_g, async_op=True)            # overlaps prepare(next) below
         if next_data is not None and not update_due:
             self._ticket = self.prepare(next_data, elapse_time)
-        if work is not None:
-            work.wait()
-        self.optimizer_step()
+        work.wait()
+        _lib.call("vn_train_step_optim", st)
         if next_data is not None and update_due:
             self._ticket = self.prepare(next_data, elapse_time)
         return self._loss_out[0]
-
-    def _bwd_hash_overlapped(self, unit, d_enc, S):
-        """DP: the hash backward is issued per level group (finest first); each finished slab of
-        the flat gradient is allreduced on a side stream while the next group scatters.  The MLP
-        gradients (already complete) go first.  The main stream joins before the optimiser."""
-        enc = self.model.pos_encoder
-        main = torch.cuda.current_stream()
-        comm = self._comm_stream
-        works = []
-
-        def reduce_slab(lo, hi):
-            ev = torch.cuda.Event()
-            ev.record(main)
-            comm.wait_event(ev)
-            with torch.cuda.stream(comm):
-                works.append(dist.all_reduce(self.flat_g[lo:hi], async_op=True))
-
-        h0, hn = self.slices[self._hash_slice_idx]
-        reduce_slab(h0 + hn, self.n_params)              # everything after the table: MLP weights
-        if h0 > 0:
-            reduce_slab(0, h0)
-        L = enc.hash_level
-        offs = [int(o) for o in enc.offsets.tolist()] + [int(enc._levels.total_entries)]
-        for lb, le in self._level_groups:
-            _lib.call("vn_hash_encode_bwd_f32_levels", unit, d_enc, enc.hash_table.grad, S, enc._levels,
-                      enc.kernel_flags, lb, le)
-            reduce_slab(h0 + 2 * offs[lb], h0 + 2 * offs[le])
-        for w in works:
-            w.wait()                                        # main stream waits for the collectives
 
     def replica_checksum(self):
         """(bitfield, parameter) checksums used to verify that DP replicas are bit-identical"""

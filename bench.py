@@ -189,6 +189,11 @@ def run_ours(a):
         ds.gen.manual_seed(1000 + rank)           # same pool on every rank, different training batches
         eng = TrainEngine(args, ds, dev, world_size=world, rank=rank, autocast=not a.no_autocast)
         host_batches = None
+        dev_batches = None
+        if not pinned:
+            # `value`: inputs already resident in HBM when the timed region starts -- the W+K batches are
+            # assembled (sampled + gathered from the ray pool) on the device beforehand
+            dev_batches = [ds(n, args.training.sampling_strategy) for _ in range(W + K + 1)]
         if pinned:
             # batches pre-assembled in pinned host memory (the reference's dataset lives on the
             # host side of the boundary); the timed region pays the H2D copy of each batch
@@ -209,7 +214,7 @@ def run_ours(a):
                 hb = host_batches[it]
                 dv = [t.to(dev, non_blocking=True) for t in hb]
                 return {"rays_o": dv[0], "rays_d": dv[1], "rgb": dv[2], "depth": {"USS": dv[3], "ToF": dv[4]}}
-            return ds(n, args.training.sampling_strategy)
+            return dev_batches[it]
 
         data = get_batch(0)
         for it in range(W + K):
@@ -222,7 +227,7 @@ def run_ours(a):
             # the next batch is fetched (H2D copy in the e2e phase) before this step is enqueued so that
             # the engine can pipeline its front half; every batch is copied exactly once, inside the
             # timed region for all timed steps but the first (whose copy replaces the last step's)
-            nxt = get_batch(it + 1) if (pinned or it + 1 < W + K) else None
+            nxt = get_batch(it + 1)
             if pinned:
                 h2d = sum(t.numel() * t.element_size() for t in host_batches[it])
             if a.autograd_step:

@@ -135,7 +135,10 @@ class TrainEngine:
         # fast-path state
         self._ws = _Workspace(self.device)
         self._counter = torch.zeros(2, dtype=torch.int32, device=self.device)
-        self._counter_host = torch.zeros(2, dtype=torch.int32).pin_memory() if self.device.type == "cuda" else None
+        cuda = self.device.type == "cuda"
+        self._counters = [torch.zeros(2, dtype=torch.int32, device=self.device) for _ in range(2)]
+        self._counter_hosts = [torch.zeros(2, dtype=torch.int32).pin_memory() for _ in range(2)] if cuda else None
+        self._prep_stream = torch.cuda.Stream(device=self.device, priority=-1) if cuda else None
         self._ticket = None
         self._prep_step = 0
         self._loss_acc = torch.zeros(8, device=self.device)
@@ -187,7 +190,7 @@ class TrainEngine:
         st.uss_tol = float(self.loss_fn.uss_depth_tol)
         st.set_ptrs(flat_p=self.flat_p, flat_g=self.flat_g, flat_m=self.flat_m, flat_v=self.flat_v,
                     loss_acc=self._loss_acc, loss_out=self._loss_out, scale_dev=self.scale, found_inf=self.found_inf,
-                    growth_tracker=self.growth_tracker, counter=self._counter)
+                    growth_tracker=self.growth_tracker)
         st.n_params = self.n_params
         esz = self.flat_p.element_size()
         st.table_off = (enc.hash_table.data_ptr() - self.flat_p.data_ptr()) // esz
@@ -200,42 +203,63 @@ class TrainEngine:
         st.lr, st.beta1, st.beta2, st.eps = self.lr, self.betas[0], self.betas[1], self.eps
         return st
 
-    def prepare(self, data, elapse_time=0.0, noise=None):
+    def prepare(self, data, elapse_time=0.0, noise=None, ready=None):
         """front half of a step, independent of the gradients in flight: (occupancy update if
         due) -> ray/AABB -> march count + scan (vn_train_step_prepare) -> async read-back of the
         sample total into pinned memory.  step_fast() enqueues it for the NEXT batch while the
         current step's backward / allreduce is still running, so the one host sync of a step
         never stalls."""
         m = self.model
-        if self._prep_step % self.grid_update_interval == 0:
-            self.occupancy_update(elapse_time)
+        update = self._prep_step % self.grid_update_interval == 0
         self._prep_step += 1
+        par = self._prep_step & 1                       # per-ray buffers are double-buffered
         ws = self._ws
+        main = torch.cuda.current_stream()
+        # the front half only needs the bitfield: run it on a high-priority side stream so that it
+        # overlaps the previous step's kernels and S is on the host before that step has finished.
+        # When the occupancy update is due it depends on the weights -> stay on the main stream.
+        side = self._prep_stream if (self._prep_stream is not None and not update) else None
         rays_o, rays_d = data['rays_o'].contiguous(), data['rays_d'].contiguous()
         N = rays_o.shape[0]
-        if noise is None:
-            noise = ws.get("noise", N)
-            noise.uniform_()                                                # ray_march.py:139
-        st = self._structs[self._prep_step & 1]
         t = self.args.training
         depth = data['depth']
+        st = self._structs[par]
         st.N = N
-        st.set_ptrs(rays_o=rays_o, rays_d=rays_d, noise=noise.contiguous(), gt_rgb=data['rgb'].contiguous(),
-                    uss=depth.get('USS') if 'USS' in t.sensors else None,
-                    tof=depth.get('ToF') if 'ToF' in t.sensors else None,
-                    rgbd=depth.get('RGBD') if 'RGBD' in t.sensors else None,
-                    hits_t=ws.get("hits", N, 2), counts=ws.get("counts", N, None, torch.int32),
-                    rays_a=ws.get("rays_a", N, 3, torch.int32),
-                    scan_tmp=ws.get("scan_tmp", _lib.scan_tmp_ints(N), None, torch.int32),
-                    bitfield=m.occupancy_grid.getBitfield(),
-                    vr_samples=ws.get("vr", N, None, torch.int32), opacity=ws.get("op", N), depth=ws.get("dp", N),
-                    rgb=ws.get("rgb", N, 3), d_rgb=ws.get("d_rgb", N, 3), d_depth=ws.get("d_dp", N),
-                    d_opacity=ws.get("d_op", N))
-        _lib.call("vn_train_step_prepare", st)
-        self._counter_host.copy_(self._counter, non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record()
-        return {"data": data, "struct": st, "event": ev, "keep": (rays_o, rays_d, noise)}
+
+        def body():
+            nz = noise
+            if update:
+                self.occupancy_update(elapse_time)
+            if nz is None:
+                nz = ws.get(f"noise{par}", N)
+                nz.uniform_()                                               # ray_march.py:139
+            st.set_ptrs(rays_o=rays_o, rays_d=rays_d, noise=nz.contiguous(), gt_rgb=data['rgb'].contiguous(),
+                        uss=depth.get('USS') if 'USS' in t.sensors else None,
+                        tof=depth.get('ToF') if 'ToF' in t.sensors else None,
+                        rgbd=depth.get('RGBD') if 'RGBD' in t.sensors else None,
+                        hits_t=ws.get(f"hits{par}", N, 2), counts=ws.get(f"counts{par}", N, None, torch.int32),
+                        rays_a=ws.get(f"rays_a{par}", N, 3, torch.int32),
+                        scan_tmp=ws.get(f"scan_tmp{par}", _lib.scan_tmp_ints(N), None, torch.int32),
+                        counter=self._counters[par], bitfield=m.occupancy_grid.getBitfield(),
+                        vr_samples=ws.get("vr", N, None, torch.int32), opacity=ws.get("op", N), depth=ws.get("dp", N),
+                        rgb=ws.get("rgb", N, 3), d_rgb=ws.get("d_rgb", N, 3), d_depth=ws.get("d_dp", N),
+                        d_opacity=ws.get("d_op", N))
+            _lib.call("vn_train_step_prepare", st)
+            self._counter_hosts[par].copy_(self._counters[par], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            return ev, nz
+
+        if side is None:
+            ev, nz = body()
+        else:
+            if ready is None:                                               # the batch itself (H2D copy / gather)
+                ready = torch.cuda.Event(); ready.record(main)
+            side.wait_event(ready)
+            with torch.cuda.stream(side):
+                ev, nz = body()
+        return {"data": data, "struct": st, "event": ev, "par": par, "side": side is not None,
+                "keep": (rays_o, rays_d, nz)}
 
     def step_fast(self, data, elapse_time=0.0, noise=None, next_data=None):
         """The same train step as step(), enqueued by the native step runner (csrc/step.cu): no
@@ -246,12 +270,19 @@ class TrainEngine:
         flat gradient), hash bwd (ditto)] -> (allreduce flat gradient || prepare(next_data)) ->
         [optim: grad check, Adam, scaler update].  Pass next_data to software-pipeline the front
         half of the next step."""
+        ready_next = None
+        if next_data is not None:
+            # next_data was produced (gather / H2D copy) on this stream before this call: everything the
+            # next front half may depend on is older than this point, so it can overlap this step's kernels
+            ready_next = torch.cuda.Event(); ready_next.record()
         tk = self._ticket if (self._ticket is not None and self._ticket["data"] is data) else \
             self.prepare(data, elapse_time, noise)
         self._ticket = None
         st, ws = tk["struct"], self._ws
         tk["event"].synchronize()                                         # the one host sync of the step
-        S = int(self._counter_host[0])
+        if tk["side"]:
+            torch.cuda.current_stream().wait_event(tk["event"])           # main stream: front half done
+        S = int(self._counter_hosts[tk["par"]][0])
         self.last_samples = S
         st.set_ptrs(xyzs=ws.get("xyzs", S, 3), dirs=ws.get("dirs", S, 3), unit=ws.get("unit", S, 3),
                     deltas=ws.get("deltas", S), ts=ws.get("ts", S), enc=ws.get("enc", S, 32), sigmas=ws.get("sig", S),
@@ -264,7 +295,7 @@ class TrainEngine:
         if self.world_size == 1:
             _lib.call("vn_train_step_run", st, S, 0, 1)
             if next_data is not None:
-                self._ticket = self.prepare(next_data, elapse_time)
+                self._ticket = self.prepare(next_data, elapse_time, ready=None if update_due else ready_next)
             return self._loss_out[0]
         # ---- data parallel ----------------------------------------------------------------
         _lib.call("vn_train_step_run", st, S, 1, 0)
@@ -275,7 +306,7 @@ class TrainEngine:
         with torch.cuda.stream(self._comm_stream):
             work = dist.all_reduce(self.flat_g, async_op=True)            # overlaps prepare(next) below
         if next_data is not None and not update_due:
-            self._ticket = self.prepare(next_data, elapse_time)
+            self._ticket = self.prepare(next_data, elapse_time, ready=ready_next)
         work.wait()
         _lib.call("vn_train_step_optim", st)
         if next_data is not None and update_due:

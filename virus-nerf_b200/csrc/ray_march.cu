@@ -231,31 +231,50 @@ __global__ void __launch_bounds__(256) march_warp_kernel(const float* __restrict
         if (inr) occ = probe_point(c, ray, bitfield, ti, xyz, &dt, &ttar);
         const unsigned inmask = __ballot_sync(full, inr);
         const unsigned occmask = __ballot_sync(full, inr && occ);
-        int cur = 0;
-        unsigned emit = 0u;
-        bool done = false;
-        if (pending) {                                               // skip started in the previous chunk
-            const unsigned ge = __ballot_sync(full, ti >= pending_target);
-            if (ge == 0u) cur = 32; else { cur = __ffs(ge) - 1; pending = false; }
-        }
-        while (cur < 32) {
-            if (!((inmask >> cur) & 1u)) { done = true; break; }     // t >= t2
-            const int room = n_max - n - __popc(emit);
-            if (room <= 0) { done = true; break; }                   // N_samples == max_samples
-            if ((occmask >> cur) & 1u) {
-                const unsigned run = occmask >> cur;
-                int len = (~run == 0u) ? 32 : (__ffs(~run) - 1);     // consecutive occupied points
-                len = min(len, room);
-                const unsigned bits = (len >= 32) ? full : ((1u << len) - 1u);
-                emit |= bits << cur;
-                cur += len;
-            } else {
-                const float tt = __shfl_sync(full, ttar, cur);
-                unsigned ge = __ballot_sync(full, ti >= tt);
-                ge &= (cur >= 31) ? 0u : (full << (cur + 1));        // at least one step (:71)
-                if (ge == 0u) { pending = true; pending_target = tt; cur = 32; }
-                else cur = __ffs(ge) - 1;
+        // ---- emit / skip chain, resolved in parallel ------------------------------------------
+        // successor of every lattice point: the next point if it is occupied, else the first later
+        // point with t >= its skip target (binary search over the increasing lattice; 32 = beyond
+        // this chunk); out-of-range points are terminal
+        int nxt = lane + 1;
+        if (!inr) nxt = 32;
+        {
+            int lo = lane + 1, hi = 32;
+            const bool search = inr && !occ;
+#pragma unroll
+            for (int it = 0; it < 5; ++it) {
+                const int mid = (lo + hi) >> 1;
+                const float tm = __shfl_sync(full, ti, mid & 31);
+                if (search && lo < hi) { if (tm >= ttar) hi = mid; else lo = mid + 1; }
             }
+            if (search) nxt = lo;                                    // >= lane + 1: at least one step (:71)
+        }
+        int cur0 = 0;
+        if (pending) {                                               // skip started in a previous chunk
+            const unsigned ge = __ballot_sync(full, ti >= pending_target);
+            if (ge == 0u) cur0 = 32; else { cur0 = __ffs(ge) - 1; pending = false; }
+        }
+        // points visited from cur0: reachability by pointer doubling (5 rounds cover 32 points)
+        unsigned R = (cur0 < 32) ? (1u << cur0) : 0u;
+        int jump = nxt;
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+            const unsigned add = (((R >> lane) & 1u) && jump < 32) ? (1u << jump) : 0u;
+            R |= __reduce_or_sync(full, add);
+            const int j2 = __shfl_sync(full, jump, jump & 31);
+            jump = (jump < 32) ? j2 : 32;
+        }
+        bool done = (R & ~inmask) != 0u;                             // reached a point with t >= t2
+        unsigned emit = R & occmask;
+        const int room = n_max - n;
+        if (__popc(emit) >= room) {                                  // N_samples reaches max_samples (:44)
+            if (__popc(emit) > room) emit &= (2u << __fns(emit, 0, room)) - 1u;
+            done = true;
+        }
+        if (!done && R != 0u) {                                      // does the chain leave the chunk in a skip?
+            const int last = 31 - __clz(R);
+            const int lp = __shfl_sync(full, (int)(inr && !occ), last);
+            const float lt = __shfl_sync(full, ttar, last);
+            if (lp) { pending = true; pending_target = lt; }
         }
         if (WRITE) {
             if ((emit >> lane) & 1u) {

@@ -140,7 +140,7 @@ __device__ __forceinline__ void load_weight(uint8_t* smem, int off, const float*
     // [R x C] f32 row-major -> chunk-major fp16; one 16-byte chunk (8 columns of one row) per
     // thread and iteration: two LDG.128, one STS.128.  Rows >= R_valid are zero padding.
     const int chunks_per_row = C / 8;
-    for (int i = tid; i < R * chunks_per_row; i += TILE) {
+    for (int i = tid; i < R * chunks_per_row; i += blockDim.x) {
         const int r = i / chunks_per_row, c = i % chunks_per_row;
         float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (r < R_valid) {
@@ -252,13 +252,46 @@ __device__ __forceinline__ void mask_store(uint8_t* smem, int off_dst, int off_a
     }
 }
 
+// 256 threads per tile: thread (row = tid & 127, half = tid >> 7) owns one half of the columns
+// of sample row `row` in every epilogue (warps w and w + 4 both address TMEM lanes 32*(w&3)..),
+// which doubles the warps in flight per tile and halves the serial epilogue work per thread.
+constexpr int NTHREADS = 256;
+
+// relu -> fp16 -> this thread's column half of a 64-wide operand buffer
+__device__ __forceinline__ void relu_store_half(uint8_t* smem, int off, int r, int half, const float* v32) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        float t[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[j] = fmaxf(v32[8 * c + j], 0.0f);
+        st_row8(smem, off, r, 4 * half + c, t);
+    }
+}
+// g * (act > 0) -> fp16, this thread's column half
+__device__ __forceinline__ void mask_store_half(uint8_t* smem, int off_dst, int off_act, int r, int half, const float* g32) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const uint4 a = ld_chunk(smem, off_act, r, 4 * half + c);
+        const __half2* h = reinterpret_cast<const __half2*>(&a);
+        float t[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = __half22float2(h[j]);
+            t[2 * j] = f.x > 0.0f ? g32[8 * c + 2 * j] : 0.0f;
+            t[2 * j + 1] = f.y > 0.0f ? g32[8 * c + 2 * j + 1] : 0.0f;
+        }
+        st_row8(smem, off_dst, r, 4 * half + c, t);
+    }
+}
+
 template <bool BWD>
-__global__ void __launch_bounds__(TILE) mlp_kernel(const MlpArgs a) {
+__global__ void __launch_bounds__(NTHREADS, BWD ? 2 : 3) mlp_kernel(const MlpArgs a) {
     using L = Lay<BWD>;
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_base;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row = tid & (TILE - 1), half = tid >> 7;
     const uint32_t sbase = umma::smem_u32(smem);
 
     load_weight(smem, L::W1, a.W[0], 64, 32, 64, tid);
@@ -270,21 +303,21 @@ __global__ void __launch_bounds__(TILE) mlp_kernel(const MlpArgs a) {
     if (tid == 0) { umma::mbar_init(&bar, 1); umma::mbar_fence_init(); }
     publish();
     umma::fence_after_sync();
-    Pipe p{&bar, 0u, tmem_base, (uint32_t)(warp * 32) << 16};
+    Pipe p{&bar, 0u, tmem_base, (uint32_t)((warp & 3) * 32) << 16};
     const uint32_t tmp = p.tm + TC_TMP;
 
     const int64_t n_tiles = (a.S + TILE - 1) / TILE;
-    // software prefetch: the NEXT tile's enc row / direction (and, for the backward, its output
-    // gradients) are loaded into registers while the current tile runs through the layer chain
-    struct Staged { float4 e[8]; float d[3]; float dsig; float drgb[3]; };
+    // software prefetch: the NEXT tile's half enc row / direction (and, for the backward, its
+    // output gradients) are loaded into registers while the current tile runs the layer chain
+    struct Staged { float4 e[4]; float d[3]; float dsig; float drgb[3]; };
     auto fetch = [&](int64_t tile, Staged& st) {
-        const int64_t s = tile * TILE + tid;
+        const int64_t s = tile * TILE + row;
         const bool valid = tile < n_tiles && s < a.S;
         if (valid) {
             if (a.enc_half) {
-                const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(a.enc) + s * 32);
+                const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(a.enc) + s * 32 + 16 * half);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < 2; ++q) {
                     const uint4 u = __ldg(src + q);
                     const __half2* h = reinterpret_cast<const __half2*>(&u);
                     const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]), f2 = __half22float2(h[2]), f3 = __half22float2(h[3]);
@@ -292,18 +325,18 @@ __global__ void __launch_bounds__(TILE) mlp_kernel(const MlpArgs a) {
                     st.e[2 * q + 1] = make_float4(f2.x, f2.y, f3.x, f3.y);
                 }
             } else {
-                const float4* src = reinterpret_cast<const float4*>(a.enc + s * 32);
+                const float4* src = reinterpret_cast<const float4*>(a.enc + s * 32 + 16 * half);
 #pragma unroll
-                for (int q = 0; q < 8; ++q) st.e[q] = __ldg(src + q);
+                for (int q = 0; q < 4; ++q) st.e[q] = __ldg(src + q);
             }
         } else {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) st.e[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int q = 0; q < 4; ++q) st.e[q] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         st.d[0] = 1.0f; st.d[1] = 0.0f; st.d[2] = 0.0f;
         if (valid && !a.density_only) { st.d[0] = __ldg(a.dirs + 3 * s); st.d[1] = __ldg(a.dirs + 3 * s + 1); st.d[2] = __ldg(a.dirs + 3 * s + 2); }
         st.dsig = 0.0f; st.drgb[0] = st.drgb[1] = st.drgb[2] = 0.0f;
-        if (BWD && valid) {
+        if (BWD && valid && half == 0) {
             st.dsig = __ldg(a.dsigmas + s);
             if (!a.density_only) { st.drgb[0] = __ldg(a.drgbs + 3 * s); st.drgb[1] = __ldg(a.drgbs + 3 * s + 1); st.drgb[2] = __ldg(a.drgbs + 3 * s + 2); }
         }
@@ -312,23 +345,25 @@ __global__ void __launch_bounds__(TILE) mlp_kernel(const MlpArgs a) {
     fetch(blockIdx.x, cur);
     bool first_tile = true;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, first_tile = false) {
-        const int64_t s = tile * TILE + tid;
+        const int64_t s = tile * TILE + row;
         const bool valid = s < a.S;
-        // ---- stage inputs: enc row -> X0, SH(dir) -> IN2[:, 0:16] -------------------------
+        // ---- stage inputs: half enc row -> X0, half of SH(dir) -> IN2[:, 0:16] ------------------
         {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < 2; ++c) {
                 const float v[8] = {cur.e[2 * c].x, cur.e[2 * c].y, cur.e[2 * c].z, cur.e[2 * c].w,
                                     cur.e[2 * c + 1].x, cur.e[2 * c + 1].y, cur.e[2 * c + 1].z, cur.e[2 * c + 1].w};
-                st_row8(smem, L::X0, tid, c, v);
+                st_row8(smem, L::X0, row, 2 * half + c, v);
             }
             if (!a.density_only) {
                 const float dx = cur.d[0], dy = cur.d[1], dz = cur.d[2];
                 const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);          // networks.py:160
                 float e[16];
                 sh16_half((dx / nrm + 1.0f) * 0.5f, (dy / nrm + 1.0f) * 0.5f, (dz / nrm + 1.0f) * 0.5f, e);   // :161
-                st_row8(smem, L::IN2, tid, 0, e);
-                st_row8(smem, L::IN2, tid, 1, e + 8);
+                float eh[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) eh[j] = half ? e[8 + j] : e[j];
+                st_row8(smem, L::IN2, row, half, eh);
             }
         }
         const float my_dsig = cur.dsig;
@@ -338,16 +373,16 @@ __global__ void __launch_bounds__(TILE) mlp_kernel(const MlpArgs a) {
         // ---- L1: 32 -> 64, ReLU -----------------------------------------------------------
         if (tid == 0) { umma::fence_after_sync(); mma_fwd(sbase, L::X0, L::W1, 64, 32, tmp); umma::commit(&bar); }
         wait_mma(p);
-        float acc[64];
-        read_acc<64>(p, TC_TMP, acc);
-        relu_store(smem, L::H1, tid, acc, 64);
+        float acc[32];
+        read_acc<32>(p, TC_TMP + 32 * half, acc);
+        relu_store_half(smem, L::H1, row, half, acc);
         publish();
         // ---- L2: 64 -> 16; sigma = exp(h0) ------------------------------------------------
         if (tid == 0) { umma::fence_after_sync(); mma_fwd(sbase, L::H1, L::W2, 16, 64, tmp); umma::commit(&bar); }
         wait_mma(p);
         read_acc<16>(p, TC_TMP, acc);
         const float h0 = acc[0];
-        if (!BWD && valid) {
+        if (!BWD && valid && half == 0) {
             a.sigmas[s] = expf(h0);                                            // TruncExp fwd, networks.py:23
             if (a.h_out) {
                 float4* hd = reinterpret_cast<float4*>(a.h_out + s * 16);
@@ -357,20 +392,24 @@ __global__ void __launch_bounds__(TILE) mlp_kernel(const MlpArgs a) {
         }
         float rgb[3] = {0.f, 0.f, 0.f};
         if (!a.density_only) {
-            st_row8(smem, L::IN2, tid, 2, acc);
-            st_row8(smem, L::IN2, tid, 3, acc + 8);
+            {
+                float hh[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) hh[j] = half ? acc[8 + j] : acc[j];
+                st_row8(smem, L::IN2, row, 2 + half, hh);
+            }
             publish();
             // ---- L3: [SH | h] 32 -> 64, ReLU ---------------------------------------------
             if (tid == 0) { umma::fence_after_sync(); mma_fwd(sbase, L::IN2, L::W3, 64, 32, tmp); umma::commit(&bar); }
             wait_mma(p);
-            read_acc<64>(p, TC_TMP, acc);
-            relu_store(smem, L::H3, tid, acc, 64);
+            read_acc<32>(p, TC_TMP + 32 * half, acc);
+            relu_store_half(smem, L::H3, row, half, acc);
             publish();
             // ---- L4: 64 -> 64, ReLU ------------------------------------------------------
             if (tid == 0) { umma::fence_after_sync(); mma_fwd(sbase, L::H3, L::W4, 64, 64, tmp); umma::commit(&bar); }
             wait_mma(p);
-            read_acc<64>(p, TC_TMP, acc);
-            relu_store(smem, L::H4, tid, acc, 64);
+            read_acc<32>(p, TC_TMP + 32 * half, acc);
+            relu_store_half(smem, L::H4, row, half, acc);
             publish();
             // ---- L5: 64 -> 3 (padded to 16), sigmoid -------------------------------------
             if (tid == 0) { umma::fence_after_sync(); mma_fwd(sbase, L::H4, L::W5, 16, 64, tmp); umma::commit(&bar); }
@@ -378,88 +417,86 @@ __global__ void __launch_bounds__(TILE) mlp_kernel(const MlpArgs a) {
             read_acc<16>(p, TC_TMP, acc);
 #pragma unroll
             for (int c = 0; c < 3; ++c) rgb[c] = 1.0f / (1.0f + expf(-acc[c]));
-            if (!BWD && valid) { a.rgbs[3 * s] = rgb[0]; a.rgbs[3 * s + 1] = rgb[1]; a.rgbs[3 * s + 2] = rgb[2]; }
+            if (!BWD && valid && half == 0) { a.rgbs[3 * s] = rgb[0]; a.rgbs[3 * s + 1] = rgb[1]; a.rgbs[3 * s + 2] = rgb[2]; }
         }
         if (!BWD) { umma::fence_before_sync(); continue; }
 
         // =============================== backward =========================================
         float dh_sigma = 0.0f;
-        if (valid) dh_sigma = my_dsig * expf(fminf(fmaxf(h0, -15.0f), 15.0f));   // TruncExp bwd, networks.py:28
+        if (valid && half == 0) dh_sigma = my_dsig * expf(fminf(fmaxf(h0, -15.0f), 15.0f));   // TruncExp bwd, networks.py:28
         if (!a.density_only) {
-            // d(out5) = drgb * rgb * (1 - rgb)
-            float d5[16];
+            // d(out5) = drgb * rgb * (1 - rgb) in columns 0..2 (chunk 0); chunk 1 is zero padding
+            float d5[8];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) d5[j] = 0.0f;
-            if (valid) {
+            for (int j = 0; j < 8; ++j) d5[j] = 0.0f;
+            if (valid && half == 0) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) d5[c] = my_drgb[c] * rgb[c] * (1.0f - rgb[c]);
             }
-            st_row8(smem, OFF_D5, tid, 0, d5);
-            st_row8(smem, OFF_D5, tid, 1, d5 + 8);
+            st_row8(smem, OFF_D5, row, half, d5);
             publish();
             if (tid == 0) {
                 umma::fence_after_sync();
-                mma_dgrad(sbase, OFF_D5, L::W5, 16, 64, 16, tmp);                       // dH4raw = d5 * W5
-                mma_wgrad(sbase, L::H4, OFF_D5, 16, p.tm + TC_DW5T, first_tile);        // dW5^T += H4^T d5
+                mma_dgrad(sbase, OFF_D5, L::W5, 16, 64, 16, tmp);                        // dH4raw = d5 * W5
+                mma_wgrad(sbase, L::H4, OFF_D5, 16, p.tm + TC_DW5T, first_tile);         // dW5^T += H4^T d5
                 umma::commit(&bar);
             }
             wait_mma(p);
-            read_acc<64>(p, TC_TMP, acc);
-            mask_store(smem, OFF_G, L::H4, tid, acc);                                   // dH4
+            read_acc<32>(p, TC_TMP + 32 * half, acc);
+            mask_store_half(smem, OFF_G, L::H4, row, half, acc);                         // dH4
             publish();
             if (tid == 0) {
                 umma::fence_after_sync();
-                mma_dgrad(sbase, OFF_G, L::W4, 64, 64, 64, tmp);                        // dH3raw = dH4 * W4
-                mma_wgrad(sbase, OFF_G, L::H3, 64, p.tm + TC_DW4, first_tile);          // dW4 += dH4^T H3
+                mma_dgrad(sbase, OFF_G, L::W4, 64, 64, 64, tmp);                         // dH3raw = dH4 * W4
+                mma_wgrad(sbase, OFF_G, L::H3, 64, p.tm + TC_DW4, first_tile);           // dW4 += dH4^T H3
                 umma::commit(&bar);
             }
             wait_mma(p);
-            read_acc<64>(p, TC_TMP, acc);
-            mask_store(smem, OFF_G, L::H3, tid, acc);                                   // dH3 (dH4 no longer needed)
+            read_acc<32>(p, TC_TMP + 32 * half, acc);
+            mask_store_half(smem, OFF_G, L::H3, row, half, acc);                         // dH3 (dH4 no longer needed)
             publish();
             if (tid == 0) {
                 umma::fence_after_sync();
-                mma_dgrad(sbase, OFF_G, L::W3, 64, 32, 64, tmp);                        // dIN2raw = dH3 * W3
-                mma_wgrad(sbase, OFF_G, L::IN2, 32, p.tm + TC_DW3, first_tile);         // dW3 += dH3^T [SH|h]
+                mma_dgrad(sbase, OFF_G, L::W3, 64, 32, 64, tmp);                         // dIN2raw = dH3 * W3
+                mma_wgrad(sbase, OFF_G, L::IN2, 32, p.tm + TC_DW3, first_tile);          // dW3 += dH3^T [SH|h]
                 umma::commit(&bar);
             }
             wait_mma(p);
-            read_acc<32>(p, TC_TMP, acc);                                                // cols 16..31 = d(h)
+            read_acc<16>(p, TC_TMP + 16, acc);                                           // cols 16..31 = d(h)
         } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) acc[j] = 0.0f;
+            for (int j = 0; j < 16; ++j) acc[j] = 0.0f;
         }
         {
-            float dh[16];
+            float dh[8];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) dh[j] = valid ? acc[16 + j] : 0.0f;
-            dh[0] += dh_sigma;
-            st_row8(smem, OFF_DH, tid, 0, dh);
-            st_row8(smem, OFF_DH, tid, 1, dh + 8);
+            for (int j = 0; j < 8; ++j) dh[j] = valid ? (half ? acc[8 + j] : acc[j]) : 0.0f;
+            if (half == 0) dh[0] += dh_sigma;
+            st_row8(smem, OFF_DH, row, half, dh);
         }
         publish();
         if (tid == 0) {
             umma::fence_after_sync();
-            mma_dgrad(sbase, OFF_DH, L::W2, 16, 64, 16, tmp);                           // dH1raw = dh * W2
-            mma_wgrad(sbase, L::H1, OFF_DH, 16, p.tm + TC_DW2T, first_tile);            // dW2^T += H1^T dh
+            mma_dgrad(sbase, OFF_DH, L::W2, 16, 64, 16, tmp);                            // dH1raw = dh * W2
+            mma_wgrad(sbase, L::H1, OFF_DH, 16, p.tm + TC_DW2T, first_tile);             // dW2^T += H1^T dh
             umma::commit(&bar);
         }
         wait_mma(p);
-        read_acc<64>(p, TC_TMP, acc);
-        mask_store(smem, OFF_G, L::H1, tid, acc);                                       // dH1
+        read_acc<32>(p, TC_TMP + 32 * half, acc);
+        mask_store_half(smem, OFF_G, L::H1, row, half, acc);                             // dH1
         publish();
         if (tid == 0) {
             umma::fence_after_sync();
-            mma_dgrad(sbase, OFF_G, L::W1, 64, 32, 64, tmp);                            // d(enc) = dH1 * W1
-            mma_wgrad(sbase, OFF_G, L::X0, 32, p.tm + TC_DW1, first_tile);              // dW1 += dH1^T enc
+            mma_dgrad(sbase, OFF_G, L::W1, 64, 32, 64, tmp);                             // d(enc) = dH1 * W1
+            mma_wgrad(sbase, OFF_G, L::X0, 32, p.tm + TC_DW1, first_tile);               // dW1 += dH1^T enc
             umma::commit(&bar);
         }
         wait_mma(p);
-        read_acc<32>(p, TC_TMP, acc);
+        read_acc<16>(p, TC_TMP + 16 * half, acc);
         if (valid) {
-            float4* dst = reinterpret_cast<float4*>(a.denc + s * 32);
+            float4* dst = reinterpret_cast<float4*>(a.denc + s * 32 + 16 * half);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) dst[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+            for (int q = 0; q < 4; ++q) dst[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
         }
         umma::fence_before_sync();
     }
@@ -468,21 +505,23 @@ __global__ void __launch_bounds__(TILE) mlp_kernel(const MlpArgs a) {
         // flush the weight-gradient accumulators: M = 64 layout -> row 16*warp + lane (lane < 16)
         __syncthreads();
         umma::fence_after_sync();
-        const int row = 16 * warp + lane;
-        float v[64];
-        // dW1 [64 out x 32 in]
-        read_acc<32>(p, TC_DW1, v);
-        if (lane < 16) for (int j = 0; j < 32; ++j) atomicAdd(a.dW[0] + row * 32 + j, v[j]);
-        // dW2^T [64 in x 16 out] -> dW2 [16 x 64]
-        read_acc<16>(p, TC_DW2T, v);
-        if (lane < 16) for (int j = 0; j < 16; ++j) atomicAdd(a.dW[1] + j * 64 + row, v[j]);
-        if (!a.density_only) {
-            read_acc<32>(p, TC_DW3, v);
-            if (lane < 16) for (int j = 0; j < 32; ++j) atomicAdd(a.dW[2] + row * 32 + j, v[j]);
-            read_acc<64>(p, TC_DW4, v);
-            if (lane < 16) for (int j = 0; j < 64; ++j) atomicAdd(a.dW[3] + row * 64 + j, v[j]);
-            read_acc<16>(p, TC_DW5T, v);
-            if (lane < 16) for (int j = 0; j < 3; ++j) atomicAdd(a.dW[4] + j * 64 + row, v[j]);
+        if (warp < 4) {
+            const int wrow = 16 * warp + lane;
+            float v[64];
+            // dW1 [64 out x 32 in]
+            read_acc<32>(p, TC_DW1, v);
+            if (lane < 16) for (int j = 0; j < 32; ++j) atomicAdd(a.dW[0] + wrow * 32 + j, v[j]);
+            // dW2^T [64 in x 16 out] -> dW2 [16 x 64]
+            read_acc<16>(p, TC_DW2T, v);
+            if (lane < 16) for (int j = 0; j < 16; ++j) atomicAdd(a.dW[1] + j * 64 + wrow, v[j]);
+            if (!a.density_only) {
+                read_acc<32>(p, TC_DW3, v);
+                if (lane < 16) for (int j = 0; j < 32; ++j) atomicAdd(a.dW[2] + wrow * 32 + j, v[j]);
+                read_acc<64>(p, TC_DW4, v);
+                if (lane < 16) for (int j = 0; j < 64; ++j) atomicAdd(a.dW[3] + wrow * 64 + j, v[j]);
+                read_acc<16>(p, TC_DW5T, v);
+                if (lane < 16) for (int j = 0; j < 3; ++j) atomicAdd(a.dW[4] + j * 64 + wrow, v[j]);
+            }
         }
         umma::fence_before_sync();
     }
@@ -499,11 +538,11 @@ int launch_mlp(bool bwd, const MlpArgs& a, cudaStream_t st) {
     }
     VnProfScope prof(bwd ? VN_K_MLP_BWD : VN_K_MLP_FWD, a.S, st);
     const int64_t n_tiles = (a.S + TILE - 1) / TILE;
-    const int per_sm = bwd ? 2 : 4;
+    const int per_sm = bwd ? 2 : 3;
     int64_t grid = (int64_t)vn_sm_count() * per_sm;
     if (grid > n_tiles) grid = n_tiles;
-    if (bwd) mlp_kernel<true><<<(unsigned)grid, TILE, SMEM_BWD, st>>>(a);
-    else     mlp_kernel<false><<<(unsigned)grid, TILE, SMEM_FWD, st>>>(a);
+    if (bwd) mlp_kernel<true><<<(unsigned)grid, NTHREADS, SMEM_BWD, st>>>(a);
+    else     mlp_kernel<false><<<(unsigned)grid, NTHREADS, SMEM_FWD, st>>>(a);
     VN_CHECK_LAUNCH(bwd ? "mlp_kernel<bwd>" : "mlp_kernel<fwd>");
     return VN_OK;
 }

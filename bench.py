@@ -21,6 +21,9 @@ sys.path.insert(0, ROOT)
 
 RAYS_PER_GPU = 4096
 HASH_BYTES_PER_POINT = 1164          # fwd or bwd, fp32 L16 F2 (SURVEY 8(d) / BASELINE.md section 3)
+# DRAM bytes per point of one `ncu --set full` capture (dram__bytes_read.sum + dram__bytes_write.sum over
+# S = 1 306 086 points, profiles/r1_ncu_top_kernels.md); scaled by the launch's points for `roofline.traffic`
+NCU_DRAM_BYTES_PER_POINT = {"hash_encode_bwd": 607.6, "hash_encode_fwd": 198.7}
 WORKLOAD = ("ETHZ-shaped synthetic scene, hash grid L=16 F=2 T=2^19 fp32 tables, 4096 rays/batch/GPU, RGB+USS+ToF "
             "losses, VIRUS-NeRF occupancy update every 8 steps, training from the initial (all-occupied) grid")
 
@@ -285,7 +288,11 @@ def run_ours(a):
         roof = None
         if dom and dom.startswith("hash_encode"):
             roof = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": kern[dom]["achieved_gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": kern[dom]["achieved_gbs"] / peak,
+                    "traffic": NCU_DRAM_BYTES_PER_POINT[dom] * kern[dom]["units"] / kern[dom]["launches"],
+                    "traffic_note": "DRAM bytes per launch = ncu bytes/point (profiles/r1_ncu_top_kernels.md) x mean points per "
+                                    "launch; below the algorithmic bytes because the table is L2 resident",
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": HASH_BYTES_PER_POINT * kern[dom]["units"] / kern[dom]["launches"],
                     "algorithmic_bytes_per_point": HASH_BYTES_PER_POINT}
         elif dom and dom.startswith("mlp"):
             roof = {"kernel": dom, "bound": "tensor", "achieved": kern[dom]["achieved_tflops"], "peak": tflops_peak,

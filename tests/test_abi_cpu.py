@@ -108,3 +108,19 @@ def test_product_package_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", src, flags=re.M), os.path.join(dirpath, f)
                 assert "liboracle" not in src
+
+
+def test_ctypes_struct_mirrors_match_the_header(vn, tmp_path):
+    """vn_hash_levels_t / vn_step_t as laid out by the C compiler vs the ctypes mirrors in _lib.py"""
+    import subprocess
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "virusnerf.h"\n'
+                   'int main(void){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(vn_hash_levels_t), sizeof(vn_step_t),'
+                   ' offsetof(vn_step_t, levels), offsetof(vn_step_t, loss_acc), offsetof(vn_step_t, adam_step),'
+                   ' offsetof(vn_step_t, w_off)); return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    c = [int(x) for x in subprocess.check_output([str(exe)], text=True).split()]
+    py = [ctypes.sizeof(vn.HashLevels), ctypes.sizeof(vn.Step), vn.Step.levels.offset, vn.Step.loss_acc.offset,
+          vn.Step.adam_step.offset, vn.Step.w_off.offset]
+    assert c == py, (c, py)

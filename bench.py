@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-autocast", action="store_true")
     ap.add_argument("--autograd-step", action="store_true", help="use the torch-autograd step instead of the fused step")
+    ap.add_argument("--comm", default="auto", choices=["auto", "nccl", "p2p"], help="gradient exchange (auto: p2p at >= 8 ranks)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end phase (profiling runs only)")
     return ap.parse_args()
 
@@ -190,7 +191,7 @@ def run_ours(a):
         timed region and the loss is read back to the host (end-to-end)."""
         ds = synthetic.SyntheticDataset(scene, pool_size=1 << 18, device=str(dev), pinned=False, seed=21)
         ds.gen.manual_seed(1000 + rank)           # same pool on every rank, different training batches
-        eng = TrainEngine(args, ds, dev, world_size=world, rank=rank, autocast=not a.no_autocast)
+        eng = TrainEngine(args, ds, dev, world_size=world, rank=rank, autocast=not a.no_autocast, comm=a.comm)
         host_batches = None
         dev_batches = None
         if not pinned:
@@ -251,6 +252,8 @@ def run_ours(a):
         launches = _lib.launch_count() - launches0
         samples = [int(s) for s in samples]
         same = True
+        if world > 1 and eng._p2p is not None and int(eng._p2p_err) != 0:
+            raise SystemExit("bench.py: peer-memory allreduce barrier timed out")
         if world > 1:
             c = eng.replica_checksum()
             lo, hi = c.clone(), c.clone()
@@ -307,7 +310,7 @@ def run_ours(a):
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": n, "global_rays_per_step": n * world,
                            "samples_per_step_mean": statistics.mean(samples) if samples else 0,
-                           "parallelism": f"dp{world}",
+                           "parallelism": f"dp{world}", "grad_exchange": ("none" if world == 1 else a.comm),
                            "l2_policy": "inputs larger than L2: table+grad+Adam state 183 MB and per-step sample "
                                         "buffers are streamed; a fresh ray batch every step"},
                 "roofline": roof, "kernels": kern,

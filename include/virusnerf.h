@@ -297,6 +297,24 @@ int vn_train_step_prepare(const vn_step_t* h_step, void* stream);
 int vn_train_step_run(const vn_step_t* h_step, int64_t S, int phase, int do_optim, void* stream);
 int vn_train_step_optim(const vn_step_t* h_step, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * (e) Data-parallel exchange over NVLink peer memory: two-shot sum-allreduce of the flat fp32
+ * gradient buffer with plain peer loads (reduce-scatter + all-gather, flag barriers in peer
+ * memory with time-outs).  Slice r is reduced by rank r in fixed rank order, so all replicas
+ * receive bit-identical sums.
+ *  vn_ipc_get_handle: 64-byte cudaIpcMemHandle of the allocation containing a device pointer
+ *               and the pointer's byte offset inside it.
+ *  vn_ipc_open: map a peer's allocation from its 64-byte cudaIpcMemHandle (+ byte offset).
+ *  vn_p2p_init: h_bufs / h_flags = `world` device pointers (own buffer at [rank]); flags are
+ *               int32 [world] arrays, zero-initialised; err_dev = local int32 set to 1 on a
+ *               barrier time-out.
+ *  vn_p2p_allreduce: in place over the first n floats (n % 4 == 0) of every rank's buffer;
+ *               must be enqueued by all ranks. */
+int vn_ipc_get_handle(const void* ptr, void* h_handle64_out, int64_t* h_offset_out);
+int vn_ipc_open(const void* h_handle64, int64_t offset_bytes, void** h_ptr_out);
+int vn_p2p_init(int rank, int world, void* const* h_bufs, void* const* h_flags, int* err_dev);
+int vn_p2p_allreduce(int64_t n, void* stream);
+
 /* tcgen05 self-test (development / CI): one 128 x N x K fp16 product through the tensor
  * cores in the three operand modes the fused MLP uses (0 forward A*B^T, 1 dgrad A*B,
  * 2 wgrad A^T*B); A, B fp16 row-major as stored, D [128,N] f32. */

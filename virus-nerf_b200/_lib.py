@@ -106,6 +106,7 @@ _SPECS = {
     "vn_train_step_prepare": "hs",
     "vn_train_step_run": "hliis",
     "vn_train_step_optim": "hs",
+    "vn_p2p_allreduce": "ls",
     "vn_mlp_fwd": "pip" "ppppp" "li" "ppp" "s",
     "vn_mlp_bwd": "pip" "ppppp" "li" "pp" "p" "ppppp" "s",
 }
@@ -255,4 +256,41 @@ def hash_levels(base_res, max_res, levels, max_params):
 
 def exported_symbols():
     """names declared in include/virusnerf.h (used by the CPU-side ABI test)"""
-    return ["vn_last_error", "vn_abi_version", "vn_launch_count", "vn_profile_enable", "vn_profile_count", "vn_profile_get", "vn_device_info", "vn_march_scan_tmp_ints"] + list(_SPECS)
+    return ["vn_last_error", "vn_abi_version", "vn_launch_count", "vn_ipc_get_handle", "vn_ipc_open", "vn_p2p_init", "vn_profile_enable", "vn_profile_count", "vn_profile_get", "vn_device_info", "vn_march_scan_tmp_ints"] + list(_SPECS)
+
+
+def p2p_setup(grad, flags, err, rank, world, group=None):
+    """Exchange CUDA-IPC handles of `grad` (flat fp32 gradient buffer) and `flags` (int32 [world],
+    zeros) across the ranks of a torch.distributed group and initialise the peer-memory
+    allreduce (vn_p2p_init).  Returns the list of opened peer pointers (kept alive by the caller)."""
+    import torch.distributed as dist
+    L = lib()
+
+    def share(t):
+        handle = ctypes.create_string_buffer(64)
+        off = ctypes.c_int64(0)
+        rc = L.vn_ipc_get_handle(ctypes.c_void_p(t.data_ptr()), handle, ctypes.byref(off))
+        if rc != 0:
+            raise RuntimeError(f"vn_ipc_get_handle failed (code {rc}): {last_error()}")
+        return handle.raw, int(off.value)
+
+    mine = (share(grad), share(flags))
+    everyone = [None] * world
+    dist.all_gather_object(everyone, mine, group=group)
+    bufs = (ctypes.c_void_p * world)()
+    flgs = (ctypes.c_void_p * world)()
+    for p in range(world):
+        if p == rank:
+            bufs[p], flgs[p] = grad.data_ptr(), flags.data_ptr()
+            continue
+        for (handle, off), arr in ((everyone[p][0], bufs), (everyone[p][1], flgs)):
+            out = ctypes.c_void_p()
+            rc = L.vn_ipc_open(ctypes.c_char_p(handle), ctypes.c_int64(off), ctypes.byref(out))
+            if rc != 0:
+                raise RuntimeError(f"vn_ipc_open failed (code {rc}): {last_error()}")
+            arr[p] = out.value
+    rc = L.vn_p2p_init(ctypes.c_int(rank), ctypes.c_int(world), bufs, flgs, ctypes.c_void_p(err.data_ptr()))
+    if rc != 0:
+        raise RuntimeError(f"vn_p2p_init failed (code {rc}): {last_error()}")
+    dist.barrier(group=group)
+    return bufs, flgs

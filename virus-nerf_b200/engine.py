@@ -85,7 +85,7 @@ class _Workspace:
 
 class TrainEngine:
     def __init__(self, args, dataset, device, world_size=1, rank=0, log2_T=19, max_res=1024, half_opt=False,
-                 autocast=True, seed=21, grad_scale=2.0 ** 19):
+                 autocast=True, seed=21, grad_scale=2.0 ** 19, comm="auto"):
         self.args = args
         self.device = torch.device(device)
         self.world_size, self.rank = world_size, rank
@@ -149,6 +149,13 @@ class TrainEngine:
         self._mlp_w = [pd[n].data for n in names]           # views into flat_p
         self._mlp_g = [pd[n].grad for n in names]           # views into flat_g
         self._comm_stream = torch.cuda.Stream(device=self.device) if world_size > 1 else None
+        # gradient exchange: NCCL allreduce, or the library's own peer-memory allreduce (csrc/p2p_allreduce.cu;
+        # measured on 8 B200: 0.193 ms vs 0.209 ms NCCL for the 45.7 MB buffer, slower than NCCL at 2-4 ranks)
+        self._p2p = None
+        if world_size > 1 and (comm == "p2p" or (comm == "auto" and world_size >= 8)):
+            self._p2p_flags = torch.zeros(world_size, dtype=torch.int32, device=self.device)
+            self._p2p_err = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self._p2p = _lib.p2p_setup(self.flat_g, self._p2p_flags, self._p2p_err, rank, world_size)
         self._hash_slice_idx = [i for i, p in enumerate(params) if p is enc.hash_table][0]
         self._structs = [self._new_step_struct(), self._new_step_struct()] if self.device.type == "cuda" else None
 
@@ -304,10 +311,18 @@ class TrainEngine:
         ev = torch.cuda.Event(); ev.record()
         self._comm_stream.wait_event(ev)
         with torch.cuda.stream(self._comm_stream):
-            work = dist.all_reduce(self.flat_g, async_op=True)            # overlaps prepare(next) below
+            if self._p2p is not None:                                     # own two-shot allreduce over NVLink peer memory
+                _lib.call("vn_p2p_allreduce", self.n_params)
+                work = None
+                done = torch.cuda.Event(); done.record()
+            else:
+                work = dist.all_reduce(self.flat_g, async_op=True)        # NCCL; overlaps prepare(next) below
         if next_data is not None and not update_due:
             self._ticket = self.prepare(next_data, elapse_time, ready=ready_next)
-        work.wait()
+        if work is not None:
+            work.wait()
+        else:
+            torch.cuda.current_stream().wait_event(done)
         _lib.call("vn_train_step_optim", st)
         if next_data is not None and update_due:
             self._ticket = self.prepare(next_data, elapse_time)

@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-autocast", action="store_true")
     ap.add_argument("--autograd-step", action="store_true", help="use the torch-autograd step instead of the fused step")
-    ap.add_argument("--comm", default="auto", choices=["auto", "nccl", "p2p"], help="gradient exchange (auto: p2p at >= 8 ranks)")
+    ap.add_argument("--comm", default="auto", choices=["auto", "nccl", "p2p"], help="gradient exchange (auto = nccl)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end phase (profiling runs only)")
     return ap.parse_args()
 
@@ -310,7 +310,7 @@ def run_ours(a):
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": n, "global_rays_per_step": n * world,
                            "samples_per_step_mean": statistics.mean(samples) if samples else 0,
-                           "parallelism": f"dp{world}", "grad_exchange": ("none" if world == 1 else a.comm),
+                           "parallelism": f"dp{world}", "grad_exchange": ("none" if world == 1 else ("nccl" if a.comm == "auto" else a.comm)),
                            "l2_policy": "inputs larger than L2: table+grad+Adam state 183 MB and per-step sample "
                                         "buffers are streamed; a fresh ray batch every step"},
                 "roofline": roof, "kernels": kern,

@@ -150,9 +150,9 @@ class TrainEngine:
         self._mlp_g = [pd[n].grad for n in names]           # views into flat_g
         self._comm_stream = torch.cuda.Stream(device=self.device) if world_size > 1 else None
         # gradient exchange: NCCL allreduce, or the library's own peer-memory allreduce (csrc/p2p_allreduce.cu;
-        # measured on 8 B200: 0.193 ms vs 0.209 ms NCCL for the 45.7 MB buffer, slower than NCCL at 2-4 ranks)
+        # standalone on 8 B200: 0.193 ms vs 0.209 ms NCCL for the 45.7 MB buffer; slower than NCCL at 2-4 ranks)
         self._p2p = None
-        if world_size > 1 and (comm == "p2p" or (comm == "auto" and world_size >= 8)):
+        if world_size > 1 and comm == "p2p":          # "auto" = NCCL: the two are within noise in the full step
             self._p2p_flags = torch.zeros(world_size, dtype=torch.int32, device=self.device)
             self._p2p_err = torch.zeros(1, dtype=torch.int32, device=self.device)
             self._p2p = _lib.p2p_setup(self.flat_g, self._p2p_flags, self._p2p_err, rank, world_size)

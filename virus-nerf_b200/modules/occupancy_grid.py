@@ -114,6 +114,10 @@ class OccupancyGrid(Grid):
         rays_o = data['rays_o']
         rays_d = data['rays_d']
         depth_meas = data['depth'][sensor]
+        if sensor in data.get('depth_valid_by_construction', ()):
+            # the sampler drew only pixels where this sensor has a measurement: the NaN filter of
+            # the reference (:216-222) is the identity and its boolean-mask gather (a host sync) is skipped
+            return {"batch_size": B, "rays_o": rays_o, "rays_d": rays_d, "depth_meas": depth_meas}
         valid_depth = ~torch.isnan(depth_meas)
         return {"batch_size": B, "rays_o": rays_o[valid_depth], "rays_d": rays_d[valid_depth],
                 "depth_meas": depth_meas[valid_depth]}

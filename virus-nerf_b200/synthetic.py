@@ -246,7 +246,12 @@ class SyntheticDataset:
 
     def __call__(self, batch_size, sampling_strategy=None, elapse_time=None):
         """datasets/dataset_base.py:23-76 shape: dict(rays_o, rays_d, rgb, depth{sensor: (N,)})"""
-        return self.gather(self.sample_indices(batch_size, sampling_strategy))
+        batch = self.gather(self.sample_indices(batch_size, sampling_strategy))
+        pixs = sampling_strategy.get("pixs", "random") if sampling_strategy else "random"
+        # every ray drawn from the valid-<sensor> subset carries a measurement of that sensor
+        batch["depth_valid_by_construction"] = {"valid_uss": ("USS",), "valid_tof": ("ToF",)}.get(pixs, ()) \
+            if isinstance(pixs, str) else ()
+        return batch
 
 
 def scan_rays(n=512, scale=0.5, height=0.0, origin=(0.0, 0.0)):

@@ -251,6 +251,24 @@ def run_ours(a):
             prof = _lib.profile_stop()
         launches = _lib.launch_count() - launches0
         samples = [int(s) for s in samples]
+        render_ms = None
+        if not pinned:
+            # BASELINE.json configs[4] (informational, outside the timed region): one 1920x1080 frame with
+            # the model just trained, rays sharded over the ranks in row bands, no collective
+            Wp, Hp = 1920, 1080
+            u, v = torch.meshgrid(torch.arange(Wp, device=dev, dtype=torch.float32),
+                                  torch.arange(Hp, device=dev, dtype=torch.float32), indexing="xy")
+            d = torch.stack([(u + 0.5 - Wp / 2) / 960, torch.ones_like(u), -(v + 0.5 - Hp / 2) / 960], -1).reshape(-1, 3)
+            d = (d / d.norm(dim=1, keepdim=True)).contiguous()
+            o = torch.tensor([0.0, -0.2, -0.05], device=dev).expand_as(d).contiguous()
+            eng.render_frame(o, d)                                   # warm-up
+            barrier()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record()
+            eng.render_frame(o, d)
+            r1.record()
+            barrier()
+            render_ms = max_over_ranks(r0.elapsed_time(r1))
         same = True
         if world > 1 and eng._p2p is not None and int(eng._p2p_err) != 0:
             raise SystemExit("bench.py: peer-memory allreduce barrier timed out")
@@ -259,15 +277,15 @@ def run_ours(a):
             lo, hi = c.clone(), c.clone()
             dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
             same = bool((lo == hi).all())
-        return ms, launches, samples, prof, h2d, d2h, float(loss), same
+        return ms, launches, samples, prof, h2d, d2h, float(loss), same, render_ms
 
     clocks = ClockSampler(local)
     clocks.start()
-    ms, launches, samples, prof, _, _, last_loss, replicas_same = run_phase(pinned=False)
+    ms, launches, samples, prof, _, _, last_loss, replicas_same, render_ms = run_phase(pinned=False)
     clk = clocks.stop()
     ms_e2e, h2d, d2h = ms, 0, 0
     if not a.no_e2e:
-        ms_e2e, _, _, _, h2d, d2h, _, _ = run_phase(pinned=True)
+        ms_e2e, _, _, _, h2d, d2h, _, _, _ = run_phase(pinned=True)
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -317,7 +335,10 @@ def run_ours(a):
                 "e2e": {"value": total_rays / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K},
                 "gpu_launches": launches, "clocks": clk, "final_loss": last_loss,
-                "replicas_bit_identical": replicas_same}
+                "replicas_bit_identical": replicas_same,
+                "render_1080p": {"ms_per_frame": render_ms, "rays_per_s": (1920 * 1080 / (render_ms * 1e-3)) if render_ms else None,
+                                 "note": "test-time render of one 1920x1080 frame with the trained model, rays sharded over "
+                                         "the ranks, no collective; informational, outside the timed region"}}
         if world == 1 and not a.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(a)
         print(json.dumps(line), flush=True)

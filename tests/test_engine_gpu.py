@@ -99,11 +99,17 @@ def test_render_test_matches_oracle(setup):
     with torch.no_grad():
         eng.model.xyz_encoder.output_layer.weight[0].add_(0.25)
     om.load_from(eng.model)
+    eng.model.fused_test_render = False                     # the reference's round loop (a7 + a10 kernels)
     res = render(eng.model, ro, rd, test_time=True, exp_step_factor=0.0)
     o = pipeline.render_test(om, ro.cpu(), rd.cpu(), bf)
     assert int(res["total_samples"]) == o["total_samples"]
     for k in ("opacity", "depth", "rgb"):
         np.testing.assert_allclose(N(res[k]), o[k], rtol=1e-4, atol=1e-5)
+    eng.model.fused_test_render = True                      # loop-free path: same image
+    fast = render(eng.model, ro, rd, test_time=True, exp_step_factor=0.0)
+    for k in ("opacity", "depth", "rgb"):
+        np.testing.assert_allclose(N(fast[k]), o[k], rtol=1e-4, atol=1e-5)
+    assert 0 < int(fast["total_samples"]) <= o["total_samples"]
     with torch.no_grad():
         eng.model.xyz_encoder.output_layer.weight[0].sub_(0.25)
     om.load_from(eng.model)

@@ -91,7 +91,9 @@ if "render" in which:
     d = torch.stack([(u + 0.5 - W / 2) / 960, torch.ones_like(u), -(v + 0.5 - H / 2) / 960], -1).reshape(-1, 3)
     d = d / d.norm(dim=1, keepdim=True)
     o = torch.tensor([0.0, -0.2, -0.05], device=DEV).expand_as(d).contiguous()
-    for chunk in (8192, 1 << 18, W * H):
+    for chunk, fused in ((8192, False), (8192, True), (1 << 18, True), (W * H, False), (W * H, True)):
+        eng.model.fused_test_render = fused
+
         def frame():
             tot = 0
             for s in range(0, W * H, chunk):
@@ -100,7 +102,8 @@ if "render" in which:
             return tot
         t0 = time.perf_counter(); tot = frame(); torch.cuda.synchronize(); dt = time.perf_counter() - t0
         t0 = time.perf_counter(); tot = frame(); torch.cuda.synchronize(); dt = time.perf_counter() - t0
-        rec(config="5: 1920x1080 test render (raymarching_test + composite_test loop)", chunk=chunk,
+        rec(config="5: 1920x1080 test render", path="loop-free (march all + model + composite)" if fused else
+            "reference round loop (raymarching_test + composite_test)", chunk=chunk,
             ms_per_frame=round(dt * 1e3, 1), rays_per_s=round(W * H / dt), samples=tot)
 
 if "occ" in which:

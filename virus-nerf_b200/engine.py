@@ -328,6 +328,22 @@ class TrainEngine:
             self._ticket = self.prepare(next_data, elapse_time)
         return self._loss_out[0]
 
+    @torch.no_grad()
+    def render_frame(self, rays_o, rays_d, chunk=1 << 20):
+        """Test-time render of a full frame, rays sharded over the ranks in contiguous bands with
+        no collective: this rank renders rays [rank*n/world, (rank+1)*n/world)
+        and returns (lo, hi, results) for its band."""
+        n = rays_o.shape[0]
+        lo = (n * self.rank) // self.world_size
+        hi = (n * (self.rank + 1)) // self.world_size
+        parts = []
+        for s in range(lo, hi, chunk):
+            e_ = min(s + chunk, hi)
+            parts.append(render(self.model, rays_o[s:e_], rays_d[s:e_], test_time=True,
+                                exp_step_factor=self.args.exp_step_factor))
+        out = {k: torch.cat([p[k] for p in parts]) for k in ("opacity", "depth", "rgb")} if parts else {}
+        return lo, hi, out
+
     def replica_checksum(self):
         """(bitfield, parameter) checksums used to verify that DP replicas are bit-identical"""
         bf = self.model.occupancy_grid.getBitfield().to(torch.int64)

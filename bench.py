@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--no-autocast", action="store_true")
     ap.add_argument("--autograd-step", action="store_true", help="use the torch-autograd step instead of the fused step")
     ap.add_argument("--comm", default="auto", choices=["auto", "nccl", "p2p"], help="gradient exchange (auto = nccl)")
+    ap.add_argument("--enc-layout", default="planar", choices=["planar", "rows"],
+                    help="layout of the encoding inside the fused step (rows = the reference's [S,32])")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end phase (profiling runs only)")
     return ap.parse_args()
 
@@ -191,7 +193,8 @@ def run_ours(a):
         timed region and the loss is read back to the host (end-to-end)."""
         ds = synthetic.SyntheticDataset(scene, pool_size=1 << 18, device=str(dev), pinned=False, seed=21)
         ds.gen.manual_seed(1000 + rank)           # same pool on every rank, different training batches
-        eng = TrainEngine(args, ds, dev, world_size=world, rank=rank, autocast=not a.no_autocast, comm=a.comm)
+        eng = TrainEngine(args, ds, dev, world_size=world, rank=rank, autocast=not a.no_autocast, comm=a.comm,
+                          enc_layout=a.enc_layout)
         host_batches = None
         dev_batches = None
         if not pinned:

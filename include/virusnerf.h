@@ -41,6 +41,11 @@ extern "C" {
 #define VN_HASH_LEVEL_GROUPS_8 64  /* eight levels per thread */
 #define VN_HASH_LEVEL_GROUPS_16 128 /* all (<= 16) levels per thread: every row touched once */
 #define VN_HASH_LEVEL_GROUPS_2 256 /* two levels per thread */
+#define VN_HASH_PLANAR 512 /* f32 only: out / dout are [levels/2][S] float4 planes (level pair
+                              p = levels 2p, 2p+1 of every point) instead of [S, 2*levels] rows;
+                              the layout vn_mlp_fwd/bwd read and write with enc_format = 2 */
+#define VN_HASH_TIGHT_REGS 1024 /* planar bwd: 48-register variant, 5 CTAs per SM */
+#define VN_HASH_PAIR_LOADS 2048 /* planar fwd: 16-byte loads for x / x+1 corner pairs that are neighbours */
 /* default (no GROUPS flag): 4 (backward: 2 when the table exceeds the L2, > 96 MB) */
 
 const char* vn_last_error(void);
@@ -242,7 +247,8 @@ int vn_scaler_update(float* scale, int32_t* growth_tracker, float* found_inf, fl
  * MLP.forward :271-282, with DirEncoder (spherical_harmonics.py:7-42) fused into the input
  * stage: ONE kernel on the tcgen05 tensor cores (fp16 operands, fp32 accumulation in TMEM --
  * the reference runs these layers as fp16 cuBLAS GEMMs under torch.autocast, trainer.py:104).
- *   enc [S,32] hash encoding, f32 (enc_half = 0) or fp16 (enc_half = 1); dirs [S,3] raw ray
+ *   enc [S,32] hash encoding, f32 rows (enc_format = 0), fp16 rows (1) or f32 level-pair planes
+ *   [8][S] float4 (2, the VN_HASH_PLANAR layout; denc is then written in the same layout); dirs [S,3] raw ray
  *   directions (normalised and mapped to (d+1)/2 inside, networks.py:160-161); W1 [64,32],
  *   W2 [16,64], W3 [64,32], W4 [64,64], W5 [3,64] f32 in torch Linear layout [out,in].
  * _fwd: sigmas [S] = exp(h0), rgbs [S,3] = sigmoid(...), optional h_out [S,16] (return_feat).
@@ -250,10 +256,10 @@ int vn_scaler_update(float* scale, int32_t* growth_tracker, float* found_inf, fl
  * _bwd: recomputes the forward per tile; inputs dsigmas [S], drgbs [S,3]; writes denc [S,32]
  *       f32 (gradient w.r.t. the encoding) and ACCUMULATES dW1..dW5 (same shapes as W, f32;
  *       TruncExp backward clamps h0 to [-15,15], networks.py:28). */
-int vn_mlp_fwd(const void* enc, int enc_half, const float* dirs, const float* W1, const float* W2,
+int vn_mlp_fwd(const void* enc, int enc_format, const float* dirs, const float* W1, const float* W2,
                const float* W3, const float* W4, const float* W5, int64_t S, int density_only,
                float* sigmas, float* rgbs, float* h_out, void* stream);
-int vn_mlp_bwd(const void* enc, int enc_half, const float* dirs, const float* W1, const float* W2,
+int vn_mlp_bwd(const void* enc, int enc_format, const float* dirs, const float* W1, const float* W2,
                const float* W3, const float* W4, const float* W5, int64_t S, int density_only,
                const float* dsigmas, const float* drgbs, float* denc, float* dW1, float* dW2,
                float* dW3, float* dW4, float* dW5, void* stream);

@@ -120,6 +120,33 @@ def test_fused_mlp_forward_backward(S):
         close_l2(dW[i], Wt[i].grad, 5e-2, f"dW{i + 1} vs fp32 autograd")
 
 
+@pytest.mark.parametrize("S", [1, 129, 5000])
+def test_fused_mlp_planar_layout_is_bit_identical(S):
+    """enc_format 2 ([8][S] float4 planes in, planes out) computes exactly what enc_format 0 does"""
+    from virus_nerf_b200 import _lib
+    torch.manual_seed(S + 7)
+    Wg = [w.to(DEV).contiguous() for w in _weights(S)]
+    enc = torch.rand(S, 32, device=DEV); dirs = torch.randn(S, 3, device=DEV)
+    enc_p = enc.view(S, 8, 4).permute(1, 0, 2).contiguous()
+    out = {}
+    for fmt, e in ((0, enc), (2, enc_p)):
+        sig = torch.empty(S, device=DEV); rgb = torch.empty(S, 3, device=DEV)
+        _lib.call("vn_mlp_fwd", e, fmt, dirs, *Wg, S, 0, sig, rgb, None)
+        dsig = torch.linspace(-2, 2, S, device=DEV); drgb = torch.linspace(-1, 3, 3 * S, device=DEV).view(S, 3)
+        denc = torch.zeros(S * 32, device=DEV)
+        dW = [torch.zeros_like(w) for w in Wg]
+        _lib.call("vn_mlp_bwd", e, fmt, dirs, *Wg, S, 0, dsig, drgb, denc, *dW)
+        out[fmt] = (sig, rgb, denc, dW)
+    assert torch.equal(out[0][0], out[2][0]) and torch.equal(out[0][1], out[2][1])
+    assert torch.equal(out[0][2].view(S, 8, 4).permute(1, 0, 2).reshape(-1), out[2][2])
+    if S <= 128:        # one tile: the weight-gradient accumulation order is identical too
+        for a, b in zip(out[0][3], out[2][3]):
+            assert torch.equal(a, b)
+    else:
+        for a, b in zip(out[0][3], out[2][3]):
+            close_l2(a, b, 1e-5, "dW planar vs rows")
+
+
 def test_fused_mlp_half_input_and_accumulation():
     from virus_nerf_b200 import _lib
     S = 3000

@@ -112,6 +112,50 @@ def test_hash_bwd_f32(vn, oracle_mod, flags):
     np.testing.assert_allclose(N(grad), ref, rtol=1e-4, atol=1e-6 * np.abs(ref).max())
 
 
+def _to_planes(rows):
+    """[S, 32] rows -> [8][S] float4 level-pair planes (VN_HASH_PLANAR)"""
+    S = rows.shape[0]
+    return np.ascontiguousarray(rows.reshape(S, 8, 4).transpose(1, 0, 2))
+
+
+@pytest.mark.parametrize("flags", [0, 32, 64, 128, 256])
+@pytest.mark.parametrize("S_extra", [0, 1, 31])
+def test_hash_planar_layout(vn, oracle_mod, flags, S_extra):
+    """the level-pair-plane layout of the fast step holds exactly the values of the row layout
+    (forward: bit-identical to the row kernel; backward: same gradient as the oracle), and the
+    48-register backward variant agrees with it"""
+    lv_o = oracle_mod.HashLevels(16, 1024, 16, 2 ** 19)
+    lv = vn.hash_levels(16, 1024, 16, 2 ** 19)
+    rng = np.random.default_rng(11)
+    table = rng.random(2 * lv_o.total, dtype=np.float32)
+    xyz = np.concatenate([rng.random((1000 + S_extra, 3)).astype(np.float32), ray_coherent_points(96, 64)])
+    S = xyz.shape[0]
+    rows = torch.empty(S, 32, device=DEV)
+    planes = torch.empty(8, S, 4, device=DEV)
+    vn.call("vn_hash_encode_fwd_f32", T(xyz), T(table), rows, S, lv, flags)
+    vn.call("vn_hash_encode_fwd_f32", T(xyz), T(table), planes, S, lv, flags | vn.VN_HASH_PLANAR)
+    np.testing.assert_array_equal(N(planes), _to_planes(N(rows)))
+    if flags in (0, 32, 256):
+        vn.call("vn_hash_encode_fwd_f32", T(xyz), T(table), planes, S, lv, flags | vn.VN_HASH_PLANAR | vn.VN_HASH_PAIR_LOADS)
+        np.testing.assert_array_equal(N(planes), _to_planes(N(rows)))
+    np.testing.assert_allclose(N(rows), oracle_mod.hash_fwd_f32(xyz, table, lv_o), rtol=1e-5, atol=1e-6)
+    dout = rng.normal(size=(S, 32)).astype(np.float32)
+    ref = oracle_mod.hash_bwd_f32(xyz, dout, lv_o)
+    for extra in (0, vn.VN_HASH_TIGHT_REGS):
+        grad = torch.zeros(2 * lv_o.total, device=DEV)
+        vn.call("vn_hash_encode_bwd_f32", T(xyz), T(_to_planes(dout)), grad, S, lv, flags | vn.VN_HASH_PLANAR | extra)
+        np.testing.assert_allclose(N(grad), ref, rtol=1e-4, atol=1e-6 * np.abs(ref).max())
+
+
+def test_hash_planar_rejects_odd_groups(vn):
+    lv = vn.hash_levels(16, 1024, 16, 2 ** 19)
+    x = torch.rand(64, 3, device=DEV); t = torch.rand(2 * lv.total_entries, device=DEV); o = torch.empty(8, 64, 4, device=DEV)
+    with pytest.raises(RuntimeError, match="planar"):
+        vn.call("vn_hash_encode_fwd_f32", x, t, o, 64, lv, vn.VN_HASH_PLANAR | vn.VN_HASH_LEVEL_GROUPS_1)
+    with pytest.raises(RuntimeError, match="planar"):
+        vn.call("vn_hash_encode_bwd_f32", x, o, t, 64, lv, vn.VN_HASH_PLANAR | vn.VN_HASH_NO_WARP_AGG)
+
+
 def test_hash_bwd_level_ranges(vn, oracle_mod):
     """the per-level-group launches used for the overlapped DP allreduce add up to the full backward"""
     lv_o = oracle_mod.HashLevels(16, 1024, 16, 2 ** 19)

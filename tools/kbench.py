@@ -91,6 +91,13 @@ def main():
                     for flags in (0, 256, 32):
                         ms = timeit(lambda: _lib.call("vn_hash_encode_bwd_f32", x, dout, grad, S, lv, flags))
                         rec("hash_bwd_f32", ms, state=state, S=S, log2_T=log2_T, flags=flags, gbs=round(S * 1164 / ms / 1e6, 1))
+                    # level-pair-plane layout ([8][S] float4) of the fast step
+                    for flags in (512, 512 | 256, 512 | 2048, 512 | 256 | 2048):
+                        ms = timeit(lambda: _lib.call("vn_hash_encode_fwd_f32", x, table, o, S, lv, flags))
+                        rec("hash_fwd_f32", ms, state=state, S=S, log2_T=log2_T, flags=flags, gbs=round(S * 1164 / ms / 1e6, 1))
+                    for flags in (512, 512 | 256, 512 | 1024, 512 | 256 | 1024):
+                        ms = timeit(lambda: _lib.call("vn_hash_encode_bwd_f32", x, dout, grad, S, lv, flags))
+                        rec("hash_bwd_f32", ms, state=state, S=S, log2_T=log2_T, flags=flags, gbs=round(S * 1164 / ms / 1e6, 1))
                     table_h = table.half().view(-1, 2)
                     oh = torch.empty(S, 16, 2, dtype=torch.float16, device=DEV)
                     ms = timeit(lambda: _lib.call("vn_hash_encode_fwd_f16", x, table_h, oh, S, lv, 0))
@@ -112,6 +119,10 @@ def main():
             denc = torch.empty(S, 32, device=DEV); dW = [torch.zeros_like(w) for w in W]
             ms = timeit(lambda: _lib.call("vn_mlp_bwd", enc, 0, dirs, *W, S, 0, dsig, drgb, denc, *dW))
             rec("mlp_bwd", ms, S=S, tflops=round(S * 56448 / ms / 1e9, 2), gbs=round(S * 284 / ms / 1e6, 1))
+            ms = timeit(lambda: _lib.call("vn_mlp_fwd", enc, 2, dirs, *W, S, 0, sig, rgb, None))
+            rec("mlp_fwd_planar", ms, S=S, tflops=round(S * 18816 / ms / 1e9, 2), gbs=round(S * 156 / ms / 1e6, 1))
+            ms = timeit(lambda: _lib.call("vn_mlp_bwd", enc, 2, dirs, *W, S, 0, dsig, drgb, denc, *dW))
+            rec("mlp_bwd_planar", ms, S=S, tflops=round(S * 56448 / ms / 1e9, 2), gbs=round(S * 284 / ms / 1e6, 1))
     if "adam" in which:
         n = 11429472
         p, g, m, v = (torch.randn(n, device=DEV) for _ in range(4))

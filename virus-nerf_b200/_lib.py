@@ -21,6 +21,9 @@ VN_HASH_LEVEL_GROUPS_4 = 32
 VN_HASH_LEVEL_GROUPS_8 = 64
 VN_HASH_LEVEL_GROUPS_16 = 128
 VN_HASH_LEVEL_GROUPS_2 = 256
+VN_HASH_PLANAR = 512
+VN_HASH_TIGHT_REGS = 1024
+VN_HASH_PAIR_LOADS = 2048
 
 
 class HashLevels(ctypes.Structure):

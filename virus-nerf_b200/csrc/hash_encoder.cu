@@ -125,15 +125,37 @@ __device__ __forceinline__ float2 load_entry(const __half2* t, uint32_t i) {
     return __half22float2(__ldg(t + i));
 }
 
-template <typename TT, bool DENSE>
+// PAIR (fp32 tables): the x / x+1 corners of a cell are neighbouring entries whenever their
+// indices differ only in bit 0 (see level_scatter) -- one 16-byte load instead of two 8-byte
+// loads, i.e. half the L1 wavefronts for those lanes.  Values and summation order unchanged.
+template <typename TT, bool DENSE, bool PAIR>
 __device__ __forceinline__ void level_gather(const TT* __restrict__ tbl, const Cell& c, uint32_t res, uint32_t size,
                                              uint32_t mask, float& a0, float& a1) {
     float2 v[8];
     float w[8];
+    if (PAIR && sizeof(TT) == sizeof(float2)) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        v[k] = load_entry(tbl, corner_index<DENSE>(c, k, res, size, mask));
-        w[k] = corner_weight(c, k);
+        for (int k = 0; k < 8; k += 2) {
+            const uint32_t i0 = corner_index<DENSE>(c, k, res, size, mask);
+            const uint32_t i1 = corner_index<DENSE>(c, k + 1, res, size, mask);
+            if ((i0 ^ i1) == 1u) {
+                const float4 q = __ldg(reinterpret_cast<const float4*>(tbl) + (i0 >> 1));
+                const bool lo0 = (i0 & 1u) == 0u;
+                v[k] = lo0 ? make_float2(q.x, q.y) : make_float2(q.z, q.w);
+                v[k + 1] = lo0 ? make_float2(q.z, q.w) : make_float2(q.x, q.y);
+            } else {
+                v[k] = load_entry(tbl, i0);
+                v[k + 1] = load_entry(tbl, i1);
+            }
+            w[k] = corner_weight(c, k);
+            w[k + 1] = corner_weight(c, k + 1);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            v[k] = load_entry(tbl, corner_index<DENSE>(c, k, res, size, mask));
+            w[k] = corner_weight(c, k);
+        }
     }
     if (sizeof(TT) == sizeof(float2)) {
         a0 = 0.0f; a1 = 0.0f;
@@ -152,7 +174,10 @@ __device__ __forceinline__ void level_gather(const TT* __restrict__ tbl, const C
 }
 
 // ---- forward ----------------------------------------------------------------------------
-template <typename TT, typename OT, int LPT>
+// PLANAR (f32 only, levels and LPT even): out is [levels/2][S] float4 -- plane p holds
+// (level 2p f0, f1, level 2p+1 f0, f1) of every point, so a warp's store of one plane is one
+// contiguous 512-byte run instead of 32 separate 16-byte pieces of 32 rows.
+template <typename TT, typename OT, int LPT, bool PLANAR, bool PAIR = false>
 __global__ void __launch_bounds__(256) hash_fwd_kernel(const float* __restrict__ xyz, const TT* __restrict__ table,
                                                        OT* __restrict__ out, int64_t S,
                                                        const __grid_constant__ HashParams P) {
@@ -168,16 +193,21 @@ __global__ void __launch_bounds__(256) hash_fwd_kernel(const float* __restrict__
             const Cell c = cell_of(x, y, z, P.scales[level]);
             const TT* tbl = table + P.offsets[level];
             if (level < P.begin_fast)
-                level_gather<TT, true>(tbl, c, P.res[level], P.sizes[level], 0u, acc[2 * l], acc[2 * l + 1]);
+                level_gather<TT, true, PAIR>(tbl, c, P.res[level], P.sizes[level], 0u, acc[2 * l], acc[2 * l + 1]);
             else
-                level_gather<TT, false>(tbl, c, P.res[level], P.sizes[level], P.pow2mask[level], acc[2 * l],
+                level_gather<TT, false, PAIR>(tbl, c, P.res[level], P.sizes[level], P.pow2mask[level], acc[2 * l],
                                         acc[2 * l + 1]);
         } else {
             acc[2 * l] = 0.0f; acc[2 * l + 1] = 0.0f;
         }
     }
     const int W = 2 * P.levels;
-    if (sizeof(OT) == 4) {
+    if (PLANAR) {
+        float4* o = (float4*)out + (int64_t)(level0 / 2) * S + i;
+#pragma unroll
+        for (int q = 0; q < LPT / 2; ++q)
+            if (level0 + 2 * q < P.levels) o[(int64_t)q * S] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+    } else if (sizeof(OT) == 4) {
         float* o = (float*)out + i * W + 2 * level0;
         if (LPT % 2 == 0 && (W % 4) == 0 && level0 + LPT <= P.levels) {
 #pragma unroll
@@ -306,8 +336,8 @@ __device__ __forceinline__ void level_scatter(float* __restrict__ grad_level, co
     }
 }
 
-template <typename DT, int LPT, bool AGG, bool ZERO_SKIP>
-__global__ void __launch_bounds__(256) hash_bwd_kernel(const float* __restrict__ xyz, const DT* __restrict__ dout,
+template <typename DT, int LPT, bool AGG, bool ZERO_SKIP, bool PLANAR, int MINB = 1>
+__global__ void __launch_bounds__(256, MINB) hash_bwd_kernel(const float* __restrict__ xyz, const DT* __restrict__ dout,
                                                        float* __restrict__ grad, int64_t S,
                                                        const __grid_constant__ HashParams P) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -320,7 +350,16 @@ __global__ void __launch_bounds__(256) hash_bwd_kernel(const float* __restrict__
     if (valid) {
         x = __ldg(xyz + 3 * i); y = __ldg(xyz + 3 * i + 1); z = __ldg(xyz + 3 * i + 2);
         const int W = 2 * P.levels;
-        if (sizeof(DT) == 4) {
+        if (PLANAR) {
+            // level0 is even (level_begin and LPT even): plane level0/2 + q at index i
+            const float4* dp = (const float4*)dout + (int64_t)(level0 / 2) * S + i;
+#pragma unroll
+            for (int q = 0; q < LPT / 2; ++q)
+                if (level0 + 2 * q < P.level_end) {
+                    float4 t = __ldg(dp + (int64_t)q * S);
+                    d[4 * q] = t.x; d[4 * q + 1] = t.y; d[4 * q + 2] = t.z; d[4 * q + 3] = t.w;
+                }
+        } else if (sizeof(DT) == 4) {
             const float* dp = (const float*)dout + i * W + 2 * level0;
             if (LPT % 2 == 0 && (W % 4) == 0 && level0 + LPT <= P.level_end) {
 #pragma unroll
@@ -409,12 +448,29 @@ static int launch_fwd(const float* xyz, const TT* table, OT* out, int64_t S, con
     VnProfScope prof(VN_K_HASH_FWD, S, st);
     const int lpt = pick_lpt(flags, lv, sizeof(TT), false);
     dim3 block(256), grid(vn_blocks(S, 256), (P.levels + lpt - 1) / lpt);
+    if (flags & VN_HASH_PLANAR) {
+        VN_REQUIRE(sizeof(OT) == 4 && P.levels % 2 == 0 && lpt % 2 == 0,
+                   "hash fwd: the planar layout needs f32 output, an even level count and >= 2 levels per thread");
+        if constexpr (sizeof(OT) == 4) {
+            const bool pair = (flags & VN_HASH_PAIR_LOADS) != 0;   // the level slabs are 16-byte aligned (sizes % 8 == 0)
+            switch (lpt) {
+                case 2: if (pair) hash_fwd_kernel<TT, OT, 2, true, true><<<grid, block, 0, st>>>(xyz, table, out, S, P);
+                        else hash_fwd_kernel<TT, OT, 2, true><<<grid, block, 0, st>>>(xyz, table, out, S, P); break;
+                case 4: if (pair) hash_fwd_kernel<TT, OT, 4, true, true><<<grid, block, 0, st>>>(xyz, table, out, S, P);
+                        else hash_fwd_kernel<TT, OT, 4, true><<<grid, block, 0, st>>>(xyz, table, out, S, P); break;
+                case 8: hash_fwd_kernel<TT, OT, 8, true><<<grid, block, 0, st>>>(xyz, table, out, S, P); break;
+                default: hash_fwd_kernel<TT, OT, 16, true><<<grid, block, 0, st>>>(xyz, table, out, S, P); break;
+            }
+        }
+        VN_CHECK_LAUNCH("hash_fwd_kernel<planar>");
+        return VN_OK;
+    }
     switch (lpt) {
-        case 1: hash_fwd_kernel<TT, OT, 1><<<grid, block, 0, st>>>(xyz, table, out, S, P); break;
-        case 2: hash_fwd_kernel<TT, OT, 2><<<grid, block, 0, st>>>(xyz, table, out, S, P); break;
-        case 4: hash_fwd_kernel<TT, OT, 4><<<grid, block, 0, st>>>(xyz, table, out, S, P); break;
-        case 8: hash_fwd_kernel<TT, OT, 8><<<grid, block, 0, st>>>(xyz, table, out, S, P); break;
-        default: hash_fwd_kernel<TT, OT, 16><<<grid, block, 0, st>>>(xyz, table, out, S, P); break;
+        case 1: hash_fwd_kernel<TT, OT, 1, false><<<grid, block, 0, st>>>(xyz, table, out, S, P); break;
+        case 2: hash_fwd_kernel<TT, OT, 2, false><<<grid, block, 0, st>>>(xyz, table, out, S, P); break;
+        case 4: hash_fwd_kernel<TT, OT, 4, false><<<grid, block, 0, st>>>(xyz, table, out, S, P); break;
+        case 8: hash_fwd_kernel<TT, OT, 8, false><<<grid, block, 0, st>>>(xyz, table, out, S, P); break;
+        default: hash_fwd_kernel<TT, OT, 16, false><<<grid, block, 0, st>>>(xyz, table, out, S, P); break;
     }
     VN_CHECK_LAUNCH("hash_fwd_kernel");
     return VN_OK;
@@ -436,7 +492,25 @@ static int launch_bwd(const float* xyz, const DT* dout, float* grad, int64_t S, 
     const int lpt = pick_lpt(flags, lv, 8, true);
     const bool agg = !(flags & VN_HASH_NO_WARP_AGG);
     dim3 block(256), grid(vn_blocks(S, 256), (level_end - level_begin + lpt - 1) / lpt);
-#define VN_BWD(L, A) hash_bwd_kernel<DT, L, A, ZERO_SKIP><<<grid, block, 0, st>>>(xyz, dout, grad, S, P)
+    if (flags & VN_HASH_PLANAR) {
+        VN_REQUIRE(sizeof(DT) == 4 && P.levels % 2 == 0 && lpt % 2 == 0 && level_begin % 2 == 0 && level_end % 2 == 0 && agg,
+                   "hash bwd: the planar layout needs f32 gradients, even level counts / ranges and >= 2 levels per thread");
+        if constexpr (sizeof(DT) == 4) {
+            // VN_HASH_TIGHT_REGS: 48 registers (5 CTAs per SM instead of 4) at the price of a few spilled bytes
+            const bool tight = (flags & VN_HASH_TIGHT_REGS) != 0;
+            switch (lpt) {
+                case 2: if (tight) hash_bwd_kernel<DT, 2, true, ZERO_SKIP, true, 5><<<grid, block, 0, st>>>(xyz, dout, grad, S, P);
+                        else hash_bwd_kernel<DT, 2, true, ZERO_SKIP, true><<<grid, block, 0, st>>>(xyz, dout, grad, S, P); break;
+                case 4: if (tight) hash_bwd_kernel<DT, 4, true, ZERO_SKIP, true, 5><<<grid, block, 0, st>>>(xyz, dout, grad, S, P);
+                        else hash_bwd_kernel<DT, 4, true, ZERO_SKIP, true><<<grid, block, 0, st>>>(xyz, dout, grad, S, P); break;
+                case 8: hash_bwd_kernel<DT, 8, true, ZERO_SKIP, true><<<grid, block, 0, st>>>(xyz, dout, grad, S, P); break;
+                default: hash_bwd_kernel<DT, 16, true, ZERO_SKIP, true><<<grid, block, 0, st>>>(xyz, dout, grad, S, P); break;
+            }
+        }
+        VN_CHECK_LAUNCH("hash_bwd_kernel<planar>");
+        return VN_OK;
+    }
+#define VN_BWD(L, A) hash_bwd_kernel<DT, L, A, ZERO_SKIP, false><<<grid, block, 0, st>>>(xyz, dout, grad, S, P)
     if (agg) {
         switch (lpt) { case 1: VN_BWD(1, true); break; case 2: VN_BWD(2, true); break; case 4: VN_BWD(4, true); break;
                        case 8: VN_BWD(8, true); break; default: VN_BWD(16, true); }

@@ -131,7 +131,8 @@ struct MlpArgs {
     float* denc;           // [S,32]  (BWD)
     float* dW[5];          // accumulated (BWD)
     int64_t S;
-    int enc_half;
+    int enc_half;          // enc_format == 1
+    int enc_planar;        // enc_format == 2: enc / denc are [8][S] float4 planes (VN_HASH_PLANAR)
     int density_only;
 };
 
@@ -324,6 +325,11 @@ __global__ void __launch_bounds__(NTHREADS, BWD ? 2 : 3) mlp_kernel(const MlpArg
                     st.e[2 * q] = make_float4(f0.x, f0.y, f1.x, f1.y);
                     st.e[2 * q + 1] = make_float4(f2.x, f2.y, f3.x, f3.y);
                 }
+            } else if (a.enc_planar) {
+                // planes 4*half .. 4*half+3 at index s: consecutive rows = consecutive float4
+                const float4* src = reinterpret_cast<const float4*>(a.enc) + (int64_t)(4 * half) * a.S + s;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) st.e[q] = __ldg(src + (int64_t)q * a.S);
             } else {
                 const float4* src = reinterpret_cast<const float4*>(a.enc + s * 32 + 16 * half);
 #pragma unroll
@@ -494,9 +500,15 @@ __global__ void __launch_bounds__(NTHREADS, BWD ? 2 : 3) mlp_kernel(const MlpArg
         wait_mma(p);
         read_acc<16>(p, TC_TMP + 16 * half, acc);
         if (valid) {
-            float4* dst = reinterpret_cast<float4*>(a.denc + s * 32 + 16 * half);
+            if (a.enc_planar) {
+                float4* dst = reinterpret_cast<float4*>(a.denc) + (int64_t)(4 * half) * a.S + s;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) dst[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+                for (int q = 0; q < 4; ++q) dst[(int64_t)q * a.S] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+            } else {
+                float4* dst = reinterpret_cast<float4*>(a.denc + s * 32 + 16 * half);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) dst[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+            }
         }
         umma::fence_before_sync();
     }
@@ -549,36 +561,38 @@ int launch_mlp(bool bwd, const MlpArgs& a, cudaStream_t st) {
 
 }  // namespace
 
-VN_API int vn_mlp_fwd(const void* enc, int enc_half, const float* dirs, const float* W1, const float* W2, const float* W3,
+VN_API int vn_mlp_fwd(const void* enc, int enc_format, const float* dirs, const float* W1, const float* W2, const float* W3,
                       const float* W4, const float* W5, int64_t S, int density_only, float* sigmas, float* rgbs,
                       float* h_out, void* stream) {
     VN_REQUIRE(S >= 0, "vn_mlp_fwd: S < 0");
     if (S == 0) return VN_OK;
     VN_REQUIRE(enc && W1 && W2 && sigmas, "vn_mlp_fwd: null pointer");
+    VN_REQUIRE(enc_format >= 0 && enc_format <= 2, "vn_mlp_fwd: enc_format must be 0 (f32 rows), 1 (f16 rows) or 2 (f32 planes)");
     VN_REQUIRE(density_only || (dirs && W3 && W4 && W5 && rgbs), "vn_mlp_fwd: null colour-network pointer");
     VN_REQUIRE(vn_aligned(enc, 16), "vn_mlp_fwd: enc must be 16-byte aligned");
     VN_REQUIRE(vn_aligned(W1, 16) && vn_aligned(W2, 16) && vn_aligned(W3, 16) && vn_aligned(W4, 16) && vn_aligned(W5, 16),
                "vn_mlp_fwd: weight matrices must be 16-byte aligned");
     MlpArgs a{};
-    a.enc = (const float*)enc; a.enc_half = enc_half; a.dirs = dirs;
+    a.enc = (const float*)enc; a.enc_half = enc_format == 1; a.enc_planar = enc_format == 2; a.dirs = dirs;
     a.W[0] = W1; a.W[1] = W2; a.W[2] = density_only ? W1 : W3; a.W[3] = density_only ? W1 : W4; a.W[4] = density_only ? W1 : W5;
     a.sigmas = sigmas; a.rgbs = rgbs; a.h_out = h_out; a.S = S; a.density_only = density_only;
     return launch_mlp(false, a, (cudaStream_t)stream);
 }
 
-VN_API int vn_mlp_bwd(const void* enc, int enc_half, const float* dirs, const float* W1, const float* W2, const float* W3,
+VN_API int vn_mlp_bwd(const void* enc, int enc_format, const float* dirs, const float* W1, const float* W2, const float* W3,
                       const float* W4, const float* W5, int64_t S, int density_only, const float* dsigmas,
                       const float* drgbs, float* denc, float* dW1, float* dW2, float* dW3, float* dW4, float* dW5,
                       void* stream) {
     VN_REQUIRE(S >= 0, "vn_mlp_bwd: S < 0");
     if (S == 0) return VN_OK;
     VN_REQUIRE(enc && W1 && W2 && dsigmas && denc && dW1 && dW2, "vn_mlp_bwd: null pointer");
+    VN_REQUIRE(enc_format >= 0 && enc_format <= 2, "vn_mlp_bwd: enc_format must be 0 (f32 rows), 1 (f16 rows) or 2 (f32 planes)");
     VN_REQUIRE(density_only || (dirs && W3 && W4 && W5 && drgbs && dW3 && dW4 && dW5), "vn_mlp_bwd: null colour-network pointer");
     VN_REQUIRE(vn_aligned(enc, 16) && vn_aligned(denc, 16), "vn_mlp_bwd: enc/denc must be 16-byte aligned");
     VN_REQUIRE(vn_aligned(W1, 16) && vn_aligned(W2, 16) && vn_aligned(W3, 16) && vn_aligned(W4, 16) && vn_aligned(W5, 16),
                "vn_mlp_bwd: weight matrices must be 16-byte aligned");
     MlpArgs a{};
-    a.enc = (const float*)enc; a.enc_half = enc_half; a.dirs = dirs;
+    a.enc = (const float*)enc; a.enc_half = enc_format == 1; a.enc_planar = enc_format == 2; a.dirs = dirs;
     a.W[0] = W1; a.W[1] = W2; a.W[2] = density_only ? W1 : W3; a.W[3] = density_only ? W1 : W4; a.W[4] = density_only ? W1 : W5;
     a.dsigmas = dsigmas; a.drgbs = drgbs; a.denc = denc;
     a.dW[0] = dW1; a.dW[1] = dW2; a.dW[2] = dW3; a.dW[3] = dW4; a.dW[4] = dW5;

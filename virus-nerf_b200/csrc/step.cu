@@ -32,6 +32,8 @@ VN_API int vn_train_step_run(const vn_step_t* s, int64_t S, int phase, int do_op
     float* table_grad = s->flat_g + s->table_off;
     float* sums = s->loss_acc;
     float* cnts = s->loss_acc + 4;
+    // enc / d_enc stay inside the step: use the level-pair-plane layout when the flags ask for it
+    const int enc_fmt = (s->hash_flags & VN_HASH_PLANAR) ? 2 : 0;
     if (phase == 0 || phase == 1) {
         VN_CUDA(cudaMemsetAsync(s->flat_g, 0, sizeof(float) * (size_t)s->n_params, st));
         VN_CUDA(cudaMemsetAsync(s->loss_acc, 0, sizeof(float) * 8, st));
@@ -39,7 +41,7 @@ VN_API int vn_train_step_run(const vn_step_t* s, int64_t S, int phase, int do_op
                                     s->scale, s->exp_step_factor, s->rays_a, S, s->xyzs, s->dirs, s->deltas, s->ts, s->unit,
                                     stream));
         VN_TRY(vn_hash_encode_fwd_f32(s->unit, table, s->enc, S, &s->levels, s->hash_flags, stream));
-        VN_TRY(vn_mlp_fwd(s->enc, 0, s->dirs, W[0], W[1], W[2], W[3], W[4], S, 0, s->sigmas, s->rgbs, nullptr, stream));
+        VN_TRY(vn_mlp_fwd(s->enc, enc_fmt, s->dirs, W[0], W[1], W[2], W[3], W[4], S, 0, s->sigmas, s->rgbs, nullptr, stream));
         VN_TRY(vn_composite_train_fwd(s->sigmas, s->rgbs, s->deltas, s->ts, s->rays_a, s->N, S, s->T_threshold, s->vr_samples,
                                       s->opacity, s->depth, s->rgb, s->ws, stream));
         VN_TRY(vn_loss_fwd(s->rgb, s->opacity, s->depth, s->gt_rgb, s->uss, s->tof, s->rgbd, s->N, s->bg, s->uss_tol, sums,
@@ -51,7 +53,7 @@ VN_API int vn_train_step_run(const vn_step_t* s, int64_t S, int phase, int do_op
                            s->loss_out, stream));
         VN_TRY(vn_composite_train_bwd(s->sigmas, s->rgbs, s->deltas, s->ts, s->rays_a, s->N, S, s->T_threshold, s->d_opacity,
                                       s->d_depth, s->d_rgb, nullptr, s->d_sigmas, s->d_rgbs, stream));
-        VN_TRY(vn_mlp_bwd(s->enc, 0, s->dirs, W[0], W[1], W[2], W[3], W[4], S, 0, s->d_sigmas, s->d_rgbs, s->d_enc, dW[0], dW[1],
+        VN_TRY(vn_mlp_bwd(s->enc, enc_fmt, s->dirs, W[0], W[1], W[2], W[3], W[4], S, 0, s->d_sigmas, s->d_rgbs, s->d_enc, dW[0], dW[1],
                           dW[2], dW[3], dW[4], stream));
         VN_TRY(vn_hash_encode_bwd_f32(s->unit, s->d_enc, table_grad, S, &s->levels, s->hash_flags, stream));
         if (do_optim) VN_TRY(vn_train_step_optim(s, stream));

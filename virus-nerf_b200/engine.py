@@ -85,12 +85,16 @@ class _Workspace:
 
 class TrainEngine:
     def __init__(self, args, dataset, device, world_size=1, rank=0, log2_T=19, max_res=1024, half_opt=False,
-                 autocast=True, seed=21, grad_scale=2.0 ** 19, comm="auto"):
+                 autocast=True, seed=21, grad_scale=2.0 ** 19, comm="auto", enc_layout="planar"):
         self.args = args
         self.device = torch.device(device)
         self.world_size, self.rank = world_size, rank
         self.dataset = dataset
         self.autocast = autocast
+        # layout of the encoding / its gradient INSIDE the fast step (never visible to the drop-in modules):
+        # "planar" = [8][S] float4 level-pair planes (coalesced on both sides), "rows" = the reference's [S,32]
+        assert enc_layout in ("planar", "rows")
+        self.enc_planar = enc_layout == "planar"
         torch.manual_seed(seed)          # identical replicas on every rank
         self.model = NGP(scale=args.model.scale, pos_encoder_type='hash', levels=args.model.hash_levels,
                          max_res=max_res, log2_T=log2_T, half_opt=half_opt, args=args, dataset=dataset)
@@ -205,6 +209,11 @@ class TrainEngine:
             st.w_off[i] = (w.data_ptr() - self.flat_p.data_ptr()) // esz
         st.levels = enc._levels
         st.hash_flags = enc.kernel_flags
+        if self.enc_planar:
+            # measured on B200 (profiles/r1_kbench.md): planes + 2 levels per thread + 16-byte pair loads (fwd)
+            # + the 48-register backward: fwd 0.240 -> 0.197 ms, bwd 0.417 -> 0.378 ms at 1.3 M samples
+            st.hash_flags |= (_lib.VN_HASH_PLANAR | _lib.VN_HASH_LEVEL_GROUPS_2 | _lib.VN_HASH_PAIR_LOADS |
+                              _lib.VN_HASH_TIGHT_REGS)
         t = a.training
         st.w_color, st.w_uss, st.w_tof, st.w_rgbd = t.color_loss_w, t.uss_loss_w, t.tof_loss_w, t.rgbd_loss_w
         st.lr, st.beta1, st.beta2, st.eps = self.lr, self.betas[0], self.betas[1], self.eps

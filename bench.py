@@ -39,7 +39,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-autocast", action="store_true")
     ap.add_argument("--autograd-step", action="store_true", help="use the torch-autograd step instead of the fused step")
-    ap.add_argument("--comm", default="auto", choices=["auto", "nccl", "p2p"], help="gradient exchange (auto = nccl)")
+    ap.add_argument("--comm", default="auto", choices=["auto", "nccl", "p2p", "p2p_fused"],
+                    help="gradient exchange: nccl allreduce, own peer-memory allreduce, or the sharded optimiser fused "
+                         "with the peer-memory exchange (auto = p2p_fused, nccl if peer mapping fails)")
     ap.add_argument("--enc-layout", default="planar", choices=["planar", "rows"],
                     help="layout of the encoding inside the fused step (rows = the reference's [S,32])")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end phase (profiling runs only)")
@@ -280,8 +282,11 @@ def run_ours(a):
             lo, hi = c.clone(), c.clone()
             dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
             same = bool((lo == hi).all())
+        nonlocal grad_exchange
+        grad_exchange = eng.comm
         return ms, launches, samples, prof, h2d, d2h, float(loss), same, render_ms
 
+    grad_exchange = "none"
     clocks = ClockSampler(local)
     clocks.start()
     ms, launches, samples, prof, _, _, last_loss, replicas_same, render_ms = run_phase(pinned=False)
@@ -331,7 +336,7 @@ def run_ours(a):
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": n, "global_rays_per_step": n * world,
                            "samples_per_step_mean": statistics.mean(samples) if samples else 0,
-                           "parallelism": f"dp{world}", "grad_exchange": ("none" if world == 1 else ("nccl" if a.comm == "auto" else a.comm)),
+                           "parallelism": f"dp{world}", "grad_exchange": grad_exchange,
                            "l2_policy": "inputs larger than L2: table+grad+Adam state 183 MB and per-step sample "
                                         "buffers are streamed; a fresh ray batch every step"},
                 "roofline": roof, "kernels": kern,

@@ -320,6 +320,23 @@ int vn_ipc_get_handle(const void* ptr, void* h_handle64_out, int64_t* h_offset_o
 int vn_ipc_open(const void* h_handle64, int64_t offset_bytes, void** h_ptr_out);
 int vn_p2p_init(int rank, int world, void* const* h_bufs, void* const* h_flags, int* err_dev);
 int vn_p2p_allreduce(int64_t n, void* stream);
+/* Sharded optimiser fused with the exchange (ZeRO-1 style, replaces allreduce + vn_grad_check +
+ * vn_adam_step + vn_scaler_update under data parallelism):
+ *  vn_p2p_attach: h_pbufs = `world` device pointers to the ranks' flat PARAMETER buffers (may be
+ *               NULL if only the small allreduce is used); h_mbox = `world` pointers to zeroed
+ *               fp32 mailboxes of 2 * world * 8 floats.
+ *  vn_p2p_allreduce_small: in-place sum (or max) of n <= 8 floats across the ranks through the
+ *               mailboxes -- one kernel, replaces the NCCL allreduce of the loss normalisers.
+ *  vn_p2p_reduce_adam: barrier -> rank r sums slice r of the gradient over all ranks (fixed order)
+ *               and checks it for inf/nan -> barrier + OR of the inf flags -> Adam on slice r with
+ *               rank-local m / v (only slice r of m, v is ever touched on rank r) and PUSH of the
+ *               updated parameters into every replica -> barrier -> GradScaler update (growth 2,
+ *               backoff 0.5, interval 2000).  Arithmetic identical to vn_adam_step. */
+int vn_p2p_attach(void* const* h_pbufs, void* const* h_mbox);
+int vn_p2p_allreduce_small(float* data, int n, int use_max, void* stream);
+int vn_p2p_reduce_adam(int64_t n, float* m, float* v, float lr, float beta1, float beta2, float eps,
+                       int step, float* found_inf, float* scale_dev, int32_t* growth_tracker,
+                       void* stream);
 
 /* tcgen05 self-test (development / CI): one 128 x N x K fp16 product through the tensor
  * cores in the three operand modes the fused MLP uses (0 forward A*B^T, 1 dgrad A*B,

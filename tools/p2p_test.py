@@ -1,41 +1,141 @@
-"""2..8-rank check of the peer-memory allreduce against NCCL (run under torchrun)."""
-import os, sys, time
+"""2..8-rank check of the peer-memory exchange kernels (run under torchrun):
+  * vn_p2p_allreduce against NCCL;
+  * vn_p2p_allreduce_small (mailbox sum of the loss normalisers) against NCCL;
+  * vn_p2p_reduce_adam (reduce-scatter + inf check + sharded Adam + parameter push + scaler
+    update) against vn_p2p_allreduce + vn_grad_check + vn_adam_step + vn_scaler_update: the
+    parameters must be BIT-identical on every rank, incl. a step with an injected inf.
+Prints one line per check on rank 0; exits non-zero on a mismatch."""
+import os
+import sys
+
 import torch
 import torch.distributed as dist
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from virus_nerf_b200 import _lib
+from virus_nerf_b200 import _lib  # noqa: E402
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dev = torch.device(f"cuda:{local}")
 dist.init_process_group("nccl", device_id=dev)
 n = 11429472
-g = torch.Generator(device=dev).manual_seed(rank)
-grad = torch.randn(n, device=dev, generator=g)
-ref = grad.clone()
+gen = torch.Generator(device=dev).manual_seed(rank)
+grad = torch.randn(n, device=dev, generator=gen)
+params = torch.randn(n, device=dev, generator=torch.Generator(device=dev).manual_seed(99))   # same on every rank
 flags = torch.zeros(world, dtype=torch.int32, device=dev)
 err = torch.zeros(1, dtype=torch.int32, device=dev)
-keep = _lib.p2p_setup(grad, flags, err, rank, world)
-dist.all_reduce(ref)
-_lib.call("vn_p2p_allreduce", n)
-torch.cuda.synchronize()
-assert int(err) == 0, "barrier timeout"
-diff = (grad - ref).abs().max().item()
-# bit-identical across ranks?
-lo, hi = grad.clone(), grad.clone()
-dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-same = bool(torch.equal(lo, hi))
+mbox = torch.zeros(2, world, 8, device=dev)
+keep = _lib.p2p_setup(grad, flags, err, rank, world, params=params, mbox=mbox)
+
+
+def say(msg):
+    if rank == 0:
+        print(msg, flush=True)
+
+
+def identical_everywhere(t):
+    lo, hi = t.clone(), t.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    return bool(torch.equal(lo, hi))
+
+
 def timeit(fn, reps=20):
-    for _ in range(3): fn()
+    for _ in range(3):
+        fn()
     dist.barrier(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(reps): fn()
+    for _ in range(reps):
+        fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
+
+
+ok = True
+# ---- 1. big allreduce ------------------------------------------------------------------------
+ref = grad.clone()
+dist.all_reduce(ref)
+_lib.call("vn_p2p_allreduce", n)
+torch.cuda.synchronize()
+diff = (grad - ref).abs().max().item()
+same = identical_everywhere(grad)
+ok &= same and diff < 1e-3 and int(err) == 0
+say(f"world {world}: allreduce max |p2p - nccl| = {diff:.3e}, replicas identical = {same}")
+
+# ---- 2. small allreduce ----------------------------------------------------------------------
+for it in range(5):
+    small = torch.arange(4, device=dev, dtype=torch.float32) * (rank + 1) + it
+    ref_s = small.clone(); dist.all_reduce(ref_s)
+    _lib.call("vn_p2p_allreduce_small", small, 4, 0)
+    torch.cuda.synchronize()
+    ok &= bool(torch.equal(small, ref_s)) and int(err) == 0
+say(f"world {world}: small allreduce matches nccl = {ok}")
+
+# ---- 3. fused sharded optimiser vs allreduce + dense Adam -------------------------------------
+lr, b1, b2, eps = 1e-2, 0.9, 0.999, 1e-15
+m_f, v_f = torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+m_r, v_r = torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+p_ref = params.clone()
+found_f, found_r = torch.zeros(1, device=dev), torch.zeros(1, device=dev)
+scale_f, scale_r = torch.tensor([2.0 ** 19], device=dev), torch.tensor([2.0 ** 19], device=dev)
+tr_f, tr_r = torch.zeros(1, dtype=torch.int32, device=dev), torch.zeros(1, dtype=torch.int32, device=dev)
+chunk = ((n // 4 + world - 1) // world) * 4
+lo, hi = rank * chunk, min((rank + 1) * chunk, n)
+for step in range(1, 5):
+    g0 = torch.randn(n, device=dev, generator=gen) * 2.0 ** 19
+    if step == 3 and rank == world - 1:
+        g0[12345] = float("inf")                      # GradScaler must skip this step on EVERY rank
+    # reference: allreduce (same summation order as the fused reduce-scatter) + dense optimiser
+    grad.copy_(g0)
+    _lib.call("vn_p2p_allreduce", n)
+    _lib.call("vn_grad_check", grad, n, found_r)
+    _lib.call("vn_adam_step", p_ref, grad, m_r, v_r, n, 1.0, lr, b1, b2, eps, step, found_r, scale_r)
+    _lib.call("vn_scaler_update", scale_r, tr_r, found_r, 2.0, 0.5, 2000)
+    # fused
+    grad.copy_(g0)
+    torch.cuda.synchronize(); dist.barrier()
+    _lib.call("vn_p2p_reduce_adam", n, m_f, v_f, lr, b1, b2, eps, step, found_f, scale_f, tr_f)
+    torch.cuda.synchronize()
+    eq_p = bool(torch.equal(params, p_ref))
+    eq_m = bool(torch.equal(m_f[lo:hi], m_r[lo:hi]) and torch.equal(v_f[lo:hi], v_r[lo:hi]))
+    eq_s = float(scale_f) == float(scale_r) and int(tr_f) == int(tr_r)
+    same = identical_everywhere(params)
+    ok &= eq_p and eq_m and eq_s and same and int(err) == 0
+    say(f"world {world}: fused optimiser step {step}: params == reference {eq_p}, own m/v slice {eq_m}, scaler {eq_s} "
+        f"(scale {float(scale_f):.0f}), replicas identical {same}")
+
+# ---- 4. timings --------------------------------------------------------------------------------
+grad.normal_()
 t_p2p = timeit(lambda: _lib.call("vn_p2p_allreduce", n))
 t_nccl = timeit(lambda: dist.all_reduce(ref))
-assert int(err) == 0
-if rank == 0:
-    print(f"world {world}: max |p2p - nccl| = {diff:.3e}, replicas identical = {same}, p2p {t_p2p:.4f} ms, nccl {t_nccl:.4f} ms", flush=True)
+
+
+def unfused():
+    _lib.call("vn_p2p_allreduce", n)
+    _lib.call("vn_grad_check", grad, n, found_r)
+    _lib.call("vn_adam_step", p_ref, grad, m_r, v_r, n, 1.0, lr, b1, b2, eps, 5, found_r, scale_r)
+    _lib.call("vn_scaler_update", scale_r, tr_r, found_r, 2.0, 0.5, 2000)
+
+
+def nccl_unfused():
+    dist.all_reduce(ref)
+    _lib.call("vn_grad_check", ref, n, found_r)
+    _lib.call("vn_adam_step", p_ref, ref, m_r, v_r, n, 1.0, lr, b1, b2, eps, 5, found_r, scale_r)
+    _lib.call("vn_scaler_update", scale_r, tr_r, found_r, 2.0, 0.5, 2000)
+
+
+t_unf = timeit(unfused)
+t_nccl_unf = timeit(nccl_unfused)
+t_fused = timeit(lambda: _lib.call("vn_p2p_reduce_adam", n, m_f, v_f, lr, b1, b2, eps, 5, found_f, scale_f, tr_f))
+small = torch.ones(4, device=dev)
+t_small = timeit(lambda: _lib.call("vn_p2p_allreduce_small", small, 4, 0))
+small2 = torch.ones(4, device=dev)
+t_small_nccl = timeit(lambda: dist.all_reduce(small2))
+ok &= int(err) == 0
+say(f"world {world}: allreduce p2p {t_p2p:.4f} ms, nccl {t_nccl:.4f} ms | exchange + optimiser: nccl+dense {t_nccl_unf:.4f} ms, "
+    f"p2p+dense {t_unf:.4f} ms, FUSED sharded {t_fused:.4f} ms | 4-float allreduce: mailbox {t_small:.4f} ms, nccl {t_small_nccl:.4f} ms")
+flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 dist.destroy_process_group()
+if float(flag) != 1.0:
+    raise SystemExit("p2p_test: MISMATCH")

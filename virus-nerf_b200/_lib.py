@@ -110,6 +110,8 @@ _SPECS = {
     "vn_train_step_run": "hliis",
     "vn_train_step_optim": "hs",
     "vn_p2p_allreduce": "ls",
+    "vn_p2p_allreduce_small": "piis",
+    "vn_p2p_reduce_adam": "lpp" "ffff" "i" "ppp" "s",
     "vn_mlp_fwd": "pip" "ppppp" "li" "ppp" "s",
     "vn_mlp_bwd": "pip" "ppppp" "li" "pp" "p" "ppppp" "s",
 }
@@ -259,13 +261,18 @@ def hash_levels(base_res, max_res, levels, max_params):
 
 def exported_symbols():
     """names declared in include/virusnerf.h (used by the CPU-side ABI test)"""
-    return ["vn_last_error", "vn_abi_version", "vn_launch_count", "vn_ipc_get_handle", "vn_ipc_open", "vn_p2p_init", "vn_profile_enable", "vn_profile_count", "vn_profile_get", "vn_device_info", "vn_march_scan_tmp_ints"] + list(_SPECS)
+    return ["vn_last_error", "vn_abi_version", "vn_launch_count", "vn_ipc_get_handle", "vn_ipc_open", "vn_p2p_init", "vn_p2p_attach", "vn_profile_enable", "vn_profile_count", "vn_profile_get", "vn_device_info", "vn_march_scan_tmp_ints"] + list(_SPECS)
 
 
-def p2p_setup(grad, flags, err, rank, world, group=None):
+_ipc_opened = {}   # 64-byte IPC handle -> mapped base pointer (a handle may be opened once per process)
+
+
+def p2p_setup(grad, flags, err, rank, world, group=None, params=None, mbox=None):
     """Exchange CUDA-IPC handles of `grad` (flat fp32 gradient buffer) and `flags` (int32 [world],
-    zeros) across the ranks of a torch.distributed group and initialise the peer-memory
-    allreduce (vn_p2p_init).  Returns the list of opened peer pointers (kept alive by the caller)."""
+    zeros) -- and, for the fused sharded optimiser, of `params` (flat fp32 parameter buffer) and
+    `mbox` (fp32 zeros [2, world, 8]) -- across the ranks of a torch.distributed group and
+    initialise the peer-memory exchange (vn_p2p_init / vn_p2p_attach).  Returns the lists of
+    opened peer pointers (kept alive by the caller)."""
     import torch.distributed as dist
     L = lib()
 
@@ -277,23 +284,32 @@ def p2p_setup(grad, flags, err, rank, world, group=None):
             raise RuntimeError(f"vn_ipc_get_handle failed (code {rc}): {last_error()}")
         return handle.raw, int(off.value)
 
-    mine = (share(grad), share(flags))
-    everyone = [None] * world
-    dist.all_gather_object(everyone, mine, group=group)
-    bufs = (ctypes.c_void_p * world)()
-    flgs = (ctypes.c_void_p * world)()
-    for p in range(world):
-        if p == rank:
-            bufs[p], flgs[p] = grad.data_ptr(), flags.data_ptr()
-            continue
-        for (handle, off), arr in ((everyone[p][0], bufs), (everyone[p][1], flgs)):
+    def open_peer(handle, off):
+        base = _ipc_opened.get(handle)
+        if base is None:     # tensors that share one cudaMalloc block of the caching allocator share the handle
             out = ctypes.c_void_p()
-            rc = L.vn_ipc_open(ctypes.c_char_p(handle), ctypes.c_int64(off), ctypes.byref(out))
+            rc = L.vn_ipc_open(ctypes.c_char_p(handle), ctypes.c_int64(0), ctypes.byref(out))
             if rc != 0:
                 raise RuntimeError(f"vn_ipc_open failed (code {rc}): {last_error()}")
-            arr[p] = out.value
-    rc = L.vn_p2p_init(ctypes.c_int(rank), ctypes.c_int(world), bufs, flgs, ctypes.c_void_p(err.data_ptr()))
+            base = _ipc_opened[handle] = out.value
+        return base + off
+
+    tensors = [grad, flags] + ([params, mbox] if mbox is not None else [])
+    if mbox is not None and params is None:
+        raise ValueError("p2p_setup: mbox needs params")
+    mine = tuple(share(t) for t in tensors)
+    everyone = [None] * world
+    dist.all_gather_object(everyone, mine, group=group)
+    arrs = [(ctypes.c_void_p * world)() for _ in tensors]
+    for p in range(world):
+        for k, t in enumerate(tensors):
+            arrs[k][p] = t.data_ptr() if p == rank else open_peer(*everyone[p][k])
+    rc = L.vn_p2p_init(ctypes.c_int(rank), ctypes.c_int(world), arrs[0], arrs[1], ctypes.c_void_p(err.data_ptr()))
     if rc != 0:
         raise RuntimeError(f"vn_p2p_init failed (code {rc}): {last_error()}")
+    if mbox is not None:
+        rc = L.vn_p2p_attach(arrs[2], arrs[3])
+        if rc != 0:
+            raise RuntimeError(f"vn_p2p_attach failed (code {rc}): {last_error()}")
     dist.barrier(group=group)
-    return bufs, flgs
+    return arrs

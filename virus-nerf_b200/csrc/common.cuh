@@ -113,3 +113,17 @@ __device__ __forceinline__ void vn_red_add_v4(float* addr, float a, float b, flo
 __device__ __forceinline__ void vn_red_add_v2(float* addr, float a, float b) {
     asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
 }
+
+// ---- Adam update of one element (torch.optim.Adam single-tensor path + GradScaler.unscale_),
+// shared by the single-GPU optimiser (optim.cu) and the sharded one fused with the DP exchange
+// (p2p_allreduce.cu) so that both produce the same bits.  Explicit fma / mul / add: no
+// context-dependent contraction.
+struct AdamCfg { float inv_scale, beta1, beta2, omb1, omb2, eps, step_size, bc2_sqrt; };
+
+__device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, const AdamCfg& c) {
+    g = __fmul_rn(g, c.inv_scale);                                   // GradScaler.unscale_
+    m = __fmaf_rn(__fsub_rn(g, m), c.omb1, m);                       // exp_avg.lerp_(grad, 1 - beta1)
+    v = __fmaf_rn(__fmul_rn(c.omb2, g), g, __fmul_rn(v, c.beta2));   // exp_avg_sq.mul_(b2).addcmul_(g, g, 1 - b2)
+    const float denom = __fadd_rn(__fdiv_rn(sqrtf(v), c.bc2_sqrt), c.eps);   // (sqrt / bias_correction2_sqrt).add_(eps)
+    p = __fsub_rn(p, __fmul_rn(c.step_size, __fdiv_rn(m, denom)));   // param.addcdiv_(exp_avg, denom, -step_size)
+}

@@ -28,16 +28,6 @@ VN_API int vn_grad_check(const float* g, int64_t n, float* found_inf, void* stre
     return VN_OK;
 }
 
-struct AdamCfg { float inv_scale, beta1, beta2, omb1, omb2, eps, step_size, bc2_sqrt; };
-
-__device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, const AdamCfg& c) {
-    g = g * c.inv_scale;                                  // GradScaler.unscale_
-    m = m + (g - m) * c.omb1;                             // exp_avg.lerp_(grad, 1 - beta1)
-    v = v * c.beta2 + (c.omb2 * g) * g;                   // exp_avg_sq.mul_(b2).addcmul_(g, g, 1 - b2)
-    const float denom = sqrtf(v) / c.bc2_sqrt + c.eps;    // (sqrt / bias_correction2_sqrt).add_(eps)
-    p = p - c.step_size * (m / denom);                    // param.addcdiv_(exp_avg, denom, -step_size)
-}
-
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, int64_t n, AdamCfg c,
                                                    const float* __restrict__ found_inf,

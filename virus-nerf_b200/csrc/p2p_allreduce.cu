@@ -13,13 +13,17 @@
 #include <string.h>
 
 #define VN_P2P_MAX_RANKS 8
+#define VN_P2P_MBOX 8                  // floats per rank and mailbox slot
 
 struct P2PCtx {
     int rank, world;
     float* bufs[VN_P2P_MAX_RANKS];     // peer-mapped gradient buffers (bufs[rank] = local)
     int* flags[VN_P2P_MAX_RANKS];      // peer-mapped flag arrays, [world] ints each
+    float* pbufs[VN_P2P_MAX_RANKS];    // peer-mapped parameter buffers (fused optimiser), or null
+    float* mbox[VN_P2P_MAX_RANKS];     // peer-mapped mailboxes, [2][world][VN_P2P_MBOX] floats each, or null
     int* err;                          // local device int
     int epoch;
+    int small_ops;                     // number of mailbox exchanges so far (mailbox parity)
 };
 static P2PCtx g_ctx;
 static bool g_ctx_ready = false;
@@ -67,6 +71,96 @@ __global__ void __launch_bounds__(512) p2p_all_gather_kernel(P2PCtx c, int64_t n
         dst[i] = __ldcv(src + i);
 }
 
+
+// flag barrier that also carries a small payload: rank r deposits n <= VN_P2P_MBOX floats in
+// slot [parity][r] of every peer's mailbox before it signals; after the wait each rank combines
+// the `world` slots of its own mailbox in rank order (sum, or max when `use_max`), so every
+// rank obtains the bit-identical result.  Two mailbox parities: a slot can only be overwritten
+// two exchanges later, i.e. after its reader has passed another barrier.
+__global__ void p2p_exchange_kernel(P2PCtx c, int value, int parity, float* data, int n, int use_max) {
+    const int p = threadIdx.x;
+    if (p < c.world) {
+        float* slot = c.mbox[p] + ((size_t)parity * c.world + c.rank) * VN_P2P_MBOX;
+        for (int k = 0; k < n; ++k) reinterpret_cast<volatile float*>(slot)[k] = data[k];
+        __threadfence_system();
+        volatile int* dst = c.flags[p] + c.rank;
+        *dst = value;
+        volatile int* src = c.flags[c.rank] + p;
+        const long long t0 = clock64();
+        while (*src < value) {
+            if (clock64() - t0 > (long long)4e9) { *c.err = 1; break; }
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (threadIdx.x < n) {
+        const volatile float* mine = c.mbox[c.rank] + (size_t)parity * c.world * VN_P2P_MBOX + threadIdx.x;
+        float acc = use_max ? -INFINITY : 0.0f;
+        for (int q = 0; q < c.world; ++q) {
+            const float v = mine[(size_t)q * VN_P2P_MBOX];
+            acc = use_max ? fmaxf(acc, v) : acc + v;
+        }
+        data[threadIdx.x] = acc;
+    }
+}
+
+// fused optimiser, phase A: reduce-scatter of this rank's slice (fixed rank order -> the same
+// sums the two-shot allreduce produces) into the local gradient buffer + GradScaler inf check
+__global__ void __launch_bounds__(512) p2p_reduce_check_kernel(P2PCtx c, int64_t n4, int64_t chunk4, float* found_inf) {
+    const int64_t lo = (int64_t)c.rank * chunk4;
+    const int64_t hi = min(lo + chunk4, n4);
+    bool bad = false;
+    for (int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int p = 0; p < VN_P2P_MAX_RANKS; ++p) {
+            if (p < c.world) {
+                const float4 v = __ldcv(reinterpret_cast<const float4*>(c.bufs[p]) + i);
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+        }
+        bad |= !(isfinite(acc.x) && isfinite(acc.y) && isfinite(acc.z) && isfinite(acc.w));
+        reinterpret_cast<float4*>(c.bufs[c.rank])[i] = acc;
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) *found_inf = 1.0f;
+}
+
+// fused optimiser, phase B: Adam on this rank's slice (its m / v never leave the rank) and
+// all-gather of the UPDATED PARAMETERS by pushing them into every replica over NVLink
+__global__ void __launch_bounds__(512) p2p_adam_push_kernel(P2PCtx c, int64_t n4, int64_t chunk4, float* __restrict__ m,
+                                                            float* __restrict__ v, AdamCfg cfg,
+                                                            const float* __restrict__ found_inf,
+                                                            const float* __restrict__ scale_dev) {
+    if (*found_inf != 0.0f) return;                       // GradScaler.step skips the step on every rank alike
+    cfg.inv_scale = 1.0f / *scale_dev;
+    const int64_t lo = (int64_t)c.rank * chunk4;
+    const int64_t hi = min(lo + chunk4, n4);
+    const float4* g4 = reinterpret_cast<const float4*>(c.bufs[c.rank]);
+    float4* m4 = reinterpret_cast<float4*>(m);
+    float4* v4 = reinterpret_cast<float4*>(v);
+    for (int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 P = reinterpret_cast<const float4*>(c.pbufs[c.rank])[i], M = m4[i], V = v4[i];
+        const float4 G = g4[i];
+        adam1(P.x, G.x, M.x, V.x, cfg); adam1(P.y, G.y, M.y, V.y, cfg);
+        adam1(P.z, G.z, M.z, V.z, cfg); adam1(P.w, G.w, M.w, V.w, cfg);
+        m4[i] = M; v4[i] = V;
+#pragma unroll
+        for (int q = 0; q < VN_P2P_MAX_RANKS; ++q)
+            if (q < c.world) reinterpret_cast<float4*>(c.pbufs[q])[i] = P;
+    }
+}
+
+__global__ void p2p_scaler_update_kernel(float* scale, int32_t* tracker, float* found_inf, float growth, float backoff,
+                                         int interval) {
+    if (*found_inf != 0.0f) { *scale = *scale * backoff; *tracker = 0; }
+    else {
+        const int t = *tracker + 1;
+        if (t == interval) { *scale = *scale * growth; *tracker = 0; }
+        else *tracker = t;
+    }
+    *found_inf = 0.0f;
+}
+
 // export: the 64-byte cudaIpcMemHandle_t of the allocation that contains `ptr` and ptr's offset
 // inside it (the caching allocator of the host framework sub-allocates from larger blocks)
 VN_API int vn_ipc_get_handle(const void* ptr, void* h_handle64_out, int64_t* h_offset_out) {
@@ -104,7 +198,8 @@ VN_API int vn_ipc_open(const void* h_handle64, int64_t offset_bytes, void** h_pt
 VN_API int vn_p2p_init(int rank, int world, void* const* h_bufs, void* const* h_flags, int* err_dev) {
     VN_REQUIRE(world >= 1 && world <= VN_P2P_MAX_RANKS && rank >= 0 && rank < world, "vn_p2p_init: bad rank/world");
     VN_REQUIRE(h_bufs && h_flags && err_dev, "vn_p2p_init: null argument");
-    g_ctx.rank = rank; g_ctx.world = world; g_ctx.err = err_dev; g_ctx.epoch = 0;
+    memset(&g_ctx, 0, sizeof(g_ctx));
+    g_ctx.rank = rank; g_ctx.world = world; g_ctx.err = err_dev; g_ctx.epoch = 0; g_ctx.small_ops = 0;
     for (int p = 0; p < world; ++p) {
         VN_REQUIRE(h_bufs[p] && h_flags[p], "vn_p2p_init: null peer pointer");
         VN_REQUIRE(vn_aligned(h_bufs[p], 16), "vn_p2p_init: buffers must be 16-byte aligned");
@@ -136,5 +231,67 @@ VN_API int vn_p2p_allreduce(int64_t n, void* stream) {
     VN_CHECK_LAUNCH("p2p_all_gather_kernel");
     p2p_barrier_kernel<<<1, 32, 0, st>>>(g_ctx, e + 3);                      // nobody reads my buffer any more
     VN_CHECK_LAUNCH("p2p_barrier_kernel");
+    return VN_OK;
+}
+
+VN_API int vn_p2p_attach(void* const* h_pbufs, void* const* h_mbox) {
+    VN_REQUIRE(g_ctx_ready, "vn_p2p_attach: vn_p2p_init has not been called");
+    VN_REQUIRE(h_mbox != nullptr, "vn_p2p_attach: null mailbox list");
+    for (int p = 0; p < g_ctx.world; ++p) {
+        VN_REQUIRE(h_mbox[p] && vn_aligned(h_mbox[p], 16), "vn_p2p_attach: null / misaligned mailbox");
+        g_ctx.mbox[p] = (float*)h_mbox[p];
+        if (h_pbufs) {
+            VN_REQUIRE(h_pbufs[p] && vn_aligned(h_pbufs[p], 16), "vn_p2p_attach: null / misaligned parameter buffer");
+            g_ctx.pbufs[p] = (float*)h_pbufs[p];
+        }
+    }
+    return VN_OK;
+}
+
+VN_API int vn_p2p_allreduce_small(float* data, int n, int use_max, void* stream) {
+    VN_REQUIRE(g_ctx_ready && g_ctx.mbox[0], "vn_p2p_allreduce_small: vn_p2p_init / vn_p2p_attach have not been called");
+    VN_REQUIRE(data && n >= 1 && n <= VN_P2P_MBOX, "vn_p2p_allreduce_small: n must be in [1,%d]", VN_P2P_MBOX);
+    if (g_ctx.world == 1) return VN_OK;
+    const int e = ++g_ctx.epoch;
+    const int parity = (g_ctx.small_ops++) & 1;
+    p2p_exchange_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(g_ctx, e, parity, data, n, use_max);
+    VN_CHECK_LAUNCH("p2p_exchange_kernel");
+    return VN_OK;
+}
+
+VN_API int vn_p2p_reduce_adam(int64_t n, float* m, float* v, float lr, float beta1, float beta2, float eps, int step,
+                              float* found_inf, float* scale_dev, int32_t* growth_tracker, void* stream) {
+    VN_REQUIRE(g_ctx_ready && g_ctx.mbox[0] && g_ctx.pbufs[0],
+               "vn_p2p_reduce_adam: vn_p2p_init / vn_p2p_attach (with parameter buffers) have not been called");
+    VN_REQUIRE(n >= 0 && n % 4 == 0 && step >= 1, "vn_p2p_reduce_adam: n must be a multiple of 4 floats, step >= 1");
+    VN_REQUIRE(m && v && found_inf && scale_dev && growth_tracker, "vn_p2p_reduce_adam: null pointer");
+    VN_REQUIRE(vn_aligned(m, 16) && vn_aligned(v, 16), "vn_p2p_reduce_adam: m / v must be 16-byte aligned");
+    if (n == 0) return VN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n4 = n / 4;
+    const int64_t chunk4 = (n4 + g_ctx.world - 1) / g_ctx.world;
+    const int sms = vn_sm_count();
+    AdamCfg c;
+    c.inv_scale = 1.0f;
+    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    c.beta1 = beta1; c.beta2 = beta2; c.omb1 = 1.0f - beta1; c.omb2 = 1.0f - beta2; c.eps = eps;
+    c.step_size = (float)((double)lr / bc1);
+    c.bc2_sqrt = (float)sqrt(bc2);
+    const int e = g_ctx.epoch;
+    g_ctx.epoch += 3;
+    const int parity = (g_ctx.small_ops++) & 1;
+    p2p_barrier_kernel<<<1, 32, 0, st>>>(g_ctx, e + 1);                      // every rank's gradients are complete
+    VN_CHECK_LAUNCH("p2p_barrier_kernel");
+    p2p_reduce_check_kernel<<<sms, 512, 0, st>>>(g_ctx, n4, chunk4, found_inf);
+    VN_CHECK_LAUNCH("p2p_reduce_check_kernel");
+    // every slice is reduced (nobody reads a peer's gradient after this) + global OR of the inf flags
+    p2p_exchange_kernel<<<1, 32, 0, st>>>(g_ctx, e + 2, parity, found_inf, 1, 1);
+    VN_CHECK_LAUNCH("p2p_exchange_kernel");
+    p2p_adam_push_kernel<<<sms, 512, 0, st>>>(g_ctx, n4, chunk4, m, v, c, found_inf, scale_dev);
+    VN_CHECK_LAUNCH("p2p_adam_push_kernel");
+    p2p_barrier_kernel<<<1, 32, 0, st>>>(g_ctx, e + 3);                      // every replica holds every updated slice
+    VN_CHECK_LAUNCH("p2p_barrier_kernel");
+    p2p_scaler_update_kernel<<<1, 1, 0, st>>>(scale_dev, growth_tracker, found_inf, 2.0f, 0.5f, 2000);
+    VN_CHECK_LAUNCH("p2p_scaler_update_kernel");
     return VN_OK;
 }

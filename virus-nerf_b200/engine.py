@@ -155,11 +155,30 @@ class TrainEngine:
         self._comm_stream = torch.cuda.Stream(device=self.device) if world_size > 1 else None
         # gradient exchange: NCCL allreduce, or the library's own peer-memory allreduce (csrc/p2p_allreduce.cu;
         # standalone on 8 B200: 0.193 ms vs 0.209 ms NCCL for the 45.7 MB buffer; slower than NCCL at 2-4 ranks)
+        #   "p2p_fused": sharded optimiser fused with the exchange (csrc/p2p_allreduce.cu, vn_p2p_reduce_adam):
+        #   rank r reduces slice r of the gradient over peer memory, runs Adam on it with rank-local m / v and
+        #   pushes the updated parameters into every replica; the loss normalisers go through the same mailboxes
         self._p2p = None
-        if world_size > 1 and comm == "p2p":          # "auto" = NCCL: the two are within noise in the full step
-            self._p2p_flags = torch.zeros(world_size, dtype=torch.int32, device=self.device)
-            self._p2p_err = torch.zeros(1, dtype=torch.int32, device=self.device)
-            self._p2p = _lib.p2p_setup(self.flat_g, self._p2p_flags, self._p2p_err, rank, world_size)
+        self.comm = comm if world_size > 1 else "none"
+        if world_size > 1 and comm in ("auto", "p2p", "p2p_fused"):
+            try:
+                self._p2p_flags = torch.zeros(world_size, dtype=torch.int32, device=self.device)
+                self._p2p_err = torch.zeros(1, dtype=torch.int32, device=self.device)
+                self._p2p_mbox = torch.zeros(2, world_size, 8, device=self.device)
+                self._p2p = _lib.p2p_setup(self.flat_g, self._p2p_flags, self._p2p_err, rank, world_size,
+                                           params=self.flat_p, mbox=self._p2p_mbox)
+                ok = torch.ones(1, device=self.device)
+            except RuntimeError as e:                  # e.g. no peer access between the GPUs of this box
+                if comm != "auto":
+                    raise
+                self._p2p, ok = None, torch.zeros(1, device=self.device)
+                self._p2p_warning = str(e)
+            if comm == "auto":                         # measured (profiles/r1_bench.md): fused beats NCCL + dense Adam
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)          # every rank must take the same path
+                self.comm = "p2p_fused" if float(ok) == 1.0 else "nccl"
+                if self.comm == "nccl":
+                    self._p2p = None
+        self._p2p_fused = self.comm == "p2p_fused"
         self._hash_slice_idx = [i for i, p in enumerate(params) if p is enc.hash_table][0]
         self._structs = [self._new_step_struct(), self._new_step_struct()] if self.device.type == "cuda" else None
 
@@ -315,12 +334,20 @@ class TrainEngine:
             return self._loss_out[0]
         # ---- data parallel ----------------------------------------------------------------
         _lib.call("vn_train_step_run", st, S, 1, 0)
-        dist.all_reduce(self._loss_acc[4:])                               # global normalisers
+        if self._p2p_fused:                                               # global normalisers
+            _lib.call("vn_p2p_allreduce_small", self._loss_acc[4:], 4, 0)
+        else:
+            dist.all_reduce(self._loss_acc[4:])
         _lib.call("vn_train_step_run", st, S, 2, 0)
         ev = torch.cuda.Event(); ev.record()
         self._comm_stream.wait_event(ev)
         with torch.cuda.stream(self._comm_stream):
-            if self._p2p is not None:                                     # own two-shot allreduce over NVLink peer memory
+            if self._p2p_fused:                                           # reduce-scatter + Adam + parameter push
+                _lib.call("vn_p2p_reduce_adam", self.n_params, self.flat_m, self.flat_v, self.lr, self.betas[0],
+                          self.betas[1], self.eps, self.adam_step, self.found_inf, self.scale, self.growth_tracker)
+                work = None
+                done = torch.cuda.Event(); done.record()
+            elif self._p2p is not None:                                   # own two-shot allreduce over NVLink peer memory
                 _lib.call("vn_p2p_allreduce", self.n_params)
                 work = None
                 done = torch.cuda.Event(); done.record()
@@ -332,7 +359,8 @@ class TrainEngine:
             work.wait()
         else:
             torch.cuda.current_stream().wait_event(done)
-        _lib.call("vn_train_step_optim", st)
+        if not self._p2p_fused:
+            _lib.call("vn_train_step_optim", st)
         if next_data is not None and update_due:
             self._ticket = self.prepare(next_data, elapse_time)
         return self._loss_out[0]

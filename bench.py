@@ -44,6 +44,7 @@ def parse():
                          "with the peer-memory exchange (auto = p2p_fused, nccl if peer mapping fails)")
     ap.add_argument("--enc-layout", default="planar", choices=["planar", "rows"],
                     help="layout of the encoding inside the fused step (rows = the reference's [S,32])")
+    ap.add_argument("--two-pass-march", action="store_true", help="re-march in the write pass (reference structure)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end phase (profiling runs only)")
     return ap.parse_args()
 
@@ -196,7 +197,7 @@ def run_ours(a):
         ds = synthetic.SyntheticDataset(scene, pool_size=1 << 18, device=str(dev), pinned=False, seed=21)
         ds.gen.manual_seed(1000 + rank)           # same pool on every rank, different training batches
         eng = TrainEngine(args, ds, dev, world_size=world, rank=rank, autocast=not a.no_autocast, comm=a.comm,
-                          enc_layout=a.enc_layout)
+                          enc_layout=a.enc_layout, single_pass_march=not a.two_pass_march)
         host_batches = None
         dev_batches = None
         if not pinned:

@@ -136,6 +136,20 @@ int vn_march_train_write(const float* rays_o, const float* rays_d, const float* 
                          int grid_size, float scale, float exp_step_factor, const int32_t* rays_a,
                          int64_t capacity, float* xyzs, float* dirs, float* deltas, float* ts,
                          float* xyzs_unit, void* stream);
+/* single-pass variant of a6 used by the native step runner: _count_rows = _count that also
+ * stores the t of emitted sample k of ray r in ts_rows[r * max_samples + k]; _expand = pass 2
+ * without a second march: every output of :84-124 is a function of (ray, t) -- xyz = o + t d
+ * (:45), dt = calc_dt(t) (:46) -- evaluated with the same IEEE operations, so the result is
+ * bit-identical to _write. */
+int vn_march_train_count_rows(const float* rays_o, const float* rays_d, const float* hits_t,
+                              const uint8_t* bitfield, const float* noise, int64_t N, int cascades,
+                              int grid_size, float scale, float exp_step_factor, int max_samples,
+                              int32_t* counts, int32_t* rays_a, int32_t* counter,
+                              int32_t* scan_tmp, float* ts_rows, void* stream);
+int vn_march_train_expand(const float* rays_o, const float* rays_d, const int32_t* rays_a,
+                          const float* ts_rows, int64_t N, int max_samples, int grid_size,
+                          float scale, float exp_step_factor, int64_t capacity, float* xyzs,
+                          float* dirs, float* deltas, float* ts, float* xyzs_unit, void* stream);
 
 /* a7. raymarching_test_kernel, modules/ray_march.py:198-269.  alive [A] i64; slot layout
  * n*max_samples+s; ray_indices i64, valid_mask u8 (caller zeroes), deltas/ts f32, all
@@ -296,6 +310,10 @@ typedef struct vn_step {
     float w_color, w_uss, w_tof, w_rgbd;
     float *scale_dev, *found_inf; int32_t* growth_tracker;
     float lr, beta1, beta2, eps; int32_t adam_step;
+    /* optional [N, max_samples] scratch: when set, _prepare records the sample positions along each
+     * ray (vn_march_train_count_rows) and _run expands them (vn_march_train_expand) instead of
+     * marching a second time */
+    float* ts_rows;
 } vn_step_t;
 
 int vn_train_step_prepare(const vn_step_t* h_step, void* stream);

@@ -151,8 +151,8 @@ def test_occupancy_update_runs_and_is_deterministic(setup):
     assert not torch.equal(g0, g1)
 
 
-@pytest.mark.parametrize("enc_layout", ["planar", "rows"])
-def test_fast_step_matches_autograd_step(monkeypatch, enc_layout):
+@pytest.mark.parametrize("enc_layout,single_pass", [("planar", True), ("rows", False)])
+def test_fast_step_matches_autograd_step(monkeypatch, enc_layout, single_pass):
     """the hand-chained C-ABI step (engine.step_fast) and the autograd step through the drop-in
     modules produce the same loss, gradients and parameter update (same rays, same jitter)"""
     from virus_nerf_b200 import synthetic
@@ -161,7 +161,7 @@ def test_fast_step_matches_autograd_step(monkeypatch, enc_layout):
     args = synthetic.make_args(device=DEV, batch_size=512)
     ds = synthetic.SyntheticDataset(pool_size=1 << 13, n_images=8, device=DEV)
     e1 = TrainEngine(args, ds, DEV)
-    e2 = TrainEngine(args, ds, DEV, enc_layout=enc_layout)
+    e2 = TrainEngine(args, ds, DEV, enc_layout=enc_layout, single_pass_march=single_pass)
     assert torch.equal(e1.flat_p, e2.flat_p)
     e1.step_idx = e2.step_idx = 1                       # no occupancy update (it draws random numbers)
     e1._prep_step = e2._prep_step = 1

@@ -272,6 +272,53 @@ def test_march_train_bit_exact(vn, oracle_mod, scene_rays, bf_name, scale, esf, 
     np.testing.assert_array_equal(N(dirs), o_dirs)
 
 
+@pytest.mark.parametrize("bf_name", ["carved", "full", "random"])
+@pytest.mark.parametrize("scale,esf,cascades", [(0.5, 0.0, 1), (2.0, 1 / 256, 3)])
+@pytest.mark.parametrize("tile", [1, 6])          # 6 x 3070 rays >= 16384: the thread-per-ray marcher
+def test_march_single_pass_equals_two_pass(vn, scene_rays, bf_name, scale, esf, cascades, tile):
+    """vn_march_train_count_rows + vn_march_train_expand (the fast step's single-pass march) produce
+    bit-identical rays_a / xyzs / dirs / deltas / ts / unit positions to count + write (which the tests
+    above pin to the oracle)"""
+    ro, rd, bfs = scene_rays
+    bf = bfs[bf_name]
+    if cascades > 1:
+        bf = np.concatenate([bf] + [np.random.default_rng(c).integers(0, 256, bf.shape[0]).astype(np.uint8)
+                                    for c in range(1, cascades)])
+    ro, rd = np.tile(ro, (tile, 1)), np.tile(rd, (tile, 1))
+    n = ro.shape[0]
+    o, d, b = T(ro), T(rd), T(bf)
+    noise = T(np.random.default_rng(7).random(n).astype(np.float32))
+    hits = torch.empty(n, 2, device=DEV)
+    vn.call("vn_ray_aabb", o, d, scale, n, hits)
+    res = []
+    for single in (False, True):
+        counts = torch.empty(n, dtype=torch.int32, device=DEV)
+        rays_a = torch.empty(n, 3, dtype=torch.int32, device=DEV)
+        counter = torch.zeros(2, dtype=torch.int32, device=DEV)
+        tmp = torch.empty(vn.scan_tmp_ints(n), dtype=torch.int32, device=DEV)
+        rows = torch.full((n, 1024), float("nan"), device=DEV)
+        if single:
+            vn.call("vn_march_train_count_rows", o, d, hits, b, noise, n, cascades, 128, scale, esf, 1024, counts, rays_a,
+                    counter, tmp, rows)
+        else:
+            vn.call("vn_march_train_count", o, d, hits, b, noise, n, cascades, 128, scale, esf, 1024, counts, rays_a,
+                    counter, tmp)
+        S = int(counter[0])
+        outs = [torch.full((S, 3), float("nan"), device=DEV), torch.full((S, 3), float("nan"), device=DEV),
+                torch.full((S,), float("nan"), device=DEV), torch.full((S,), float("nan"), device=DEV),
+                torch.full((S, 3), float("nan"), device=DEV)]
+        if single:
+            vn.call("vn_march_train_expand", o, d, rays_a, rows, n, 1024, 128, scale, esf, S, *outs)
+        else:
+            vn.call("vn_march_train_write", o, d, hits, b, noise, n, cascades, 128, scale, esf, rays_a, S, *outs)
+        res.append((S, rays_a, outs))
+    assert res[0][0] == res[1][0] > 0
+    assert torch.equal(res[0][1], res[1][1])
+    for a, c in zip(res[0][2], res[1][2]):
+        assert not torch.isnan(c).any()
+        assert torch.equal(a, c)
+
+
 def test_march_train_max_samples_and_empty(vn, oracle_mod, scene_rays):
     from virus_nerf_b200.modules.ray_march import raymarching_train
     ro, rd, bfs = scene_rays

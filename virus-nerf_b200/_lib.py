@@ -60,7 +60,8 @@ class Step(ctypes.Structure):
         [("loss_acc", _P), ("loss_out", _P)] +
         [("w_color", _F), ("w_uss", _F), ("w_tof", _F), ("w_rgbd", _F)] +
         [("scale_dev", _P), ("found_inf", _P), ("growth_tracker", _P)] +
-        [("lr", _F), ("beta1", _F), ("beta2", _F), ("eps", _F), ("adam_step", _I32)])
+        [("lr", _F), ("beta1", _F), ("beta2", _F), ("eps", _F), ("adam_step", _I32)] +
+        [("ts_rows", _P)])
 
     def set_ptrs(self, **tensors):
         for k, t in tensors.items():
@@ -86,6 +87,8 @@ _SPECS = {
     "vn_ray_aabb": "ppflps",
     "vn_march_train_count": "pppppliiffipppps",
     "vn_march_train_write": "ppppp" "liiff" "pl" "ppppp" "s",
+    "vn_march_train_count_rows": "pppppliiffippppps",
+    "vn_march_train_expand": "pppp" "liiff" "l" "ppppp" "s",
     "vn_march_test": "pppp" "lp" "iiffi" "ppppp" "s",
     "vn_march_test_compact": "plippppppppps",
     "vn_composite_train_fwd": "ppppp" "llf" "ppppp" "s",

@@ -287,6 +287,8 @@ __global__ void __launch_bounds__(256) march_warp_kernel(const float* __restrict
                 }
             }
         }
+        if (!WRITE && ts != nullptr && ((emit >> lane) & 1u))      // single-pass mode: row r of ts [N, max_samples]
+            ts[r * max_samples + n + __popc(emit & ((1u << lane) - 1u))] = ti;
         n += __popc(emit);
         if (done) break;
         t = t_after;
@@ -328,6 +330,7 @@ __global__ void __launch_bounds__(128) march_thread_kernel(const float* __restri
                     if (xyzs_unit) write_unit(c, xyzs_unit + 3 * s, xyz);
                 }
             }
+            if (!WRITE && ts != nullptr) ts[r * max_samples + n] = t;
             t = vn_add(t, dt); ++n;
         } else t = tn;
     }
@@ -419,10 +422,10 @@ __global__ void __launch_bounds__(256) fill_rays_a_kernel(const int32_t* __restr
     if (r == N - 1) { counter[0] = st + cnt; counter[1] = (int32_t)N; }
 }
 
-VN_API int vn_march_train_count(const float* rays_o, const float* rays_d, const float* hits_t, const uint8_t* bitfield,
-                                const float* noise, int64_t N, int cascades, int grid_size, float scale,
-                                float exp_step_factor, int max_samples, int32_t* counts, int32_t* rays_a,
-                                int32_t* counter, int32_t* scan_tmp, void* stream) {
+static int march_count_impl(const float* rays_o, const float* rays_d, const float* hits_t, const uint8_t* bitfield,
+                            const float* noise, int64_t N, int cascades, int grid_size, float scale,
+                            float exp_step_factor, int max_samples, int32_t* counts, int32_t* rays_a,
+                            int32_t* counter, int32_t* scan_tmp, float* ts_rows, void* stream) {
     VN_REQUIRE(N >= 0, "vn_march_train_count: N < 0");
     VN_REQUIRE(counter != nullptr, "vn_march_train_count: null counter");
     cudaStream_t st = (cudaStream_t)stream;
@@ -437,17 +440,84 @@ VN_API int vn_march_train_count(const float* rays_o, const float* rays_d, const 
     if (N < kWarpMarchMaxRays)
         march_warp_kernel<false><<<vn_blocks(N * 32, 256), 256, 0, st>>>(rays_o, rays_d, (const float2*)hits_t, bitfield,
                                                                          noise, N, c, max_samples, counts, nullptr, 0,
-                                                                         nullptr, nullptr, nullptr, nullptr, nullptr);
+                                                                         nullptr, nullptr, nullptr, ts_rows, nullptr);
     else
         march_thread_kernel<false><<<vn_blocks(N, 128), 128, 0, st>>>(rays_o, rays_d, (const float2*)hits_t, bitfield, noise,
                                                                       N, c, max_samples, counts, nullptr, 0, nullptr,
-                                                                      nullptr, nullptr, nullptr, nullptr);
+                                                                      nullptr, nullptr, ts_rows, nullptr);
     VN_CHECK_LAUNCH("march kernel <count>");
     int32_t* starts = scan_tmp;
     int rc = exclusive_scan_i32(counts, starts, N, scan_tmp + round_up4(N), st);
     if (rc) return rc;
     fill_rays_a_kernel<<<vn_blocks(N, 256), 256, 0, st>>>(counts, starts, N, rays_a, counter);
     VN_CHECK_LAUNCH("fill_rays_a_kernel");
+    return VN_OK;
+}
+
+VN_API int vn_march_train_count(const float* rays_o, const float* rays_d, const float* hits_t, const uint8_t* bitfield,
+                                const float* noise, int64_t N, int cascades, int grid_size, float scale,
+                                float exp_step_factor, int max_samples, int32_t* counts, int32_t* rays_a,
+                                int32_t* counter, int32_t* scan_tmp, void* stream) {
+    return march_count_impl(rays_o, rays_d, hits_t, bitfield, noise, N, cascades, grid_size, scale, exp_step_factor,
+                            max_samples, counts, rays_a, counter, scan_tmp, nullptr, stream);
+}
+
+// ---- a6, single-pass variant: the count pass also records the t of every emitted sample in
+// row r of ts_rows [N, max_samples]; pass 2 then needs no second march -- every output of
+// ray_march.py:84-124 is a function of (ray, t): xyz = o + t d (:45), dt = calc_dt(t) (:46).
+VN_API int vn_march_train_count_rows(const float* rays_o, const float* rays_d, const float* hits_t,
+                                     const uint8_t* bitfield, const float* noise, int64_t N, int cascades, int grid_size,
+                                     float scale, float exp_step_factor, int max_samples, int32_t* counts,
+                                     int32_t* rays_a, int32_t* counter, int32_t* scan_tmp, float* ts_rows, void* stream) {
+    VN_REQUIRE(N == 0 || ts_rows != nullptr, "vn_march_train_count_rows: null ts_rows");
+    return march_count_impl(rays_o, rays_d, hits_t, bitfield, noise, N, cascades, grid_size, scale, exp_step_factor,
+                            max_samples, counts, rays_a, counter, scan_tmp, ts_rows, stream);
+}
+
+// warp per ray: sample k of ray r -> row rays_a[r,1] + k of the packed outputs
+__global__ void __launch_bounds__(256) march_expand_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                           const int32_t* __restrict__ rays_a, const float* __restrict__ ts_rows,
+                                                           int64_t N, int max_samples, const MarchCfg c, int64_t capacity,
+                                                           float* __restrict__ xyzs, float* __restrict__ dirs,
+                                                           float* __restrict__ deltas, float* __restrict__ ts,
+                                                           float* __restrict__ xyzs_unit) {
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= N) return;
+    const int64_t start = rays_a[3 * r + 1];
+    const int n = rays_a[3 * r + 2];
+    if (n == 0) return;
+    float o[3], d[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { o[k] = __ldg(rays_o + 3 * r + k); d[k] = __ldg(rays_d + 3 * r + k); }
+    const float* row = ts_rows + r * max_samples;
+    for (int k = lane; k < n; k += 32) {
+        const int64_t s = start + k;
+        if (s >= capacity) break;
+        const float t = __ldg(row + k);
+        float xyz[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) xyz[j] = vn_add(o[j], vn_mul(t, d[j]));               // ray_march.py:45
+        xyzs[3 * s] = xyz[0]; xyzs[3 * s + 1] = xyz[1]; xyzs[3 * s + 2] = xyz[2];
+        dirs[3 * s] = d[0]; dirs[3 * s + 1] = d[1]; dirs[3 * s + 2] = d[2];
+        ts[s] = t; deltas[s] = vn_calc_dt(t, c.esf, c.dt_max);                            // :46
+        if (xyzs_unit) write_unit(c, xyzs_unit + 3 * s, xyz);
+    }
+}
+
+VN_API int vn_march_train_expand(const float* rays_o, const float* rays_d, const int32_t* rays_a, const float* ts_rows,
+                                 int64_t N, int max_samples, int grid_size, float scale, float exp_step_factor,
+                                 int64_t capacity, float* xyzs, float* dirs, float* deltas, float* ts, float* xyzs_unit,
+                                 void* stream) {
+    VN_REQUIRE(N >= 0 && capacity >= 0 && max_samples >= 0, "vn_march_train_expand: negative size");
+    if (N == 0 || capacity == 0) return VN_OK;
+    VN_REQUIRE(rays_o && rays_d && rays_a && ts_rows && xyzs && dirs && deltas && ts, "vn_march_train_expand: null pointer");
+    VN_REQUIRE(grid_size >= 1 && grid_size <= 1024, "vn_march_train_expand: bad grid_size");
+    const MarchCfg c = make_cfg(1, grid_size, scale, exp_step_factor);
+    VnProfScope prof(VN_K_MARCH_WRITE, capacity, (cudaStream_t)stream);
+    march_expand_kernel<<<vn_blocks(N * 32, 256), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, rays_a, ts_rows, N, max_samples,
+                                                                                c, capacity, xyzs, dirs, deltas, ts, xyzs_unit);
+    VN_CHECK_LAUNCH("march_expand_kernel");
     return VN_OK;
 }
 

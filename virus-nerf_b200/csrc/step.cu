@@ -7,9 +7,14 @@
 VN_API int vn_train_step_prepare(const vn_step_t* s, void* stream) {
     VN_REQUIRE(s != nullptr, "vn_train_step_prepare: null step");
     VN_TRY(vn_ray_aabb(s->rays_o, s->rays_d, s->scale, s->N, s->hits_t, stream));
-    VN_TRY(vn_march_train_count(s->rays_o, s->rays_d, s->hits_t, s->bitfield, s->noise, s->N, s->cascades, s->grid_size,
-                                s->scale, s->exp_step_factor, s->max_samples, s->counts, s->rays_a, s->counter,
-                                s->scan_tmp, stream));
+    if (s->ts_rows)     // single-pass march: the count pass records the sample positions along each ray
+        VN_TRY(vn_march_train_count_rows(s->rays_o, s->rays_d, s->hits_t, s->bitfield, s->noise, s->N, s->cascades,
+                                         s->grid_size, s->scale, s->exp_step_factor, s->max_samples, s->counts, s->rays_a,
+                                         s->counter, s->scan_tmp, s->ts_rows, stream));
+    else
+        VN_TRY(vn_march_train_count(s->rays_o, s->rays_d, s->hits_t, s->bitfield, s->noise, s->N, s->cascades, s->grid_size,
+                                    s->scale, s->exp_step_factor, s->max_samples, s->counts, s->rays_a, s->counter,
+                                    s->scan_tmp, stream));
     return VN_OK;
 }
 
@@ -37,9 +42,13 @@ VN_API int vn_train_step_run(const vn_step_t* s, int64_t S, int phase, int do_op
     if (phase == 0 || phase == 1) {
         VN_CUDA(cudaMemsetAsync(s->flat_g, 0, sizeof(float) * (size_t)s->n_params, st));
         VN_CUDA(cudaMemsetAsync(s->loss_acc, 0, sizeof(float) * 8, st));
-        VN_TRY(vn_march_train_write(s->rays_o, s->rays_d, s->hits_t, s->bitfield, s->noise, s->N, s->cascades, s->grid_size,
-                                    s->scale, s->exp_step_factor, s->rays_a, S, s->xyzs, s->dirs, s->deltas, s->ts, s->unit,
-                                    stream));
+        if (s->ts_rows)
+            VN_TRY(vn_march_train_expand(s->rays_o, s->rays_d, s->rays_a, s->ts_rows, s->N, s->max_samples, s->grid_size,
+                                         s->scale, s->exp_step_factor, S, s->xyzs, s->dirs, s->deltas, s->ts, s->unit, stream));
+        else
+            VN_TRY(vn_march_train_write(s->rays_o, s->rays_d, s->hits_t, s->bitfield, s->noise, s->N, s->cascades,
+                                        s->grid_size, s->scale, s->exp_step_factor, s->rays_a, S, s->xyzs, s->dirs, s->deltas,
+                                        s->ts, s->unit, stream));
         VN_TRY(vn_hash_encode_fwd_f32(s->unit, table, s->enc, S, &s->levels, s->hash_flags, stream));
         VN_TRY(vn_mlp_fwd(s->enc, enc_fmt, s->dirs, W[0], W[1], W[2], W[3], W[4], S, 0, s->sigmas, s->rgbs, nullptr, stream));
         VN_TRY(vn_composite_train_fwd(s->sigmas, s->rgbs, s->deltas, s->ts, s->rays_a, s->N, S, s->T_threshold, s->vr_samples,

@@ -85,7 +85,8 @@ class _Workspace:
 
 class TrainEngine:
     def __init__(self, args, dataset, device, world_size=1, rank=0, log2_T=19, max_res=1024, half_opt=False,
-                 autocast=True, seed=21, grad_scale=2.0 ** 19, comm="auto", enc_layout="planar"):
+                 autocast=True, seed=21, grad_scale=2.0 ** 19, comm="auto", enc_layout="planar",
+                 single_pass_march=True):
         self.args = args
         self.device = torch.device(device)
         self.world_size, self.rank = world_size, rank
@@ -95,6 +96,9 @@ class TrainEngine:
         # "planar" = [8][S] float4 level-pair planes (coalesced on both sides), "rows" = the reference's [S,32]
         assert enc_layout in ("planar", "rows")
         self.enc_planar = enc_layout == "planar"
+        # single-pass march of the fast step: the count pass stores t of every sample in a [N, 1024] scratch and
+        # the write pass only expands it (bit-identical to re-marching); capped at 64 Ki rays (256 MB scratch x 2)
+        self.single_pass_march = single_pass_march
         torch.manual_seed(seed)          # identical replicas on every rank
         self.model = NGP(scale=args.model.scale, pos_encoder_type='hash', levels=args.model.hash_levels,
                          max_res=max_res, log2_T=log2_T, half_opt=half_opt, args=args, dataset=dataset)
@@ -276,6 +280,7 @@ class TrainEngine:
                         rays_a=ws.get(f"rays_a{par}", N, 3, torch.int32),
                         scan_tmp=ws.get(f"scan_tmp{par}", _lib.scan_tmp_ints(N), None, torch.int32),
                         counter=self._counters[par], bitfield=m.occupancy_grid.getBitfield(),
+                        ts_rows=ws.get(f"ts_rows{par}", N * 1024) if (self.single_pass_march and N <= 65536) else None,
                         vr_samples=ws.get("vr", N, None, torch.int32), opacity=ws.get("op", N), depth=ws.get("dp", N),
                         rgb=ws.get("rgb", N, 3), d_rgb=ws.get("d_rgb", N, 3), d_depth=ws.get("d_dp", N),
                         d_opacity=ws.get("d_op", N))

@@ -356,6 +356,51 @@ int vn_p2p_reduce_adam(int64_t n, float* m, float* v, float lr, float beta1, flo
                        int step, float* found_inf, float* scale_dev, int32_t* growth_tracker,
                        void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * (f) row 2. Batch assembly on the device -- the gather half of DatasetBase.__call__
+ * (datasets/dataset_base.py:23-76), _calcRayPoses (:194-243) and get_rays
+ * (datasets/ray_utils.py:51-80): rays_o = c2w[:, 3], rays_d = directions[pix] @ c2w[:, :3]^T,
+ * rgb / depth gathers.  img_idxs, pix_idxs [B] i32 (the Sampler's dtype, training/sampler.py:111);
+ * poses [N_img,3,4]; cam_slot [N_img] = row of directions [n_cams, HW, 3] of the image's camera
+ * (the sensor_ids == id masks of :218-231); rgbs [N_img, HW, rgb_stride >= 3]; depth0..3 up to four
+ * [N_img, HW] sensor maps (NULL = absent, then out_depthK must be NULL).  An out-of-range index or
+ * camera leaves NaN in the ray (:207-208) and sets err[0] = 1 (err may be NULL).
+ * ------------------------------------------------------------------------------------- */
+int vn_batch_assemble(const int32_t* img_idxs, const int32_t* pix_idxs, int64_t B, const float* poses,
+                      const int32_t* cam_slot, int64_t n_imgs, const float* directions, int n_cams,
+                      int64_t HW, const float* rgbs, int rgb_stride, const float* depth0,
+                      const float* depth1, const float* depth2, const float* depth3,
+                      const int32_t* sensor_ids, const float* times, float* rays_o, float* rays_d,
+                      float* rgb, float* out_depth0, float* out_depth1, float* out_depth2,
+                      float* out_depth3, int32_t* ids_out, float* time_out, int32_t* err, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * (f) row 3. NGPGrid, modules/ngp_grid.py:37-152 (the Instant-NGP baseline grid of the ablation).
+ *  vn_ngp_sample_occupied: indices2 = nonzero(occ > thr)[randint(len, (M,))] (:53-60) without the
+ *      host sync of nonzero: indices_out[i] = Morton index of the (rand_idx[i] mod count)-th
+ *      occupied cell, -1 when none is occupied.  tmp: >= vn_ngp_select_tmp_ints(n_cells) i32.
+ *  vn_ngp_cell_positions: xyzs_w = (coords/(G-1)*2-1)*span + (noise*2-1)*half_cell (:139-143), one
+ *      IEEE operation per torch op; span = (float)(s - s/G), half_cell = (float)(s/G).
+ *  vn_ngp_grid_update: tmp[indices] = sigmas (duplicates: largest position wins, the CPU
+ *      index_put_ order; indices < 0 are skipped), then occ = occ < 0 ? occ : max(occ * decay, tmp)
+ *      (:148-152) and tmp is re-zeroed.  winner: [n_cells] i32 filled with -1 (restored on exit);
+ *      decay_cells: optional per-cell decay (the `erode` branch, :146-147).
+ *  vn_ngp_threshold_pack: thr_out = (mean(occ[occ > 0]), min(mean, density_threshold)) (:155-156,
+ *      deterministic double-precision mean) and bitfield = packbits(occ, threshold) (:159-163) over
+ *      n_cells_total cells.  scratch: >= vn_ngp_threshold_tmp_bytes() bytes, 8-byte aligned.
+ * ------------------------------------------------------------------------------------- */
+int64_t vn_ngp_select_tmp_ints(int64_t n_cells);
+int vn_ngp_sample_occupied(const float* occ, int64_t n_cells, float threshold, const int64_t* rand_idx,
+                           int64_t M, int32_t* tmp, int64_t* indices_out, void* stream);
+int vn_ngp_cell_positions(const int32_t* coords, const float* noise, int64_t M, int grid_size,
+                          float span, float half_cell, float* xyzs_w, void* stream);
+int vn_ngp_grid_update(float* occ, float* tmp, int32_t* winner, int64_t n_cells, const int64_t* indices,
+                       const float* sigmas, int64_t M, float decay, const float* decay_cells,
+                       void* stream);
+int64_t vn_ngp_threshold_tmp_bytes(void);
+int vn_ngp_threshold_pack(const float* occ, int64_t n_cells_total, float density_threshold,
+                          void* scratch, float* thr_out, uint8_t* bitfield, void* stream);
+
 /* tcgen05 self-test (development / CI): one 128 x N x K fp16 product through the tensor
  * cores in the three operand modes the fused MLP uses (0 forward A*B^T, 1 dgrad A*B,
  * 2 wgrad A^T*B); A, B fp16 row-major as stored, D [128,N] f32. */

@@ -115,6 +115,11 @@ _SPECS = {
     "vn_p2p_allreduce": "ls",
     "vn_p2p_allreduce_small": "piis",
     "vn_p2p_reduce_adam": "lpp" "ffff" "i" "ppp" "s",
+    "vn_batch_assemble": "ppl" "ppl" "pil" "pi" "pppp" "pp" "ppp" "pppp" "pp" "p" "s",
+    "vn_ngp_sample_occupied": "plfplpps",
+    "vn_ngp_cell_positions": "ppliffps",
+    "vn_ngp_grid_update": "ppplpplfps",
+    "vn_ngp_threshold_pack": "plfppps",
     "vn_mlp_fwd": "pip" "ppppp" "li" "ppp" "s",
     "vn_mlp_bwd": "pip" "ppppp" "li" "pp" "p" "ppppp" "s",
 }
@@ -144,6 +149,8 @@ def lib():
         L.vn_last_error.restype = ctypes.c_char_p
         L.vn_abi_version.restype = ctypes.c_int
         L.vn_march_scan_tmp_ints.restype = ctypes.c_int64
+        L.vn_ngp_select_tmp_ints.restype = ctypes.c_int64
+        L.vn_ngp_threshold_tmp_bytes.restype = ctypes.c_int64
         L.vn_march_scan_tmp_ints.argtypes = [ctypes.c_int64]
         L.vn_launch_count.restype = ctypes.c_int64
         for name, spec in _SPECS.items():
@@ -247,6 +254,14 @@ def launch_count():
     return int(lib().vn_launch_count())
 
 
+def ngp_select_tmp_ints(n_cells):
+    return int(lib().vn_ngp_select_tmp_ints(ctypes.c_int64(int(n_cells))))
+
+
+def ngp_threshold_tmp_bytes():
+    return int(lib().vn_ngp_threshold_tmp_bytes())
+
+
 def scan_tmp_ints(n):
     return int(lib().vn_march_scan_tmp_ints(ctypes.c_int64(int(n))))
 
@@ -264,7 +279,8 @@ def hash_levels(base_res, max_res, levels, max_params):
 
 def exported_symbols():
     """names declared in include/virusnerf.h (used by the CPU-side ABI test)"""
-    return ["vn_last_error", "vn_abi_version", "vn_launch_count", "vn_ipc_get_handle", "vn_ipc_open", "vn_p2p_init", "vn_p2p_attach", "vn_profile_enable", "vn_profile_count", "vn_profile_get", "vn_device_info", "vn_march_scan_tmp_ints"] + list(_SPECS)
+    return ["vn_last_error", "vn_abi_version", "vn_launch_count", "vn_ipc_get_handle", "vn_ipc_open", "vn_p2p_init", "vn_p2p_attach", "vn_profile_enable", "vn_profile_count", "vn_profile_get", "vn_device_info", "vn_march_scan_tmp_ints",
+            "vn_ngp_select_tmp_ints", "vn_ngp_threshold_tmp_bytes"] + list(_SPECS)
 
 
 _ipc_opened = {}   # 64-byte IPC handle -> mapped base pointer (a handle may be opened once per process)

@@ -111,7 +111,10 @@ class TrainEngine:
         self.model.fused_mlp = self.model.fused_mlp and autocast   # fp32 mode (tests): torch.nn.Linear fp32
         self.loss_fn = Loss(args)
         self.step_idx = 0
-        self.grid_update_interval = args.occ_grid.update_interval
+        self.grid_type = getattr(args.model, "grid_type", "occ")
+        # trainer_base.py:85-88
+        self.grid_update_interval = (args.ngp_grid if self.grid_type == "ngp" else args.occ_grid).update_interval
+        self._grid_updates = 0
         self.lr, self.betas, self.eps = args.training.lr, (0.9, 0.999), 1e-15   # trainer.py:53-57
 
         # ---- flat parameter / gradient / Adam state ------------------------------------
@@ -188,8 +191,15 @@ class TrainEngine:
 
     # ------------------------------------------------------------------------------------
     def occupancy_update(self, elapse_time=0.0):
+        """trainer.py:106-119"""
+        step = self._grid_updates * self.grid_update_interval          # the train step this update belongs to
+        self._grid_updates += 1
         with torch.autocast(device_type='cuda', dtype=torch.float16, enabled=self.autocast):
-            self.model.updateOccGrid(density_threshold=0.5, elapse_time=elapse_time)
+            if self.grid_type == "ngp":
+                self.model.updateNeRFGrid(density_threshold=0.01 * 1024 / 3 ** 0.5,
+                                          warmup=step < self.args.ngp_grid.warmup_steps)
+            else:
+                self.model.updateOccGrid(density_threshold=0.5, elapse_time=elapse_time)
 
     def forward_loss(self, data):
         with torch.autocast(device_type='cuda', dtype=torch.float16, enabled=self.autocast):

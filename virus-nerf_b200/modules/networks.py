@@ -194,9 +194,11 @@ class NGP(nn.Module):
             from .occupancy_grid import OccupancyGrid
             self.occupancy_grid = OccupancyGrid(args=args, grid_size=self.grid_size, scene=scene, dataset=dataset,
                                                 fct_density=self.density)
+        elif args is not None and self.args.model.grid_type == 'ngp':                  # networks.py:117-122
+            from .ngp_grid import NGPGrid
+            self.occupancy_grid = NGPGrid(args=args, grid_size=self.grid_size, fct_density=self.density)
         elif args is not None:
-            raise NotImplementedError(f"grid_type {self.args.model.grid_type} not implemented "
-                                      "(NGPGrid is a 'next' row, SURVEY section 8(f))")
+            raise NotImplementedError(f"grid_type {self.args.model.grid_type} not implemented")
 
     def density(self, x, return_feat=False):
         """networks.py:134-148"""
@@ -230,6 +232,10 @@ class NGP(nn.Module):
         return sigmas, rgbs
 
     @torch.no_grad()
+    def updateNeRFGrid(self, density_threshold, warmup=False, decay=0.95, erode=False):
+        """networks.py:166-178"""
+        self.occupancy_grid.update(density_threshold=density_threshold, warmup=warmup, decay=decay, erode=erode)
+
     def updateOccGrid(self, density_threshold: float, elapse_time: float):
         """networks.py:180-191"""
         self.occupancy_grid.update(elapse_time=elapse_time)

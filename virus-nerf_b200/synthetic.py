@@ -32,6 +32,7 @@ def make_args(device="cuda", scale=0.5, sensors=("USS", "ToF"), grid_type="occ",
         training=SimpleNamespace(sensors=list(sensors), batch_size=batch_size, lr=lr, debug_mode=False,
                                  color_loss_w=1.0, tof_loss_w=50.0, uss_loss_w=50.0, rgbd_loss_w=100.0,
                                  sampling_strategy={"imgs": "all", "pixs": {"valid_uss": 0.4, "valid_tof": 0.4}}),
+        ngp_grid=SimpleNamespace(update_interval=16, warmup_steps=256),     # args/ethz_usstof_win.json:61-65
         occ_grid=SimpleNamespace(batch_size=occ_batch_size, update_interval=update_interval,
                                  decay_warmup_steps=decay_warmup_steps, batch_ratio_ray_update=0.5,
                                  false_detection_prob_every_m=0.3, std_every_m=0.2, nerf_pos_noise_every_m=0.2,

@@ -58,6 +58,11 @@ int64_t vn_launch_count(void);
  * bwd, 2 MLP fwd, 3 MLP bwd, 4 march count, 5 march write, 6 composite fwd, 7 composite bwd,
  * 8 Adam. */
 int vn_profile_enable(int on);
+/* the same restricted to the kernel ids whose bit is set in `mask` (bit k = kernel id k) */
+int vn_profile_enable_mask(unsigned mask);
+/* programmatic dependent launch between the kernels of the train step (default on; VN_PDL=0 in the
+ * environment or vn_set_pdl(0) launches them with plain stream order) */
+int vn_set_pdl(int on);
 int vn_profile_count(void);
 int vn_profile_get(int i, int* h_kernel_id, int64_t* h_size, float* h_ms);
 /* SM count / device name of the current device; proves the library talks to a GPU */

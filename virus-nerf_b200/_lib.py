@@ -184,9 +184,20 @@ KERNEL_NAMES = ["hash_encode_fwd", "hash_encode_bwd", "mlp_fwd", "mlp_bwd", "mar
                 "composite_fwd", "composite_bwd", "adam"]
 
 
-def profile_start():
-    """bracket every major kernel launch with CUDA events on the launching stream (vn_profile_*)"""
-    lib().vn_profile_enable(1)
+def profile_start(kernels=None):
+    """bracket the launches of the major kernels (all, or the named ones) with CUDA events on the
+    launching stream (vn_profile_*)"""
+    if kernels is None:
+        lib().vn_profile_enable(1)
+    else:
+        mask = 0
+        for k in kernels:
+            mask |= 1 << KERNEL_NAMES.index(k)
+        lib().vn_profile_enable_mask(ctypes.c_uint(mask))
+
+
+def set_pdl(on):
+    lib().vn_set_pdl(ctypes.c_int(1 if on else 0))
 
 
 def profile_stop():
@@ -279,7 +290,7 @@ def hash_levels(base_res, max_res, levels, max_params):
 
 def exported_symbols():
     """names declared in include/virusnerf.h (used by the CPU-side ABI test)"""
-    return ["vn_last_error", "vn_abi_version", "vn_launch_count", "vn_ipc_get_handle", "vn_ipc_open", "vn_p2p_init", "vn_p2p_attach", "vn_profile_enable", "vn_profile_count", "vn_profile_get", "vn_device_info", "vn_march_scan_tmp_ints",
+    return ["vn_last_error", "vn_abi_version", "vn_launch_count", "vn_ipc_get_handle", "vn_ipc_open", "vn_p2p_init", "vn_p2p_attach", "vn_profile_enable", "vn_profile_enable_mask", "vn_set_pdl", "vn_profile_count", "vn_profile_get", "vn_device_info", "vn_march_scan_tmp_ints",
             "vn_ngp_select_tmp_ints", "vn_ngp_threshold_tmp_bytes"] + list(_SPECS)
 
 

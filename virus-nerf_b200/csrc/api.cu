@@ -1,6 +1,7 @@
 // api.cu -- error plumbing and device queries of the C ABI (include/virusnerf.h).
 #include "common.cuh"
 #include <string.h>
+#include <stdlib.h>
 
 static thread_local char g_err[512] = "";
 unsigned long long g_vn_launches = 0;
@@ -41,7 +42,9 @@ VN_API int vn_device_info(int* sm_count, int* cc_major, int* cc_minor, char* nam
 }
 
 // ---- in-stream kernel timing -----------------------------------------------------------------
-bool g_vn_profiling = false;
+unsigned g_vn_profiling = 0u;
+static bool pdl_from_env() { const char* e = getenv("VN_PDL"); return !(e && e[0] == '0'); }
+bool g_vn_pdl = pdl_from_env();
 namespace {
 struct ProfRec { int id; int64_t size; cudaEvent_t e0, e1; };
 const int kMaxRecs = 8192;
@@ -50,7 +53,7 @@ int g_nrecs = 0, g_nevents = 0;
 }
 
 void vn_prof_begin(int kernel_id, int64_t size, cudaStream_t st) {
-    if (g_nrecs >= kMaxRecs) { g_vn_profiling = false; return; }
+    if (g_nrecs >= kMaxRecs) { g_vn_profiling = 0u; return; }
     ProfRec& r = g_recs[g_nrecs];
     if (g_nrecs >= g_nevents) { cudaEventCreate(&r.e0); cudaEventCreate(&r.e1); ++g_nevents; }
     r.id = kernel_id; r.size = size;
@@ -62,7 +65,9 @@ void vn_prof_end(cudaStream_t st) {
     ++g_nrecs;
 }
 
-VN_API int vn_profile_enable(int on) { g_vn_profiling = on != 0; if (on) g_nrecs = 0; return VN_OK; }
+VN_API int vn_profile_enable(int on) { g_vn_profiling = on ? 0xffffffffu : 0u; if (on) g_nrecs = 0; return VN_OK; }
+VN_API int vn_profile_enable_mask(unsigned mask) { g_vn_profiling = mask; if (mask) g_nrecs = 0; return VN_OK; }
+VN_API int vn_set_pdl(int on) { g_vn_pdl = on != 0; return VN_OK; }
 VN_API int vn_profile_count(void) { return g_nrecs; }
 VN_API int vn_profile_get(int i, int* kernel_id, int64_t* size, float* ms) {
     VN_REQUIRE(i >= 0 && i < g_nrecs && kernel_id && size && ms, "vn_profile_get: bad index");

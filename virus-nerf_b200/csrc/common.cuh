@@ -44,14 +44,36 @@ extern unsigned long long g_vn_launches;   // kernels launched by this library (
 // ---- optional in-stream kernel timing (CUDA events around a launch; see vn_profile_*) ----
 enum { VN_K_HASH_FWD = 0, VN_K_HASH_BWD, VN_K_MLP_FWD, VN_K_MLP_BWD, VN_K_MARCH_COUNT, VN_K_MARCH_WRITE, VN_K_COMP_FWD,
        VN_K_COMP_BWD, VN_K_ADAM, VN_K_COUNT };
-extern bool g_vn_profiling;
+extern unsigned g_vn_profiling;           // bit k set: kernel id k is timed
 void vn_prof_begin(int kernel_id, int64_t size, cudaStream_t st);
 void vn_prof_end(cudaStream_t st);
 struct VnProfScope {
     cudaStream_t st; bool on;
-    VnProfScope(int id, int64_t size, cudaStream_t s) : st(s), on(g_vn_profiling) { if (on) vn_prof_begin(id, size, st); }
+    VnProfScope(int id, int64_t size, cudaStream_t s) : st(s), on((g_vn_profiling >> id) & 1u) { if (on) vn_prof_begin(id, size, st); }
     ~VnProfScope() { if (on) vn_prof_end(st); }
 };
+
+// ---- programmatic dependent launch (PDL): the kernels of the train step are launched with
+// programmaticStreamSerialization so that the launch latency and the prologue of kernel k+1
+// (index math, weight staging, TMEM allocation) overlap the tail of kernel k.  Every such kernel
+// executes vn_pdl_wait() before it touches memory a predecessor may still be writing (or reading)
+// and vn_pdl_trigger() as early as possible.  VN_PDL=0 in the environment turns the attribute off.
+extern bool g_vn_pdl;
+template <typename... KArgs, typename... Args>
+static inline void vn_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                 Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = g_vn_pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);     // errors surface through cudaGetLastError()
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void vn_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void vn_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
 
 static inline bool vn_aligned(const void* p, size_t a) { return ((uintptr_t)p % a) == 0; }
 static inline unsigned vn_blocks(int64_t n, int per_block) { return (unsigned)((n + per_block - 1) / per_block); }

@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(const float* __restr
                                                             float T_thr, int32_t* __restrict__ total_samples,
                                                             float* __restrict__ opacity, float* __restrict__ depth,
                                                             float* __restrict__ rgb, float* __restrict__ ws) {
+    vn_pdl_trigger(); vn_pdl_wait();          // PDL: see common.cuh
     const int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (n >= N) return;
@@ -100,7 +101,7 @@ VN_API int vn_composite_train_fwd(const float* sigmas, const float* rgbs, const 
     VN_REQUIRE(rays_a && total_samples && opacity && depth && rgb, "vn_composite_train_fwd: null pointer");
     VN_REQUIRE(S == 0 || (sigmas && rgbs && deltas && ts && ws), "vn_composite_train_fwd: null sample pointer");
     VnProfScope prof(VN_K_COMP_FWD, S, (cudaStream_t)stream);
-    composite_fwd_kernel<<<vn_blocks(N * 32, 256), 256, 0, (cudaStream_t)stream>>>(sigmas, rgbs, deltas, ts, rays_a, N, S,
+    vn_launch_pdl(composite_fwd_kernel, dim3(vn_blocks(N * 32, 256)), dim3(256), 0, (cudaStream_t)stream, sigmas, rgbs, deltas, ts, rays_a, N, S,
                                                                                  T_threshold, total_samples, opacity,
                                                                                  depth, rgb, ws);
     VN_CHECK_LAUNCH("composite_fwd_kernel");
@@ -120,6 +121,7 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(const float* __restr
                                                             const float* __restrict__ dL_ddepth, const float* __restrict__ dL_drgb,
                                                             const float* __restrict__ dL_dws, float* __restrict__ dsigmas,
                                                             float* __restrict__ drgbs) {
+    vn_pdl_trigger(); vn_pdl_wait();          // PDL: see common.cuh
     const int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (n >= N) return;
@@ -210,7 +212,7 @@ VN_API int vn_composite_train_bwd(const float* sigmas, const float* rgbs, const 
     VN_REQUIRE(sigmas && rgbs && deltas && ts && rays_a && dL_dopacity && dL_ddepth && dL_drgb && dsigmas && drgbs,
                "vn_composite_train_bwd: null pointer");
     VnProfScope prof(VN_K_COMP_BWD, S, (cudaStream_t)stream);
-    composite_bwd_kernel<<<vn_blocks(N * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+    vn_launch_pdl(composite_bwd_kernel, dim3(vn_blocks(N * 32, 256)), dim3(256), 0, (cudaStream_t)stream, 
         sigmas, rgbs, deltas, ts, rays_a, N, S, T_threshold, dL_dopacity, dL_ddepth, dL_drgb, dL_dws, dsigmas, drgbs);
     VN_CHECK_LAUNCH("composite_bwd_kernel");
     return VN_OK;

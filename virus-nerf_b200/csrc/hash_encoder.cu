@@ -181,6 +181,7 @@ template <typename TT, typename OT, int LPT, bool PLANAR, bool PAIR = false>
 __global__ void __launch_bounds__(256) hash_fwd_kernel(const float* __restrict__ xyz, const TT* __restrict__ table,
                                                        OT* __restrict__ out, int64_t S,
                                                        const __grid_constant__ HashParams P) {
+    vn_pdl_trigger(); vn_pdl_wait();          // PDL: see common.cuh
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= S) return;
     const int level0 = blockIdx.y * LPT;
@@ -340,6 +341,7 @@ template <typename DT, int LPT, bool AGG, bool ZERO_SKIP, bool PLANAR, int MINB 
 __global__ void __launch_bounds__(256, MINB) hash_bwd_kernel(const float* __restrict__ xyz, const DT* __restrict__ dout,
                                                        float* __restrict__ grad, int64_t S,
                                                        const __grid_constant__ HashParams P) {
+    vn_pdl_trigger(); vn_pdl_wait();          // PDL: see common.cuh
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < S;
     const int level0 = P.level_begin + blockIdx.y * LPT;
@@ -454,23 +456,23 @@ static int launch_fwd(const float* xyz, const TT* table, OT* out, int64_t S, con
         if constexpr (sizeof(OT) == 4) {
             const bool pair = (flags & VN_HASH_PAIR_LOADS) != 0;   // the level slabs are 16-byte aligned (sizes % 8 == 0)
             switch (lpt) {
-                case 2: if (pair) hash_fwd_kernel<TT, OT, 2, true, true><<<grid, block, 0, st>>>(xyz, table, out, S, P);
-                        else hash_fwd_kernel<TT, OT, 2, true><<<grid, block, 0, st>>>(xyz, table, out, S, P); break;
-                case 4: if (pair) hash_fwd_kernel<TT, OT, 4, true, true><<<grid, block, 0, st>>>(xyz, table, out, S, P);
-                        else hash_fwd_kernel<TT, OT, 4, true><<<grid, block, 0, st>>>(xyz, table, out, S, P); break;
-                case 8: hash_fwd_kernel<TT, OT, 8, true><<<grid, block, 0, st>>>(xyz, table, out, S, P); break;
-                default: hash_fwd_kernel<TT, OT, 16, true><<<grid, block, 0, st>>>(xyz, table, out, S, P); break;
+                case 2: if (pair) vn_launch_pdl(hash_fwd_kernel<TT, OT, 2, true, true>, dim3(grid), dim3(block), 0, st, xyz, table, out, S, P);
+                        else vn_launch_pdl(hash_fwd_kernel<TT, OT, 2, true>, dim3(grid), dim3(block), 0, st, xyz, table, out, S, P); break;
+                case 4: if (pair) vn_launch_pdl(hash_fwd_kernel<TT, OT, 4, true, true>, dim3(grid), dim3(block), 0, st, xyz, table, out, S, P);
+                        else vn_launch_pdl(hash_fwd_kernel<TT, OT, 4, true>, dim3(grid), dim3(block), 0, st, xyz, table, out, S, P); break;
+                case 8: vn_launch_pdl(hash_fwd_kernel<TT, OT, 8, true>, dim3(grid), dim3(block), 0, st, xyz, table, out, S, P); break;
+                default: vn_launch_pdl(hash_fwd_kernel<TT, OT, 16, true>, dim3(grid), dim3(block), 0, st, xyz, table, out, S, P); break;
             }
         }
         VN_CHECK_LAUNCH("hash_fwd_kernel<planar>");
         return VN_OK;
     }
     switch (lpt) {
-        case 1: hash_fwd_kernel<TT, OT, 1, false><<<grid, block, 0, st>>>(xyz, table, out, S, P); break;
-        case 2: hash_fwd_kernel<TT, OT, 2, false><<<grid, block, 0, st>>>(xyz, table, out, S, P); break;
-        case 4: hash_fwd_kernel<TT, OT, 4, false><<<grid, block, 0, st>>>(xyz, table, out, S, P); break;
-        case 8: hash_fwd_kernel<TT, OT, 8, false><<<grid, block, 0, st>>>(xyz, table, out, S, P); break;
-        default: hash_fwd_kernel<TT, OT, 16, false><<<grid, block, 0, st>>>(xyz, table, out, S, P); break;
+        case 1: vn_launch_pdl(hash_fwd_kernel<TT, OT, 1, false>, dim3(grid), dim3(block), 0, st, xyz, table, out, S, P); break;
+        case 2: vn_launch_pdl(hash_fwd_kernel<TT, OT, 2, false>, dim3(grid), dim3(block), 0, st, xyz, table, out, S, P); break;
+        case 4: vn_launch_pdl(hash_fwd_kernel<TT, OT, 4, false>, dim3(grid), dim3(block), 0, st, xyz, table, out, S, P); break;
+        case 8: vn_launch_pdl(hash_fwd_kernel<TT, OT, 8, false>, dim3(grid), dim3(block), 0, st, xyz, table, out, S, P); break;
+        default: vn_launch_pdl(hash_fwd_kernel<TT, OT, 16, false>, dim3(grid), dim3(block), 0, st, xyz, table, out, S, P); break;
     }
     VN_CHECK_LAUNCH("hash_fwd_kernel");
     return VN_OK;
@@ -499,18 +501,18 @@ static int launch_bwd(const float* xyz, const DT* dout, float* grad, int64_t S, 
             // VN_HASH_TIGHT_REGS: 48 registers (5 CTAs per SM instead of 4) at the price of a few spilled bytes
             const bool tight = (flags & VN_HASH_TIGHT_REGS) != 0;
             switch (lpt) {
-                case 2: if (tight) hash_bwd_kernel<DT, 2, true, ZERO_SKIP, true, 5><<<grid, block, 0, st>>>(xyz, dout, grad, S, P);
-                        else hash_bwd_kernel<DT, 2, true, ZERO_SKIP, true><<<grid, block, 0, st>>>(xyz, dout, grad, S, P); break;
-                case 4: if (tight) hash_bwd_kernel<DT, 4, true, ZERO_SKIP, true, 5><<<grid, block, 0, st>>>(xyz, dout, grad, S, P);
-                        else hash_bwd_kernel<DT, 4, true, ZERO_SKIP, true><<<grid, block, 0, st>>>(xyz, dout, grad, S, P); break;
-                case 8: hash_bwd_kernel<DT, 8, true, ZERO_SKIP, true><<<grid, block, 0, st>>>(xyz, dout, grad, S, P); break;
-                default: hash_bwd_kernel<DT, 16, true, ZERO_SKIP, true><<<grid, block, 0, st>>>(xyz, dout, grad, S, P); break;
+                case 2: if (tight) vn_launch_pdl(hash_bwd_kernel<DT, 2, true, ZERO_SKIP, true, 5>, dim3(grid), dim3(block), 0, st, xyz, dout, grad, S, P);
+                        else vn_launch_pdl(hash_bwd_kernel<DT, 2, true, ZERO_SKIP, true>, dim3(grid), dim3(block), 0, st, xyz, dout, grad, S, P); break;
+                case 4: if (tight) vn_launch_pdl(hash_bwd_kernel<DT, 4, true, ZERO_SKIP, true, 5>, dim3(grid), dim3(block), 0, st, xyz, dout, grad, S, P);
+                        else vn_launch_pdl(hash_bwd_kernel<DT, 4, true, ZERO_SKIP, true>, dim3(grid), dim3(block), 0, st, xyz, dout, grad, S, P); break;
+                case 8: vn_launch_pdl(hash_bwd_kernel<DT, 8, true, ZERO_SKIP, true>, dim3(grid), dim3(block), 0, st, xyz, dout, grad, S, P); break;
+                default: vn_launch_pdl(hash_bwd_kernel<DT, 16, true, ZERO_SKIP, true>, dim3(grid), dim3(block), 0, st, xyz, dout, grad, S, P); break;
             }
         }
         VN_CHECK_LAUNCH("hash_bwd_kernel<planar>");
         return VN_OK;
     }
-#define VN_BWD(L, A) hash_bwd_kernel<DT, L, A, ZERO_SKIP, false><<<grid, block, 0, st>>>(xyz, dout, grad, S, P)
+#define VN_BWD(L, A) vn_launch_pdl(hash_bwd_kernel<DT, L, A, ZERO_SKIP, false>, dim3(grid), dim3(block), 0, st, xyz, dout, grad, S, P)
     if (agg) {
         switch (lpt) { case 1: VN_BWD(1, true); break; case 2: VN_BWD(2, true); break; case 4: VN_BWD(4, true); break;
                        case 8: VN_BWD(8, true); break; default: VN_BWD(16, true); }

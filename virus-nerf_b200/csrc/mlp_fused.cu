@@ -287,6 +287,7 @@ __device__ __forceinline__ void mask_store_half(uint8_t* smem, int off_dst, int 
 
 template <bool BWD>
 __global__ void __launch_bounds__(NTHREADS, BWD ? 2 : 3) mlp_kernel(const MlpArgs a) {
+    vn_pdl_trigger();                         // PDL: the wait follows the prologue
     using L = Lay<BWD>;
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar;
@@ -348,6 +349,9 @@ __global__ void __launch_bounds__(NTHREADS, BWD ? 2 : 3) mlp_kernel(const MlpArg
         }
     };
     Staged cur;
+    // everything above read only the weights (final since the previous optimiser step, which every
+    // predecessor in the stream has transitively waited for) -- from here on the producer's outputs
+    vn_pdl_wait();
     fetch(blockIdx.x, cur);
     bool first_tile = true;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, first_tile = false) {
@@ -553,8 +557,8 @@ int launch_mlp(bool bwd, const MlpArgs& a, cudaStream_t st) {
     const int per_sm = bwd ? 2 : 3;
     int64_t grid = (int64_t)vn_sm_count() * per_sm;
     if (grid > n_tiles) grid = n_tiles;
-    if (bwd) mlp_kernel<true><<<(unsigned)grid, NTHREADS, SMEM_BWD, st>>>(a);
-    else     mlp_kernel<false><<<(unsigned)grid, NTHREADS, SMEM_FWD, st>>>(a);
+    if (bwd) vn_launch_pdl(mlp_kernel<true>, dim3((unsigned)grid), dim3(NTHREADS), SMEM_BWD, st, a);
+    else     vn_launch_pdl(mlp_kernel<false>, dim3((unsigned)grid), dim3(NTHREADS), SMEM_FWD, st, a);
     VN_CHECK_LAUNCH(bwd ? "mlp_kernel<bwd>" : "mlp_kernel<fwd>");
     return VN_OK;
 }

@@ -5,6 +5,7 @@
 
 __global__ void __launch_bounds__(256) grad_check_kernel(const float4* __restrict__ g4, const float* __restrict__ g, int64_t n,
                                                          float* __restrict__ found_inf) {
+    vn_pdl_trigger(); vn_pdl_wait();          // PDL: see common.cuh
     const int64_t n4 = n / 4;
     bool bad = false;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -23,7 +24,7 @@ VN_API int vn_grad_check(const float* g, int64_t n, float* found_inf, void* stre
     const int64_t cap = (int64_t)vn_sm_count() * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    grad_check_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)g, g, n, found_inf);
+    vn_launch_pdl(grad_check_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, (const float4*)g, g, n, found_inf);
     VN_CHECK_LAUNCH("grad_check_kernel");
     return VN_OK;
 }
@@ -32,6 +33,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
                                                    float* __restrict__ v, int64_t n, AdamCfg c,
                                                    const float* __restrict__ found_inf,
                                                    const float* __restrict__ scale_dev) {
+    vn_pdl_trigger(); vn_pdl_wait();          // PDL: see common.cuh
     if (found_inf && *found_inf != 0.0f) return;          // GradScaler.step skips the optimizer step
     if (scale_dev) c.inv_scale = 1.0f / *scale_dev;
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -61,12 +63,13 @@ VN_API int vn_adam_step(float* p, const float* g, float* m, float* v, int64_t n,
     c.step_size = (float)((double)lr / bc1);
     c.bc2_sqrt = (float)sqrt(bc2);
     VnProfScope prof(VN_K_ADAM, n, (cudaStream_t)stream);
-    adam_kernel<<<vn_blocks((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, c, found_inf, scale_dev);
+    vn_launch_pdl(adam_kernel, dim3(vn_blocks((n + 3) / 4, 256)), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, n, c, found_inf, scale_dev);
     VN_CHECK_LAUNCH("adam_kernel");
     return VN_OK;
 }
 
 __global__ void scaler_update_kernel(float* scale, int32_t* tracker, float* found_inf, float growth, float backoff, int interval) {
+    vn_pdl_trigger(); vn_pdl_wait();          // PDL: see common.cuh
     if (*found_inf != 0.0f) { *scale = *scale * backoff; *tracker = 0; }
     else {
         const int t = *tracker + 1;
@@ -79,7 +82,7 @@ __global__ void scaler_update_kernel(float* scale, int32_t* tracker, float* foun
 VN_API int vn_scaler_update(float* scale, int32_t* growth_tracker, float* found_inf, float growth_factor,
                             float backoff_factor, int growth_interval, void* stream) {
     VN_REQUIRE(scale && growth_tracker && found_inf, "vn_scaler_update: null pointer");
-    scaler_update_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(scale, growth_tracker, found_inf, growth_factor, backoff_factor, growth_interval);
+    vn_launch_pdl(scaler_update_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, scale, growth_tracker, found_inf, growth_factor, backoff_factor, growth_interval);
     VN_CHECK_LAUNCH("scaler_update_kernel");
     return VN_OK;
 }
@@ -108,6 +111,7 @@ __global__ void __launch_bounds__(256) loss_fwd_kernel(const float* __restrict__
                                                        const float* __restrict__ uss, const float* __restrict__ tof,
                                                        const float* __restrict__ rgbd, int64_t N, float bg, float uss_tol,
                                                        float* __restrict__ sums, float* __restrict__ counts) {
+    vn_pdl_trigger(); vn_pdl_wait();          // PDL: see common.cuh
     __shared__ float sm[8][8];
     float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // sums[4], counts[4]
     for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
@@ -141,6 +145,7 @@ __global__ void __launch_bounds__(256) loss_bwd_kernel(const float* __restrict__
                                                        const float* __restrict__ scale_dev, float* __restrict__ dL_drgb,
                                                        float* __restrict__ dL_ddepth, float* __restrict__ dL_dopacity,
                                                        float* __restrict__ loss_out) {
+    vn_pdl_trigger(); vn_pdl_wait();          // PDL: see common.cuh
     const float scale = scale_dev ? *scale_dev : 1.0f;
     const float c0 = counts[0], c1 = counts[1], c2 = counts[2], c3 = counts[3];
     // d(mean)/dx = 2 x / count; empty masks contribute nothing (loss.py:140-141, 186-190)
@@ -169,7 +174,7 @@ VN_API int vn_loss_fwd(const float* rgb, const float* opacity, const float* dept
     VN_REQUIRE(rgb && opacity && depth && gt_rgb, "vn_loss_fwd: null pointer");
     int64_t blocks = (N + 255) / 256;
     if (blocks > 2 * vn_sm_count()) blocks = 2 * vn_sm_count();
-    loss_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(rgb, opacity, depth, gt_rgb, uss, tof, rgbd, N, bg,
+    vn_launch_pdl(loss_fwd_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, rgb, opacity, depth, gt_rgb, uss, tof, rgbd, N, bg,
                                                                       uss_tol, sums, counts);
     VN_CHECK_LAUNCH("loss_fwd_kernel");
     return VN_OK;
@@ -182,7 +187,7 @@ VN_API int vn_loss_bwd(const float* rgb, const float* opacity, const float* dept
     VN_REQUIRE(N >= 0 && sums && counts, "vn_loss_bwd: bad arguments");
     if (N == 0) return VN_OK;
     VN_REQUIRE(rgb && opacity && depth && gt_rgb && dL_drgb && dL_ddepth && dL_dopacity, "vn_loss_bwd: null pointer");
-    loss_bwd_kernel<<<vn_blocks(N, 256), 256, 0, (cudaStream_t)stream>>>(rgb, opacity, depth, gt_rgb, uss, tof, rgbd, N, bg,
+    vn_launch_pdl(loss_bwd_kernel, dim3(vn_blocks(N, 256)), dim3(256), 0, (cudaStream_t)stream, rgb, opacity, depth, gt_rgb, uss, tof, rgbd, N, bg,
                                                                        uss_tol, sums, counts, w_color, w_uss, w_tof, w_rgbd,
                                                                        scale_dev, dL_drgb, dL_ddepth, dL_dopacity, loss_out);
     VN_CHECK_LAUNCH("loss_bwd_kernel");

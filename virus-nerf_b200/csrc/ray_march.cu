@@ -481,6 +481,7 @@ __global__ void __launch_bounds__(256) march_expand_kernel(const float* __restri
                                                            float* __restrict__ xyzs, float* __restrict__ dirs,
                                                            float* __restrict__ deltas, float* __restrict__ ts,
                                                            float* __restrict__ xyzs_unit) {
+    vn_pdl_trigger(); vn_pdl_wait();          // PDL: see common.cuh
     const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (r >= N) return;
@@ -515,7 +516,7 @@ VN_API int vn_march_train_expand(const float* rays_o, const float* rays_d, const
     VN_REQUIRE(grid_size >= 1 && grid_size <= 1024, "vn_march_train_expand: bad grid_size");
     const MarchCfg c = make_cfg(1, grid_size, scale, exp_step_factor);
     VnProfScope prof(VN_K_MARCH_WRITE, capacity, (cudaStream_t)stream);
-    march_expand_kernel<<<vn_blocks(N * 32, 256), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, rays_a, ts_rows, N, max_samples,
+    vn_launch_pdl(march_expand_kernel, dim3(vn_blocks(N * 32, 256)), dim3(256), 0, (cudaStream_t)stream, rays_o, rays_d, rays_a, ts_rows, N, max_samples,
                                                                                 c, capacity, xyzs, dirs, deltas, ts, xyzs_unit);
     VN_CHECK_LAUNCH("march_expand_kernel");
     return VN_OK;

@@ -45,6 +45,7 @@ extern "C" {
                               p = levels 2p, 2p+1 of every point) instead of [S, 2*levels] rows;
                               the layout vn_mlp_fwd/bwd read and write with enc_format = 2 */
 #define VN_HASH_TIGHT_REGS 1024 /* planar bwd: 48-register variant, 5 CTAs per SM */
+#define VN_HASH_SKIP_ZERO_GRADS 4096 /* f32 bwd: do not scatter (level, sample) pairs whose gradient is exactly 0 */
 #define VN_HASH_PAIR_LOADS 2048 /* planar fwd: 16-byte loads for x / x+1 corner pairs that are neighbours */
 /* default (no GROUPS flag): 4 (backward: 2 when the table exceeds the L2, > 96 MB) */
 

@@ -140,8 +140,10 @@ def test_hash_planar_layout(vn, oracle_mod, flags, S_extra):
         np.testing.assert_array_equal(N(planes), _to_planes(N(rows)))
     np.testing.assert_allclose(N(rows), oracle_mod.hash_fwd_f32(xyz, table, lv_o), rtol=1e-5, atol=1e-6)
     dout = rng.normal(size=(S, 32)).astype(np.float32)
+    dout[rng.random(S) < 0.4] = 0.0                      # samples behind an opaque surface: exactly zero gradient
+    dout[::5, 4:8] = 0.0
     ref = oracle_mod.hash_bwd_f32(xyz, dout, lv_o)
-    for extra in (0, vn.VN_HASH_TIGHT_REGS):
+    for extra in (0, vn.VN_HASH_TIGHT_REGS, vn.VN_HASH_TIGHT_REGS | vn.VN_HASH_SKIP_ZERO_GRADS, vn.VN_HASH_SKIP_ZERO_GRADS):
         grad = torch.zeros(2 * lv_o.total, device=DEV)
         vn.call("vn_hash_encode_bwd_f32", T(xyz), T(_to_planes(dout)), grad, S, lv, flags | vn.VN_HASH_PLANAR | extra)
         np.testing.assert_allclose(N(grad), ref, rtol=1e-4, atol=1e-6 * np.abs(ref).max())

@@ -24,6 +24,7 @@ VN_HASH_LEVEL_GROUPS_2 = 256
 VN_HASH_PLANAR = 512
 VN_HASH_TIGHT_REGS = 1024
 VN_HASH_PAIR_LOADS = 2048
+VN_HASH_SKIP_ZERO_GRADS = 4096
 
 
 class HashLevels(ctypes.Structure):

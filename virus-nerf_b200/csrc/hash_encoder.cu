@@ -539,6 +539,9 @@ VN_API int vn_hash_encode_fwd_f32(const float* xyz, const float* table, float* o
 VN_API int vn_hash_encode_bwd_f32(const float* xyz, const float* dout, float* grad, int64_t S,
                                   const vn_hash_levels_t* lv, int flags, void* stream) {
     VN_HASH_ARGCHECK("vn_hash_encode_bwd_f32", xyz, grad, dout);
+    // VN_HASH_SKIP_ZERO_GRADS: samples behind an opaque surface have an exactly zero gradient (the compositor
+    // stops at T <= 1e-4); not scattering their zeros leaves every sum unchanged
+    if (flags & VN_HASH_SKIP_ZERO_GRADS) return launch_bwd<float, true>(xyz, dout, grad, S, lv, flags, (cudaStream_t)stream);
     return launch_bwd<float, false>(xyz, dout, grad, S, lv, flags, (cudaStream_t)stream);
 }
 

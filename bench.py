@@ -23,8 +23,12 @@ RAYS_PER_GPU = 4096
 HASH_BYTES_PER_POINT = 1164          # fwd or bwd, fp32 L16 F2 (SURVEY 8(d) / BASELINE.md section 3)
 # DRAM bytes per point of one `ncu --set full` capture (dram__bytes_read.sum + dram__bytes_write.sum over
 # S = 1 306 086 points, profiles/r1_ncu_top_kernels.md); scaled by the launch's points for `roofline.traffic`
-ROOFLINE_KERNEL = "hash_encode_bwd"   # the dominant kernel of the step (verified by the breakdown)
-NCU_DRAM_BYTES_PER_POINT = {"hash_encode_bwd": 607.6, "hash_encode_fwd": 198.7}
+# the two candidates for "dominant kernel of the step" (DESIGN.md section 4): both are bracketed with CUDA events
+# INSIDE the timed region and the one with the larger total there is the roofline kernel
+ROOFLINE_CANDIDATES = ("hash_encode_bwd", "mlp_bwd")
+# DRAM bytes per point / sample from the ncu --set full capture of this round's kernels
+# (profiles/r1_ncu_top_kernels.md: dram__bytes_read.sum + dram__bytes_write.sum over 1 306 081 samples)
+NCU_DRAM_BYTES_PER_POINT = {"hash_encode_bwd": 188.9, "hash_encode_fwd": 148.1, "mlp_fwd": 152.9, "mlp_bwd": 253.1}
 WORKLOAD = ("ETHZ-shaped synthetic scene, hash grid L=16 F=2 T=2^19 fp32 tables, 4096 rays/batch/GPU, RGB+USS+ToF "
             "losses, VIRUS-NeRF occupancy update every 8 steps, training from the initial (all-occupied) grid")
 
@@ -235,7 +239,7 @@ def run_ours(a):
                 if not pinned:
                     # only the dominant kernel is bracketed with events inside the timed region (an event between
                     # two kernels serialises them); the full per-kernel table comes from the untimed steps below
-                    _lib.profile_start([ROOFLINE_KERNEL])
+                    _lib.profile_start(list(ROOFLINE_CANDIDATES))
                 ev0.record()
             # the next batch is fetched (H2D copy in the e2e phase) before this step is enqueued so that
             # the engine can pipeline its front half; every batch is copied exactly once, inside the
@@ -266,7 +270,7 @@ def run_ours(a):
                 eng.step_fast(dev_batches[it % len(dev_batches)], next_data=nxt) if not a.autograd_step else eng.step(dev_batches[it % len(dev_batches)])
             torch.cuda.synchronize()
             prof = _lib.profile_stop()
-            prof["__timed__" + ROOFLINE_KERNEL] = prof_dom.get(ROOFLINE_KERNEL, [])
+            prof["__timed__"] = {k: prof_dom.get(k, []) for k in ROOFLINE_CANDIDATES}
         samples = [int(s) for s in samples]
         render_ms = None
         if not pinned:
@@ -314,7 +318,7 @@ def run_ours(a):
         # roofline of the dominant kernel: algorithmic bytes / measured kernel time (CUDA events
         # around the launches, on the launching stream)
         kern = {}
-        timed_dom = prof.pop("__timed__" + ROOFLINE_KERNEL, [])
+        timed = prof.pop("__timed__", {})
         for name, calls in prof.items():
             t_ms = sum(c[0] for c in calls); pts = sum(c[1] for c in calls)
             if t_ms > 0:
@@ -326,31 +330,37 @@ def run_ours(a):
                     flop = 18816 if name == "mlp_fwd" else 56448
                     kern[name]["achieved_tflops"] = pts * flop / (t_ms * 1e-3) / 1e12
         tflops_peak = peaks_tensor()
-        dom = max(kern, key=lambda k: kern[k]["ms_total"]) if kern else None
+        # kernels timed live inside the timed region: totals there decide which one dominates the step
+        live = {}
+        for name, calls in timed.items():
+            t_ms = sum(c[0] for c in calls); pts = sum(c[1] for c in calls)
+            if t_ms > 0:
+                live[name] = (t_ms, pts, len(calls))
+                kern.setdefault(name, {}).update({"ms_total_timed_region": round(t_ms, 4), "launches_timed_region": len(calls),
+                                                  "units_timed_region": pts, "share_of_timed_step": round(t_ms / ms, 4)})
+        dom = max(live, key=lambda k: live[k][0]) if live else None
         roof = None
-        if timed_dom and dom == ROOFLINE_KERNEL:
-            # the dominant kernel, timed live inside the timed region
-            t_ms = sum(c[0] for c in timed_dom); pts = sum(c[1] for c in timed_dom)
+        if dom and dom.startswith("hash_encode"):
+            t_ms, pts, nl = live[dom]
             gbs = pts * HASH_BYTES_PER_POINT / (t_ms * 1e-3) / 1e9
-            kern[dom].update({"ms_total_timed_region": round(t_ms, 4), "launches_timed_region": len(timed_dom),
-                              "share_of_step": round(t_ms / ms, 4), "achieved_gbs": gbs})
-            roof = {"kernel": dom, "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s",
-                    "frac": gbs / peak, "measured": "CUDA events around every launch of this kernel inside the timed region",
-                    "traffic": NCU_DRAM_BYTES_PER_POINT[dom] * pts / len(timed_dom),
+            roof = {"kernel": dom, "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                    "measured": "CUDA events around every launch of this kernel inside the timed region",
+                    "traffic": NCU_DRAM_BYTES_PER_POINT[dom] * pts / nl,
                     "traffic_note": "DRAM bytes per launch = ncu bytes/point (profiles/r1_ncu_top_kernels.md) x mean points per "
-                                    "launch; below the algorithmic bytes because the table is L2 resident",
-                    "peak_source": peak_src, "algorithmic_bytes_per_launch": HASH_BYTES_PER_POINT * pts / len(timed_dom),
-                    "algorithmic_bytes_per_point": HASH_BYTES_PER_POINT}
-        elif dom and dom.startswith("hash_encode"):
-            roof = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": kern[dom]["achieved_gbs"] / peak, "traffic": None, "peak_source": peak_src,
-                    "measured": "untimed breakdown steps", "algorithmic_bytes_per_point": HASH_BYTES_PER_POINT}
+                                    "launch; far below the algorithmic bytes because the table and its gradient are L2 resident",
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": HASH_BYTES_PER_POINT * pts / nl,
+                    "algorithmic_bytes_per_point": HASH_BYTES_PER_POINT,
+                    "runner_up": {k: round(v[0], 4) for k, v in live.items() if k != dom}}
         elif dom and dom.startswith("mlp"):
-            roof = {"kernel": dom, "bound": "tensor", "achieved": kern[dom]["achieved_tflops"], "peak": tflops_peak,
-                    "unit": "TFLOP/s", "frac": kern[dom]["achieved_tflops"] / tflops_peak, "traffic": None,
-                    "peak_source": "bf16_tflops_sustained, " + peak_src}
+            t_ms, pts, nl = live[dom]
+            tf = pts * 56448 / (t_ms * 1e-3) / 1e12
+            roof = {"kernel": dom, "bound": "tensor", "achieved": tf, "peak": tflops_peak, "unit": "TFLOP/s",
+                    "frac": tf / tflops_peak, "traffic": NCU_DRAM_BYTES_PER_POINT[dom] * pts / nl,
+                    "measured": "CUDA events around every launch of this kernel inside the timed region",
+                    "peak_source": "bf16_tflops_sustained, " + peak_src,
+                    "runner_up": {k: round(v[0], 4) for k, v in live.items() if k != dom}}
         for k in ("hash_encode_fwd", "hash_encode_bwd"):
-            if k in kern:
+            if k in kern and "achieved_gbs" in kern[k]:
                 kern[k]["frac_of_hbm_peak"] = kern[k]["achieved_gbs"] / peak
         line = {"metric": "train_rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": K,
                 "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

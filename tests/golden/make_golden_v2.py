@@ -149,6 +149,14 @@ def main():
     G["f3_all_indices"] = morton3D(grid.grid_coords).long().numpy()
     G["f3_all_coords"] = grid.grid_coords.numpy()
 
+    # ---------------- f4: evaluation inputs (helpers/geometric_fcts.py) ----------------------
+    from helpers.geometric_fcts import createScanRays, createScanPos
+    origins = rng.uniform(-0.3, 0.3, (3, 3)).astype(np.float32)
+    so, sd = createScanRays(rays_o=torch.from_numpy(origins), angle_res=48)
+    G["f4_origins"], G["f4_scan_o"], G["f4_scan_d"] = origins, so.numpy(), sd.numpy()
+    G["f4_scan_pos"] = createScanPos(res_map=9, height_c=-0.05, num_avg_heights=3, tolerance_c=0.02, cube_min=-0.5,
+                                     cube_max=0.5, device="cpu").numpy()
+
     out_path = os.path.join(HERE, "golden_v2.npz")
     np.savez_compressed(out_path, **G)
     print("wrote", out_path, len(G), "arrays")

@@ -115,6 +115,42 @@ def test_render_test_matches_oracle(setup):
     om.load_from(eng.model)
 
 
+def test_evaluation_consumers_match_oracle(setup, tmp_path):
+    """lidar-like scan rendering (d_z = 0 rays, trainer.py:574-629), the density-map slice
+    (trainer_base.py:92-140) and the .pth checkpoint round trip, against the oracle pipeline"""
+    eng, om, ds, bf, args, pipeline = setup
+    from virus_nerf_b200.training import evaluation as ev
+    from virus_nerf_b200.modules.networks import NGP
+    with torch.no_grad():
+        eng.model.xyz_encoder.output_layer.weight[0].add_(0.25)
+    om.load_from(eng.model)
+    origins = torch.tensor([[0.05, -0.1, -0.05], [-0.2, 0.15, -0.05]], device=DEV)
+    ro, rd, depth = ev.evaluation_depth_nerf(eng.model, origins, angle_res=96, batch_size=64)
+    assert ro.shape == (192, 3) and (rd[:, 2] == 0).all()
+    o = pipeline.render_test(om, torch.from_numpy(ro), torch.from_numpy(rd), bf)
+    np.testing.assert_allclose(depth, o["depth"], rtol=1e-4, atol=1e-5)
+    dm, dm_thr = ev.interfere_density_map(eng.model, res_map=24, height_c=-0.05, num_avg_heights=3, tolerance_c=0.02,
+                                          threshold=1.0, cube_min=-0.5, cube_max=0.5, batch_size=500)
+    pos = ev.createScanPos(24, -0.05, 3, 0.02, -0.5, 0.5, "cpu")
+    ref = om.density(pos).detach().numpy().reshape(-1, 3).max(1).reshape(24, 24)
+    np.testing.assert_allclose(dm, ref, rtol=1e-4, atol=1e-6)
+    assert set(np.unique(dm_thr)) <= {0.0, 1.0} and ((dm >= 1.0) == (dm_thr == 1.0)).all()
+    # checkpoint: the reference's state-dict keys, readable by a freshly built model
+    path = ev.save_checkpoint(eng.model, str(tmp_path))
+    sd = torch.load(path, map_location="cpu")
+    assert "pos_encoder.hash_table" in sd and "rgb_net.output_layer.weight" in sd
+    fresh = NGP(scale=args.model.scale, pos_encoder_type='hash', levels=16, max_res=1024, log2_T=19, args=args,
+                dataset=ds).to(DEV)
+    ev.load_checkpoint(fresh, path)
+    fresh.occupancy_grid.bitfield = eng.model.occupancy_grid.bitfield
+    fresh.fused_mlp = eng.model.fused_mlp
+    _, _, depth2 = ev.evaluation_depth_nerf(fresh, origins, angle_res=96, batch_size=64)
+    np.testing.assert_array_equal(depth2, depth)
+    with torch.no_grad():
+        eng.model.xyz_encoder.output_layer.weight[0].sub_(0.25)
+    om.load_from(eng.model)
+
+
 def test_train_steps_track_oracle(setup, monkeypatch):
     """three optimiser steps (no grid update in between): losses and parameters track the CPU
     trainer (fp32, Adam eps 1e-15; the GPU side goes through GradScaler 2^19 + fused Adam)"""

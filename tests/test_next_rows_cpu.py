@@ -79,3 +79,15 @@ def test_ngp_grid_oracle_matches_reference(g2, oracle_mod, tag):
     if not np.array_equal(bf, ref_bf):       # a cell within rounding of the mean may flip: allow only those
         diff = np.unpackbits(bf ^ ref_bf, bitorder="little").nonzero()[0]
         assert np.allclose(after[diff], float(t), rtol=1e-6)
+
+
+def test_evaluation_inputs_match_reference(g2):
+    """createScanRays / createScanPos (helpers/geometric_fcts.py:77-150) as the reference computes them"""
+    from virus_nerf_b200.training.evaluation import createScanRays, createScanPos
+    so, sd = createScanRays(torch.from_numpy(g2["f4_origins"]), angle_res=48)
+    np.testing.assert_array_equal(so.numpy(), g2["f4_scan_o"])
+    np.testing.assert_array_equal(sd.numpy(), g2["f4_scan_d"])
+    assert (sd[:, 2] == 0).all()
+    pos = createScanPos(res_map=9, height_c=-0.05, num_avg_heights=3, tolerance_c=0.02, cube_min=-0.5, cube_max=0.5,
+                        device="cpu")
+    np.testing.assert_array_equal(pos.numpy(), g2["f4_scan_pos"])

@@ -7,7 +7,9 @@ from virus_nerf_b200 import _lib, synthetic
 from virus_nerf_b200.modules.intersection import ray_aabb_intersection
 from virus_nerf_b200.modules.ray_march import raymarching_train
 DEV = "cuda:0"
-flags = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+# default: the fast step's flags (planes, 2 levels per thread, 16-byte pair loads, 48-register bwd, zero skip)
+flags = int(sys.argv[1]) if len(sys.argv) > 1 else (512 | 256 | 2048 | 1024 | 4096)
+fmt = 2 if flags & 512 else 0
 ds = synthetic.SyntheticDataset(pool_size=1 << 16, device=DEV)
 b = ds(4096, {"pixs": {"valid_uss": 0.4, "valid_tof": 0.4}})
 bf = torch.full((128 ** 3 // 8,), 255, dtype=torch.uint8, device=DEV)
@@ -27,7 +29,7 @@ dW = [torch.zeros_like(w) for w in W]
 for _ in range(3):
     _lib.call("vn_hash_encode_fwd_f32", x, table, o, S, lv, flags)
     _lib.call("vn_hash_encode_bwd_f32", x, dout, grad, S, lv, flags)
-    _lib.call("vn_mlp_fwd", o, 0, dirs, *W, S, 0, sig, rgb, None)
-    _lib.call("vn_mlp_bwd", o, 0, dirs, *W, S, 0, dsig, drgb, denc, *dW)
+    _lib.call("vn_mlp_fwd", o, fmt, dirs, *W, S, 0, sig, rgb, None)
+    _lib.call("vn_mlp_bwd", o, fmt, dirs, *W, S, 0, dsig, drgb, denc, *dW)
 torch.cuda.synchronize()
 print("S", S)

@@ -29,6 +29,7 @@ static P2PCtx g_ctx;
 static bool g_ctx_ready = false;
 
 __global__ void p2p_barrier_kernel(P2PCtx c, int value) {
+    vn_pdl_trigger(); vn_pdl_wait();          // PDL: may be pre-launched behind the kernel that produces the data
     const int p = threadIdx.x;
     if (p < c.world) {
         __threadfence_system();
@@ -78,6 +79,7 @@ __global__ void __launch_bounds__(512) p2p_all_gather_kernel(P2PCtx c, int64_t n
 // rank obtains the bit-identical result.  Two mailbox parities: a slot can only be overwritten
 // two exchanges later, i.e. after its reader has passed another barrier.
 __global__ void p2p_exchange_kernel(P2PCtx c, int value, int parity, float* data, int n, int use_max) {
+    vn_pdl_trigger(); vn_pdl_wait();          // PDL: `data` comes from the preceding kernel
     const int p = threadIdx.x;
     if (p < c.world) {
         float* slot = c.mbox[p] + ((size_t)parity * c.world + c.rank) * VN_P2P_MBOX;
@@ -254,7 +256,7 @@ VN_API int vn_p2p_allreduce_small(float* data, int n, int use_max, void* stream)
     if (g_ctx.world == 1) return VN_OK;
     const int e = ++g_ctx.epoch;
     const int parity = (g_ctx.small_ops++) & 1;
-    p2p_exchange_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(g_ctx, e, parity, data, n, use_max);
+    vn_launch_pdl(p2p_exchange_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, g_ctx, e, parity, data, n, use_max);
     VN_CHECK_LAUNCH("p2p_exchange_kernel");
     return VN_OK;
 }
@@ -280,7 +282,7 @@ VN_API int vn_p2p_reduce_adam(int64_t n, float* m, float* v, float lr, float bet
     const int e = g_ctx.epoch;
     g_ctx.epoch += 3;
     const int parity = (g_ctx.small_ops++) & 1;
-    p2p_barrier_kernel<<<1, 32, 0, st>>>(g_ctx, e + 1);                      // every rank's gradients are complete
+    vn_launch_pdl(p2p_barrier_kernel, dim3(1), dim3(32), 0, st, g_ctx, e + 1);                      // every rank's gradients are complete
     VN_CHECK_LAUNCH("p2p_barrier_kernel");
     p2p_reduce_check_kernel<<<sms, 512, 0, st>>>(g_ctx, n4, chunk4, found_inf);
     VN_CHECK_LAUNCH("p2p_reduce_check_kernel");

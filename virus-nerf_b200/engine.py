@@ -355,27 +355,29 @@ class TrainEngine:
         else:
             dist.all_reduce(self._loss_acc[4:])
         _lib.call("vn_train_step_run", st, S, 2, 0)
-        ev = torch.cuda.Event(); ev.record()
-        self._comm_stream.wait_event(ev)
-        with torch.cuda.stream(self._comm_stream):
-            if self._p2p_fused:                                           # reduce-scatter + Adam + parameter push
-                _lib.call("vn_p2p_reduce_adam", self.n_params, self.flat_m, self.flat_v, self.lr, self.betas[0],
-                          self.betas[1], self.eps, self.adam_step, self.found_inf, self.scale, self.growth_tracker)
-                work = None
-                done = torch.cuda.Event(); done.record()
-            elif self._p2p is not None:                                   # own two-shot allreduce over NVLink peer memory
-                _lib.call("vn_p2p_allreduce", self.n_params)
-                work = None
-                done = torch.cuda.Event(); done.record()
-            else:
-                work = dist.all_reduce(self.flat_g, async_op=True)        # NCCL; overlaps prepare(next) below
-        if next_data is not None and not update_due:
-            self._ticket = self.prepare(next_data, elapse_time, ready=ready_next)
-        if work is not None:
-            work.wait()
+        if self._p2p_fused:
+            # reduce-scatter + inf check + sharded Adam + parameter push + scaler update, on the main stream: the next
+            # step's main-stream work needs its result anyway, only the front half of the next step (side stream) overlaps
+            _lib.call("vn_p2p_reduce_adam", self.n_params, self.flat_m, self.flat_v, self.lr, self.betas[0],
+                      self.betas[1], self.eps, self.adam_step, self.found_inf, self.scale, self.growth_tracker)
+            if next_data is not None and not update_due:
+                self._ticket = self.prepare(next_data, elapse_time, ready=ready_next)
         else:
-            torch.cuda.current_stream().wait_event(done)
-        if not self._p2p_fused:
+            ev = torch.cuda.Event(); ev.record()
+            self._comm_stream.wait_event(ev)
+            with torch.cuda.stream(self._comm_stream):
+                if self._p2p is not None:                                 # own two-shot allreduce over NVLink peer memory
+                    _lib.call("vn_p2p_allreduce", self.n_params)
+                    work = None
+                    done = torch.cuda.Event(); done.record()
+                else:
+                    work = dist.all_reduce(self.flat_g, async_op=True)    # NCCL; overlaps prepare(next) below
+            if next_data is not None and not update_due:
+                self._ticket = self.prepare(next_data, elapse_time, ready=ready_next)
+            if work is not None:
+                work.wait()
+            else:
+                torch.cuda.current_stream().wait_event(done)
             _lib.call("vn_train_step_optim", st)
         if next_data is not None and update_due:
             self._ticket = self.prepare(next_data, elapse_time)

@@ -38,6 +38,53 @@ def test_library_exports_every_declared_symbol(vn):
     assert L.vn_abi_version() == 1
 
 
+def test_ctypes_call_specs_match_the_header_prototypes(vn):
+    """every entry of _lib._SPECS (one character per argument) against the parameter list of the
+    prototype in include/virusnerf.h: pointer / int64 / int / float / double / stream, in order"""
+    h = open(os.path.join(ROOT, "include", "virusnerf.h")).read()
+    h = re.sub(r"/\*.*?\*/", "", h, flags=re.S)
+    protos = dict(re.findall(r"\bint\s+(vn_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", h, flags=re.S))
+
+    def kind(param):
+        param = " ".join(param.split())
+        name = param.split()[-1].lstrip("*")
+        if "*" in param:
+            if name == "stream":
+                return "s"
+            return "h" if name.startswith("h_") else "p"
+        t = param.rsplit(" ", 1)[0].replace("const ", "")
+        return {"int64_t": "l", "int": "i", "int32_t": "i", "unsigned": "i", "float": "f", "double": "d"}[t]
+
+    checked = 0
+    for name, spec in vn._SPECS.items():
+        assert name in protos, name
+        params = [q for q in protos[name].split(",") if q.strip() and q.strip() != "void"]
+        kinds = "".join(kind(q) for q in params)
+        # host-struct pointers are declared with an h_ prefix or as const vn_*_t* (passed as 'h')
+        norm = lambda k: k.replace("h", "p")
+        assert norm(kinds) == norm(spec), (name, kinds, spec)
+        checked += 1
+    assert checked >= 45
+
+
+def test_next_row_mirrors_expose_the_reference_api():
+    from virus_nerf_b200.modules import ngp_grid, networks
+    from virus_nerf_b200.datasets import dataset_base
+    from virus_nerf_b200.training import sampler, evaluation
+    for name in ("sample_uniform_and_occupied_cells", "mark_invisible_cells", "update", "getBitfield", "getAllCells",
+                 "updateBitfield", "morton2bitfield"):
+        assert hasattr(ngp_grid.NGPGrid, name), name
+    assert hasattr(networks.NGP, "updateNeRFGrid") and hasattr(networks.NGP, "updateOccGrid")
+    for name in ("__call__", "_calcRayPoses", "to", "getMeanHeight", "__len__"):
+        assert hasattr(dataset_base.DatasetBase, name), name
+    for name in ("__call__", "getValidImgIdxs", "_imgIdxs", "_pixIdxs", "_pixStrategyRandom", "_pixStrategyEntireImg",
+                 "_pixStrategyClosest", "_pixStrategyValidDepth"):
+        assert hasattr(sampler.Sampler, name), name
+    for name in ("createScanRays", "createScanPos", "batchify_render", "batchify_density", "interfere_density_map",
+                 "evaluation_depth_nerf", "save_checkpoint", "load_checkpoint"):
+        assert callable(getattr(evaluation, name)), name
+
+
 def test_only_sm100a_code_in_the_library(vn):
     import subprocess
     out = subprocess.run(["cuobjdump", "--list-elf", vn.LIB_PATH], capture_output=True, text=True).stdout
@@ -115,12 +162,12 @@ def test_ctypes_struct_mirrors_match_the_header(vn, tmp_path):
     import subprocess
     src = tmp_path / "sz.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "virusnerf.h"\n'
-                   'int main(void){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(vn_hash_levels_t), sizeof(vn_step_t),'
+                   'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(vn_hash_levels_t), sizeof(vn_step_t),'
                    ' offsetof(vn_step_t, levels), offsetof(vn_step_t, loss_acc), offsetof(vn_step_t, adam_step),'
-                   ' offsetof(vn_step_t, w_off)); return 0;}\n')
+                   ' offsetof(vn_step_t, w_off), offsetof(vn_step_t, ts_rows)); return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     c = [int(x) for x in subprocess.check_output([str(exe)], text=True).split()]
     py = [ctypes.sizeof(vn.HashLevels), ctypes.sizeof(vn.Step), vn.Step.levels.offset, vn.Step.loss_acc.offset,
-          vn.Step.adam_step.offset, vn.Step.w_off.offset]
+          vn.Step.adam_step.offset, vn.Step.w_off.offset, vn.Step.ts_rows.offset]
     assert c == py, (c, py)

@@ -70,3 +70,59 @@ def test_dp_loss_and_gradient_match_single_process():
     loss.backward()
     assert abs(loss_dp - float(loss)) <= 1e-5 * abs(float(loss))
     np.testing.assert_allclose(g_dp, w.grad.numpy(), rtol=1e-4, atol=1e-6)
+
+
+# ---- sharded optimiser protocol (vn_p2p_reduce_adam): slice partition + equivalence with the dense step ----------
+def _sharded_worker(rank, world, port, n, q):
+    sys.path.insert(0, ROOT)
+    import oracle
+    from virus_nerf_b200 import _lib
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(5)
+    p = rng.normal(size=n).astype(np.float32)                     # identical replicas
+    m = np.zeros(n, np.float32); v = np.zeros(n, np.float32)      # only the own slice is ever touched
+    lo, hi = _lib.p2p_slice(n, rank, world)
+    for step in range(1, 4):
+        g = torch.from_numpy(np.random.default_rng(100 * step + rank).normal(size=n).astype(np.float32))
+        # reduce-scatter: rank r needs only slice r of the sum (gloo: allreduce, then keep the slice)
+        dist.all_reduce(g)
+        ps, ms, vs = p[lo:hi].copy(), m[lo:hi].copy(), v[lo:hi].copy()
+        if hi > lo:
+            oracle.adam_step(ps, g.numpy()[lo:hi].copy(), ms, vs, 1.0, 1e-2, 0.9, 0.999, 1e-15, step)
+        m[lo:hi], v[lo:hi] = ms, vs
+        # parameter push: every replica receives every owner's updated slice
+        mine = torch.zeros(n); mine[lo:hi] = torch.from_numpy(ps)
+        dist.all_reduce(mine)                                     # slices are disjoint: the sum is the concatenation
+        p = mine.numpy().copy()
+    q.put((rank, p, lo, hi))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [4096, 4 * 1001])                   # 1001 float4 chunks: ragged slices
+def test_sharded_optimiser_protocol_equals_dense_adam(n, oracle_mod):
+    from virus_nerf_b200 import _lib
+    world = 2
+    # the slices tile [0, n) exactly, for every world size the library supports
+    for w in range(1, 9):
+        edges = [_lib.p2p_slice(n, r, w) for r in range(w)]
+        assert edges[0][0] == 0 and edges[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(edges, edges[1:])) and all(lo % 4 == 0 and hi % 4 == 0 for lo, hi in edges)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000) + (n % 7)
+    procs = [ctx.Process(target=_sharded_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    outs = sorted([q.get(timeout=120) for _ in range(world)], key=lambda o: o[0])
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    np.testing.assert_array_equal(outs[0][1], outs[1][1])                   # replicas bit-identical
+    # dense reference: the same summed gradients through one Adam over the whole buffer
+    rng = np.random.default_rng(5)
+    p = rng.normal(size=n).astype(np.float32); m = np.zeros(n, np.float32); v = np.zeros(n, np.float32)
+    for step in range(1, 4):
+        g = sum(np.random.default_rng(100 * step + r).normal(size=n).astype(np.float32) for r in range(world))
+        oracle_mod.adam_step(p, g.astype(np.float32), m, v, 1.0, 1e-2, 0.9, 0.999, 1e-15, step)
+    np.testing.assert_array_equal(outs[0][1], p)

@@ -295,6 +295,16 @@ def exported_symbols():
             "vn_ngp_select_tmp_ints", "vn_ngp_threshold_tmp_bytes"] + list(_SPECS)
 
 
+def p2p_slice(n, rank, world):
+    """[lo, hi) in floats of the slice of an n-float buffer (n % 4 == 0) that rank `rank` reduces and
+    optimises in vn_p2p_reduce_adam / vn_p2p_allreduce: float4 chunks of ceil(n/4 / world), the last
+    slices may be short or empty (csrc/p2p_allreduce.cu)"""
+    n4 = n // 4
+    chunk4 = (n4 + world - 1) // world
+    lo = min(rank * chunk4, n4)
+    return 4 * lo, 4 * min(lo + chunk4, n4)
+
+
 _ipc_opened = {}   # 64-byte IPC handle -> mapped base pointer (a handle may be opened once per process)
 
 

@@ -223,3 +223,26 @@ def test_loss_against_reference(G):
     np.testing.assert_allclose(float(per_term[0]) * 1.0, float(G["loss_color"]), rtol=1e-6)
     np.testing.assert_allclose(float(per_term[1]) * 50.0, float(G["loss_uss_w"]), rtol=1e-6)
     np.testing.assert_allclose(float(per_term[2]) * 50.0, float(G["loss_tof_w"]), rtol=1e-6)
+
+
+def test_adam_against_torch_optim(oracle_mod):
+    """row f1: the optimiser restatement (GradScaler.unscale_ + torch.optim.Adam(eps=1e-15), trainer.py:49-57,
+    138-141) against torch's own Adam -- the reference's actual dependency for this row -- over several steps"""
+    import torch
+    rng = np.random.default_rng(8)
+    n, scale = 4099, 2.0 ** 19
+    p0 = rng.normal(size=n).astype(np.float32)
+    param = torch.nn.Parameter(torch.from_numpy(p0.copy()))
+    opt = torch.optim.Adam([param], lr=5e-3, eps=1e-15)
+    p, m, v = p0.copy(), np.zeros(n, np.float32), np.zeros(n, np.float32)
+    for step in range(1, 7):
+        g_scaled = (rng.normal(size=n) * scale * 10.0 ** rng.integers(-3, 2)).astype(np.float32)
+        g_scaled[rng.random(n) < 0.1] = 0.0                               # untouched table entries still move (m / v decay)
+        param.grad = torch.from_numpy(g_scaled) * (1.0 / scale)           # unscale_: exact, the scale is a power of two
+        opt.step()
+        oracle_mod.adam_step(p, g_scaled, m, v, 1.0 / scale, 5e-3, 0.9, 0.999, 1e-15, step)
+        np.testing.assert_allclose(p, param.detach().numpy(), rtol=2e-6, atol=1e-7)
+    st = opt.state[param]
+    # lerp cancels where g and m are close: absolute tolerance relative to the largest moment
+    np.testing.assert_allclose(m, st["exp_avg"].numpy(), rtol=2e-6, atol=1e-6 * float(np.abs(m).max()))
+    np.testing.assert_allclose(v, st["exp_avg_sq"].numpy(), rtol=2e-6, atol=1e-6 * float(np.abs(v).max()))

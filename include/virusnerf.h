@@ -253,10 +253,15 @@ int vn_loss_bwd(const float* rgb, const float* opacity, const float* depth, cons
  * vn_grad_check when a scaled gradient is non-finite; the step kernel skips the update when
  * it is non-zero (GradScaler.step semantics).  step is the 1-based Adam step count.  When
  * scale_dev (device, [1] f32) is non-NULL the unscale factor is 1 / scale_dev[0] (the
- * GradScaler's device-side scale) and inv_scale is ignored. */
+ * GradScaler's device-side scale) and inv_scale is ignored.
+ * The hyper-parameters are doubles: torch derives 1 - beta1, 1 - beta2, lr / bias_correction1 and
+ * sqrt(bias_correction2) in python doubles and rounds ONCE to f32 when the scalar meets the f32
+ * tensor (1 - beta2 = 0.001f, not 1.0f - 0.999f); vn_adam_config (host only) returns those six f32
+ * constants (beta2, 1-beta1, 1-beta2, eps, step_size, bias_correction2_sqrt) for inspection. */
 int vn_grad_check(const float* g, int64_t n, float* found_inf, void* stream);
-int vn_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float inv_scale, float lr,
-                 float beta1, float beta2, float eps, int step, const float* found_inf,
+int vn_adam_config(double lr, double beta1, double beta2, double eps, int step, float* h_out6);
+int vn_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float inv_scale, double lr,
+                 double beta1, double beta2, double eps, int step, const float* found_inf,
                  const float* scale_dev, void* stream);
 /* GradScaler.update() on device (torch _amp_update_scale_): scale [1] f32, growth_tracker
  * [1] i32; found_inf is reset to 0 afterwards. */
@@ -315,7 +320,7 @@ typedef struct vn_step {
     float *loss_acc /* [8]: sums[4], counts[4] */, *loss_out /* [1] */;
     float w_color, w_uss, w_tof, w_rgbd;
     float *scale_dev, *found_inf; int32_t* growth_tracker;
-    float lr, beta1, beta2, eps; int32_t adam_step;
+    double lr, beta1, beta2, eps; int32_t adam_step;
     /* optional [N, max_samples] scratch: when set, _prepare records the sample positions along each
      * ray (vn_march_train_count_rows) and _run expands them (vn_march_train_expand) instead of
      * marching a second time */
@@ -358,7 +363,7 @@ int vn_p2p_allreduce(int64_t n, void* stream);
  *               backoff 0.5, interval 2000).  Arithmetic identical to vn_adam_step. */
 int vn_p2p_attach(void* const* h_pbufs, void* const* h_mbox);
 int vn_p2p_allreduce_small(float* data, int n, int use_max, void* stream);
-int vn_p2p_reduce_adam(int64_t n, float* m, float* v, float lr, float beta1, float beta2, float eps,
+int vn_p2p_reduce_adam(int64_t n, float* m, float* v, double lr, double beta1, double beta2, double eps,
                        int step, float* found_inf, float* scale_dev, int32_t* growth_tracker,
                        void* stream);
 

@@ -49,6 +49,7 @@ def _c(a, dt):
 
 f32, i32, i64, u8, u32 = np.float32, np.int32, np.int64, np.uint8, np.uint32
 cf = ctypes.c_float
+cd = ctypes.c_double
 ci = ctypes.c_int
 cl = ctypes.c_int64
 
@@ -314,5 +315,5 @@ def adam_step(p, g, m, v, inv_scale, lr, beta1, beta2, eps, step):
     for a in (p, m, v):
         assert a.dtype == f32 and a.flags["C_CONTIGUOUS"]
     g = _c(g, f32)
-    return int(lib().vo_adam_step(_p(p), _p(g), _p(m), _p(v), cl(p.size), cf(inv_scale), cf(lr),
-                                  cf(beta1), cf(beta2), cf(eps), ci(step)))
+    return int(lib().vo_adam_step(_p(p), _p(g), _p(m), _p(v), cl(p.size), cf(inv_scale), cd(lr),
+                                  cd(beta1), cd(beta2), cd(eps), ci(step)))

@@ -801,16 +801,19 @@ VO_API void vo_occ_decay_pack(float* grid, int grid_size, float decay /*1.0 = no
 // (the step is then skipped, as GradScaler.step does).
 // ------------------------------------------------------------------------------------
 VO_API int vo_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float inv_scale,
-                        float lr, float beta1, float beta2, float eps, int step) {
+                        double lr, double beta1, double beta2, double eps, int step) {
     for (int64_t i = 0; i < n; ++i) if (!std::isfinite(g[i] * inv_scale)) return 1;
-    double bc1 = 1.0 - std::pow((double)beta1, step), bc2 = 1.0 - std::pow((double)beta2, step);
-    float step_size = (float)((double)lr / bc1);
-    float bc2_sqrt = (float)std::sqrt(bc2);
+    // torch (_single_tensor_adam): python-double arithmetic on the hyper-parameters, one rounding to f32
+    // where the scalar meets the f32 tensor
+    double bc1 = 1.0 - std::pow(beta1, step), bc2 = 1.0 - std::pow(beta2, step);
+    const float step_size = (float)(lr / bc1);
+    const float bc2_sqrt = (float)std::sqrt(bc2);
+    const float b2 = (float)beta2, omb1 = (float)(1.0 - beta1), omb2 = (float)(1.0 - beta2), epsf = (float)eps;
     for (int64_t i = 0; i < n; ++i) {
         float gi = g[i] * inv_scale;
-        m[i] = m[i] + (gi - m[i]) * (1.0f - beta1);          // torch: exp_avg.lerp_(grad, 1-beta1)
-        v[i] = v[i] * beta2 + (1.0f - beta2) * gi * gi;      // exp_avg_sq.mul_(b2).addcmul_(g,g,1-b2)
-        float denom = sqrtf(v[i]) / bc2_sqrt + eps;
+        m[i] = std::fmaf(gi - m[i], omb1, m[i]);             // torch: exp_avg.lerp_(grad, 1-beta1)
+        v[i] = std::fmaf(omb2 * gi, gi, v[i] * b2);          // exp_avg_sq.mul_(b2).addcmul_(g,g,1-b2)
+        float denom = sqrtf(v[i]) / bc2_sqrt + epsf;
         p[i] = p[i] - step_size * (m[i] / denom);
     }
     return 0;

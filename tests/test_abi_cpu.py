@@ -67,6 +67,18 @@ def test_ctypes_call_specs_match_the_header_prototypes(vn):
     assert checked >= 45
 
 
+def test_adam_constants_follow_torch_rounding(vn):
+    """vn_adam_config (host): python-double arithmetic on the hyper-parameters, one rounding to f32 -- what
+    torch.optim.Adam's single-tensor path feeds its kernels (1 - beta2 is 0.001f, not 1.0f - 0.999f)"""
+    import math
+    lr, b1, b2, eps = 5e-3, 0.9, 0.999, 1e-15
+    for step in (1, 2, 7, 100, 5000):
+        got = np.array(vn.adam_config(lr, b1, b2, eps, step), np.float32)
+        want = np.array([b2, 1 - b1, 1 - b2, eps, lr / (1 - b1 ** step), math.sqrt(1 - b2 ** step)]).astype(np.float32)
+        np.testing.assert_array_equal(got, want)
+    assert np.float32(1 - b2) != np.float32(1) - np.float32(b2)        # the distinction this entry point exists for
+
+
 def test_next_row_mirrors_expose_the_reference_api():
     from virus_nerf_b200.modules import ngp_grid, networks
     from virus_nerf_b200.datasets import dataset_base

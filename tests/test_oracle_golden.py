@@ -245,4 +245,4 @@ def test_adam_against_torch_optim(oracle_mod):
     st = opt.state[param]
     # lerp cancels where g and m are close: absolute tolerance relative to the largest moment
     np.testing.assert_allclose(m, st["exp_avg"].numpy(), rtol=2e-6, atol=1e-6 * float(np.abs(m).max()))
-    np.testing.assert_allclose(v, st["exp_avg_sq"].numpy(), rtol=2e-6, atol=1e-6 * float(np.abs(v).max()))
+    np.testing.assert_allclose(v, st["exp_avg_sq"].numpy(), rtol=2e-6, atol=1e-7 * float(np.abs(v).max()))

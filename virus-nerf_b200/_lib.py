@@ -41,7 +41,7 @@ class HashLevels(ctypes.Structure):
     ]
 
 
-_P, _F, _I32, _I64 = ctypes.c_void_p, ctypes.c_float, ctypes.c_int32, ctypes.c_int64
+_P, _F, _I32, _I64, _D = ctypes.c_void_p, ctypes.c_float, ctypes.c_int32, ctypes.c_int64, ctypes.c_double
 
 
 class Step(ctypes.Structure):
@@ -61,7 +61,7 @@ class Step(ctypes.Structure):
         [("loss_acc", _P), ("loss_out", _P)] +
         [("w_color", _F), ("w_uss", _F), ("w_tof", _F), ("w_rgbd", _F)] +
         [("scale_dev", _P), ("found_inf", _P), ("growth_tracker", _P)] +
-        [("lr", _F), ("beta1", _F), ("beta2", _F), ("eps", _F), ("adam_step", _I32)] +
+        [("lr", _D), ("beta1", _D), ("beta2", _D), ("eps", _D), ("adam_step", _I32)] +
         [("ts_rows", _P)])
 
     def set_ptrs(self, **tensors):
@@ -107,7 +107,7 @@ _SPECS = {
     "vn_loss_fwd": "ppppppp" "lff" "pp" "s",
     "vn_loss_bwd": "ppppppp" "lff" "pp" "ffff" "p" "pppp" "s",
     "vn_grad_check": "plps",
-    "vn_adam_step": "ppppl" "fffff" "ipps",
+    "vn_adam_step": "ppppl" "f" "dddd" "ipps",
     "vn_scaler_update": "pppffis",
     "vn_umma_selftest": "iiippps",
     "vn_train_step_prepare": "hs",
@@ -115,7 +115,7 @@ _SPECS = {
     "vn_train_step_optim": "hs",
     "vn_p2p_allreduce": "ls",
     "vn_p2p_allreduce_small": "piis",
-    "vn_p2p_reduce_adam": "lpp" "ffff" "i" "ppp" "s",
+    "vn_p2p_reduce_adam": "lpp" "dddd" "i" "ppp" "s",
     "vn_batch_assemble": "ppl" "ppl" "pil" "pi" "pppp" "pp" "ppp" "pppp" "pp" "p" "s",
     "vn_ngp_sample_occupied": "plfplpps",
     "vn_ngp_cell_positions": "ppliffps",
@@ -266,6 +266,18 @@ def launch_count():
     return int(lib().vn_launch_count())
 
 
+def adam_config(lr, beta1, beta2, eps, step):
+    """the six f32 constants of one Adam step (beta2, 1-beta1, 1-beta2, eps, step_size, bias_correction2_sqrt)
+    as the kernels receive them (host only)"""
+    out = (ctypes.c_float * 6)()
+    L = lib()
+    L.vn_adam_config.argtypes = [ctypes.c_double] * 4 + [ctypes.c_int, ctypes.c_void_p]
+    rc = L.vn_adam_config(lr, beta1, beta2, eps, int(step), ctypes.cast(out, ctypes.c_void_p))
+    if rc != 0:
+        raise RuntimeError(last_error())
+    return list(out)
+
+
 def ngp_select_tmp_ints(n_cells):
     return int(lib().vn_ngp_select_tmp_ints(ctypes.c_int64(int(n_cells))))
 
@@ -291,7 +303,7 @@ def hash_levels(base_res, max_res, levels, max_params):
 
 def exported_symbols():
     """names declared in include/virusnerf.h (used by the CPU-side ABI test)"""
-    return ["vn_last_error", "vn_abi_version", "vn_launch_count", "vn_ipc_get_handle", "vn_ipc_open", "vn_p2p_init", "vn_p2p_attach", "vn_profile_enable", "vn_profile_enable_mask", "vn_set_pdl", "vn_profile_count", "vn_profile_get", "vn_device_info", "vn_march_scan_tmp_ints",
+    return ["vn_last_error", "vn_abi_version", "vn_launch_count", "vn_ipc_get_handle", "vn_ipc_open", "vn_p2p_init", "vn_p2p_attach", "vn_profile_enable", "vn_profile_enable_mask", "vn_set_pdl", "vn_profile_count", "vn_profile_get", "vn_device_info", "vn_march_scan_tmp_ints", "vn_adam_config",
             "vn_ngp_select_tmp_ints", "vn_ngp_threshold_tmp_bytes"] + list(_SPECS)
 
 

@@ -142,6 +142,22 @@ __device__ __forceinline__ void vn_red_add_v2(float* addr, float a, float b) {
 // context-dependent contraction.
 struct AdamCfg { float inv_scale, beta1, beta2, omb1, omb2, eps, step_size, bc2_sqrt; };
 
+// the f32 constants torch's single-tensor Adam hands to its kernels: python-double arithmetic on the
+// hyper-parameters first, ONE rounding to f32 when the scalar meets the f32 tensor -- in particular
+// 1 - beta2 = f32(1 - 0.999) = 0.001f, not 1.0f - 0.999f (which is 1.3e-5 smaller)
+#include <math.h>
+static inline AdamCfg vn_make_adam_cfg(double lr, double beta1, double beta2, double eps, int step, float inv_scale) {
+    AdamCfg c;
+    const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+    c.inv_scale = inv_scale;
+    c.beta1 = (float)beta1; c.beta2 = (float)beta2;                 // exp_avg_sq.mul_(beta2)
+    c.omb1 = (float)(1.0 - beta1); c.omb2 = (float)(1.0 - beta2);   // lerp_(grad, 1 - beta1); addcmul_(..., value=1 - beta2)
+    c.eps = (float)eps;
+    c.step_size = (float)(lr / bc1);                                // addcdiv_(..., value=-step_size)
+    c.bc2_sqrt = (float)sqrt(bc2);                                  // exp_avg_sq.sqrt() / bias_correction2_sqrt
+    return c;
+}
+
 __device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, const AdamCfg& c) {
     g = __fmul_rn(g, c.inv_scale);                                   // GradScaler.unscale_
     m = __fmaf_rn(__fsub_rn(g, m), c.omb1, m);                       // exp_avg.lerp_(grad, 1 - beta1)

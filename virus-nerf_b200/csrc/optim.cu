@@ -48,20 +48,22 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
     }
 }
 
-VN_API int vn_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float inv_scale, float lr, float beta1,
-                        float beta2, float eps, int step, const float* found_inf, const float* scale_dev,
+VN_API int vn_adam_config(double lr, double beta1, double beta2, double eps, int step, float* h_out6) {
+    VN_REQUIRE(h_out6 != nullptr && step >= 1, "vn_adam_config: bad arguments");
+    const AdamCfg c = vn_make_adam_cfg(lr, beta1, beta2, eps, step, 1.0f);
+    h_out6[0] = c.beta2; h_out6[1] = c.omb1; h_out6[2] = c.omb2; h_out6[3] = c.eps; h_out6[4] = c.step_size; h_out6[5] = c.bc2_sqrt;
+    return VN_OK;
+}
+
+VN_API int vn_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float inv_scale, double lr, double beta1,
+                        double beta2, double eps, int step, const float* found_inf, const float* scale_dev,
                         void* stream) {
     VN_REQUIRE(n >= 0 && step >= 1, "vn_adam_step: bad n/step");
     if (n == 0) return VN_OK;
     VN_REQUIRE(p && g && m && v, "vn_adam_step: null pointer");
     VN_REQUIRE(vn_aligned(p, 16) && vn_aligned(g, 16) && vn_aligned(m, 16) && vn_aligned(v, 16),
                "vn_adam_step: buffers must be 16-byte aligned");
-    AdamCfg c;
-    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
-    c.inv_scale = inv_scale; c.beta1 = beta1; c.beta2 = beta2;
-    c.omb1 = 1.0f - beta1; c.omb2 = 1.0f - beta2; c.eps = eps;
-    c.step_size = (float)((double)lr / bc1);
-    c.bc2_sqrt = (float)sqrt(bc2);
+    const AdamCfg c = vn_make_adam_cfg(lr, beta1, beta2, eps, step, inv_scale);
     VnProfScope prof(VN_K_ADAM, n, (cudaStream_t)stream);
     vn_launch_pdl(adam_kernel, dim3(vn_blocks((n + 3) / 4, 256)), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, n, c, found_inf, scale_dev);
     VN_CHECK_LAUNCH("adam_kernel");

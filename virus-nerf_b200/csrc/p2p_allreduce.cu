@@ -261,7 +261,7 @@ VN_API int vn_p2p_allreduce_small(float* data, int n, int use_max, void* stream)
     return VN_OK;
 }
 
-VN_API int vn_p2p_reduce_adam(int64_t n, float* m, float* v, float lr, float beta1, float beta2, float eps, int step,
+VN_API int vn_p2p_reduce_adam(int64_t n, float* m, float* v, double lr, double beta1, double beta2, double eps, int step,
                               float* found_inf, float* scale_dev, int32_t* growth_tracker, void* stream) {
     VN_REQUIRE(g_ctx_ready && g_ctx.mbox[0] && g_ctx.pbufs[0],
                "vn_p2p_reduce_adam: vn_p2p_init / vn_p2p_attach (with parameter buffers) have not been called");
@@ -273,12 +273,7 @@ VN_API int vn_p2p_reduce_adam(int64_t n, float* m, float* v, float lr, float bet
     const int64_t n4 = n / 4;
     const int64_t chunk4 = (n4 + g_ctx.world - 1) / g_ctx.world;
     const int sms = vn_sm_count();
-    AdamCfg c;
-    c.inv_scale = 1.0f;
-    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
-    c.beta1 = beta1; c.beta2 = beta2; c.omb1 = 1.0f - beta1; c.omb2 = 1.0f - beta2; c.eps = eps;
-    c.step_size = (float)((double)lr / bc1);
-    c.bc2_sqrt = (float)sqrt(bc2);
+    const AdamCfg c = vn_make_adam_cfg(lr, beta1, beta2, eps, step, 1.0f);
     const int e = g_ctx.epoch;
     g_ctx.epoch += 3;
     const int parity = (g_ctx.small_ops++) & 1;

@@ -75,7 +75,7 @@ __global__ void scaler_update_kernel(float* scale, int32_t* tracker, float* foun
     if (*found_inf != 0.0f) { *scale = *scale * backoff; *tracker = 0; }
     else {
         const int t = *tracker + 1;
-        if (t == interval) { *scale = *scale * growth; *tracker = 0; }
+        if (t == interval) { const float grown = *scale * growth; if (isfinite(grown)) *scale = grown; *tracker = 0; }   // torch _amp_update_scale_
         else *tracker = t;
     }
     *found_inf = 0.0f;

@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--comm", default="auto", choices=["auto", "nccl", "p2p", "p2p_fused"],
                     help="gradient exchange: nccl allreduce, own peer-memory allreduce, or the sharded optimiser fused "
                          "with the peer-memory exchange (auto = p2p_fused, nccl if peer mapping fails)")
-    ap.add_argument("--enc-layout", default="planar", choices=["planar", "rows"],
+    ap.add_argument("--enc-layout", default="chunks", choices=["chunks", "planar", "rows"],
                     help="layout of the encoding inside the fused step (rows = the reference's [S,32])")
     ap.add_argument("--two-pass-march", action="store_true", help="re-march in the write pass (reference structure)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end phase (profiling runs only)")

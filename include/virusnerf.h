@@ -47,6 +47,10 @@ extern "C" {
 #define VN_HASH_TIGHT_REGS 1024 /* planar bwd: 48-register variant, 5 CTAs per SM */
 #define VN_HASH_SKIP_ZERO_GRADS 4096 /* f32 bwd: do not scatter (level, sample) pairs whose gradient is exactly 0 */
 #define VN_HASH_PAIR_LOADS 2048 /* planar fwd: 16-byte loads for x / x+1 corner pairs that are neighbours */
+#define VN_HASH_F16_CHUNKS 8192 /* fwd (f32 or f16 table): out is [levels/4][S] x 16 B "chunk planes": plane c holds
+                                  levels 4c..4c+3 of every point as 8 fp16 values = one row of one column chunk of the
+                                  fused MLP's tensor-core operand (vn_mlp_fwd enc_format 3, vn_mlp_bwd 3 / 4); bwd
+                                  (vn_hash_encode_bwd_f16): dout is in the same layout */
 /* default (no GROUPS flag): 4 (backward: 2 when the table exceeds the L2, > 96 MB) */
 
 const char* vn_last_error(void);
@@ -273,7 +277,9 @@ int vn_scaler_update(float* scale, int32_t* growth_tracker, float* found_inf, fl
  * stage: ONE kernel on the tcgen05 tensor cores (fp16 operands, fp32 accumulation in TMEM --
  * the reference runs these layers as fp16 cuBLAS GEMMs under torch.autocast, trainer.py:104).
  *   enc [S,32] hash encoding, f32 rows (enc_format = 0), fp16 rows (1) or f32 level-pair planes
- *   [8][S] float4 (2, the VN_HASH_PLANAR layout; denc is then written in the same layout); dirs [S,3] raw ray
+ *   [8][S] float4 (2, the VN_HASH_PLANAR layout; denc is then written in the same layout), or fp16 chunk
+ *   planes [4][S] x 16 B (3, the VN_HASH_F16_CHUNKS layout: tiles are bulk-copied straight into the tensor-core
+ *   operand; vn_mlp_bwd writes denc as f32 planes for enc_format 3 and as fp16 chunk planes for 4); dirs [S,3] raw ray
  *   directions (normalised and mapped to (d+1)/2 inside, networks.py:160-161); W1 [64,32],
  *   W2 [16,64], W3 [64,32], W4 [64,64], W5 [3,64] f32 in torch Linear layout [out,in].
  * _fwd: sigmas [S] = exp(h0), rgbs [S,3] = sigmoid(...), optional h_out [S,16] (return_feat).

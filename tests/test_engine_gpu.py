@@ -187,7 +187,7 @@ def test_occupancy_update_runs_and_is_deterministic(setup):
     assert not torch.equal(g0, g1)
 
 
-@pytest.mark.parametrize("enc_layout,single_pass", [("planar", True), ("rows", False)])
+@pytest.mark.parametrize("enc_layout,single_pass", [("chunks", True), ("planar", True), ("rows", False)])
 def test_fast_step_matches_autograd_step(monkeypatch, enc_layout, single_pass):
     """the hand-chained C-ABI step (engine.step_fast) and the autograd step through the drop-in
     modules produce the same loss, gradients and parameter update (same rays, same jitter)"""

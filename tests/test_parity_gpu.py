@@ -149,6 +149,29 @@ def test_hash_planar_layout(vn, oracle_mod, flags, S_extra):
         np.testing.assert_allclose(N(grad), ref, rtol=1e-4, atol=1e-6 * np.abs(ref).max())
 
 
+@pytest.mark.parametrize("flags", [0, 64, 128, 2048])
+@pytest.mark.parametrize("S_extra", [0, 1, 31])
+def test_hash_f16_chunk_layout(vn, oracle_mod, flags, S_extra):
+    """VN_HASH_F16_CHUNKS: plane c of the output holds levels 4c..4c+3 of every point as fp16 -- exactly the
+    row kernel's fp32 values rounded to nearest fp16 (where autocast rounds the Linear input)"""
+    lv = vn.hash_levels(16, 1024, 16, 2 ** 19)
+    rng = np.random.default_rng(12)
+    table = rng.random(2 * lv.total_entries, dtype=np.float32) * 2 - 1
+    xyz = np.concatenate([rng.random((1000 + S_extra, 3)).astype(np.float32), ray_coherent_points(96, 64)])
+    S = xyz.shape[0]
+    rows = torch.empty(S, 32, device=DEV)
+    chunks = torch.empty(4, S, 8, device=DEV, dtype=torch.float16)
+    vn.call("vn_hash_encode_fwd_f32", T(xyz), T(table), rows, S, lv, 0)
+    vn.call("vn_hash_encode_fwd_f32", T(xyz), T(table), chunks, S, lv, flags | vn.VN_HASH_F16_CHUNKS)
+    np.testing.assert_array_equal(N(chunks), N(rows.half().view(S, 4, 8).permute(1, 0, 2)))
+    # half-precision table (hash_encoder_half.py): same layout, the half kernel's own arithmetic
+    table_h = T(table).half().view(-1, 2)
+    rows_h = torch.empty(S, 16, 2, dtype=torch.float16, device=DEV)
+    vn.call("vn_hash_encode_fwd_f16", T(xyz), table_h, rows_h, S, lv, 0)
+    vn.call("vn_hash_encode_fwd_f16", T(xyz), table_h, chunks, S, lv, (flags & ~2048) | vn.VN_HASH_F16_CHUNKS)
+    np.testing.assert_array_equal(N(chunks), N(rows_h.view(S, 4, 8).permute(1, 0, 2)))
+
+
 def test_hash_planar_rejects_odd_groups(vn):
     lv = vn.hash_levels(16, 1024, 16, 2 ** 19)
     x = torch.rand(64, 3, device=DEV); t = torch.rand(2 * lv.total_entries, device=DEV); o = torch.empty(8, 64, 4, device=DEV)

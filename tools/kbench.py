@@ -110,7 +110,7 @@ def main():
         g = torch.Generator().manual_seed(0)
         xav = lambda o, i: ((torch.rand(o, i, generator=g) * 2 - 1) * (6.0 / (i + o)) ** 0.5).to(DEV)
         W = [xav(64, 32), xav(16, 64), xav(64, 32), xav(64, 64), xav(3, 64)]
-        for S in (69710, 1 << 20):
+        for S in (69710, 933574, 1 << 20):
             enc = torch.rand(S, 32, device=DEV); dirs = torch.randn(S, 3, device=DEV)
             sig = torch.empty(S, device=DEV); rgb = torch.empty(S, 3, device=DEV)
             ms = timeit(lambda: _lib.call("vn_mlp_fwd", enc, 0, dirs, *W, S, 0, sig, rgb, None))
@@ -119,6 +119,11 @@ def main():
             denc = torch.empty(S, 32, device=DEV); dW = [torch.zeros_like(w) for w in W]
             ms = timeit(lambda: _lib.call("vn_mlp_bwd", enc, 0, dirs, *W, S, 0, dsig, drgb, denc, *dW))
             rec("mlp_bwd", ms, S=S, tflops=round(S * 56448 / ms / 1e9, 2), gbs=round(S * 284 / ms / 1e6, 1))
+            enc_c = enc.half().view(S, 4, 8).permute(1, 0, 2).contiguous()
+            ms = timeit(lambda: _lib.call("vn_mlp_fwd", enc_c, 3, dirs, *W, S, 0, sig, rgb, None))
+            rec("mlp_fwd_chunks", ms, S=S, tflops=round(S * 18816 / ms / 1e9, 2), gbs=round(S * 92 / ms / 1e6, 1))
+            ms = timeit(lambda: _lib.call("vn_mlp_bwd", enc_c, 3, dirs, *W, S, 0, dsig, drgb, denc, *dW))
+            rec("mlp_bwd_chunks", ms, S=S, tflops=round(S * 56448 / ms / 1e9, 2), gbs=round(S * 220 / ms / 1e6, 1))
             ms = timeit(lambda: _lib.call("vn_mlp_fwd", enc, 2, dirs, *W, S, 0, sig, rgb, None))
             rec("mlp_fwd_planar", ms, S=S, tflops=round(S * 18816 / ms / 1e9, 2), gbs=round(S * 156 / ms / 1e6, 1))
             ms = timeit(lambda: _lib.call("vn_mlp_bwd", enc, 2, dirs, *W, S, 0, dsig, drgb, denc, *dW))

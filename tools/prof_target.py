@@ -8,8 +8,9 @@ from virus_nerf_b200.modules.intersection import ray_aabb_intersection
 from virus_nerf_b200.modules.ray_march import raymarching_train
 DEV = "cuda:0"
 # default: the fast step's flags (planes, 2 levels per thread, 16-byte pair loads, 48-register bwd, zero skip)
-flags = int(sys.argv[1]) if len(sys.argv) > 1 else (512 | 256 | 2048 | 1024 | 4096)
-fmt = 2 if flags & 512 else 0
+# round 2: + 8192 = fp16 operand chunks out of the hash forward, bulk-copied by the fused MLP (enc_format 3)
+flags = int(sys.argv[1]) if len(sys.argv) > 1 else (512 | 256 | 2048 | 1024 | 4096 | 8192)
+fmt = 3 if flags & 8192 else (2 if flags & 512 else 0)
 ds = synthetic.SyntheticDataset(pool_size=1 << 16, device=DEV)
 b = ds(4096, {"pixs": {"valid_uss": 0.4, "valid_tof": 0.4}})
 bf = torch.full((128 ** 3 // 8,), 255, dtype=torch.uint8, device=DEV)

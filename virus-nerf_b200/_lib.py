@@ -25,6 +25,7 @@ VN_HASH_PLANAR = 512
 VN_HASH_TIGHT_REGS = 1024
 VN_HASH_PAIR_LOADS = 2048
 VN_HASH_SKIP_ZERO_GRADS = 4096
+VN_HASH_F16_CHUNKS = 8192
 
 
 class HashLevels(ctypes.Structure):

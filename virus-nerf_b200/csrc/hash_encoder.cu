@@ -177,7 +177,11 @@ __device__ __forceinline__ void level_gather(const TT* __restrict__ tbl, const C
 // PLANAR (f32 only, levels and LPT even): out is [levels/2][S] float4 -- plane p holds
 // (level 2p f0, f1, level 2p+1 f0, f1) of every point, so a warp's store of one plane is one
 // contiguous 512-byte run instead of 32 separate 16-byte pieces of 32 rows.
-template <typename TT, typename OT, int LPT, bool PLANAR, bool PAIR = false>
+// CHUNK (LPT % 4 == 0, levels % 4 == 0): out is [levels/4][S] x 16 B -- plane c holds levels 4c .. 4c+3 of
+// every point as 8 fp16 values, which is one row of one column chunk of the fused MLP's UMMA operand
+// (umma.cuh): a 128-sample tile of a plane is 2 KB of contiguous, ready-to-multiply operand.  The fp32
+// sums are rounded to fp16 exactly where torch.autocast rounds the Linear input.
+template <typename TT, typename OT, int LPT, bool PLANAR, bool PAIR = false, bool CHUNK = false>
 __global__ void __launch_bounds__(256) hash_fwd_kernel(const float* __restrict__ xyz, const TT* __restrict__ table,
                                                        OT* __restrict__ out, int64_t S,
                                                        const __grid_constant__ HashParams P) {
@@ -203,7 +207,18 @@ __global__ void __launch_bounds__(256) hash_fwd_kernel(const float* __restrict__
         }
     }
     const int W = 2 * P.levels;
-    if (PLANAR) {
+    if (CHUNK) {
+        uint4* o = (uint4*)out + (int64_t)(level0 / 4) * S + i;
+#pragma unroll
+        for (int q = 0; q < LPT / 4; ++q) {
+            if (level0 + 4 * q < P.levels) {
+                __half2 h[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(acc[8 * q + 2 * j], acc[8 * q + 2 * j + 1]);
+                o[(int64_t)q * S] = *reinterpret_cast<const uint4*>(h);
+            }
+        }
+    } else if (PLANAR) {
         float4* o = (float4*)out + (int64_t)(level0 / 2) * S + i;
 #pragma unroll
         for (int q = 0; q < LPT / 2; ++q)
@@ -430,6 +445,7 @@ __global__ void f32_to_f16_kernel(const float* __restrict__ src, __half* __restr
 // resident; the backward prefers 2 when it is not (T = 2^22).  8 / 16 levels per thread touch
 // every output row only once (less DRAM traffic) but lose more to occupancy than they gain.
 static int pick_lpt(int flags, const vn_hash_levels_t* lv, size_t entry_bytes, bool backward) {
+    if (!backward && (flags & VN_HASH_F16_CHUNKS)) return (flags & VN_HASH_LEVEL_GROUPS_8) ? 8 : ((flags & VN_HASH_LEVEL_GROUPS_16) ? 16 : 4);
     if (flags & VN_HASH_LEVEL_GROUPS_1) return 1;
     if (flags & VN_HASH_LEVEL_GROUPS_2) return 2;
     if (flags & VN_HASH_LEVEL_GROUPS_4) return 4;
@@ -450,6 +466,20 @@ static int launch_fwd(const float* xyz, const TT* table, OT* out, int64_t S, con
     VnProfScope prof(VN_K_HASH_FWD, S, st);
     const int lpt = pick_lpt(flags, lv, sizeof(TT), false);
     dim3 block(256), grid(vn_blocks(S, 256), (P.levels + lpt - 1) / lpt);
+    if (flags & VN_HASH_F16_CHUNKS) {
+        VN_REQUIRE(P.levels % 4 == 0 && lpt % 4 == 0, "hash fwd: the f16 chunk layout needs levels %% 4 == 0 and >= 4 levels per thread");
+        VN_REQUIRE(vn_aligned(out, 16), "hash fwd: the f16 chunk layout needs a 16-byte aligned output");
+        const bool pair = (flags & VN_HASH_PAIR_LOADS) != 0 && sizeof(TT) == 8;
+        switch (lpt) {
+            case 4: if (pair) vn_launch_pdl(hash_fwd_kernel<TT, OT, 4, false, true, true>, dim3(grid), dim3(block), 0, st, xyz, table, out, S, P);
+                    else vn_launch_pdl(hash_fwd_kernel<TT, OT, 4, false, false, true>, dim3(grid), dim3(block), 0, st, xyz, table, out, S, P); break;
+            case 8: if (pair) vn_launch_pdl(hash_fwd_kernel<TT, OT, 8, false, true, true>, dim3(grid), dim3(block), 0, st, xyz, table, out, S, P);
+                    else vn_launch_pdl(hash_fwd_kernel<TT, OT, 8, false, false, true>, dim3(grid), dim3(block), 0, st, xyz, table, out, S, P); break;
+            default: vn_launch_pdl(hash_fwd_kernel<TT, OT, 16, false, false, true>, dim3(grid), dim3(block), 0, st, xyz, table, out, S, P); break;
+        }
+        VN_CHECK_LAUNCH("hash_fwd_kernel<f16 chunks>");
+        return VN_OK;
+    }
     if (flags & VN_HASH_PLANAR) {
         VN_REQUIRE(sizeof(OT) == 4 && P.levels % 2 == 0 && lpt % 2 == 0,
                    "hash fwd: the planar layout needs f32 output, an even level count and >= 2 levels per thread");

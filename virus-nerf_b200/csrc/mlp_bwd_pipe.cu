@@ -1,0 +1,656 @@
+// mlp_bwd_pipe.cu -- backward of the fused NGP MLPs (modules/networks.py:134-164, 195-282 under
+// torch.autocast(float16)) as a warp-specialised, software-pipelined tcgen05 kernel.
+//
+// Same mathematics, operand layouts and rounding points as mlp_kernel<true> (mlp_fused.cu); what
+// changes is how the per-tile latency chain (10 dependent MMA rounds) is hidden:
+//
+//   * ONE persistent CTA per SM: 3 tile chains x 256 epilogue threads + 2 MMA-issuing warps.
+//     Each chain owns one 128-sample tile at a time; while chain A waits for its MMAs, chains B
+//     and C run their epilogues, so three tiles are in flight per SM and the tensor pipe always
+//     has a queue.  The 20 KB of fp16 weights and the five weight-gradient accumulators in TMEM
+//     are shared by the chains (single issuer => the accumulating MMAs are ordered).
+//   * a chain publishes its operands with fence.proxy.async + one red.release per warp on a
+//     shared-memory counter; the issuers walk a FIXED schedule (tile, round, chain 0/1/2), wait
+//     for the chain's counter with plain ld.acquire, issue the round's tcgen05.mma with
+//     immediate descriptors and commit to the chain's mbarrier.  (A first version with one
+//     issuer that dispatched on a per-chain round number spent ~960 cycles per round in
+//     bookkeeping and was the bottleneck: profiles/r2_mlp_bwd.md.)  Warp 24 issues the MMAs a
+//     chain waits for, warp 25 the weight-gradient products.
+//   * inputs arrive by bulk async copies (cp.async.bulk -> mbarrier complete_tx) one tile ahead:
+//     the encoding as fp16 in the UMMA core-matrix layout straight from the hash kernel
+//     (enc_fmt 3: [4][S] x 16 B chunk planes -- four 2 KB copies are the whole X0 operand), the
+//     ray directions and the output gradients as flat 1.5 KB / 0.5 KB runs.  No register
+//     staging, no cvt / st.shared pass over the inputs.
+//   * 60 KB of activations per tile instead of 88: masked gradients overwrite their activations
+//     in place, d(h) overwrites h inside the [SH | h] operand, and H1 is RECOMPUTED (one extra
+//     32->64 MMA, issued in the shadow of the dgrad3 / wgrad3 round) instead of being kept, so
+//     H1 / H4 / dH4 / dH1 share one buffer.
+//   * epilogues work on packed halves: cvt.rn.relu.f16x2.f32 for the ReLU, a half2 compare mask
+//     + AND for the ReLU backward.
+//
+// Rounds per tile (chain-local buffers X0, IN2 = [SH16 | h16], HA, HB, D5; TMEM scratch TMP):
+//   r1  TMP[0:64]  = X0  W1^T          -> HA = relu                       (H1)
+//   r2  TMP[0:16]  = HA  W2^T          -> IN2[:,16:32] = h, keep dsigma*exp(h0)
+//   r3  TMP[0:64]  = IN2 W3^T          -> HB = relu                       (H3)
+//   r4  TMP[0:64]  = HB  W4^T          -> HA = relu                       (H4)
+//   r5  TMP[0:16]  = HA  W5^T          -> rgb = sigmoid, D5 = drgb rgb (1-rgb)
+//   r6  TMP[0:64]  = D5  W5 ; dW5^T += HA^T D5      -> HA = TMP * (HA > 0)  (dH4, in place)
+//   r7  TMP[0:64]  = HA  W4 ; dW4   += HA^T HB      -> HB = TMP * (HB > 0)  (dH3, in place)
+//   r8  TMP[64:80] = HB  W3[:,16:32] ; dW3 += HB^T IN2 ; TMP[0:64] = X0 W1^T
+//                                       -> IN2[:,16:32] = d(h) (+ sigma term), HA = relu (H1 again)
+//   r9  TMP[0:64]  = dh  W2 ; dW2^T += HA^T dh      -> HA = TMP * (HA > 0)  (dH1, in place)
+//   r10 TMP[0:32]  = HA  W1 ; dW1   += HA^T X0      -> d(enc) to global
+#include "mlp_common.cuh"
+
+namespace mlp {
+namespace {
+
+constexpr int NCH = 3;                          // tile chains per CTA
+constexpr int CH_THREADS = 256;                 // (row, column half) threads of a chain
+constexpr int MMA_WARP = NCH * CH_THREADS / 32; // warp 24: forward / dgrad MMAs (the chains' critical path)
+constexpr int WG_WARP = MMA_WARP + 1;           // warp 25: weight-gradient MMAs (all accumulating MMAs from one thread)
+constexpr int NTHR = NCH * CH_THREADS + 64;     // 832
+// per-chain shared memory (bytes)
+constexpr int C_X0 = 0;                         // 2 x [128 x 32] fp16 (double-buffered input tile)
+constexpr int C_IN2 = C_X0 + 2 * 8192;          // [128 x 32]
+constexpr int C_HA = C_IN2 + 8192;              // [128 x 64]
+constexpr int C_HB = C_HA + 16384;              // [128 x 64]
+constexpr int C_D5 = C_HB + 16384;              // [128 x 16]
+constexpr int C_AUX = C_D5 + 4096;              // 2 x (dirs 1536 | drgb 1536 | dsig 512)
+constexpr int AUX_DIRS = 0, AUX_DRGB = 1536, AUX_DSIG = 3072, AUX_SIZE = 3584;
+constexpr int C_SIZE = C_AUX + 2 * AUX_SIZE;    // 68 608
+static_assert(C_SIZE % 1024 == 0, "chain stride must keep the operand alignment");
+// shared weights
+constexpr int W_BASE = NCH * C_SIZE;
+constexpr int W1_OFF = W_BASE;                  // [64 x 32]
+constexpr int W2_OFF = W1_OFF + 64 * 32 * 2;    // [16 x 64]
+constexpr int W3_OFF = W2_OFF + 16 * 64 * 2;    // [64 x 32]
+constexpr int W4_OFF = W3_OFF + 64 * 32 * 2;    // [64 x 64]
+constexpr int W5_OFF = W4_OFF + 64 * 64 * 2;    // [16 x 64], rows 3..15 zero
+constexpr int SMEM_PIPE = W5_OFF + 16 * 64 * 2; // 226 304 bytes
+static_assert(SMEM_PIPE <= 227 * 1024 - 256, "shared memory budget");
+// TMEM columns: chain scratch c * 96 (+0: 64-wide accumulator, +64: 16-wide d(h)), then the shared
+// weight-gradient accumulators (M = 64 layout)
+constexpr int T_CH = 96;
+constexpr int T_DW1 = NCH * T_CH, T_DW3 = T_DW1 + 32, T_DW4 = T_DW3 + 32, T_DW2T = T_DW4 + 64, T_DW5T = T_DW2T + 16;
+static_assert(T_DW5T + 16 <= 512, "TMEM budget");
+constexpr int ROUNDS = 10;
+
+// ---- small PTX helpers ---------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(umma::smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+                 "l"(src), "r"(bytes), "r"(umma::smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void red_release_inc(uint32_t* p) {
+    asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(umma::smem_u32(p)) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(umma::smem_u32(p)) : "memory");
+    return v;
+}
+// two fp32 -> packed fp16 (lo in bits 0..15), round to nearest; RELU: negative -> +0
+template <bool RELU>
+__device__ __forceinline__ uint32_t pack2(uint32_t lo_bits, uint32_t hi_bits) {
+    uint32_t d;
+    if (RELU) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(hi_bits)), "f"(__uint_as_float(lo_bits)));
+    else      asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(hi_bits)), "f"(__uint_as_float(lo_bits)));
+    return d;
+}
+// 0xffff per half where act > 0
+__device__ __forceinline__ uint32_t gt0_mask(uint32_t act2) {
+    const __half2 z = __float2half2_rn(0.0f);
+    return __hgt2_mask(*reinterpret_cast<const __half2*>(&act2), z);
+}
+template <int N>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t* r);
+template <>
+__device__ __forceinline__ void tmem_ld<8>(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+template <>
+__device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+template <>
+__device__ __forceinline__ void tmem_ld<32>(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+
+// ---- descriptors with everything but the chain base folded into immediates ------------------------
+// a16 = shared-memory byte address >> 4 (< 2^14 for the whole 227 KB window, so adding k-steps never
+// carries into the LBO field).  K-major operand of R stored rows: LBO = R*16 (next 8 columns), SBO =
+// 128 (next 8 rows), one K=16 step = 2*LBO.  MN-major: LBO = 128, SBO = R*16, one K step = 256 B.
+template <int R>
+__device__ __forceinline__ uint64_t dK(uint32_t a16, int k) {
+    const uint32_t lo = a16 + (uint32_t)(k * 2 * R + (R << 16));
+    return ((uint64_t)(0x4000u | 8u) << 32) | lo;
+}
+template <int R>
+__device__ __forceinline__ uint64_t dMN(uint32_t a16, int k) {
+    const uint32_t lo = a16 + (uint32_t)(k * 16 + (8 << 16));
+    return ((uint64_t)(0x4000u | (uint32_t)R) << 32) | lo;
+}
+
+// ---- the MMA issuers: one round of one chain, round number known at compile time ---------------------
+// cb16 / x16: chain base and this tile's X0 buffer (>> 4); w16: weights; tm: the chain's TMEM scratch
+template <int R>
+__device__ __forceinline__ void issue_main(uint32_t cb16, uint32_t x16, uint32_t w16, uint32_t tm) {
+    constexpr uint32_t IN2 = C_IN2 >> 4, HA = C_HA >> 4, HB = C_HB >> 4, D5 = C_D5 >> 4;
+    constexpr uint32_t W1 = (W1_OFF - W_BASE) >> 4, W2 = (W2_OFF - W_BASE) >> 4, W3 = (W3_OFF - W_BASE) >> 4,
+                       W4 = (W4_OFF - W_BASE) >> 4, W5 = (W5_OFF - W_BASE) >> 4;
+    constexpr uint32_t I_F64 = umma::instr_desc_f16(128, 64, 0, 0), I_F16 = umma::instr_desc_f16(128, 16, 0, 0);
+    constexpr uint32_t I_D64 = umma::instr_desc_f16(128, 64, 0, 1), I_D32 = umma::instr_desc_f16(128, 32, 0, 1),
+                       I_D16 = umma::instr_desc_f16(128, 16, 0, 1);
+    if (R == 0) {          // r1: H1raw = X0 W1^T
+#pragma unroll
+        for (int k = 0; k < 2; ++k) umma::mma_f16(tm, dK<128>(x16, k), dK<64>(w16 + W1, k), I_F64, k > 0);
+    } else if (R == 1) {   // r2: h = H1 W2^T
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma::mma_f16(tm, dK<128>(cb16 + HA, k), dK<16>(w16 + W2, k), I_F16, k > 0);
+    } else if (R == 2) {   // r3: H3raw = IN2 W3^T
+#pragma unroll
+        for (int k = 0; k < 2; ++k) umma::mma_f16(tm, dK<128>(cb16 + IN2, k), dK<64>(w16 + W3, k), I_F64, k > 0);
+    } else if (R == 3) {   // r4: H4raw = H3 W4^T
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma::mma_f16(tm, dK<128>(cb16 + HB, k), dK<64>(w16 + W4, k), I_F64, k > 0);
+    } else if (R == 4) {   // r5: out = H4 W5^T
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma::mma_f16(tm, dK<128>(cb16 + HA, k), dK<16>(w16 + W5, k), I_F16, k > 0);
+    } else if (R == 5) {   // r6: dH4raw = D5 W5
+        umma::mma_f16(tm, dK<128>(cb16 + D5, 0), dMN<16>(w16 + W5, 0), I_D64, false);
+    } else if (R == 6) {   // r7: dH3raw = dH4 W4
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma::mma_f16(tm, dK<128>(cb16 + HA, k), dMN<64>(w16 + W4, k), I_D64, k > 0);
+    } else if (R == 7) {   // r8: d(h)raw = dH3 W3[:,16:32] ; H1raw = X0 W1^T (recomputed)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma::mma_f16(tm + 64, dK<128>(cb16 + HB, k), dMN<64>(w16 + W3 + 128, k), I_D16, k > 0);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) umma::mma_f16(tm, dK<128>(x16, k), dK<64>(w16 + W1, k), I_F64, k > 0);
+    } else if (R == 8) {   // r9: dH1raw = dh W2       (dh = IN2[:,16:32], a [128 x 16] operand at +4096 B)
+        umma::mma_f16(tm, dK<128>(cb16 + IN2 + 256, 0), dMN<16>(w16 + W2, 0), I_D64, false);
+    } else {               // r10: d(enc) = dH1 W1
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma::mma_f16(tm, dK<128>(cb16 + HA, k), dMN<64>(w16 + W1, k), I_D32, k > 0);
+    }
+}
+// the weight-gradient product of rounds r6 .. r10 (R = 5 .. 9); acc0: accumulate into what is there
+template <int R>
+__device__ __forceinline__ void issue_wgrad(uint32_t cb16, uint32_t x16, uint32_t tmem0, bool acc0) {
+    constexpr uint32_t IN2 = C_IN2 >> 4, HA = C_HA >> 4, HB = C_HB >> 4, D5 = C_D5 >> 4;
+    constexpr uint32_t I_W64 = umma::instr_desc_f16(64, 64, 1, 1), I_W32 = umma::instr_desc_f16(64, 32, 1, 1),
+                       I_W16 = umma::instr_desc_f16(64, 16, 1, 1);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const bool acc = k > 0 || acc0;
+        if (R == 5)      umma::mma_f16(tmem0 + T_DW5T, dMN<128>(cb16 + HA, k), dMN<128>(cb16 + D5, k), I_W16, acc);         // dW5^T += H4^T D5
+        else if (R == 6) umma::mma_f16(tmem0 + T_DW4, dMN<128>(cb16 + HA, k), dMN<128>(cb16 + HB, k), I_W64, acc);          // dW4 += dH4^T H3
+        else if (R == 7) umma::mma_f16(tmem0 + T_DW3, dMN<128>(cb16 + HB, k), dMN<128>(cb16 + IN2, k), I_W32, acc);         // dW3 += dH3^T IN2
+        else if (R == 8) umma::mma_f16(tmem0 + T_DW2T, dMN<128>(cb16 + HA, k), dMN<128>(cb16 + IN2 + 256, k), I_W16, acc);  // dW2^T += H1^T dh
+        else             umma::mma_f16(tmem0 + T_DW1, dMN<128>(cb16 + HA, k), dMN<128>(x16, k), I_W32, acc);                // dW1 += dH1^T X0
+    }
+}
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+// ---- epilogue pieces (thread = sample row x column half) --------------------------------------------
+// 32 accumulator columns -> ReLU -> fp16 -> chunks 4*half .. 4*half+3 of a 64-wide operand buffer
+__device__ __forceinline__ void epi_relu32(uint32_t taddr, uint8_t* buf, int row, int half) {
+    uint32_t r[32];
+    tmem_ld<32>(taddr, r);
+    umma::tmem_ld_wait();
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        uint4 u;
+        u.x = pack2<true>(r[8 * c], r[8 * c + 1]); u.y = pack2<true>(r[8 * c + 2], r[8 * c + 3]);
+        u.z = pack2<true>(r[8 * c + 4], r[8 * c + 5]); u.w = pack2<true>(r[8 * c + 6], r[8 * c + 7]);
+        *reinterpret_cast<uint4*>(buf + (4 * half + c) * (TILE * 16) + row * 16) = u;
+    }
+}
+// in place: buf holds the activation H (fp16); it is replaced by fp16(g) where H > 0, else 0
+// (the buffer is an operand of the round's weight-gradient product: the stores wait for it on `wg_bar`)
+__device__ __forceinline__ void epi_mask32(uint32_t taddr, uint8_t* buf, int row, int half, uint64_t* wg_bar, uint32_t& wg_phase) {
+    uint32_t r[32];
+    tmem_ld<32>(taddr, r);
+    uint4 a[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) a[c] = *reinterpret_cast<const uint4*>(buf + (4 * half + c) * (TILE * 16) + row * 16);
+    umma::tmem_ld_wait();
+    umma::mbar_wait(wg_bar, wg_phase);
+    wg_phase ^= 1u;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        uint4 u;
+        u.x = pack2<false>(r[8 * c], r[8 * c + 1]) & gt0_mask(a[c].x);
+        u.y = pack2<false>(r[8 * c + 2], r[8 * c + 3]) & gt0_mask(a[c].y);
+        u.z = pack2<false>(r[8 * c + 4], r[8 * c + 5]) & gt0_mask(a[c].z);
+        u.w = pack2<false>(r[8 * c + 6], r[8 * c + 7]) & gt0_mask(a[c].w);
+        *reinterpret_cast<uint4*>(buf + (4 * half + c) * (TILE * 16) + row * 16) = u;
+    }
+}
+__device__ __forceinline__ uint4 pack8(const float* v) {
+    uint4 u;
+    u.x = pack2<false>(__float_as_uint(v[0]), __float_as_uint(v[1])); u.y = pack2<false>(__float_as_uint(v[2]), __float_as_uint(v[3]));
+    u.z = pack2<false>(__float_as_uint(v[4]), __float_as_uint(v[5])); u.w = pack2<false>(__float_as_uint(v[6]), __float_as_uint(v[7]));
+    return u;
+}
+
+struct Shared {
+    uint64_t in_full[NCH][2];   // bulk copies of a tile's inputs landed (tx count)
+    uint64_t done[NCH];         // the chain's current forward / dgrad round has completed (tcgen05.commit of warp 24)
+    uint64_t done_wg[NCH];      // ... and the weight-gradient product of the round (rounds r6 .. r10, warp 25)
+    uint32_t posted[4];         // per chain: warps that have published operands (8 per round)
+    uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(NTHR, 1) mlp_bwd_pipe_kernel(const MlpArgs a) {
+    vn_pdl_trigger();
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ Shared sh;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t sbase = umma::smem_u32(smem);
+
+    // ---- prologue (overlaps the predecessor's tail under PDL): weights, barriers, TMEM ------------
+    load_weight(smem, W1_OFF, a.W[0], 64, 32, 64, tid);
+    load_weight(smem, W2_OFF, a.W[1], 16, 64, 16, tid);
+    load_weight(smem, W3_OFF, a.W[2], 64, 32, 64, tid);
+    load_weight(smem, W4_OFF, a.W[3], 64, 64, 64, tid);
+    load_weight(smem, W5_OFF, a.W[4], 16, 64, 3, tid);
+    // chunk 1 of every chain's D5 operand (columns 8..15 of d(out5)) is zero for ever
+    for (int i = tid; i < NCH * TILE; i += NTHR)
+        *reinterpret_cast<uint4*>(smem + (i / TILE) * C_SIZE + C_D5 + TILE * 16 + (i % TILE) * 16) = make_uint4(0u, 0u, 0u, 0u);
+    if (warp == MMA_WARP) umma::tmem_alloc(&sh.tmem_base, 512);
+    if (tid == 0) {
+        for (int c = 0; c < NCH; ++c) {
+            umma::mbar_init(&sh.in_full[c][0], 1); umma::mbar_init(&sh.in_full[c][1], 1);
+            umma::mbar_init(&sh.done[c], 1); umma::mbar_init(&sh.done_wg[c], 1);
+            sh.posted[c] = 0u;
+        }
+        sh.posted[3] = 0u;
+        umma::mbar_fence_init();
+    }
+    umma::fence_async_smem();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem0 = sh.tmem_base;
+
+    const int64_t n_tiles = (a.S + TILE - 1) / TILE;
+    const int64_t stride = (int64_t)NCH * gridDim.x;
+    const bool fmt3 = a.enc_fmt == 3;
+    // flat 16-byte-aligned input arrays can be bulk-copied tile-wise (full tiles only)
+    const bool bulk_small = ((reinterpret_cast<uintptr_t>(a.dirs) | reinterpret_cast<uintptr_t>(a.drgbs) |
+                              reinterpret_cast<uintptr_t>(a.dsigmas)) & 15u) == 0;
+
+    if (warp >= MMA_WARP) {
+        // ============================ MMA issuers ==============================================
+        // Both warps walk the SAME fixed schedule -- tile t, round r, chain c = 0, 1, 2 -- and block on the
+        // chain's request counter: no dispatch logic, every descriptor is an immediate added to the chain base.
+        // The chains are symmetric, so the fixed order settles into a software pipeline with the three chains a
+        // third of a round apart.  Warp 24 issues what a chain is waiting for (forward, dgrad), warp 25 the
+        // weight-gradient products (all accumulating MMAs come from one thread, hence ordered).  The whole warp
+        // runs the uniform control flow; one elected lane issues.
+        uint32_t nt[NCH];
+        uint32_t max_t = 0;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const int64_t first = (int64_t)c * gridDim.x + blockIdx.x;
+            nt[c] = first < n_tiles ? (uint32_t)((n_tiles - first + stride - 1) / stride) : 0u;
+            max_t = nt[c] > max_t ? nt[c] : max_t;
+        }
+        const uint32_t posted0 = umma::smem_u32(&sh.posted[0]);
+        const uint32_t done0 = umma::smem_u32(warp == MMA_WARP ? &sh.done[0] : &sh.done_wg[0]);
+        const uint32_t s16 = sbase >> 4, w16 = (sbase + W_BASE) >> 4;
+        auto wait_posted = [&](int c, uint32_t target) {
+            uint32_t v;
+            do {
+                asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(posted0 + 4u * c) : "memory");
+            } while (v < target);
+            umma::fence_after_sync();
+        };
+        auto commit_to = [&](int c) {
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(done0 + 8u * c) : "memory");
+        };
+        uint32_t target = 8u;          // 8 warps per chain publish every round
+        for (uint32_t t = 0; t < max_t; ++t) {
+            const uint32_t xo = (t & 1u) * (8192u >> 4);
+            if (warp == MMA_WARP) {
+#define VN_MAIN_ROUND(R)                                                                                              \
+    _Pragma("unroll") for (int c = 0; c < NCH; ++c) {                                                                 \
+        if (t < nt[c]) {                                                                                              \
+            wait_posted(c, target + 8u * (R));                                                                        \
+            if (elect_one()) {                                                                                        \
+                const uint32_t cb16 = s16 + (uint32_t)c * (C_SIZE >> 4);                                              \
+                issue_main<R>(cb16, cb16 + xo, w16, tmem0 + (uint32_t)c * T_CH);                                      \
+                commit_to(c);                                                                                         \
+            }                                                                                                         \
+            __syncwarp();                                                                                             \
+        }                                                                                                             \
+    }
+                VN_MAIN_ROUND(0) VN_MAIN_ROUND(1) VN_MAIN_ROUND(2) VN_MAIN_ROUND(3) VN_MAIN_ROUND(4)
+                VN_MAIN_ROUND(5) VN_MAIN_ROUND(6) VN_MAIN_ROUND(7) VN_MAIN_ROUND(8) VN_MAIN_ROUND(9)
+#undef VN_MAIN_ROUND
+            } else {
+#define VN_WG_ROUND(R)                                                                                                \
+    _Pragma("unroll") for (int c = 0; c < NCH; ++c) {                                                                 \
+        if (t < nt[c]) {                                                                                              \
+            wait_posted(c, target + 8u * (R));                                                                        \
+            if (elect_one()) {                                                                                        \
+                const uint32_t cb16 = s16 + (uint32_t)c * (C_SIZE >> 4);                                              \
+                issue_wgrad<R>(cb16, cb16 + xo, tmem0, !(t == 0 && c == 0));                                          \
+                commit_to(c);                                                                                         \
+            }                                                                                                         \
+            __syncwarp();                                                                                             \
+        }                                                                                                             \
+    }
+                VN_WG_ROUND(5) VN_WG_ROUND(6) VN_WG_ROUND(7) VN_WG_ROUND(8) VN_WG_ROUND(9)
+#undef VN_WG_ROUND
+            }
+            target += 8u * ROUNDS;
+        }
+    } else {
+        // ============================ tile chains ==============================================
+        const int c = warp >> 3, q = warp & 3, half = (warp >> 2) & 1;
+        const int row = 32 * q + lane;
+        const int ct = tid - c * CH_THREADS;
+        uint8_t* cs = smem + c * C_SIZE;
+        const uint32_t cs32 = sbase + (uint32_t)c * C_SIZE;
+        const uint32_t tm = tmem0 + (uint32_t)c * T_CH + ((uint32_t)(32 * q) << 16);
+        uint64_t* done = &sh.done[c];
+        uint64_t* done_wg = &sh.done_wg[c];
+        uint32_t* posted = &sh.posted[c];
+        uint32_t done_phase = 0u, wg_phase = 0u, in_phase = 0u;   // in_phase: bit p = parity to wait for on in_full[c][p]
+
+        auto post = [&]() {          // operands written -> visible to the tensor core; one arrival per warp
+            umma::fence_async_smem();
+            umma::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) red_release_inc(posted);
+        };
+        auto wait_done = [&]() {
+            umma::mbar_wait(done, done_phase);
+            done_phase ^= 1u;
+            umma::fence_after_sync();
+        };
+        // the round's weight-gradient product has read its operands: they may be overwritten
+        auto wait_wgrad = [&]() {
+            umma::mbar_wait(done_wg, wg_phase);
+            wg_phase ^= 1u;
+        };
+        // which inputs of tile t travel by bulk copy (identical on the issuing and the waiting side)
+        auto tile_rows = [&](int64_t t) { const int64_t left = a.S - t * TILE; return (int)(left < TILE ? left : TILE); };
+        auto issue_loads = [&](int64_t t, int p) {      // one thread per chain
+            const int rows = tile_rows(t);
+            const bool small = bulk_small && rows == TILE;
+            if (!fmt3 && !small) return;
+            uint64_t* bar = &sh.in_full[c][p];
+            mbar_expect_tx(bar, (fmt3 ? 4u * rows * 16u : 0u) + (small ? (uint32_t)AUX_SIZE : 0u));
+            if (fmt3) {
+                const uint4* src = reinterpret_cast<const uint4*>(a.enc) + t * TILE;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) bulk_g2s(cs32 + C_X0 + p * 8192 + k * 2048, src + (int64_t)k * a.S, rows * 16u, bar);
+            }
+            if (small) {
+                const uint32_t aux = cs32 + C_AUX + p * AUX_SIZE;
+                bulk_g2s(aux + AUX_DIRS, a.dirs + t * TILE * 3, 1536u, bar);
+                bulk_g2s(aux + AUX_DRGB, a.drgbs + t * TILE * 3, 1536u, bar);
+                bulk_g2s(aux + AUX_DSIG, a.dsigmas + t * TILE, 512u, bar);
+            }
+        };
+
+        const int64_t first = (int64_t)c * gridDim.x + blockIdx.x;
+        // everything above read only the weights; from here on the producers' outputs
+        vn_pdl_wait();
+        if (ct == 0 && first < n_tiles) issue_loads(first, 0);
+        int it = 0;
+        for (int64_t tile = first; tile < n_tiles; tile += stride, ++it) {
+            const int p = it & 1;
+            if (ct == 0 && tile + stride < n_tiles) issue_loads(tile + stride, p ^ 1);   // one tile ahead
+            const int rows = tile_rows(tile);
+            const bool small = bulk_small && rows == TILE;
+            const int64_t s = tile * TILE + row;
+            const bool valid = row < rows;
+            const uint8_t* aux = cs + C_AUX + p * AUX_SIZE;
+            uint8_t* x0 = cs + C_X0 + p * 8192;
+            if (fmt3 || small) {
+                umma::mbar_wait(&sh.in_full[c][p], (in_phase >> p) & 1u);
+                in_phase ^= 1u << p;
+            }
+            // ---- stage: X0 (unless it arrived by bulk copy), SH(dir) -> IN2[:, 0:16] -----------------
+            if (fmt3) {
+                if (!valid) {          // tail tile: rows the copy did not write must be finite (they meet zero gradients in the wgrads)
+                    *reinterpret_cast<uint4*>(x0 + (2 * half) * (TILE * 16) + row * 16) = make_uint4(0u, 0u, 0u, 0u);
+                    *reinterpret_cast<uint4*>(x0 + (2 * half + 1) * (TILE * 16) + row * 16) = make_uint4(0u, 0u, 0u, 0u);
+                }
+            } else {
+                float e[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) e[k] = 0.0f;
+                if (valid) {
+                    if (a.enc_fmt == 1) {
+                        const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(a.enc) + s * 32 + 16 * half);
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) {
+                            const uint4 u = __ldg(src + k);
+                            const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); e[8 * k + 2 * j] = f.x; e[8 * k + 2 * j + 1] = f.y; }
+                        }
+                    } else {
+                        const float4* src = a.enc_fmt == 2 ? reinterpret_cast<const float4*>(a.enc) + (int64_t)(4 * half) * a.S + s
+                                                           : reinterpret_cast<const float4*>(a.enc + s * 32 + 16 * half);
+                        const int64_t step = a.enc_fmt == 2 ? a.S : 1;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const float4 f = __ldg(src + k * step);
+                            e[4 * k] = f.x; e[4 * k + 1] = f.y; e[4 * k + 2] = f.z; e[4 * k + 3] = f.w;
+                        }
+                    }
+                }
+                *reinterpret_cast<uint4*>(x0 + (2 * half) * (TILE * 16) + row * 16) = pack8(e);
+                *reinterpret_cast<uint4*>(x0 + (2 * half + 1) * (TILE * 16) + row * 16) = pack8(e + 8);
+            }
+            {
+                float dx = 1.0f, dy = 0.0f, dz = 0.0f;
+                if (small) {
+                    const float* d = reinterpret_cast<const float*>(aux + AUX_DIRS) + 3 * row;
+                    dx = d[0]; dy = d[1]; dz = d[2];
+                } else if (valid) {
+                    dx = __ldg(a.dirs + 3 * s); dy = __ldg(a.dirs + 3 * s + 1); dz = __ldg(a.dirs + 3 * s + 2);
+                }
+                const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);                                    // networks.py:160
+                float e[16];
+                sh16_half((dx / nrm + 1.0f) * 0.5f, (dy / nrm + 1.0f) * 0.5f, (dz / nrm + 1.0f) * 0.5f, e);   // :161
+                float eh[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) eh[k] = half ? e[8 + k] : e[k];
+                *reinterpret_cast<uint4*>(cs + C_IN2 + half * (TILE * 16) + row * 16) = pack8(eh);
+            }
+            post();                                                        // -> r1
+            // ---- r1: H1 -----------------------------------------------------------------------------
+            wait_done();
+            epi_relu32(tm + 32 * half, cs + C_HA, row, half);
+            post();                                                        // -> r2
+            // ---- r2: h; sigma-branch gradient seed ----------------------------------------------------
+            wait_done();
+            float dh_sigma = 0.0f;
+            {
+                uint32_t r[8];
+                tmem_ld<8>(tm + 8 * half, r);
+                umma::tmem_ld_wait();
+                uint4 u;
+                u.x = pack2<false>(r[0], r[1]); u.y = pack2<false>(r[2], r[3]); u.z = pack2<false>(r[4], r[5]); u.w = pack2<false>(r[6], r[7]);
+                *reinterpret_cast<uint4*>(cs + C_IN2 + (2 + half) * (TILE * 16) + row * 16) = u;
+                if (half == 0 && valid) {
+                    const float dsig = small ? reinterpret_cast<const float*>(aux + AUX_DSIG)[row] : __ldg(a.dsigmas + s);
+                    dh_sigma = dsig * expf(fminf(fmaxf(__uint_as_float(r[0]), -15.0f), 15.0f));          // TruncExp bwd, networks.py:28
+                }
+            }
+            post();                                                        // -> r3
+            // ---- r3: H3 -----------------------------------------------------------------------------
+            wait_done();
+            epi_relu32(tm + 32 * half, cs + C_HB, row, half);
+            post();                                                        // -> r4
+            // ---- r4: H4 -----------------------------------------------------------------------------
+            wait_done();
+            epi_relu32(tm + 32 * half, cs + C_HA, row, half);
+            post();                                                        // -> r5
+            // ---- r5: rgb -> d(out5) -----------------------------------------------------------------
+            wait_done();
+            if (half == 0) {
+                uint32_t r[8];
+                tmem_ld<8>(tm, r);
+                umma::tmem_ld_wait();
+                float d5[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if (valid) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const float g = small ? reinterpret_cast<const float*>(aux + AUX_DRGB)[3 * row + k] : __ldg(a.drgbs + 3 * s + k);
+                        const float rgb = 1.0f / (1.0f + expf(-__uint_as_float(r[k])));
+                        d5[k] = g * rgb * (1.0f - rgb);
+                    }
+                }
+                *reinterpret_cast<uint4*>(cs + C_D5 + row * 16) = pack8(d5);
+            }
+            post();                                                        // -> r6
+            // ---- r6: dH4 ----------------------------------------------------------------------------
+            wait_done();
+            epi_mask32(tm + 32 * half, cs + C_HA, row, half, done_wg, wg_phase);
+            post();                                                        // -> r7
+            // ---- r7: dH3 ----------------------------------------------------------------------------
+            wait_done();
+            epi_mask32(tm + 32 * half, cs + C_HB, row, half, done_wg, wg_phase);
+            post();                                                        // -> r8
+            // ---- r8: d(h) into IN2[:,16:32]; H1 again -----------------------------------------------
+            wait_done();
+            {
+                uint32_t r[8];
+                tmem_ld<8>(tm + 64 + 8 * half, r);
+                umma::tmem_ld_wait();
+                float dh[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) dh[k] = valid ? __uint_as_float(r[k]) : 0.0f;
+                if (half == 0) dh[0] += dh_sigma;
+                wait_wgrad();                                              // dW3 has read IN2
+                *reinterpret_cast<uint4*>(cs + C_IN2 + (2 + half) * (TILE * 16) + row * 16) = pack8(dh);
+            }
+            epi_relu32(tm + 32 * half, cs + C_HA, row, half);
+            post();                                                        // -> r9
+            // ---- r9: dH1 ----------------------------------------------------------------------------
+            wait_done();
+            epi_mask32(tm + 32 * half, cs + C_HA, row, half, done_wg, wg_phase);
+            post();                                                        // -> r10
+            // ---- r10: d(enc) ------------------------------------------------------------------------
+            wait_done();
+            {
+                uint32_t r[16];
+                tmem_ld<16>(tm + 16 * half, r);
+                umma::tmem_ld_wait();
+                if (valid) {
+                    if (a.denc_fmt == 2) {
+                        float4* dst = reinterpret_cast<float4*>(a.denc) + (int64_t)(4 * half) * a.S + s;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            dst[(int64_t)k * a.S] = make_float4(__uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1]),
+                                                               __uint_as_float(r[4 * k + 2]), __uint_as_float(r[4 * k + 3]));
+                    } else if (a.denc_fmt == 3) {
+                        uint4* dst = reinterpret_cast<uint4*>(a.denc) + (int64_t)(2 * half) * a.S + s;
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) {
+                            uint4 u;
+                            u.x = pack2<false>(r[8 * k], r[8 * k + 1]); u.y = pack2<false>(r[8 * k + 2], r[8 * k + 3]);
+                            u.z = pack2<false>(r[8 * k + 4], r[8 * k + 5]); u.w = pack2<false>(r[8 * k + 6], r[8 * k + 7]);
+                            dst[(int64_t)k * a.S] = u;
+                        }
+                    } else {
+                        float4* dst = reinterpret_cast<float4*>(a.denc + s * 32 + 16 * half);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            dst[k] = make_float4(__uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1]), __uint_as_float(r[4 * k + 2]),
+                                                 __uint_as_float(r[4 * k + 3]));
+                    }
+                }
+            }
+            wait_wgrad();                                                  // dW1 has read HA and this tile's X0
+            umma::fence_before_sync();
+        }
+    }
+
+    // ---- flush the weight-gradient accumulators (M = 64 layout: row i sits in TMEM lane 32*(i/16) + i%16) ----
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    if (blockIdx.x < n_tiles && warp < 24) {
+        // warps with the same (warp & 3) address the same TMEM lanes; the six warp groups split the columns
+        const int q = warp & 3, grp = warp >> 2;
+        const int wrow = 16 * q + lane;
+        const uint32_t tl = tmem0 + ((uint32_t)(32 * q) << 16);
+        uint32_t v[32];
+        if (grp == 0) {                       // dW1 [64 out x 32 in]
+            tmem_ld<32>(tl + T_DW1, v); umma::tmem_ld_wait();
+            if (lane < 16) for (int j = 0; j < 32; ++j) atomicAdd(a.dW[0] + wrow * 32 + j, __uint_as_float(v[j]));
+        } else if (grp == 1) {                // dW3 [64 x 32]
+            tmem_ld<32>(tl + T_DW3, v); umma::tmem_ld_wait();
+            if (lane < 16) for (int j = 0; j < 32; ++j) atomicAdd(a.dW[2] + wrow * 32 + j, __uint_as_float(v[j]));
+        } else if (grp == 2 || grp == 3) {    // dW4 [64 x 64], 32 columns each
+            const int c0 = 32 * (grp - 2);
+            tmem_ld<32>(tl + T_DW4 + c0, v); umma::tmem_ld_wait();
+            if (lane < 16) for (int j = 0; j < 32; ++j) atomicAdd(a.dW[3] + wrow * 64 + c0 + j, __uint_as_float(v[j]));
+        } else if (grp == 4) {                // dW2^T [64 in x 16 out] -> dW2 [16 x 64]
+            tmem_ld<16>(tl + T_DW2T, v); umma::tmem_ld_wait();
+            if (lane < 16) for (int j = 0; j < 16; ++j) atomicAdd(a.dW[1] + j * 64 + wrow, __uint_as_float(v[j]));
+        } else {                              // dW5^T [64 in x 16] -> dW5 [3 x 64]
+            tmem_ld<8>(tl + T_DW5T, v); umma::tmem_ld_wait();
+            if (lane < 16) for (int j = 0; j < 3; ++j) atomicAdd(a.dW[4] + j * 64 + wrow, __uint_as_float(v[j]));
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == MMA_WARP) umma::tmem_dealloc(tmem0, 512);
+}
+
+}  // namespace
+
+int launch_mlp_bwd_pipe(const MlpArgs& a, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        VN_CUDA(cudaFuncSetAttribute(mlp_bwd_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_PIPE));
+        attr_set = true;
+    }
+    VnProfScope prof(VN_K_MLP_BWD, a.S, st);
+    const int64_t n_tiles = (a.S + TILE - 1) / TILE;
+    int64_t grid = vn_sm_count();
+    if (grid > n_tiles) grid = n_tiles;
+    vn_launch_pdl(mlp_bwd_pipe_kernel, dim3((unsigned)grid), dim3(NTHR), SMEM_PIPE, st, a);
+    VN_CHECK_LAUNCH("mlp_bwd_pipe_kernel");
+    return VN_OK;
+}
+
+}  // namespace mlp

@@ -3,6 +3,8 @@
 // launches of modules/networks.py:134-164, 195-282 and modules/spherical_harmonics.py.
 #include "common.cuh"
 #include "umma.cuh"
+#include "mlp_common.cuh"
+#include <stdlib.h>
 
 // ---- UMMA self-test: one 128 x N x K product in each operand mode the fused kernels use ----
 // mode 0 (forward):  D[128,N] = A[128,K] * B[N,K]^T          A, B K-major
@@ -83,8 +85,7 @@ VN_API int vn_umma_selftest(int mode, int N, int K, const void* A, const void* B
 // operands, M = 64), flushing them with one atomicAdd pass at the end.
 // =========================================================================================
 namespace {
-
-constexpr int TILE = 128;
+using namespace mlp;
 // shared-memory operand buffers (bytes)
 constexpr int SZ_X0 = TILE * 32 * 2, SZ_H = TILE * 64 * 2, SZ_16 = TILE * 16 * 2;
 constexpr int OFF_X0 = 0;
@@ -119,67 +120,12 @@ constexpr int TC_TMP = 0;                    // 64-column scratch accumulator
 constexpr int TC_DW1 = 64, TC_DW3 = 96, TC_DW4 = 128, TC_DW2T = 192, TC_DW5T = 208;   // wgrad accumulators
 constexpr int TMEM_FWD = 64, TMEM_BWD = 256;
 
-struct MlpArgs {
-    const float* enc;      // [S,32] f32 (or fp16 when enc_half)
-    const float* dirs;     // [S,3]
-    const float* W[5];     // torch Linear layout [out,in] f32
-    float* sigmas;         // [S]
-    float* rgbs;           // [S,3]
-    float* h_out;          // [S,16] or null: the density net's feature vector (return_feat)
-    const float* dsigmas;  // [S]     (BWD)
-    const float* drgbs;    // [S,3]   (BWD)
-    float* denc;           // [S,32]  (BWD)
-    float* dW[5];          // accumulated (BWD)
-    int64_t S;
-    int enc_half;          // enc_format == 1
-    int enc_planar;        // enc_format == 2: enc / denc are [8][S] float4 planes (VN_HASH_PLANAR)
-    int density_only;
-};
-
-__device__ __forceinline__ void load_weight(uint8_t* smem, int off, const float* __restrict__ W, int R, int C, int R_valid,
-                                            int tid) {
-    // [R x C] f32 row-major -> chunk-major fp16; one 16-byte chunk (8 columns of one row) per
-    // thread and iteration: two LDG.128, one STS.128.  Rows >= R_valid are zero padding.
-    const int chunks_per_row = C / 8;
-    for (int i = tid; i < R * chunks_per_row; i += blockDim.x) {
-        const int r = i / chunks_per_row, c = i % chunks_per_row;
-        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (r < R_valid) {
-            const float4* src = reinterpret_cast<const float4*>(W + (size_t)r * C + 8 * c);
-            const float4 lo = __ldg(src), hi = __ldg(src + 1);
-            v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
-        }
-        umma::st_chunk(reinterpret_cast<__half*>(smem + off), R, r, c, v);
-    }
-}
-
 // this thread's row of a 128-row operand buffer: 8 fp16 of column chunk c
 __device__ __forceinline__ uint4 ld_chunk(const uint8_t* smem, int off, int r, int c) {
     return *reinterpret_cast<const uint4*>(smem + off + c * TILE * 16 + r * 16);
 }
 __device__ __forceinline__ void st_row8(uint8_t* smem, int off, int r, int c, const float* v8) {
     umma::st_chunk(reinterpret_cast<__half*>(smem + off), TILE, r, c, v8);
-}
-
-__device__ __forceinline__ void sh16_half(float x, float y, float z, float* e) {
-    // spherical_harmonics.py:16-42
-    const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
-    e[0] = 0.28209479177387814f;
-    e[1] = -0.48860251190291987f * y;
-    e[2] = 0.48860251190291987f * z;
-    e[3] = -0.48860251190291987f * x;
-    e[4] = 1.0925484305920792f * xy;
-    e[5] = -1.0925484305920792f * yz;
-    e[6] = 0.94617469575755997f * z2 - 0.31539156525251999f;
-    e[7] = -1.0925484305920792f * xz;
-    e[8] = 0.54627421529603959f * x2 - 0.54627421529603959f * y2;
-    e[9] = 0.59004358992664352f * y * (-3.0f * x2 + y2);
-    e[10] = 2.8906114426405538f * xy * z;
-    e[11] = 0.45704579946446572f * y * (1.0f - 5.0f * z2);
-    e[12] = 0.3731763325901154f * z * (5.0f * z2 - 3.0f);
-    e[13] = 0.45704579946446572f * x * (1.0f - 5.0f * z2);
-    e[14] = 1.4453057213202769f * z * (x2 - y2);
-    e[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
 }
 
 struct Pipe {
@@ -316,7 +262,18 @@ __global__ void __launch_bounds__(NTHREADS, BWD ? 2 : 3) mlp_kernel(const MlpArg
         const int64_t s = tile * TILE + row;
         const bool valid = tile < n_tiles && s < a.S;
         if (valid) {
-            if (a.enc_half) {
+            if (a.enc_fmt == 3) {
+                // f16 chunk planes [4][S] x 16 B: chunks 2*half, 2*half+1 of this row
+                const uint4* src = reinterpret_cast<const uint4*>(a.enc) + (int64_t)(2 * half) * a.S + s;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const uint4 u = __ldg(src + (int64_t)q * a.S);
+                    const __half2* h = reinterpret_cast<const __half2*>(&u);
+                    const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]), f2 = __half22float2(h[2]), f3 = __half22float2(h[3]);
+                    st.e[2 * q] = make_float4(f0.x, f0.y, f1.x, f1.y);
+                    st.e[2 * q + 1] = make_float4(f2.x, f2.y, f3.x, f3.y);
+                }
+            } else if (a.enc_half) {
                 const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(a.enc) + s * 32 + 16 * half);
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
@@ -565,19 +522,23 @@ int launch_mlp(bool bwd, const MlpArgs& a, cudaStream_t st) {
 
 }  // namespace
 
+static bool mlp_pipe_from_env() { const char* e = getenv("VN_MLP_PIPE"); return !(e && e[0] == '0'); }
+static bool g_mlp_pipe = mlp_pipe_from_env();
+
 VN_API int vn_mlp_fwd(const void* enc, int enc_format, const float* dirs, const float* W1, const float* W2, const float* W3,
                       const float* W4, const float* W5, int64_t S, int density_only, float* sigmas, float* rgbs,
                       float* h_out, void* stream) {
     VN_REQUIRE(S >= 0, "vn_mlp_fwd: S < 0");
     if (S == 0) return VN_OK;
     VN_REQUIRE(enc && W1 && W2 && sigmas, "vn_mlp_fwd: null pointer");
-    VN_REQUIRE(enc_format >= 0 && enc_format <= 2, "vn_mlp_fwd: enc_format must be 0 (f32 rows), 1 (f16 rows) or 2 (f32 planes)");
+    VN_REQUIRE(enc_format >= 0 && enc_format <= 3,
+               "vn_mlp_fwd: enc_format must be 0 (f32 rows), 1 (f16 rows), 2 (f32 planes) or 3 (f16 chunk planes)");
     VN_REQUIRE(density_only || (dirs && W3 && W4 && W5 && rgbs), "vn_mlp_fwd: null colour-network pointer");
     VN_REQUIRE(vn_aligned(enc, 16), "vn_mlp_fwd: enc must be 16-byte aligned");
     VN_REQUIRE(vn_aligned(W1, 16) && vn_aligned(W2, 16) && vn_aligned(W3, 16) && vn_aligned(W4, 16) && vn_aligned(W5, 16),
                "vn_mlp_fwd: weight matrices must be 16-byte aligned");
     MlpArgs a{};
-    a.enc = (const float*)enc; a.enc_half = enc_format == 1; a.enc_planar = enc_format == 2; a.dirs = dirs;
+    a.enc = (const float*)enc; a.enc_half = enc_format == 1; a.enc_planar = enc_format == 2; a.enc_fmt = enc_format; a.dirs = dirs;
     a.W[0] = W1; a.W[1] = W2; a.W[2] = density_only ? W1 : W3; a.W[3] = density_only ? W1 : W4; a.W[4] = density_only ? W1 : W5;
     a.sigmas = sigmas; a.rgbs = rgbs; a.h_out = h_out; a.S = S; a.density_only = density_only;
     return launch_mlp(false, a, (cudaStream_t)stream);
@@ -590,7 +551,10 @@ VN_API int vn_mlp_bwd(const void* enc, int enc_format, const float* dirs, const 
     VN_REQUIRE(S >= 0, "vn_mlp_bwd: S < 0");
     if (S == 0) return VN_OK;
     VN_REQUIRE(enc && W1 && W2 && dsigmas && denc && dW1 && dW2, "vn_mlp_bwd: null pointer");
-    VN_REQUIRE(enc_format >= 0 && enc_format <= 2, "vn_mlp_bwd: enc_format must be 0 (f32 rows), 1 (f16 rows) or 2 (f32 planes)");
+    VN_REQUIRE(enc_format >= 0 && enc_format <= 4,
+               "vn_mlp_bwd: enc_format must be 0 (f32 rows), 1 (f16 rows), 2 (f32 planes), 3 (f16 chunk planes in, f32 planes out) "
+               "or 4 (f16 chunk planes in and out)");
+    VN_REQUIRE(!(density_only && enc_format >= 3), "vn_mlp_bwd: the density-only backward takes enc_format 0..2");
     VN_REQUIRE(density_only || (dirs && W3 && W4 && W5 && drgbs && dW3 && dW4 && dW5), "vn_mlp_bwd: null colour-network pointer");
     VN_REQUIRE(vn_aligned(enc, 16) && vn_aligned(denc, 16), "vn_mlp_bwd: enc/denc must be 16-byte aligned");
     VN_REQUIRE(vn_aligned(W1, 16) && vn_aligned(W2, 16) && vn_aligned(W3, 16) && vn_aligned(W4, 16) && vn_aligned(W5, 16),
@@ -601,5 +565,10 @@ VN_API int vn_mlp_bwd(const void* enc, int enc_format, const float* dirs, const 
     a.dsigmas = dsigmas; a.drgbs = drgbs; a.denc = denc;
     a.dW[0] = dW1; a.dW[1] = dW2; a.dW[2] = dW3; a.dW[3] = dW4; a.dW[4] = dW5;
     a.S = S; a.density_only = density_only;
+    a.enc_fmt = enc_format >= 3 ? 3 : enc_format;
+    a.denc_fmt = enc_format == 4 ? 3 : (enc_format >= 2 ? 2 : 0);
+    // the pipelined three-chain kernel (mlp_bwd_pipe.cu) is the backward; the serial kernel remains for the
+    // density-only variant and as the A/B baseline (VN_MLP_PIPE=0)
+    if (!density_only && (g_mlp_pipe || enc_format >= 3)) return launch_mlp_bwd_pipe(a, (cudaStream_t)stream);
     return launch_mlp(true, a, (cudaStream_t)stream);
 }

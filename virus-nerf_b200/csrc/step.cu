@@ -38,7 +38,11 @@ VN_API int vn_train_step_run(const vn_step_t* s, int64_t S, int phase, int do_op
     float* sums = s->loss_acc;
     float* cnts = s->loss_acc + 4;
     // enc / d_enc stay inside the step: use the level-pair-plane layout when the flags ask for it
-    const int enc_fmt = (s->hash_flags & VN_HASH_PLANAR) ? 2 : 0;
+    // VN_HASH_F16_CHUNKS: the hash forward emits fp16 operand chunks that the MLP kernels bulk-copy (enc_format 3,
+    // d_enc stays f32 planes); else f32 planes (2) or rows (0)
+    const int enc_fmt = (s->hash_flags & VN_HASH_F16_CHUNKS) ? 3 : ((s->hash_flags & VN_HASH_PLANAR) ? 2 : 0);
+    VN_REQUIRE(!(s->hash_flags & VN_HASH_F16_CHUNKS) || (s->hash_flags & VN_HASH_PLANAR),
+               "vn_train_step_run: VN_HASH_F16_CHUNKS needs VN_HASH_PLANAR (d_enc planes)");
     if (phase == 0 || phase == 1) {
         VN_CUDA(cudaMemsetAsync(s->flat_g, 0, sizeof(float) * (size_t)s->n_params, st));
         VN_CUDA(cudaMemsetAsync(s->loss_acc, 0, sizeof(float) * 8, st));

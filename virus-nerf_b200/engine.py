@@ -85,7 +85,7 @@ class _Workspace:
 
 class TrainEngine:
     def __init__(self, args, dataset, device, world_size=1, rank=0, log2_T=19, max_res=1024, half_opt=False,
-                 autocast=True, seed=21, grad_scale=2.0 ** 19, comm="auto", enc_layout="planar",
+                 autocast=True, seed=21, grad_scale=2.0 ** 19, comm="auto", enc_layout="chunks",
                  single_pass_march=True):
         self.args = args
         self.device = torch.device(device)
@@ -94,8 +94,9 @@ class TrainEngine:
         self.autocast = autocast
         # layout of the encoding / its gradient INSIDE the fast step (never visible to the drop-in modules):
         # "planar" = [8][S] float4 level-pair planes (coalesced on both sides), "rows" = the reference's [S,32]
-        assert enc_layout in ("planar", "rows")
-        self.enc_planar = enc_layout == "planar"
+        assert enc_layout in ("chunks", "planar", "rows")
+        self.enc_planar = enc_layout in ("planar", "chunks")
+        self.enc_chunks = enc_layout == "chunks" and autocast
         # single-pass march of the fast step: the count pass stores t of every sample in a [N, 1024] scratch and
         # the write pass only expands it (bit-identical to re-marching); capped at 64 Ki rays (256 MB scratch x 2)
         self.single_pass_march = single_pass_march
@@ -248,6 +249,10 @@ class TrainEngine:
             # + no scatter of exactly-zero gradients (41 % of the samples after 200 steps: tools/zero_frac.py)
             st.hash_flags |= (_lib.VN_HASH_PLANAR | _lib.VN_HASH_LEVEL_GROUPS_2 | _lib.VN_HASH_PAIR_LOADS |
                               _lib.VN_HASH_TIGHT_REGS | _lib.VN_HASH_SKIP_ZERO_GRADS)
+            # round 2: the forward encoding leaves the hash kernel as fp16 tensor-core operand chunks (rounded
+            # where autocast rounds the Linear input) and the MLP kernels pull tiles in with bulk async copies
+            if self.enc_chunks:
+                st.hash_flags |= _lib.VN_HASH_F16_CHUNKS
         t = a.training
         st.w_color, st.w_uss, st.w_tof, st.w_rgbd = t.color_loss_w, t.uss_loss_w, t.tof_loss_w, t.rgbd_loss_w
         st.lr, st.beta1, st.beta2, st.eps = self.lr, self.betas[0], self.betas[1], self.eps

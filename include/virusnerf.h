@@ -160,6 +160,14 @@ int vn_march_train_expand(const float* rays_o, const float* rays_d, const int32_
                           const float* ts_rows, int64_t N, int max_samples, int grid_size,
                           float scale, float exp_step_factor, int64_t capacity, float* xyzs,
                           float* dirs, float* deltas, float* ts, float* xyzs_unit, void* stream);
+/* the same, and additionally the direction encoding SH16((d/|d|+1)/2) of every sample (a function of the ray,
+ * evaluated once per ray: networks.py:160-161, spherical_harmonics.py:16-42) as two fp16 operand-chunk planes
+ * sh_planes[0][s], sh_planes[1][s] (16 B each, plane stride sh_stride samples) -- planes 4 and 5 of the fused MLP's
+ * enc_format 5 input */
+int vn_march_train_expand_sh(const float* rays_o, const float* rays_d, const int32_t* rays_a,
+                          const float* ts_rows, int64_t N, int max_samples, int grid_size,
+                          float scale, float exp_step_factor, int64_t capacity, float* xyzs,
+                          float* dirs, float* deltas, float* ts, float* xyzs_unit, void* sh_planes, int64_t sh_stride, void* stream);
 
 /* a7. raymarching_test_kernel, modules/ray_march.py:198-269.  alive [A] i64; slot layout
  * n*max_samples+s; ray_indices i64, valid_mask u8 (caller zeroes), deltas/ts f32, all
@@ -279,7 +287,9 @@ int vn_scaler_update(float* scale, int32_t* growth_tracker, float* found_inf, fl
  *   enc [S,32] hash encoding, f32 rows (enc_format = 0), fp16 rows (1) or f32 level-pair planes
  *   [8][S] float4 (2, the VN_HASH_PLANAR layout; denc is then written in the same layout), or fp16 chunk
  *   planes [4][S] x 16 B (3, the VN_HASH_F16_CHUNKS layout: tiles are bulk-copied straight into the tensor-core
- *   operand; vn_mlp_bwd writes denc as f32 planes for enc_format 3 and as fp16 chunk planes for 4); dirs [S,3] raw ray
+ *   operand), or the same followed by the two SH planes of vn_march_train_expand_sh ([6][S] x 16 B, enc_format 5:
+ *   the whole network input arrives in operand layout, dirs is ignored).  vn_mlp_bwd writes denc as f32 planes for
+ *   enc_format 3 / 5 and, with VN_MLP_DENC_F16 (8) added to enc_format, as fp16 chunk planes [4][S]; dirs [S,3] raw ray
  *   directions (normalised and mapped to (d+1)/2 inside, networks.py:160-161); W1 [64,32],
  *   W2 [16,64], W3 [64,32], W4 [64,64], W5 [3,64] f32 in torch Linear layout [out,in].
  * _fwd: sigmas [S] = exp(h0), rgbs [S,3] = sigmoid(...), optional h_out [S,16] (return_feat).
@@ -287,6 +297,7 @@ int vn_scaler_update(float* scale, int32_t* growth_tracker, float* found_inf, fl
  * _bwd: recomputes the forward per tile; inputs dsigmas [S], drgbs [S,3]; writes denc [S,32]
  *       f32 (gradient w.r.t. the encoding) and ACCUMULATES dW1..dW5 (same shapes as W, f32;
  *       TruncExp backward clamps h0 to [-15,15], networks.py:28). */
+#define VN_MLP_DENC_F16 8
 int vn_mlp_fwd(const void* enc, int enc_format, const float* dirs, const float* W1, const float* W2,
                const float* W3, const float* W4, const float* W5, int64_t S, int density_only,
                float* sigmas, float* rgbs, float* h_out, void* stream);

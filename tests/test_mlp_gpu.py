@@ -165,24 +165,38 @@ def test_fused_mlp_chunk_plane_format(S):
     enc_c = _to_chunks(enc16)
     dsig = torch.randn(S, device=DEV) * 3; drgb = torch.randn(S, 3, device=DEV) * 3
     res = {}
-    for fmt, e in ((1, enc16), (3, enc_c), (4, enc_c)):
+    # enc_format 5: the direction encoding arrives as two more operand planes (what vn_march_train_expand_sh emits)
+    d = dirs / dirs.norm(dim=1, keepdim=True)
+    import oracle
+    sh16 = torch.from_numpy(oracle.sh_encode(((d + 1) / 2).cpu().numpy())).to(DEV).half()
+    enc_c5 = torch.cat([enc_c, sh16.view(S, 2, 8).permute(1, 0, 2)], 0).contiguous()
+    F16 = 8                                                   # VN_MLP_DENC_F16
+    for fmt, e in ((1, enc16), (3, enc_c), (3 | F16, enc_c), (5, enc_c5), (5 | F16, enc_c5)):
         sig = torch.empty(S, device=DEV); rgb = torch.empty(S, 3, device=DEV)
-        _lib.call("vn_mlp_fwd", e, min(fmt, 3), dirs, *Wg, S, 0, sig, rgb, None)
-        denc = torch.zeros(S * 32, device=DEV) if fmt != 4 else torch.zeros(S * 32, device=DEV, dtype=torch.float16)
+        _lib.call("vn_mlp_fwd", e, fmt & 7, dirs if (fmt & 7) != 5 else None, *Wg, S, 0, sig, rgb, None)
+        denc = torch.zeros(S * 32, device=DEV) if not fmt & F16 else torch.zeros(S * 32, device=DEV, dtype=torch.float16)
         dW = [torch.zeros_like(w) for w in Wg]
-        _lib.call("vn_mlp_bwd", e, fmt, dirs, *Wg, S, 0, dsig, drgb, denc, *dW)
+        _lib.call("vn_mlp_bwd", e, fmt, dirs if (fmt & 7) != 5 else None, *Wg, S, 0, dsig, drgb, denc, *dW)
         res[fmt] = (sig, rgb, denc, dW)
     assert torch.equal(res[1][0], res[3][0]) and torch.equal(res[1][1], res[3][1])
     rows = res[1][2].view(S, 32)
     planes = res[3][2].view(8, S, 4).permute(1, 0, 2).reshape(S, 32)
     assert torch.equal(rows, planes)
-    chunks = res[4][2].view(4, S, 8).permute(1, 0, 2).reshape(S, 32)
+    chunks = res[3 | F16][2].view(4, S, 8).permute(1, 0, 2).reshape(S, 32)
     assert torch.equal(chunks, rows.half())
     for a, b in zip(res[1][3], res[3][3]):
         if S <= 128:
             assert torch.equal(a, b)
         else:
             close_l2(a, b, 1e-5, "dW chunks vs rows")
+    # precomputed SH (oracle's fp32 SH rounded to fp16; the kernel's own SH may differ in the last fp16 bit)
+    close(res[5][0], res[3][0], 1e-6, "sigma fmt 5 vs 3")
+    close(res[5][1], res[3][1], 2e-3, "rgb fmt 5 vs 3")
+    close(res[5][2].view(8, S, 4).permute(1, 0, 2).reshape(S, 32), rows, 2e-3, "denc fmt 5 vs 3")
+    assert torch.equal(res[5 | F16][2].view(4, S, 8).permute(1, 0, 2).reshape(S, 32),
+                       res[5][2].view(8, S, 4).permute(1, 0, 2).reshape(S, 32).half())
+    for a, b in zip(res[5][3], res[3][3]):
+        close_l2(a, b, 2e-3, "dW fmt 5 vs 3")
 
 
 def test_fused_mlp_pipelined_backward_equals_serial_kernel(monkeypatch):

@@ -124,6 +124,11 @@ def main():
             rec("mlp_fwd_chunks", ms, S=S, tflops=round(S * 18816 / ms / 1e9, 2), gbs=round(S * 92 / ms / 1e6, 1))
             ms = timeit(lambda: _lib.call("vn_mlp_bwd", enc_c, 3, dirs, *W, S, 0, dsig, drgb, denc, *dW))
             rec("mlp_bwd_chunks", ms, S=S, tflops=round(S * 56448 / ms / 1e9, 2), gbs=round(S * 220 / ms / 1e6, 1))
+            enc_c5 = torch.cat([enc_c, torch.rand(2, S, 8, device=DEV).half()], 0).contiguous()
+            ms = timeit(lambda: _lib.call("vn_mlp_fwd", enc_c5, 5, None, *W, S, 0, sig, rgb, None))
+            rec("mlp_fwd_chunks_sh", ms, S=S, tflops=round(S * 18816 / ms / 1e9, 2), gbs=round(S * 112 / ms / 1e6, 1))
+            ms = timeit(lambda: _lib.call("vn_mlp_bwd", enc_c5, 5, None, *W, S, 0, dsig, drgb, denc, *dW))
+            rec("mlp_bwd_chunks_sh", ms, S=S, tflops=round(S * 56448 / ms / 1e9, 2), gbs=round(S * 240 / ms / 1e6, 1))
             ms = timeit(lambda: _lib.call("vn_mlp_fwd", enc, 2, dirs, *W, S, 0, sig, rgb, None))
             rec("mlp_fwd_planar", ms, S=S, tflops=round(S * 18816 / ms / 1e9, 2), gbs=round(S * 156 / ms / 1e6, 1))
             ms = timeit(lambda: _lib.call("vn_mlp_bwd", enc, 2, dirs, *W, S, 0, dsig, drgb, denc, *dW))

@@ -91,6 +91,7 @@ _SPECS = {
     "vn_march_train_write": "ppppp" "liiff" "pl" "ppppp" "s",
     "vn_march_train_count_rows": "pppppliiffippppps",
     "vn_march_train_expand": "pppp" "liiff" "l" "ppppp" "s",
+    "vn_march_train_expand_sh": "pppp" "liiff" "l" "ppppp" "pl" "s",
     "vn_march_test": "pppp" "lp" "iiffi" "ppppp" "s",
     "vn_march_test_compact": "plippppppppps",
     "vn_composite_train_fwd": "ppppp" "llf" "ppppp" "s",

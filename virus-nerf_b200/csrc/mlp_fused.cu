@@ -257,12 +257,12 @@ __global__ void __launch_bounds__(NTHREADS, BWD ? 2 : 3) mlp_kernel(const MlpArg
     const int64_t n_tiles = (a.S + TILE - 1) / TILE;
     // software prefetch: the NEXT tile's half enc row / direction (and, for the backward, its
     // output gradients) are loaded into registers while the current tile runs the layer chain
-    struct Staged { float4 e[4]; float d[3]; float dsig; float drgb[3]; };
+    struct Staged { float4 e[4]; float d[3]; float dsig; float drgb[3]; uint4 sh; };
     auto fetch = [&](int64_t tile, Staged& st) {
         const int64_t s = tile * TILE + row;
         const bool valid = tile < n_tiles && s < a.S;
         if (valid) {
-            if (a.enc_fmt == 3) {
+            if (a.enc_fmt == 3 || a.enc_fmt == 5) {
                 // f16 chunk planes [4][S] x 16 B: chunks 2*half, 2*half+1 of this row
                 const uint4* src = reinterpret_cast<const uint4*>(a.enc) + (int64_t)(2 * half) * a.S + s;
 #pragma unroll
@@ -298,7 +298,10 @@ __global__ void __launch_bounds__(NTHREADS, BWD ? 2 : 3) mlp_kernel(const MlpArg
             for (int q = 0; q < 4; ++q) st.e[q] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         st.d[0] = 1.0f; st.d[1] = 0.0f; st.d[2] = 0.0f;
-        if (valid && !a.density_only) { st.d[0] = __ldg(a.dirs + 3 * s); st.d[1] = __ldg(a.dirs + 3 * s + 1); st.d[2] = __ldg(a.dirs + 3 * s + 2); }
+        st.sh = make_uint4(0u, 0u, 0u, 0u);
+        if (a.enc_fmt == 5) {          // planes 4, 5: the direction encoding, already an operand chunk (vn_march_train_expand_sh)
+            if (valid && !a.density_only) st.sh = __ldg(reinterpret_cast<const uint4*>(a.enc) + (int64_t)(4 + half) * a.S + s);
+        } else if (valid && !a.density_only) { st.d[0] = __ldg(a.dirs + 3 * s); st.d[1] = __ldg(a.dirs + 3 * s + 1); st.d[2] = __ldg(a.dirs + 3 * s + 2); }
         st.dsig = 0.0f; st.drgb[0] = st.drgb[1] = st.drgb[2] = 0.0f;
         if (BWD && valid && half == 0) {
             st.dsig = __ldg(a.dsigmas + s);
@@ -322,7 +325,9 @@ __global__ void __launch_bounds__(NTHREADS, BWD ? 2 : 3) mlp_kernel(const MlpArg
                                     cur.e[2 * c + 1].x, cur.e[2 * c + 1].y, cur.e[2 * c + 1].z, cur.e[2 * c + 1].w};
                 st_row8(smem, L::X0, row, 2 * half + c, v);
             }
-            if (!a.density_only) {
+            if (!a.density_only && a.enc_fmt == 5) {
+                *reinterpret_cast<uint4*>(smem + L::IN2 + half * (TILE * 16) + row * 16) = cur.sh;
+            } else if (!a.density_only) {
                 const float dx = cur.d[0], dy = cur.d[1], dz = cur.d[2];
                 const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);          // networks.py:160
                 float e[16];
@@ -531,9 +536,10 @@ VN_API int vn_mlp_fwd(const void* enc, int enc_format, const float* dirs, const 
     VN_REQUIRE(S >= 0, "vn_mlp_fwd: S < 0");
     if (S == 0) return VN_OK;
     VN_REQUIRE(enc && W1 && W2 && sigmas, "vn_mlp_fwd: null pointer");
-    VN_REQUIRE(enc_format >= 0 && enc_format <= 3,
-               "vn_mlp_fwd: enc_format must be 0 (f32 rows), 1 (f16 rows), 2 (f32 planes) or 3 (f16 chunk planes)");
-    VN_REQUIRE(density_only || (dirs && W3 && W4 && W5 && rgbs), "vn_mlp_fwd: null colour-network pointer");
+    VN_REQUIRE((enc_format >= 0 && enc_format <= 3) || enc_format == 5,
+               "vn_mlp_fwd: enc_format must be 0 (f32 rows), 1 (f16 rows), 2 (f32 planes), 3 (f16 chunk planes) or 5 (f16 chunk "
+               "planes + SH planes)");
+    VN_REQUIRE(density_only || ((dirs || enc_format == 5) && W3 && W4 && W5 && rgbs), "vn_mlp_fwd: null colour-network pointer");
     VN_REQUIRE(vn_aligned(enc, 16), "vn_mlp_fwd: enc must be 16-byte aligned");
     VN_REQUIRE(vn_aligned(W1, 16) && vn_aligned(W2, 16) && vn_aligned(W3, 16) && vn_aligned(W4, 16) && vn_aligned(W5, 16),
                "vn_mlp_fwd: weight matrices must be 16-byte aligned");
@@ -551,11 +557,13 @@ VN_API int vn_mlp_bwd(const void* enc, int enc_format, const float* dirs, const 
     VN_REQUIRE(S >= 0, "vn_mlp_bwd: S < 0");
     if (S == 0) return VN_OK;
     VN_REQUIRE(enc && W1 && W2 && dsigmas && denc && dW1 && dW2, "vn_mlp_bwd: null pointer");
-    VN_REQUIRE(enc_format >= 0 && enc_format <= 4,
+    const int base_fmt = enc_format & ~VN_MLP_DENC_F16;
+    const bool denc_f16 = (enc_format & VN_MLP_DENC_F16) != 0;
+    VN_REQUIRE(enc_format >= 0 && ((base_fmt >= 0 && base_fmt <= 3) || base_fmt == 5) && (!denc_f16 || base_fmt == 3 || base_fmt == 5),
                "vn_mlp_bwd: enc_format must be 0 (f32 rows), 1 (f16 rows), 2 (f32 planes), 3 (f16 chunk planes in, f32 planes out) "
-               "or 4 (f16 chunk planes in and out)");
+               "or 5 (f16 chunk + SH planes in, f32 planes out); + VN_MLP_DENC_F16 (formats 3, 5): f16 chunk planes out");
     VN_REQUIRE(!(density_only && enc_format >= 3), "vn_mlp_bwd: the density-only backward takes enc_format 0..2");
-    VN_REQUIRE(density_only || (dirs && W3 && W4 && W5 && drgbs && dW3 && dW4 && dW5), "vn_mlp_bwd: null colour-network pointer");
+    VN_REQUIRE(density_only || ((dirs || base_fmt == 5) && W3 && W4 && W5 && drgbs && dW3 && dW4 && dW5), "vn_mlp_bwd: null colour-network pointer");
     VN_REQUIRE(vn_aligned(enc, 16) && vn_aligned(denc, 16), "vn_mlp_bwd: enc/denc must be 16-byte aligned");
     VN_REQUIRE(vn_aligned(W1, 16) && vn_aligned(W2, 16) && vn_aligned(W3, 16) && vn_aligned(W4, 16) && vn_aligned(W5, 16),
                "vn_mlp_bwd: weight matrices must be 16-byte aligned");
@@ -565,8 +573,8 @@ VN_API int vn_mlp_bwd(const void* enc, int enc_format, const float* dirs, const 
     a.dsigmas = dsigmas; a.drgbs = drgbs; a.denc = denc;
     a.dW[0] = dW1; a.dW[1] = dW2; a.dW[2] = dW3; a.dW[3] = dW4; a.dW[4] = dW5;
     a.S = S; a.density_only = density_only;
-    a.enc_fmt = enc_format >= 3 ? 3 : enc_format;
-    a.denc_fmt = enc_format == 4 ? 3 : (enc_format >= 2 ? 2 : 0);
+    a.enc_fmt = base_fmt;
+    a.denc_fmt = denc_f16 ? 3 : (base_fmt >= 2 ? 2 : 0);
     // the pipelined three-chain kernel (mlp_bwd_pipe.cu) is the backward; the serial kernel remains for the
     // density-only variant and as the A/B baseline (VN_MLP_PIPE=0)
     if (!density_only && (g_mlp_pipe || enc_format >= 3)) return launch_mlp_bwd_pipe(a, (cudaStream_t)stream);

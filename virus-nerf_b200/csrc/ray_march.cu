@@ -5,6 +5,7 @@
 // bit-exact against the oracle), so every float expression is written with explicit
 // round-to-nearest intrinsics in the reference's source order (no FMA contraction).
 #include "common.cuh"
+#include "mlp_common.cuh"
 
 struct MarchCfg {
     int cascades;
@@ -480,7 +481,8 @@ __global__ void __launch_bounds__(256) march_expand_kernel(const float* __restri
                                                            int64_t N, int max_samples, const MarchCfg c, int64_t capacity,
                                                            float* __restrict__ xyzs, float* __restrict__ dirs,
                                                            float* __restrict__ deltas, float* __restrict__ ts,
-                                                           float* __restrict__ xyzs_unit) {
+                                                           float* __restrict__ xyzs_unit, uint4* __restrict__ sh_planes,
+                                                           int64_t sh_stride) {
     vn_pdl_trigger(); vn_pdl_wait();          // PDL: see common.cuh
     const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -491,6 +493,19 @@ __global__ void __launch_bounds__(256) march_expand_kernel(const float* __restri
     float o[3], d[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) { o[k] = __ldg(rays_o + 3 * r + k); d[k] = __ldg(rays_d + 3 * r + k); }
+    // the direction encoding is a function of the RAY: evaluate SH16((d/|d| + 1)/2) once (networks.py:160-161,
+    // spherical_harmonics.py:16-42 -- the expression sequence of the fused MLP's input stage) and hand every
+    // sample its copy as two fp16 operand chunks, so that the MLP kernels bulk-copy instead of recomputing it
+    uint4 sh_lo = make_uint4(0u, 0u, 0u, 0u), sh_hi = sh_lo;
+    if (sh_planes) {
+        const float nrm = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        float e[16];
+        mlp::sh16_half((d[0] / nrm + 1.0f) * 0.5f, (d[1] / nrm + 1.0f) * 0.5f, (d[2] / nrm + 1.0f) * 0.5f, e);
+        __half2 h[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) h[j] = __floats2half2_rn(e[2 * j], e[2 * j + 1]);
+        sh_lo = *reinterpret_cast<const uint4*>(h); sh_hi = *reinterpret_cast<const uint4*>(h + 4);
+    }
     const float* row = ts_rows + r * max_samples;
     for (int k = lane; k < n; k += 32) {
         const int64_t s = start + k;
@@ -503,13 +518,37 @@ __global__ void __launch_bounds__(256) march_expand_kernel(const float* __restri
         dirs[3 * s] = d[0]; dirs[3 * s + 1] = d[1]; dirs[3 * s + 2] = d[2];
         ts[s] = t; deltas[s] = vn_calc_dt(t, c.esf, c.dt_max);                            // :46
         if (xyzs_unit) write_unit(c, xyzs_unit + 3 * s, xyz);
+        if (sh_planes) { sh_planes[s] = sh_lo; sh_planes[sh_stride + s] = sh_hi; }
     }
 }
+
+static int march_expand_launch(const float* rays_o, const float* rays_d, const int32_t* rays_a, const float* ts_rows,
+                               int64_t N, int max_samples, int grid_size, float scale, float exp_step_factor,
+                               int64_t capacity, float* xyzs, float* dirs, float* deltas, float* ts, float* xyzs_unit,
+                               void* sh_planes, int64_t sh_stride, void* stream);
 
 VN_API int vn_march_train_expand(const float* rays_o, const float* rays_d, const int32_t* rays_a, const float* ts_rows,
                                  int64_t N, int max_samples, int grid_size, float scale, float exp_step_factor,
                                  int64_t capacity, float* xyzs, float* dirs, float* deltas, float* ts, float* xyzs_unit,
                                  void* stream) {
+    return march_expand_launch(rays_o, rays_d, rays_a, ts_rows, N, max_samples, grid_size, scale, exp_step_factor, capacity,
+                               xyzs, dirs, deltas, ts, xyzs_unit, nullptr, 0, stream);
+}
+
+VN_API int vn_march_train_expand_sh(const float* rays_o, const float* rays_d, const int32_t* rays_a, const float* ts_rows,
+                                    int64_t N, int max_samples, int grid_size, float scale, float exp_step_factor,
+                                    int64_t capacity, float* xyzs, float* dirs, float* deltas, float* ts, float* xyzs_unit,
+                                    void* sh_planes, int64_t sh_stride, void* stream) {
+    VN_REQUIRE(sh_planes && vn_aligned(sh_planes, 16) && sh_stride >= capacity,
+               "vn_march_train_expand_sh: sh_planes must be 16-byte aligned with a plane stride >= capacity");
+    return march_expand_launch(rays_o, rays_d, rays_a, ts_rows, N, max_samples, grid_size, scale, exp_step_factor, capacity,
+                               xyzs, dirs, deltas, ts, xyzs_unit, sh_planes, sh_stride, stream);
+}
+
+static int march_expand_launch(const float* rays_o, const float* rays_d, const int32_t* rays_a, const float* ts_rows,
+                               int64_t N, int max_samples, int grid_size, float scale, float exp_step_factor,
+                               int64_t capacity, float* xyzs, float* dirs, float* deltas, float* ts, float* xyzs_unit,
+                               void* sh_planes, int64_t sh_stride, void* stream) {
     VN_REQUIRE(N >= 0 && capacity >= 0 && max_samples >= 0, "vn_march_train_expand: negative size");
     if (N == 0 || capacity == 0) return VN_OK;
     VN_REQUIRE(rays_o && rays_d && rays_a && ts_rows && xyzs && dirs && deltas && ts, "vn_march_train_expand: null pointer");
@@ -517,7 +556,7 @@ VN_API int vn_march_train_expand(const float* rays_o, const float* rays_d, const
     const MarchCfg c = make_cfg(1, grid_size, scale, exp_step_factor);
     VnProfScope prof(VN_K_MARCH_WRITE, capacity, (cudaStream_t)stream);
     vn_launch_pdl(march_expand_kernel, dim3(vn_blocks(N * 32, 256)), dim3(256), 0, (cudaStream_t)stream, rays_o, rays_d, rays_a, ts_rows, N, max_samples,
-                                                                                c, capacity, xyzs, dirs, deltas, ts, xyzs_unit);
+                                                                                c, capacity, xyzs, dirs, deltas, ts, xyzs_unit, (uint4*)sh_planes, sh_stride);
     VN_CHECK_LAUNCH("march_expand_kernel");
     return VN_OK;
 }

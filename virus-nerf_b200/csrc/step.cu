@@ -40,13 +40,19 @@ VN_API int vn_train_step_run(const vn_step_t* s, int64_t S, int phase, int do_op
     // enc / d_enc stay inside the step: use the level-pair-plane layout when the flags ask for it
     // VN_HASH_F16_CHUNKS: the hash forward emits fp16 operand chunks that the MLP kernels bulk-copy (enc_format 3,
     // d_enc stays f32 planes); else f32 planes (2) or rows (0)
-    const int enc_fmt = (s->hash_flags & VN_HASH_F16_CHUNKS) ? 3 : ((s->hash_flags & VN_HASH_PLANAR) ? 2 : 0);
+    // (5 when the single-pass march also emits the per-ray direction encoding as two more operand planes)
+    const bool chunks = (s->hash_flags & VN_HASH_F16_CHUNKS) != 0;
+    const int enc_fmt = chunks ? (s->ts_rows ? 5 : 3) : ((s->hash_flags & VN_HASH_PLANAR) ? 2 : 0);
     VN_REQUIRE(!(s->hash_flags & VN_HASH_F16_CHUNKS) || (s->hash_flags & VN_HASH_PLANAR),
                "vn_train_step_run: VN_HASH_F16_CHUNKS needs VN_HASH_PLANAR (d_enc planes)");
     if (phase == 0 || phase == 1) {
         VN_CUDA(cudaMemsetAsync(s->flat_g, 0, sizeof(float) * (size_t)s->n_params, st));
         VN_CUDA(cudaMemsetAsync(s->loss_acc, 0, sizeof(float) * 8, st));
-        if (s->ts_rows)
+        if (s->ts_rows && chunks)      // enc = [4 hash planes | 2 SH planes][S] x 16 B
+            VN_TRY(vn_march_train_expand_sh(s->rays_o, s->rays_d, s->rays_a, s->ts_rows, s->N, s->max_samples, s->grid_size,
+                                            s->scale, s->exp_step_factor, S, s->xyzs, s->dirs, s->deltas, s->ts, s->unit,
+                                            (char*)s->enc + (size_t)S * 64, S, stream));
+        else if (s->ts_rows)
             VN_TRY(vn_march_train_expand(s->rays_o, s->rays_d, s->rays_a, s->ts_rows, s->N, s->max_samples, s->grid_size,
                                          s->scale, s->exp_step_factor, S, s->xyzs, s->dirs, s->deltas, s->ts, s->unit, stream));
         else

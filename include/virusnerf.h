@@ -279,6 +279,18 @@ int vn_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float 
  * [1] i32; found_inf is reset to 0 afterwards. */
 int vn_scaler_update(float* scale, int32_t* growth_tracker, float* found_inf, float growth_factor,
                      float backoff_factor, int growth_interval, void* stream);
+/* Optimiser step count on the device (torch's GradScaler.step skips optimizer.step() on an overflow, so Adam's
+ * state['step'] only advances on applied steps -- training/trainer.py:140-141): opt_state = 4 floats {lr / (1 - beta1^t),
+ * sqrt(1 - beta2^t) for the NEXT step t, bit pattern of the int32 count of applied steps, unused}.
+ * vn_opt_state_init sets it for `applied_steps` steps already taken; vn_adam_step_dev takes its bias corrections from
+ * it; vn_scaler_update_dev advances it when found_inf == 0 (double-precision arithmetic, one thread). */
+int vn_opt_state_init(float* opt_state, int applied_steps, double lr, double beta1, double beta2, void* stream);
+int vn_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1,
+                     double beta2, double eps, const float* opt_state, const float* found_inf,
+                     const float* scale_dev, void* stream);
+int vn_scaler_update_dev(float* scale, int32_t* growth_tracker, float* found_inf, float growth_factor,
+                         float backoff_factor, int growth_interval, float* opt_state, double lr,
+                         double beta1, double beta2, void* stream);
 
 /* a12 (+a11 fused). NGP.density / NGP.forward dense part, modules/networks.py:134-164 and
  * MLP.forward :271-282, with DirEncoder (spherical_harmonics.py:7-42) fused into the input
@@ -342,6 +354,14 @@ typedef struct vn_step {
      * ray (vn_march_train_count_rows) and _run expands them (vn_march_train_expand) instead of
      * marching a second time */
     float* ts_rows;
+    /* half-precision encoder inside the step (modules/hash_encoder_half.py:112-213, 364-368): when table_h != NULL
+     * the step converts the fp32 table to fp16 (the reference's hash_table.to(float16) per forward), encodes with the
+     * half kernel, and the fused MLP backward hands fp16 gradients (what autocast produces) to the half backward
+     * kernel (zero-skip rule, fp32 accumulation straight into flat_g).  Needs VN_HASH_F16_CHUNKS | VN_HASH_PLANAR. */
+    void* table_h;    /* [total_entries, 2] fp16 scratch */
+    /* device-side optimiser step counter (torch Adam's state['step']): int32[1], advanced by the optimiser only when
+     * the step is not skipped (found_inf == 0); NULL = use the host counter adam_step */
+    float* step_dev;  /* the 4-float optimiser state of vn_opt_state_init */
 } vn_step_t;
 
 int vn_train_step_prepare(const vn_step_t* h_step, void* stream);

@@ -218,6 +218,89 @@ def test_fast_step_matches_autograd_step(monkeypatch, enc_layout, single_pass):
     assert int(e1.last_samples) == int(e2.last_samples) > 0
 
 
+def test_fast_step_half_encoder_matches_autograd_step(monkeypatch):
+    """BASELINE config 3's half-precision encoder (hash_encoder_half.py) inside the native step runner: fp16 table
+    copy per step, half forward kernel, fp16 encoding gradients into the half backward kernel (zero-skip, fp32
+    accumulation into the flat gradient) == the same step through the drop-in half module and torch autograd"""
+    from virus_nerf_b200 import synthetic
+    from virus_nerf_b200.engine import TrainEngine
+    from virus_nerf_b200.modules import ray_march, rendering
+    args = synthetic.make_args(device=DEV, batch_size=512)
+    ds = synthetic.SyntheticDataset(pool_size=1 << 13, n_images=8, device=DEV)
+    e1 = TrainEngine(args, ds, DEV, half_opt=True)
+    e2 = TrainEngine(args, ds, DEV, half_opt=True)
+    assert type(e2.model.pos_encoder).__module__.endswith("hash_encoder_half") and e2._table_h is not None
+    # the reference initialises the half table with U(-1e-4, 1e-4): give the encoding some signal
+    with torch.no_grad():
+        torch.manual_seed(4)
+        t = (torch.rand_like(e1.model.pos_encoder.hash_table) * 2 - 1) * 0.5
+        e1.model.pos_encoder.hash_table.copy_(t); e2.model.pos_encoder.hash_table.copy_(t)
+    assert torch.equal(e1.flat_p, e2.flat_p)
+    e1.step_idx = e2.step_idx = 1
+    e1._prep_step = e2._prep_step = 1
+    bf = torch.from_numpy(synthetic.morton_pack(ds.scene.occupancy_bitfield(128))).to(DEV)
+    e1.model.occupancy_grid.bitfield = bf; e2.model.occupancy_grid.bitfield = bf
+    orig = ray_march.raymarching_train
+    for it in range(2):
+        data = ds(512, args.training.sampling_strategy)
+        noise = torch.rand(512, device=DEV)
+        monkeypatch.setattr(rendering, "raymarching_train", lambda *a, **k: orig(*a, noise=noise, **k))
+        l1 = float(e1.step(data))
+        l2 = float(e2.step_fast(data, noise=noise))
+        assert abs(l1 - l2) <= 1e-5 * abs(l1), (l1, l2)
+        g1, g2 = e1.flat_g, e2.flat_g
+        assert float(g1.norm()) > 0
+        assert float((g1 - g2).norm() / g1.norm()) < 1e-4
+        assert float((e1.flat_p - e2.flat_p).abs().max()) < 1e-4
+    assert int(e1.last_samples) == int(e2.last_samples) > 0
+
+
+def test_half_engine_rejects_other_layouts():
+    from virus_nerf_b200 import synthetic
+    from virus_nerf_b200.engine import TrainEngine
+    args = synthetic.make_args(device=DEV, batch_size=64)
+    ds = synthetic.SyntheticDataset(pool_size=1 << 10, n_images=4, device=DEV)
+    with pytest.raises(ValueError, match="half_opt"):
+        TrainEngine(args, ds, DEV, half_opt=True, enc_layout="rows")
+
+
+def test_skipped_step_does_not_advance_adam(monkeypatch):
+    """torch semantics of GradScaler.step + Adam: a step with a non-finite gradient is skipped, the scale backs off,
+    and Adam's step count (bias corrections) does NOT advance -- checked against torch.optim.Adam + torch GradScaler
+    arithmetic on the same gradients (the host-side counter advanced on skipped steps)"""
+    from virus_nerf_b200 import _lib
+    torch.manual_seed(0)
+    n = 4096
+    p = torch.randn(n, device=DEV); g = torch.zeros(n, device=DEV)
+    m = torch.zeros(n, device=DEV); v = torch.zeros(n, device=DEV)
+    scale = torch.tensor([2.0 ** 19], device=DEV); tracker = torch.zeros(1, dtype=torch.int32, device=DEV)
+    found = torch.zeros(1, device=DEV); state = torch.zeros(4, device=DEV)
+    lr, b1, b2, eps = 5e-3, 0.9, 0.999, 1e-15
+    _lib.call("vn_opt_state_init", state, 0, lr, b1, b2)
+    ref_p = p.clone().cpu().requires_grad_(True)
+    opt = torch.optim.Adam([ref_p], lr=lr, betas=(b1, b2), eps=eps)
+    ref_scale = 2.0 ** 19
+    grads = [torch.randn(n), torch.randn(n), torch.randn(n), torch.randn(n)]
+    grads[0][17] = float("inf"); grads[2][5] = float("nan")          # steps 1 and 3 overflow
+    applied = 0
+    for k, gk in enumerate(grads):
+        g.copy_((gk * ref_scale).to(DEV))
+        _lib.call("vn_grad_check", g, n, found)
+        _lib.call("vn_adam_step_dev", p, g, m, v, n, lr, b1, b2, eps, state, found, scale)
+        _lib.call("vn_scaler_update_dev", scale, tracker, found, 2.0, 0.5, 2000, state, lr, b1, b2)
+        if torch.isfinite(gk).all():
+            ref_p.grad = (gk * ref_scale) * (1.0 / ref_scale)
+            opt.step(); applied += 1
+        else:
+            ref_scale *= 0.5
+        assert float(scale) == ref_scale
+        assert int(state[2:3].view(torch.int32)) == applied
+    assert applied == 2 and opt.state[ref_p]["step"] == 2
+    np.testing.assert_allclose(p.cpu().numpy(), ref_p.detach().numpy(), rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(m.cpu().numpy(), opt.state[ref_p]["exp_avg"].numpy(), rtol=2e-6, atol=1e-9)
+    np.testing.assert_allclose(v.cpu().numpy(), opt.state[ref_p]["exp_avg_sq"].numpy(), rtol=2e-6, atol=1e-12)
+
+
 def test_pipelined_steps_equal_unpipelined():
     """step_fast(data, next_data=...) (front half of the next step enqueued early) is the same
     computation as calling step_fast(data) step by step"""

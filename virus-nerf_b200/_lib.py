@@ -63,7 +63,7 @@ class Step(ctypes.Structure):
         [("w_color", _F), ("w_uss", _F), ("w_tof", _F), ("w_rgbd", _F)] +
         [("scale_dev", _P), ("found_inf", _P), ("growth_tracker", _P)] +
         [("lr", _D), ("beta1", _D), ("beta2", _D), ("eps", _D), ("adam_step", _I32)] +
-        [("ts_rows", _P)])
+        [("ts_rows", _P), ("table_h", _P), ("step_dev", _P)])
 
     def set_ptrs(self, **tensors):
         for k, t in tensors.items():
@@ -111,6 +111,9 @@ _SPECS = {
     "vn_grad_check": "plps",
     "vn_adam_step": "ppppl" "f" "dddd" "ipps",
     "vn_scaler_update": "pppffis",
+    "vn_opt_state_init": "piddds",
+    "vn_adam_step_dev": "ppppl" "dddd" "ppps",
+    "vn_scaler_update_dev": "pppffi" "pddd" "s",
     "vn_umma_selftest": "iiippps",
     "vn_train_step_prepare": "hs",
     "vn_train_step_run": "hliis",

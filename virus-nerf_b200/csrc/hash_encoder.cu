@@ -352,7 +352,8 @@ __device__ __forceinline__ void level_scatter(float* __restrict__ grad_level, co
     }
 }
 
-template <typename DT, int LPT, bool AGG, bool ZERO_SKIP, bool PLANAR, int MINB = 1>
+// CHUNK (DT = __half): dout is the fused MLP's fp16 chunk-plane gradient [levels/4][S] x 16 B (VN_HASH_F16_CHUNKS)
+template <typename DT, int LPT, bool AGG, bool ZERO_SKIP, bool PLANAR, int MINB = 1, bool CHUNK = false>
 __global__ void __launch_bounds__(256, MINB) hash_bwd_kernel(const float* __restrict__ xyz, const DT* __restrict__ dout,
                                                        float* __restrict__ grad, int64_t S,
                                                        const __grid_constant__ HashParams P) {
@@ -388,6 +389,28 @@ __global__ void __launch_bounds__(256, MINB) hash_bwd_kernel(const float* __rest
 #pragma unroll
                 for (int l = 0; l < LPT; ++l)
                     if (level0 + l < P.level_end) { float2 t = __ldg((const float2*)dp + l); d[2 * l] = t.x; d[2 * l + 1] = t.y; }
+            }
+        } else if (CHUNK) {
+            // level l of point i: half2 number (l & 3) of the 16-byte element i of plane l >> 2
+            if (LPT == 4 && (level0 & 3) == 0 && level0 + 4 <= P.level_end) {
+                const uint4 u = __ldg((const uint4*)dout + (int64_t)(level0 >> 2) * S + i);
+                const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                for (int l = 0; l < 4; ++l) { const float2 t = __half22float2(h[l]); d[2 * l] = t.x; d[2 * l + 1] = t.y; }
+            } else if (LPT == 2 && (level0 & 1) == 0 && level0 + 2 <= P.level_end) {
+                const uint2 u = __ldg((const uint2*)dout + ((int64_t)(level0 >> 2) * S + i) * 2 + ((level0 >> 1) & 1));
+                const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                for (int l = 0; l < 2; ++l) { const float2 t = __half22float2(h[l]); d[2 * l] = t.x; d[2 * l + 1] = t.y; }
+            } else {
+#pragma unroll
+                for (int l = 0; l < LPT; ++l) {
+                    const int level = level0 + l;
+                    if (level < P.level_end) {
+                        const float2 t = __half22float2(__ldg((const __half2*)dout + ((int64_t)(level >> 2) * S + i) * 4 + (level & 3)));
+                        d[2 * l] = t.x; d[2 * l + 1] = t.y;
+                    }
+                }
             }
         } else {
             const __half2* dp = (const __half2*)dout + i * P.levels + level0;
@@ -524,6 +547,19 @@ static int launch_bwd(const float* xyz, const DT* dout, float* grad, int64_t S, 
     const int lpt = pick_lpt(flags, lv, 8, true);
     const bool agg = !(flags & VN_HASH_NO_WARP_AGG);
     dim3 block(256), grid(vn_blocks(S, 256), (level_end - level_begin + lpt - 1) / lpt);
+    if (sizeof(DT) == 2 && (flags & VN_HASH_F16_CHUNKS)) {
+        VN_REQUIRE(P.levels % 4 == 0 && agg && vn_aligned(dout, 16), "hash bwd: the f16 chunk layout needs levels %% 4 == 0, "
+                   "warp aggregation and a 16-byte aligned gradient");
+        if constexpr (sizeof(DT) == 2) {
+            switch (lpt) {
+                case 2: vn_launch_pdl(hash_bwd_kernel<DT, 2, true, ZERO_SKIP, false, 5, true>, dim3(grid), dim3(block), 0, st, xyz, dout, grad, S, P); break;
+                case 4: vn_launch_pdl(hash_bwd_kernel<DT, 4, true, ZERO_SKIP, false, 5, true>, dim3(grid), dim3(block), 0, st, xyz, dout, grad, S, P); break;
+                default: VN_REQUIRE(false, "hash bwd: the f16 chunk layout takes 2 or 4 levels per thread");
+            }
+        }
+        VN_CHECK_LAUNCH("hash_bwd_kernel<f16 chunks>");
+        return VN_OK;
+    }
     if (flags & VN_HASH_PLANAR) {
         VN_REQUIRE(sizeof(DT) == 4 && P.levels % 2 == 0 && lpt % 2 == 0 && level_begin % 2 == 0 && level_end % 2 == 0 && agg,
                    "hash bwd: the planar layout needs f32 gradients, even level counts / ranges and >= 2 levels per thread");

@@ -32,10 +32,12 @@ VN_API int vn_grad_check(const float* g, int64_t n, float* found_inf, void* stre
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, int64_t n, AdamCfg c,
                                                    const float* __restrict__ found_inf,
-                                                   const float* __restrict__ scale_dev) {
+                                                   const float* __restrict__ scale_dev,
+                                                   const float* __restrict__ opt_state) {
     vn_pdl_trigger(); vn_pdl_wait();          // PDL: see common.cuh
     if (found_inf && *found_inf != 0.0f) return;          // GradScaler.step skips the optimizer step
     if (scale_dev) c.inv_scale = 1.0f / *scale_dev;
+    if (opt_state) { c.step_size = opt_state[0]; c.bc2_sqrt = opt_state[1]; }   // bias corrections of the device-side step count
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i + 3 < n) {
         float4 P = *(float4*)(p + i), M = *(float4*)(m + i), V = *(float4*)(v + i);
@@ -65,15 +67,56 @@ VN_API int vn_adam_step(float* p, const float* g, float* m, float* v, int64_t n,
                "vn_adam_step: buffers must be 16-byte aligned");
     const AdamCfg c = vn_make_adam_cfg(lr, beta1, beta2, eps, step, inv_scale);
     VnProfScope prof(VN_K_ADAM, n, (cudaStream_t)stream);
-    vn_launch_pdl(adam_kernel, dim3(vn_blocks((n + 3) / 4, 256)), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, n, c, found_inf, scale_dev);
+    vn_launch_pdl(adam_kernel, dim3(vn_blocks((n + 3) / 4, 256)), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, n, c, found_inf, scale_dev,
+                  (const float*)nullptr);
     VN_CHECK_LAUNCH("adam_kernel");
     return VN_OK;
 }
 
-__global__ void scaler_update_kernel(float* scale, int32_t* tracker, float* found_inf, float growth, float backoff, int interval) {
+// ---- optimiser step count on the device ------------------------------------------------------------
+// torch's GradScaler.step() skips optimizer.step() when an inf was found, so Adam's state['step'] -- and with it
+// the bias corrections -- only advances on steps that are applied.  A host-side counter cannot know that without a
+// sync; opt_state = {step_size = lr / (1 - beta1^t), sqrt(1 - beta2^t), bit pattern of the int32 number of APPLIED
+// steps, unused} lives on the device: the scaler update advances the count when found_inf == 0 and derives the two
+// constants of the NEXT step in double precision (the arithmetic of vn_make_adam_cfg), one thread.
+__device__ __forceinline__ void opt_state_set(float* opt_state, int applied, double lr, double beta1, double beta2) {
+    const double t = (double)(applied + 1);
+    opt_state[0] = (float)(lr / (1.0 - pow(beta1, t)));
+    opt_state[1] = (float)sqrt(1.0 - pow(beta2, t));
+    opt_state[2] = __int_as_float(applied);
+}
+__global__ void opt_state_init_kernel(float* opt_state, int applied, double lr, double beta1, double beta2) {
+    opt_state_set(opt_state, applied, lr, beta1, beta2);
+    opt_state[3] = 0.0f;
+}
+VN_API int vn_opt_state_init(float* opt_state, int applied_steps, double lr, double beta1, double beta2, void* stream) {
+    VN_REQUIRE(opt_state && applied_steps >= 0, "vn_opt_state_init: bad arguments");
+    opt_state_init_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(opt_state, applied_steps, lr, beta1, beta2);
+    VN_CHECK_LAUNCH("opt_state_init_kernel");
+    return VN_OK;
+}
+
+VN_API int vn_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2,
+                            double eps, const float* opt_state, const float* found_inf, const float* scale_dev, void* stream) {
+    VN_REQUIRE(n >= 0 && opt_state, "vn_adam_step_dev: bad n / null optimiser state");
+    if (n == 0) return VN_OK;
+    VN_REQUIRE(p && g && m && v, "vn_adam_step_dev: null pointer");
+    VN_REQUIRE(vn_aligned(p, 16) && vn_aligned(g, 16) && vn_aligned(m, 16) && vn_aligned(v, 16),
+               "vn_adam_step_dev: buffers must be 16-byte aligned");
+    const AdamCfg c = vn_make_adam_cfg(lr, beta1, beta2, eps, 1, 1.0f);          // step-dependent fields come from opt_state
+    VnProfScope prof(VN_K_ADAM, n, (cudaStream_t)stream);
+    vn_launch_pdl(adam_kernel, dim3(vn_blocks((n + 3) / 4, 256)), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, n, c, found_inf, scale_dev,
+                  opt_state);
+    VN_CHECK_LAUNCH("adam_kernel");
+    return VN_OK;
+}
+
+__global__ void scaler_update_kernel(float* scale, int32_t* tracker, float* found_inf, float growth, float backoff, int interval,
+                                     float* opt_state, double lr, double beta1, double beta2) {
     vn_pdl_trigger(); vn_pdl_wait();          // PDL: see common.cuh
     if (*found_inf != 0.0f) { *scale = *scale * backoff; *tracker = 0; }
     else {
+        if (opt_state) opt_state_set(opt_state, __float_as_int(opt_state[2]) + 1, lr, beta1, beta2);   // the step was applied
         const int t = *tracker + 1;
         if (t == interval) { const float grown = *scale * growth; if (isfinite(grown)) *scale = grown; *tracker = 0; }   // torch _amp_update_scale_
         else *tracker = t;
@@ -84,7 +127,18 @@ __global__ void scaler_update_kernel(float* scale, int32_t* tracker, float* foun
 VN_API int vn_scaler_update(float* scale, int32_t* growth_tracker, float* found_inf, float growth_factor,
                             float backoff_factor, int growth_interval, void* stream) {
     VN_REQUIRE(scale && growth_tracker && found_inf, "vn_scaler_update: null pointer");
-    vn_launch_pdl(scaler_update_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, scale, growth_tracker, found_inf, growth_factor, backoff_factor, growth_interval);
+    vn_launch_pdl(scaler_update_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, scale, growth_tracker, found_inf, growth_factor, backoff_factor, growth_interval,
+                  (float*)nullptr, 0.0, 0.0, 0.0);
+    VN_CHECK_LAUNCH("scaler_update_kernel");
+    return VN_OK;
+}
+
+VN_API int vn_scaler_update_dev(float* scale, int32_t* growth_tracker, float* found_inf, float growth_factor,
+                                float backoff_factor, int growth_interval, float* opt_state, double lr, double beta1,
+                                double beta2, void* stream) {
+    VN_REQUIRE(scale && growth_tracker && found_inf && opt_state, "vn_scaler_update_dev: null pointer");
+    vn_launch_pdl(scaler_update_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, scale, growth_tracker, found_inf, growth_factor, backoff_factor, growth_interval,
+                  opt_state, lr, beta1, beta2);
     VN_CHECK_LAUNCH("scaler_update_kernel");
     return VN_OK;
 }

@@ -21,6 +21,13 @@ VN_API int vn_train_step_prepare(const vn_step_t* s, void* stream) {
 VN_API int vn_train_step_optim(const vn_step_t* s, void* stream) {
     VN_REQUIRE(s != nullptr, "vn_train_step_optim: null step");
     VN_TRY(vn_grad_check(s->flat_g, s->n_params, s->found_inf, stream));
+    if (s->step_dev) {       // step count on the device: skipped steps do not advance Adam's bias corrections
+        VN_TRY(vn_adam_step_dev(s->flat_p, s->flat_g, s->flat_m, s->flat_v, s->n_params, s->lr, s->beta1, s->beta2, s->eps,
+                                (const float*)s->step_dev, s->found_inf, s->scale_dev, stream));
+        VN_TRY(vn_scaler_update_dev(s->scale_dev, s->growth_tracker, s->found_inf, 2.0f, 0.5f, 2000, (float*)s->step_dev, s->lr,
+                                    s->beta1, s->beta2, stream));
+        return VN_OK;
+    }
     VN_TRY(vn_adam_step(s->flat_p, s->flat_g, s->flat_m, s->flat_v, s->n_params, 1.0f, s->lr, s->beta1, s->beta2, s->eps,
                         s->adam_step, s->found_inf, s->scale_dev, stream));
     VN_TRY(vn_scaler_update(s->scale_dev, s->growth_tracker, s->found_inf, 2.0f, 0.5f, 2000, stream));
@@ -43,6 +50,8 @@ VN_API int vn_train_step_run(const vn_step_t* s, int64_t S, int phase, int do_op
     // (5 when the single-pass march also emits the per-ray direction encoding as two more operand planes)
     const bool chunks = (s->hash_flags & VN_HASH_F16_CHUNKS) != 0;
     const int enc_fmt = chunks ? (s->ts_rows ? 5 : 3) : ((s->hash_flags & VN_HASH_PLANAR) ? 2 : 0);
+    const bool half_enc = s->table_h != nullptr;       // hash_encoder_half.py inside the step
+    VN_REQUIRE(!half_enc || chunks, "vn_train_step_run: the half-precision encoder needs VN_HASH_F16_CHUNKS");
     VN_REQUIRE(!(s->hash_flags & VN_HASH_F16_CHUNKS) || (s->hash_flags & VN_HASH_PLANAR),
                "vn_train_step_run: VN_HASH_F16_CHUNKS needs VN_HASH_PLANAR (d_enc planes)");
     if (phase == 0 || phase == 1) {
@@ -59,7 +68,12 @@ VN_API int vn_train_step_run(const vn_step_t* s, int64_t S, int phase, int do_op
             VN_TRY(vn_march_train_write(s->rays_o, s->rays_d, s->hits_t, s->bitfield, s->noise, s->N, s->cascades,
                                         s->grid_size, s->scale, s->exp_step_factor, s->rays_a, S, s->xyzs, s->dirs, s->deltas,
                                         s->ts, s->unit, stream));
-        VN_TRY(vn_hash_encode_fwd_f32(s->unit, table, s->enc, S, &s->levels, s->hash_flags, stream));
+        if (half_enc) {
+            VN_TRY(vn_f32_to_f16(table, s->table_h, 2 * s->levels.total_entries, stream));       // hash_encoder_half.py:367
+            VN_TRY(vn_hash_encode_fwd_f16(s->unit, s->table_h, s->enc, S, &s->levels, s->hash_flags, stream));
+        } else {
+            VN_TRY(vn_hash_encode_fwd_f32(s->unit, table, s->enc, S, &s->levels, s->hash_flags, stream));
+        }
         VN_TRY(vn_mlp_fwd(s->enc, enc_fmt, s->dirs, W[0], W[1], W[2], W[3], W[4], S, 0, s->sigmas, s->rgbs, nullptr, stream));
         VN_TRY(vn_composite_train_fwd(s->sigmas, s->rgbs, s->deltas, s->ts, s->rays_a, s->N, S, s->T_threshold, s->vr_samples,
                                       s->opacity, s->depth, s->rgb, s->ws, stream));
@@ -72,9 +86,10 @@ VN_API int vn_train_step_run(const vn_step_t* s, int64_t S, int phase, int do_op
                            s->loss_out, stream));
         VN_TRY(vn_composite_train_bwd(s->sigmas, s->rgbs, s->deltas, s->ts, s->rays_a, s->N, S, s->T_threshold, s->d_opacity,
                                       s->d_depth, s->d_rgb, nullptr, s->d_sigmas, s->d_rgbs, stream));
-        VN_TRY(vn_mlp_bwd(s->enc, enc_fmt, s->dirs, W[0], W[1], W[2], W[3], W[4], S, 0, s->d_sigmas, s->d_rgbs, s->d_enc, dW[0], dW[1],
-                          dW[2], dW[3], dW[4], stream));
-        VN_TRY(vn_hash_encode_bwd_f32(s->unit, s->d_enc, table_grad, S, &s->levels, s->hash_flags, stream));
+        VN_TRY(vn_mlp_bwd(s->enc, half_enc ? (enc_fmt | VN_MLP_DENC_F16) : enc_fmt, s->dirs, W[0], W[1], W[2], W[3], W[4], S, 0,
+                          s->d_sigmas, s->d_rgbs, s->d_enc, dW[0], dW[1], dW[2], dW[3], dW[4], stream));
+        if (half_enc) VN_TRY(vn_hash_encode_bwd_f16(s->unit, s->d_enc, table_grad, S, &s->levels, s->hash_flags, stream));
+        else          VN_TRY(vn_hash_encode_bwd_f32(s->unit, s->d_enc, table_grad, S, &s->levels, s->hash_flags, stream));
         if (do_optim) VN_TRY(vn_train_step_optim(s, stream));
     }
     return VN_OK;

@@ -117,6 +117,9 @@ class TrainEngine:
         self.grid_update_interval = (args.ngp_grid if self.grid_type == "ngp" else args.occ_grid).update_interval
         self._grid_updates = 0
         self.lr, self.betas, self.eps = args.training.lr, (0.9, 0.999), 1e-15   # trainer.py:53-57
+        self.half_opt = bool(half_opt)
+        if self.half_opt and not (enc_layout == "chunks" and autocast):
+            raise ValueError("TrainEngine: half_opt needs enc_layout='chunks' and autocast (the fp16 operand-chunk path)")
 
         # ---- flat parameter / gradient / Adam state ------------------------------------
         params = [p for p in self.model.parameters() if p.requires_grad]
@@ -142,7 +145,14 @@ class TrainEngine:
         self.scale = torch.tensor([grad_scale], device=self.device)
         self.growth_tracker = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.found_inf = torch.zeros(1, device=self.device)
-        self.adam_step = 0
+        self.adam_step = 0        # host-side count of optimiser CALLS (diagnostic only: the bias corrections follow opt_state)
+        # Adam's state['step'] on the device: advanced only by steps that are applied (GradScaler skips on overflow)
+        self.opt_state = torch.zeros(4, device=self.device)
+        if self.device.type == "cuda":
+            _lib.call("vn_opt_state_init", self.opt_state, 0, self.lr, self.betas[0], self.betas[1])
+        # fp16 copy of the table, re-materialised every forward (hash_encoder_half.py:367), for the fast step
+        self._table_h = (torch.empty(self.model.pos_encoder.hash_table.numel(), dtype=torch.float16, device=self.device)
+                         if self.half_opt else None)
         self.last_samples = 0
         # fast-path state
         self._ws = _Workspace(self.device)
@@ -256,6 +266,7 @@ class TrainEngine:
         t = a.training
         st.w_color, st.w_uss, st.w_tof, st.w_rgbd = t.color_loss_w, t.uss_loss_w, t.tof_loss_w, t.rgbd_loss_w
         st.lr, st.beta1, st.beta2, st.eps = self.lr, self.betas[0], self.betas[1], self.eps
+        st.set_ptrs(step_dev=self.opt_state, table_h=self._table_h)
         return st
 
     def prepare(self, data, elapse_time=0.0, noise=None, ready=None):
@@ -280,6 +291,14 @@ class TrainEngine:
         depth = data['depth']
         st = self._structs[par]
         st.N = N
+        # every tensor whose pointer goes into the struct stays alive in the ticket (a .contiguous() copy made on the side
+        # stream would otherwise be freed before the main-stream kernels read it) and must be float32
+        gt_rgb = data['rgb'].contiguous()
+        dep = {k: (depth[k].contiguous() if (k in t.sensors and depth.get(k) is not None) else None) for k in ('USS', 'ToF', 'RGBD')}
+        for name, ten in [('rays_o', rays_o), ('rays_d', rays_d), ('rgb', gt_rgb)] + [(k, v) for k, v in dep.items() if v is not None]:
+            if ten.dtype != torch.float32:
+                raise TypeError(f"TrainEngine.prepare: {name} must be float32, got {ten.dtype}")
+        keep = [rays_o, rays_d]
 
         def body():
             nz = noise
@@ -288,10 +307,10 @@ class TrainEngine:
             if nz is None:
                 nz = ws.get(f"noise{par}", N)
                 nz.uniform_()                                               # ray_march.py:139
-            st.set_ptrs(rays_o=rays_o, rays_d=rays_d, noise=nz.contiguous(), gt_rgb=data['rgb'].contiguous(),
-                        uss=depth.get('USS') if 'USS' in t.sensors else None,
-                        tof=depth.get('ToF') if 'ToF' in t.sensors else None,
-                        rgbd=depth.get('RGBD') if 'RGBD' in t.sensors else None,
+            nz = nz.contiguous()
+            keep.extend([nz, gt_rgb] + [d for d in dep.values() if d is not None])
+            st.set_ptrs(rays_o=rays_o, rays_d=rays_d, noise=nz, gt_rgb=gt_rgb,
+                        uss=dep['USS'], tof=dep['ToF'], rgbd=dep['RGBD'],
                         hits_t=ws.get(f"hits{par}", N, 2), counts=ws.get(f"counts{par}", N, None, torch.int32),
                         rays_a=ws.get(f"rays_a{par}", N, 3, torch.int32),
                         scan_tmp=ws.get(f"scan_tmp{par}", _lib.scan_tmp_ints(N), None, torch.int32),
@@ -314,8 +333,7 @@ class TrainEngine:
             side.wait_event(ready)
             with torch.cuda.stream(side):
                 ev, nz = body()
-        return {"data": data, "struct": st, "event": ev, "par": par, "side": side is not None,
-                "keep": (rays_o, rays_d, nz)}
+        return {"data": data, "struct": st, "event": ev, "par": par, "side": side is not None, "keep": keep}
 
     def step_fast(self, data, elapse_time=0.0, noise=None, next_data=None):
         """The same train step as step(), enqueued by the native step runner (csrc/step.cu): no
@@ -414,6 +432,11 @@ class TrainEngine:
         """grad_scaler.step(optimizer); grad_scaler.update() (trainer.py:140-141), fused"""
         self.adam_step += 1
         _lib.call("vn_grad_check", self.flat_g, self.n_params, self.found_inf)
-        _lib.call("vn_adam_step", self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.n_params,
-                  1.0, self.lr, self.betas[0], self.betas[1], self.eps, self.adam_step, self.found_inf, self.scale)
-        _lib.call("vn_scaler_update", self.scale, self.growth_tracker, self.found_inf, 2.0, 0.5, 2000)
+        _lib.call("vn_adam_step_dev", self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.n_params,
+                  self.lr, self.betas[0], self.betas[1], self.eps, self.opt_state, self.found_inf, self.scale)
+        _lib.call("vn_scaler_update_dev", self.scale, self.growth_tracker, self.found_inf, 2.0, 0.5, 2000,
+                  self.opt_state, self.lr, self.betas[0], self.betas[1])
+
+    def applied_steps(self):
+        """number of optimiser steps that were applied (torch Adam's state['step']); synchronises"""
+        return int(self.opt_state[2:3].view(torch.int32).item())

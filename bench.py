@@ -21,14 +21,9 @@ sys.path.insert(0, ROOT)
 
 RAYS_PER_GPU = 4096
 HASH_BYTES_PER_POINT = 1164          # fwd or bwd, fp32 L16 F2 (SURVEY 8(d) / BASELINE.md section 3)
-# DRAM bytes per point of one `ncu --set full` capture (dram__bytes_read.sum + dram__bytes_write.sum over
-# S = 1 306 086 points, profiles/r1_ncu_top_kernels.md); scaled by the launch's points for `roofline.traffic`
 # the two candidates for "dominant kernel of the step" (DESIGN.md section 4): both are bracketed with CUDA events
 # INSIDE the timed region and the one with the larger total there is the roofline kernel
 ROOFLINE_CANDIDATES = ("hash_encode_bwd", "mlp_bwd")
-# DRAM bytes per point / sample from the ncu --set full capture of this round's kernels
-# (profiles/r1_ncu_top_kernels.md: dram__bytes_read.sum + dram__bytes_write.sum over 1 306 081 samples)
-NCU_DRAM_BYTES_PER_POINT = {"hash_encode_bwd": 188.9, "hash_encode_fwd": 148.1, "mlp_fwd": 152.9, "mlp_bwd": 253.1}
 WORKLOAD = ("ETHZ-shaped synthetic scene, hash grid L=16 F=2 T=2^19 fp32 tables, 4096 rays/batch/GPU, RGB+USS+ToF "
             "losses, VIRUS-NeRF occupancy update every 8 steps, training from the initial (all-occupied) grid")
 
@@ -40,7 +35,13 @@ def parse():
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rays", type=int, default=RAYS_PER_GPU)
-    ap.add_argument("--cpu-rays", type=int, default=512, help="rays per step of the bounded CPU sample")
+    ap.add_argument("--cpu-rays", type=int, default=RAYS_PER_GPU,
+                    help="rays per step of the CPU arm (default: the full 4096-ray batch of the GPU arm's config)")
+    ap.add_argument("--windows", type=int, default=5, help="repetitions of the K-step timed window (median reported)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --rays per GPU; strong: --rays is ONE global batch, rank r takes its contiguous shard")
+    ap.add_argument("--no-extra", action="store_true", help="skip extra_configs (configs 3 and 5)")
+    ap.add_argument("--no-config3", action="store_true", help="skip the T=2^22 / 2^18-ray / half-encoder configuration")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-autocast", action="store_true")
     ap.add_argument("--autograd-step", action="store_true", help="use the torch-autograd step instead of the fused step")
@@ -162,6 +163,33 @@ def run_reference(a):
 
 
 # ----------------------------------------------------------------------------------------
+def _snapshot(eng):
+    """everything a train step changes: parameters, Adam moments, scaler / optimiser state, occupancy grid, RNG streams"""
+    import torch
+    og = eng.model.occupancy_grid
+    snap = {"t": [x.clone() for x in (eng.flat_p, eng.flat_m, eng.flat_v, eng.scale, eng.growth_tracker, eng.found_inf,
+                                      eng.opt_state)],
+            "grid": og.occ_3d_grid.clone(), "bf": og.getBitfield().clone(), "update_step": og.update_step,
+            "ints": (eng.step_idx, eng._prep_step, eng._grid_updates, eng.adam_step),
+            "rng": torch.cuda.get_rng_state(eng.device),
+            "gen": og.dataset.gen.get_state() if getattr(og, "dataset", None) is not None else None}
+    return snap
+
+
+def _restore(eng, snap):
+    import torch
+    og = eng.model.occupancy_grid
+    for dst, src in zip((eng.flat_p, eng.flat_m, eng.flat_v, eng.scale, eng.growth_tracker, eng.found_inf, eng.opt_state),
+                        snap["t"]):
+        dst.copy_(src)
+    og.occ_3d_grid.copy_(snap["grid"]); og.bitfield = snap["bf"].clone(); og.update_step = snap["update_step"]
+    eng.step_idx, eng._prep_step, eng._grid_updates, eng.adam_step = snap["ints"]
+    eng._ticket = None                                   # it was prepared with the bitfield of the previous window
+    torch.cuda.set_rng_state(snap["rng"], eng.device)
+    if snap["gen"] is not None:
+        og.dataset.gen.set_state(snap["gen"])
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -178,10 +206,13 @@ def run_ours(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()
-    n = a.rays
+    strong = a.scaling == "strong"
+    n_global = a.rays if strong else a.rays * world         # strong: --rays is the GLOBAL batch, split over the ranks
+    lo, hi = (n_global * rank) // world, (n_global * (rank + 1)) // world
+    n = hi - lo if strong else a.rays                       # rays of this rank per step
     args = synthetic.make_args(device=str(dev), batch_size=n)
     scene = synthetic.RoomScene()
-    K, W = a.steps, a.warmup
+    K, W, R = a.steps, a.warmup, max(1, a.windows)
 
     def barrier():
         if world > 1:
@@ -195,128 +226,143 @@ def run_ours(a):
             return float(t)
         return ms
 
+    def check_p2p(eng):
+        if world > 1 and eng._p2p is not None and int(eng._p2p_err) != 0:
+            raise SystemExit("bench.py: peer-memory exchange barrier timed out")
+
+    def make_batches(ds, count, n_rank, strategy, shard=None):
+        """weak: every rank draws its own batches; strong (shard=(lo, hi, n_global)): every rank draws the SAME global
+        batch (identically seeded sampler) and keeps its contiguous shard"""
+        out = []
+        for _ in range(count):
+            if shard is None:
+                out.append(ds(n_rank, strategy))
+            else:
+                b = ds(shard[2], strategy)
+                sl = slice(shard[0], shard[1])
+                out.append({"rays_o": b["rays_o"][sl].contiguous(), "rays_d": b["rays_d"][sl].contiguous(),
+                            "rgb": b["rgb"][sl].contiguous(), "depth": {k: v[sl].contiguous() for k, v in b["depth"].items()}})
+        return out
+
     def run_phase(pinned):
-        """W warm-up + K timed steps from a fresh model.  pinned=False: the ray pool is resident
-        in HBM; pinned=True: every step's batch is copied from pinned host memory inside the
-        timed region and the loss is read back to the host (end-to-end)."""
+        """W warm-up steps, then R windows of K timed steps, every window from the SAME restored state and over the same
+        K batches (so the windows are repetitions of one measurement).  pinned=False: the batches are resident in HBM;
+        pinned=True: every step's batch is copied from pinned host memory inside the timed region and the loss is read
+        back to the host (end-to-end)."""
         ds = synthetic.SyntheticDataset(scene, pool_size=1 << 18, device=str(dev), pinned=False, seed=21)
-        ds.gen.manual_seed(1000 + rank)           # same pool on every rank, different training batches
+        ds.gen.manual_seed(1000 + (0 if strong else rank))    # same pool on every rank; weak: different training batches
         eng = TrainEngine(args, ds, dev, world_size=world, rank=rank, autocast=not a.no_autocast, comm=a.comm,
                           enc_layout=a.enc_layout, single_pass_march=not a.two_pass_march)
+        batches = make_batches(ds, W + K + 1, n, args.training.sampling_strategy, (lo, hi, n_global) if strong else None)
+        noises = None
+        if strong:          # the jitter of the GLOBAL batch, so that N ranks march exactly the samples one rank would
+            gen = torch.Generator(device=dev); gen.manual_seed(9)
+            noises = [torch.rand(n_global, device=dev, generator=gen)[lo:hi].contiguous() for _ in batches]
         host_batches = None
-        dev_batches = None
-        if not pinned:
-            # `value`: inputs already resident in HBM when the timed region starts -- the W+K batches are
-            # assembled (sampled + gathered from the ray pool) on the device beforehand
-            dev_batches = [ds(n, args.training.sampling_strategy) for _ in range(W + K + 1)]
         if pinned:
-            # batches pre-assembled in pinned host memory (the reference's dataset lives on the
-            # host side of the boundary); the timed region pays the H2D copy of each batch
             # ONE flat pinned buffer per batch: rays_o | rays_d | rgb | USS | ToF  (11 n floats, one H2D copy per step)
             host_batches = []
-            for _ in range(W + K + 1):
-                b = ds(n, args.training.sampling_strategy)
+            for b in batches:
                 flat = [b["rays_o"], b["rays_d"], b["rgb"], b["depth"]["USS"], b["depth"]["ToF"]]
                 host_batches.append(torch.cat([t.reshape(-1).float() for t in flat]).cpu().pin_memory())
             loss_host = torch.zeros(1).pin_memory()
         h2d = d2h = 0
-        samples = []
-        prof = {}
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        launches0 = 0
+
         def get_batch(it):
             if pinned:
                 buf = host_batches[it].to(dev, non_blocking=True)
                 ro, rd, rgb_t = buf[0:3 * n].view(n, 3), buf[3 * n:6 * n].view(n, 3), buf[6 * n:9 * n].view(n, 3)
                 return {"rays_o": ro, "rays_d": rd, "rgb": rgb_t, "depth": {"USS": buf[9 * n:10 * n], "ToF": buf[10 * n:11 * n]}}
-            return dev_batches[it]
+            return batches[it]
 
-        data = get_batch(0)
-        for it in range(W + K):
-            if it == W:
-                barrier()
-                launches0 = _lib.launch_count()
-                if not pinned:
-                    # only the dominant kernel is bracketed with events inside the timed region (an event between
-                    # two kernels serialises them); the full per-kernel table comes from the untimed steps below
-                    _lib.profile_start(list(ROOFLINE_CANDIDATES))
-                ev0.record()
-            # the next batch is fetched (H2D copy in the e2e phase) before this step is enqueued so that
-            # the engine can pipeline its front half; every batch is copied exactly once, inside the
-            # timed region for all timed steps but the first (whose copy replaces the last step's)
-            nxt = get_batch(it + 1)
-            if pinned:
-                h2d = host_batches[it].numel() * host_batches[it].element_size()
-            if a.autograd_step:
-                loss = eng.step(data)
-            else:
-                loss = eng.step_fast(data, next_data=nxt)
-            data = nxt
-            if pinned:
-                loss_host.copy_(loss.reshape(1), non_blocking=True)      # D2H read of the step's result (pinned, in stream)
-                d2h = 4
-            if it >= W:
-                samples.append(eng.last_samples)
-        ev1.record()
-        barrier()
-        ms = max_over_ranks(ev0.elapsed_time(ev1))
-        launches = _lib.launch_count() - launches0
+        def steps(first, count):
+            nonlocal h2d, d2h
+            smp, loss = [], None
+            data = get_batch(first)
+            for it in range(first, first + count):
+                # the next batch is fetched (H2D copy in the e2e phase) before this step is enqueued so that the
+                # engine can pipeline its front half; every batch is copied exactly once per window
+                nxt = get_batch(it + 1)
+                if pinned:
+                    h2d = host_batches[it].numel() * host_batches[it].element_size()
+                if a.autograd_step:
+                    loss = eng.step(data)
+                elif noises is not None:
+                    loss = eng.step_fast(data, noise=noises[it], next_data=nxt, next_noise=noises[it + 1])
+                else:
+                    loss = eng.step_fast(data, next_data=nxt)
+                data = nxt
+                if pinned:
+                    loss_host.copy_(loss.reshape(1), non_blocking=True)   # D2H read of the step's result (pinned, in stream)
+                    d2h = 4
+                smp.append(eng.last_samples)
+            return smp, loss
+
+        steps(0, W)
+        torch.cuda.synchronize()
+        snap = _snapshot(eng)
+        window_ms, samples, launches, loss = [], [], 0, None
+        live_prof = {}
+        for w in range(R):
+            _restore(eng, snap)
+            barrier()
+            launches0 = _lib.launch_count()
+            if not pinned:
+                # only the candidate dominant kernels are bracketed with events inside the timed region (an event between
+                # two kernels serialises them); the full per-kernel table comes from the untimed steps below
+                _lib.profile_start(list(ROOFLINE_CANDIDATES))
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            samples, loss = steps(W, K)
+            ev1.record()
+            barrier()
+            window_ms.append(max_over_ranks(ev0.elapsed_time(ev1)))
+            launches = _lib.launch_count() - launches0
+            if not pinned:
+                for k, v in _lib.profile_stop().items():
+                    live_prof.setdefault(k, []).extend(v)
+        check_p2p(eng)
+        prof = {}
         if not pinned:
-            prof_dom = _lib.profile_stop()
             # untimed breakdown: the same K steps again with every major kernel timed
+            _restore(eng, snap)
             _lib.profile_start()
-            for it in range(K):
-                nxt = dev_batches[(it + 1) % len(dev_batches)]
-                eng.step_fast(dev_batches[it % len(dev_batches)], next_data=nxt) if not a.autograd_step else eng.step(dev_batches[it % len(dev_batches)])
+            steps(W, K)
             torch.cuda.synchronize()
             prof = _lib.profile_stop()
-            prof["__timed__"] = {k: prof_dom.get(k, []) for k in ROOFLINE_CANDIDATES}
-        samples = [int(s) for s in samples]
-        render_ms = None
-        if not pinned:
-            # BASELINE.json configs[4] (informational, outside the timed region): one 1920x1080 frame with
-            # the model just trained, rays sharded over the ranks in row bands, no collective
-            Wp, Hp = 1920, 1080
-            u, v = torch.meshgrid(torch.arange(Wp, device=dev, dtype=torch.float32),
-                                  torch.arange(Hp, device=dev, dtype=torch.float32), indexing="xy")
-            d = torch.stack([(u + 0.5 - Wp / 2) / 960, torch.ones_like(u), -(v + 0.5 - Hp / 2) / 960], -1).reshape(-1, 3)
-            d = (d / d.norm(dim=1, keepdim=True)).contiguous()
-            o = torch.tensor([0.0, -0.2, -0.05], device=dev).expand_as(d).contiguous()
-            eng.render_frame(o, d)                                   # warm-up
-            barrier()
-            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            r0.record()
-            eng.render_frame(o, d)
-            r1.record()
-            barrier()
-            render_ms = max_over_ranks(r0.elapsed_time(r1))
+            prof["__timed__"] = {k: live_prof.get(k, []) for k in ROOFLINE_CANDIDATES}
         same = True
-        if world > 1 and eng._p2p is not None and int(eng._p2p_err) != 0:
-            raise SystemExit("bench.py: peer-memory allreduce barrier timed out")
         if world > 1:
             c = eng.replica_checksum()
-            lo, hi = c.clone(), c.clone()
-            dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-            same = bool((lo == hi).all())
-        nonlocal grad_exchange
-        grad_exchange = eng.comm
-        return ms, launches, samples, prof, h2d, d2h, float(loss), same, render_ms
+            clo, chi = c.clone(), c.clone()
+            dist.all_reduce(clo, op=dist.ReduceOp.MIN); dist.all_reduce(chi, op=dist.ReduceOp.MAX)
+            same = bool((clo == chi).all())
+        return {"window_ms": window_ms, "launches": launches, "samples": [int(x) for x in samples], "prof": prof, "h2d": h2d,
+                "d2h": d2h, "loss": float(loss), "same": same, "eng": eng, "comm": eng.comm}
 
-    grad_exchange = "none"
     clocks = ClockSampler(local)
     clocks.start()
-    ms, launches, samples, prof, _, _, last_loss, replicas_same, render_ms = run_phase(pinned=False)
+    ph = run_phase(pinned=False)
     clk = clocks.stop()
-    ms_e2e, h2d, d2h = ms, 0, 0
-    if not a.no_e2e:
-        ms_e2e, _, _, _, h2d, d2h, _, _, _ = run_phase(pinned=True)
+    eng = ph["eng"]
+    extra = {} if a.no_extra else extra_configs(a, eng, scene, dev, world, rank, barrier, max_over_ranks, make_batches, check_p2p)
+    del eng
+    ph["eng"] = None
+    torch.cuda.empty_cache()
+    ph_e2e = None if a.no_e2e else run_phase(pinned=True)
+    if ph_e2e is not None:
+        ph_e2e["eng"] = None
 
     if rank == 0:
         peak, peak_src = peaks()
-        total_rays = n * world * K
+        ms = statistics.median(ph["window_ms"])                 # K steps
+        ms_e2e = statistics.median(ph_e2e["window_ms"]) if ph_e2e else ms
+        total_rays = n_global * K
         value = total_rays / (ms * 1e-3)
-        # roofline of the dominant kernel: algorithmic bytes / measured kernel time (CUDA events
-        # around the launches, on the launching stream)
+        prof, samples = ph["prof"], ph["samples"]
+        traffic = ncu_traffic()
+        # roofline of the dominant kernel: algorithmic bytes / measured kernel time (CUDA events around the launches,
+        # on the launching stream)
         kern = {}
         timed = prof.pop("__timed__", {})
         for name, calls in prof.items():
@@ -326,67 +372,200 @@ def run_ours(a):
                               "share_of_step": round(t_ms / ms, 4)}
                 if name.startswith("hash_encode"):
                     kern[name]["achieved_gbs"] = pts * HASH_BYTES_PER_POINT / (t_ms * 1e-3) / 1e9
+                    kern[name]["frac_of_hbm_peak"] = kern[name]["achieved_gbs"] / peak
                 if name.startswith("mlp"):
                     flop = 18816 if name == "mlp_fwd" else 56448
                     kern[name]["achieved_tflops"] = pts * flop / (t_ms * 1e-3) / 1e12
         tflops_peak = peaks_tensor()
-        # kernels timed live inside the timed region: totals there decide which one dominates the step
+        # kernels timed live inside the timed windows: totals there decide which one dominates the step
         live = {}
         for name, calls in timed.items():
             t_ms = sum(c[0] for c in calls); pts = sum(c[1] for c in calls)
             if t_ms > 0:
                 live[name] = (t_ms, pts, len(calls))
                 kern.setdefault(name, {}).update({"ms_total_timed_region": round(t_ms, 4), "launches_timed_region": len(calls),
-                                                  "units_timed_region": pts, "share_of_timed_step": round(t_ms / ms, 4)})
+                                                  "units_timed_region": pts, "ms_per_launch_timed_region": round(t_ms / len(calls), 5),
+                                                  "share_of_timed_step": round(t_ms / (ms * R), 4)})
         dom = max(live, key=lambda k: live[k][0]) if live else None
         roof = None
         if dom and dom.startswith("hash_encode"):
             t_ms, pts, nl = live[dom]
             gbs = pts * HASH_BYTES_PER_POINT / (t_ms * 1e-3) / 1e9
+            tr = traffic.get(dom)
             roof = {"kernel": dom, "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
-                    "measured": "CUDA events around every launch of this kernel inside the timed region",
-                    "traffic": NCU_DRAM_BYTES_PER_POINT[dom] * pts / nl,
-                    "traffic_note": "DRAM bytes per launch = ncu bytes/point (profiles/r1_ncu_top_kernels.md) x mean points per "
-                                    "launch; far below the algorithmic bytes because the table and its gradient are L2 resident",
+                    "measured": f"CUDA events around every launch of this kernel inside the {R} timed windows ({nl} launches)",
+                    "traffic": (tr["dram_bytes_per_point"] * pts / nl) if tr else None,
+                    "traffic_note": (f"DRAM bytes per launch = dram__bytes_read.sum + dram__bytes_write.sum per point of this round's "
+                                     f"ncu --set full capture ({tr['source']}) x mean points per launch; far below the algorithmic "
+                                     f"bytes because the table and its gradient are L2 resident") if tr else "no ncu capture",
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": HASH_BYTES_PER_POINT * pts / nl,
                     "algorithmic_bytes_per_point": HASH_BYTES_PER_POINT,
-                    "runner_up": {k: round(v[0], 4) for k, v in live.items() if k != dom}}
+                    "runner_up": {k: round(v[0] / v[2], 5) for k, v in live.items() if k != dom}}
         elif dom and dom.startswith("mlp"):
             t_ms, pts, nl = live[dom]
             tf = pts * 56448 / (t_ms * 1e-3) / 1e12
+            tr = traffic.get(dom)
             roof = {"kernel": dom, "bound": "tensor", "achieved": tf, "peak": tflops_peak, "unit": "TFLOP/s",
-                    "frac": tf / tflops_peak, "traffic": NCU_DRAM_BYTES_PER_POINT[dom] * pts / nl,
-                    "measured": "CUDA events around every launch of this kernel inside the timed region",
+                    "frac": tf / tflops_peak, "traffic": (tr["dram_bytes_per_point"] * pts / nl) if tr else None,
+                    "measured": f"CUDA events around every launch of this kernel inside the {R} timed windows ({nl} launches)",
                     "peak_source": "bf16_tflops_sustained, " + peak_src,
-                    "runner_up": {k: round(v[0], 4) for k, v in live.items() if k != dom}}
-        for k in ("hash_encode_fwd", "hash_encode_bwd"):
-            if k in kern and "achieved_gbs" in kern[k]:
-                kern[k]["frac_of_hbm_peak"] = kern[k]["achieved_gbs"] / peak
+                    "runner_up": {k: round(v[0] / v[2], 5) for k, v in live.items() if k != dom}}
+        spread = lambda xs: (max(xs) - min(xs)) / statistics.median(xs)
         line = {"metric": "train_rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": K,
-                "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if strong else "weak",
+                "vs_baseline": None,
                 "dtype": "f32 tables/encoder/composite, fp16-autocast MLP" if not a.no_autocast else "f32",
                 "data": "synthetic",
-                "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": n, "global_rays_per_step": n * world,
+                "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": n, "global_rays_per_step": n_global,
                            "samples_per_step_mean": statistics.mean(samples) if samples else 0,
-                           "parallelism": f"dp{world}", "grad_exchange": grad_exchange,
+                           "parallelism": f"dp{world}", "grad_exchange": ph["comm"],
                            "l2_policy": "inputs larger than L2: table+grad+Adam state 183 MB and per-step sample "
                                         "buffers are streamed; a fresh ray batch every step"},
+                "windows": {"count": R, "what": f"the K = {K} timed steps are repeated {R} times, every window from the same "
+                                               "restored state (parameters, Adam moments, scaler, occupancy grid, RNG) over the same "
+                                               "batches; value / ms_per_step = median window, max over ranks per window",
+                            "ms_per_step": [round(x / K, 5) for x in ph["window_ms"]], "spread": round(spread(ph["window_ms"]), 4),
+                            "e2e_ms_per_step": [round(x / K, 5) for x in ph_e2e["window_ms"]] if ph_e2e else None},
                 "roofline": roof, "kernels": kern,
-                "kernels_note": "per-kernel table: K untimed steps after the timed region with CUDA events around every major "
-                                "launch (share_of_step relative to the timed ms/step); the roofline kernel is also timed inside "
-                                "the timed region",
-                "e2e": {"value": total_rays / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": h2d,
-                        "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K},
-                "gpu_launches": launches, "clocks": clk, "final_loss": last_loss,
-                "replicas_bit_identical": replicas_same,
-                "render_1080p": {"ms_per_frame": render_ms, "rays_per_s": (1920 * 1080 / (render_ms * 1e-3)) if render_ms else None,
-                                 "note": "test-time render of one 1920x1080 frame with the trained model, rays sharded over "
-                                         "the ranks, no collective; informational, outside the timed region"}}
+                "kernels_note": "per-kernel table: K untimed steps after the timed windows with CUDA events around every major "
+                                "launch (share_of_step relative to the timed ms/step); the roofline candidates are also timed "
+                                "inside the timed windows",
+                "e2e": {"value": total_rays / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": ph_e2e["h2d"] if ph_e2e else 0,
+                        "d2h_bytes_per_step": ph_e2e["d2h"] if ph_e2e else 0, "ms_per_step": ms_e2e / K},
+                "gpu_launches": ph["launches"], "clocks": clk, "final_loss": ph["loss"],
+                "replicas_bit_identical": ph["same"] and (ph_e2e["same"] if ph_e2e else True),
+                "extra_configs": extra}
+        if "render_1080p" in extra:
+            line["render_1080p"] = extra["render_1080p"]
         if world == 1 and not a.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(a)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def ncu_traffic():
+    """DRAM bytes per point of this round's `ncu --set full` captures (profiles/r2_ncu_traffic.json, written from the
+    .ncu-rep files by tools/ncu_traffic.py)"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+def extra_configs(a, eng, scene, dev, world, rank, barrier, max_over_ranks, make_batches, check_p2p):
+    """BASELINE.json configs[2] and [4], untimed by the headline (after its timed windows, before the end-to-end phase):
+    config 5 = 1080p test-time frame (rays sharded, no collective) + occupancy-update sweep; config 3 = Robot@Home2-shaped
+    scene, T = 2^22, 2^18 rays per step split over the ranks (strong scaling), half-precision encoder."""
+    import torch
+    from virus_nerf_b200 import _lib, synthetic
+    from virus_nerf_b200.engine import TrainEngine
+    from virus_nerf_b200.modules.occupancy_grid import OccupancyGrid
+    out = {}
+
+    def timed(fn, reps=3):
+        fn(); barrier()
+        ts = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); barrier()
+            ts.append(max_over_ranks(e0.elapsed_time(e1)))
+        return statistics.median(ts)
+
+    # ---- config 5a: one 1920x1080 frame, (i) with the grid as trained so far, (ii) with the scene's carved grid
+    Wp, Hp = 1920, 1080
+    u, v = torch.meshgrid(torch.arange(Wp, device=dev, dtype=torch.float32),
+                          torch.arange(Hp, device=dev, dtype=torch.float32), indexing="xy")
+    d = torch.stack([(u + 0.5 - Wp / 2) / 960, torch.ones_like(u), -(v + 0.5 - Hp / 2) / 960], -1).reshape(-1, 3)
+    d = (d / d.norm(dim=1, keepdim=True)).contiguous()
+    o = torch.tensor([0.0, -0.2, -0.05], device=dev).expand_as(d).contiguous()
+    og = eng.model.occupancy_grid
+    ms_trained = timed(lambda: eng.render_frame(o, d))
+    bf_keep = og.getBitfield().clone()
+    og.bitfield = torch.from_numpy(synthetic.morton_pack(scene.occupancy_bitfield(128))).to(dev)
+    ms_carved = timed(lambda: eng.render_frame(o, d))
+    og.bitfield = bf_keep
+    out["render_1080p"] = {"ms_per_frame": ms_carved, "rays_per_s": 1920 * 1080 / (ms_carved * 1e-3),
+                           "ms_per_frame_grid_as_trained": ms_trained, "n_gpus": world,
+                           "note": "test-time render of one 1920x1080 frame (raymarching_test + fused MLP + composite_test), rays "
+                                   "sharded over the ranks in bands, no collective; carved = the synthetic scene's occupancy "
+                                   "(room shell + boxes), grid_as_trained = the grid after the benchmark's few dozen steps"}
+
+    # ---- config 5b: occupancy-grid update (OccupancyGrid.update: ray update + NeRF update + decay + bitfield), rank 0's clock
+    sweep = []
+    for G in (128, 256):
+        for B in (1024, 8192, 65536):
+            args_g = synthetic.make_args(device=str(dev), occ_batch_size=B)
+            ds_g = synthetic.SyntheticDataset(scene, pool_size=1 << 18, device=str(dev), seed=5)
+            grid = OccupancyGrid(args=args_g, grid_size=G, dataset=ds_g, fct_density=eng.model.density)
+            n0 = _lib.launch_count()
+            grid.update(elapse_time=0.0)
+            per_update = _lib.launch_count() - n0
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(5):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); grid.update(elapse_time=0.0); e1.record(); torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            sweep.append({"grid": G, "rays": B, "ms_per_update": round(statistics.median(ts), 4), "kernels_per_update": per_update})
+            del grid
+    out["occupancy_update_sweep"] = sweep
+
+    # ---- config 3: RH2-shaped (RGBD + USS + ToF), T = 2^22, 2^18 rays per step over all ranks, half-precision encoder
+    if not a.no_config3:
+        n3 = 1 << 18
+        lo3, hi3 = (n3 * rank) // world, (n3 * (rank + 1)) // world
+        args3 = synthetic.make_args(device=str(dev), batch_size=hi3 - lo3, sensors=("RGBD", "USS", "ToF"))
+        args3.training.sampling_strategy = {"imgs": "all", "pixs": "random"}
+        ds3 = synthetic.SyntheticDataset(scene, kind="rh2", pool_size=1 << 19, device=str(dev), seed=33)
+        ds3.gen.manual_seed(77)                                              # the same global batches on every rank
+        eng3 = TrainEngine(args3, ds3, dev, world_size=world, rank=rank, log2_T=22, half_opt=True, comm=a.comm)
+        W3, K3 = 2, 4
+        b3 = make_batches(ds3, W3 + K3 + 1, hi3 - lo3, args3.training.sampling_strategy, (lo3, hi3, n3))
+        gen = torch.Generator(device=dev); gen.manual_seed(5)
+        noise3 = [torch.rand(n3, device=dev, generator=gen)[lo3:hi3].contiguous() for _ in b3]   # same jitter as the 1-GPU run
+        losses = []
+        for it in range(W3):
+            losses.append(float(eng3.step_fast(b3[it], noise=noise3[it])))
+        barrier()
+        _lib.profile_start(["hash_encode_fwd", "hash_encode_bwd", "mlp_fwd", "mlp_bwd"])
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        smp = []
+        for it in range(W3, W3 + K3):
+            losses.append(eng3.step_fast(b3[it], noise=noise3[it]).clone())
+            smp.append(eng3.last_samples)
+        e1.record()
+        barrier()
+        ms3 = max_over_ranks(e0.elapsed_time(e1))
+        prof3 = _lib.profile_stop()
+        check_p2p(eng3)
+        peak, _ = peaks()
+        k3 = {}
+        for name, calls in prof3.items():
+            t_ms = sum(c[0] for c in calls); pts = sum(c[1] for c in calls)
+            if t_ms > 0:
+                k3[name] = {"ms_per_launch": round(t_ms / len(calls), 4), "points": pts // len(calls)}
+                if name.startswith("hash_encode"):
+                    # algorithmic bytes per point, half encoder (BASELINE.md section 3): fwd 588 (fp16 table reads + fp16 out),
+                    # bwd 1100 (fp32 scatter); reported next to the fp32 figure of the headline
+                    bpp = 588 if name == "hash_encode_fwd" else 1100
+                    k3[name]["achieved_gbs"] = round(pts * bpp / (t_ms * 1e-3) / 1e9, 1)
+                    k3[name]["frac_of_hbm_peak"] = round(k3[name]["achieved_gbs"] / peak, 4)
+                    k3[name]["algorithmic_bytes_per_point"] = bpp
+        out["config3_rh2_T22_half"] = {
+            "metric": "train_rays_per_sec", "value": n3 * K3 / (ms3 * 1e-3), "unit": "rays/s", "ms_per_step": ms3 / K3,
+            "n_gpus": world, "scaling": "strong", "global_rays_per_step": n3, "rays_per_step_per_gpu": hi3 - lo3,
+            "samples_per_step_per_gpu": int(statistics.mean(smp)), "steps": K3, "warmup": W3,
+            "encoder": "half (fp16 table copy per step, fp16 encoding and encoding gradient, fp32 scatter)", "log2_T": 22,
+            "table_mb_fp32": round(eng3.model.pos_encoder.hash_table.numel() * 4 / 2 ** 20, 1), "grad_exchange": eng3.comm,
+            "losses": [round(float(x), 6) for x in losses], "kernels": k3,
+            "note": "one globally seeded batch per step, rank r trains on rays [r N/n, (r+1) N/n) with the jitter of the global "
+                    "batch: `losses` must agree between N = 1 and N > 1 (global loss normalisers, summed gradients)"}
+        del eng3
+        torch.cuda.empty_cache()
+    return out
 
 
 def cpu_baseline(a):

@@ -335,7 +335,7 @@ class TrainEngine:
                 ev, nz = body()
         return {"data": data, "struct": st, "event": ev, "par": par, "side": side is not None, "keep": keep}
 
-    def step_fast(self, data, elapse_time=0.0, noise=None, next_data=None):
+    def step_fast(self, data, elapse_time=0.0, noise=None, next_data=None, next_noise=None):
         """The same train step as step(), enqueued by the native step runner (csrc/step.cu): no
         autograd graph, no torch glue, persistent workspace, three host calls per step:
         [prepare: aabb, march count + scan] -> host reads S -> [run: march write (also emits
@@ -369,7 +369,7 @@ class TrainEngine:
         if self.world_size == 1:
             _lib.call("vn_train_step_run", st, S, 0, 1)
             if next_data is not None:
-                self._ticket = self.prepare(next_data, elapse_time, ready=None if update_due else ready_next)
+                self._ticket = self.prepare(next_data, elapse_time, noise=next_noise, ready=None if update_due else ready_next)
             return self._loss_out[0]
         # ---- data parallel ----------------------------------------------------------------
         _lib.call("vn_train_step_run", st, S, 1, 0)
@@ -384,7 +384,7 @@ class TrainEngine:
             _lib.call("vn_p2p_reduce_adam", self.n_params, self.flat_m, self.flat_v, self.lr, self.betas[0],
                       self.betas[1], self.eps, self.adam_step, self.found_inf, self.scale, self.growth_tracker)
             if next_data is not None and not update_due:
-                self._ticket = self.prepare(next_data, elapse_time, ready=ready_next)
+                self._ticket = self.prepare(next_data, elapse_time, noise=next_noise, ready=ready_next)
         else:
             ev = torch.cuda.Event(); ev.record()
             self._comm_stream.wait_event(ev)
@@ -396,14 +396,14 @@ class TrainEngine:
                 else:
                     work = dist.all_reduce(self.flat_g, async_op=True)    # NCCL; overlaps prepare(next) below
             if next_data is not None and not update_due:
-                self._ticket = self.prepare(next_data, elapse_time, ready=ready_next)
+                self._ticket = self.prepare(next_data, elapse_time, noise=next_noise, ready=ready_next)
             if work is not None:
                 work.wait()
             else:
                 torch.cuda.current_stream().wait_event(done)
             _lib.call("vn_train_step_optim", st)
         if next_data is not None and update_due:
-            self._ticket = self.prepare(next_data, elapse_time)
+            self._ticket = self.prepare(next_data, elapse_time, noise=next_noise)
         return self._loss_out[0]
 
     @torch.no_grad()

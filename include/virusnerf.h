@@ -47,6 +47,8 @@ extern "C" {
 #define VN_HASH_TIGHT_REGS 1024 /* planar bwd: 48-register variant, 5 CTAs per SM */
 #define VN_HASH_SKIP_ZERO_GRADS 4096 /* f32 bwd: do not scatter (level, sample) pairs whose gradient is exactly 0 */
 #define VN_HASH_PAIR_LOADS 2048 /* planar fwd: 16-byte loads for x / x+1 corner pairs that are neighbours */
+#define VN_HASH_FUSED_SCATTER 16384 /* native step runner: MLP backward and hash backward run as one kernel
+                                       (vn_mlp_bwd_scatter); needs VN_HASH_F16_CHUNKS */
 #define VN_HASH_F16_CHUNKS 8192 /* fwd (f32 or f16 table): out is [levels/4][S] x 16 B "chunk planes": plane c holds
                                   levels 4c..4c+3 of every point as 8 fp16 values = one row of one column chunk of the
                                   fused MLP's tensor-core operand (vn_mlp_fwd enc_format 3, vn_mlp_bwd 3 / 4); bwd
@@ -234,6 +236,11 @@ int vn_occ_calc_pos_prob(const float* rays_o, const float* rays_d, const float* 
 int vn_occ_ray_prob(const float* meas, const float* dists, int64_t N, int M, int I, float p_false,
                     float std_every_m, float prob_min, float* probs_occ, float* probs_emp,
                     void* stream);
+/* the same with return_probs=True (:387-388): terms [4][N,M] = P[meas=dist|emp], P[meas=dist|occ],
+ * P[meas not< dist|emp], P[meas not< dist|occ] (the plotting / analysis path of the reference) */
+int vn_occ_ray_prob_terms(const float* meas, const float* dists, int64_t N, int M, int I, float p_false,
+                          float std_every_m, float prob_min, float* probs_occ, float* probs_emp,
+                          float* terms, void* stream);
 int vn_occ_nerf_prob(const float* density, int64_t n, double thr_max, float slope, float* scratch,
                      float* probs_occ, float* probs_emp, void* stream);
 int vn_occ_bayes_update(float* grid, int grid_size, const int32_t* cell_idxs, int64_t n,
@@ -317,6 +324,18 @@ int vn_mlp_bwd(const void* enc, int enc_format, const float* dirs, const float* 
                const float* W3, const float* W4, const float* W5, int64_t S, int density_only,
                const float* dsigmas, const float* drgbs, float* denc, float* dW1, float* dW2,
                float* dW3, float* dW4, float* dW5, void* stream);
+/* a12 + a3 / a4 fused: vn_mlp_bwd followed by vn_hash_encode_bwd_* as ONE kernel (enc_format 3 or 5, 16 levels x 2
+ * features).  The gradient w.r.t. the encoding never leaves the SM: every thread of the MLP epilogue reads its levels of
+ * d(enc) back from tensor memory and runs the warp-aggregated scatter of hash_encoder.py:264-277 /
+ * hash_encoder_half.py:164-213 (zero-skip rule, f32 red.global.add) into table_grad [total_entries,2], ACCUMULATING like
+ * vn_hash_encode_bwd_f32.  xyz [S,3] = the unit-cube positions the forward encoded; round_f16 != 0 rounds d(enc) to
+ * fp16 first (the half-precision encoder's gradient dtype).  Equivalent to vn_mlp_bwd(enc_format [+ VN_MLP_DENC_F16])
+ * + vn_hash_encode_bwd_f32 / _f16 up to the summation order of the atomics. */
+int vn_mlp_bwd_scatter(const void* enc, int enc_format, const float* dirs, const float* W1, const float* W2,
+                       const float* W3, const float* W4, const float* W5, int64_t S, const float* dsigmas,
+                       const float* drgbs, const float* xyz, const vn_hash_levels_t* lv, int round_f16,
+                       float* table_grad, float* dW1, float* dW2, float* dW3, float* dW4, float* dW5,
+                       void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Native step runner (caller side): the body of Trainer.train()'s loop

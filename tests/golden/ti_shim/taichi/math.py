@@ -41,6 +41,10 @@ class _VT(_VecType):
 vec2 = _VT(2, np.float32)
 vec3 = _VT(3, np.float32)
 uvec3 = _VT(3, np.uint32)
+ivec3 = _VT(3, np.int32)       # imported (not executed) by modules/triplane.py
+ivec2 = _VT(2, np.int32)
+uvec2 = _VT(2, np.uint32)
+vec4 = _VT(4, np.float32)
 
 
 def clamp(x, xmin, xmax):

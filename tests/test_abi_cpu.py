@@ -183,3 +183,94 @@ def test_ctypes_struct_mirrors_match_the_header(vn, tmp_path):
     py = [ctypes.sizeof(vn.HashLevels), ctypes.sizeof(vn.Step), vn.Step.levels.offset, vn.Step.loss_acc.offset,
           vn.Step.adam_step.offset, vn.Step.w_off.offset, vn.Step.ts_rows.offset]
     assert c == py, (c, py)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# names of the reference that have no host-side mirror, with the reason (everything else in signatures.json must exist)
+NOT_MIRRORED = {
+    # Taichi field <-> torch copies: the product keeps every tensor in torch device memory, there is no second runtime
+    "modules.utils": {"ti2torch", "ti2torch_grad", "ti2torch_vec", "ti2torch_grad_vec", "torch2ti", "torch2ti_grad",
+                      "torch2ti_vec", "torch2ti_grad_vec", "random_initialize",
+                      # @ti.func device helpers: they live inside the CUDA kernels (csrc/common.cuh)
+                      "calc_dt", "mip_from_dt", "mip_from_pos", "frexp_bit", "scalbn",
+                      # @ti.kernel bodies behind morton3D / morton3D_invert: replaced by C-ABI entries
+                      "morton3D_kernel", "morton3D_invert_kernel",
+                      # deployment export / plotting helpers outside the hot path (SURVEY section 8 "out of scope")
+                      "save_deployment_model", "depth2img"},
+    # kernel factories / raw kernels replaced by C-ABI entries (include/virusnerf.h cites each)
+    "modules.hash_encoder": {"build_hash_encoder_kernel"},
+    "modules.hash_encoder_half": {"build_hash_encoder_kernel"},
+    "modules.intersection": {"ray_aabb_intersect"},
+    "modules.ray_march": {"raymarching_train_kernel", "raymarching_test_kernel"},
+    "modules.spherical_harmonics": {"dir_encoder"},
+    "modules.volume_train": {"volume_rendering_kernel"},
+}
+# methods that exist in the reference class but are plotting / dataset-file plumbing outside the path
+METHODS_NOT_MIRRORED = {
+    ("datasets.dataset_base", "DatasetBase"): {"getMeanHeight", "getSyncIdxs", "reduceImgHeight"},
+    ("modules.networks", "TruncExp"): {"forward", "backward"},       # fused into the MLP epilogue (kernel side)
+}
+
+
+def _params_of(fn):
+    import inspect
+    fn = getattr(fn, "__func__", fn)
+    return [(p.name, p.kind.name, p.default) for p in inspect.signature(fn).parameters.values()]
+
+
+def _check_params(where, ref_params, mine, errors):
+    """same parameter names in the same order and the same literal defaults; the mirror may append optional parameters
+    and may give a default to a parameter the reference requires (both keep every reference call valid)"""
+    import inspect
+    names = [p[0] for p in mine]
+    ref_names = [p[0] for p in ref_params]
+    if any(p[1] in ("VAR_POSITIONAL", "VAR_KEYWORD") for p in ref_params):
+        return
+    if names[:len(ref_names)] != ref_names:
+        errors.append(f"{where}: reference {ref_names} vs mirror {names}")
+        return
+    for p in mine[len(ref_names):]:
+        if p[2] is inspect.Parameter.empty and p[1] not in ("VAR_POSITIONAL", "VAR_KEYWORD"):
+            errors.append(f"{where}: extra parameter {p[0]} of the mirror has no default")
+    for (rn, _, rdef), (mn, _, mdef) in zip(ref_params, mine):
+        if rdef not in ("<required>", "<object>") and repr(mdef) != rdef:
+            errors.append(f"{where}: default of {rn}: reference {rdef} vs mirror {mdef!r}")
+
+
+def test_mirrors_match_the_reference_signatures():
+    """every public function / class / method the reference defines on the path exists in the mirror package with the
+    same parameter list (tests/golden/signatures.json = inspect.signature over /root/reference, made by
+    tests/golden/make_signatures.py)"""
+    import importlib
+    import inspect
+    import json
+    sigs = json.load(open(os.path.join(ROOT, "tests", "golden", "signatures.json")))
+    checked, errors = 0, []
+    for ref_mod, entry in sigs.items():
+        mod = importlib.import_module("virus_nerf_b200." + entry["mirror"])
+        skip = NOT_MIRRORED.get(ref_mod, set())
+        for name, d in entry["members"].items():
+            if name in skip:
+                continue
+            if not hasattr(mod, name):
+                errors.append(f"{ref_mod}.{name} has no mirror in virus_nerf_b200.{entry['mirror']}")
+                continue
+            obj = getattr(mod, name)
+            if d["kind"] == "function":
+                _check_params(f"{ref_mod}.{name}", d["params"], _params_of(obj), errors)
+                checked += 1
+                continue
+            assert inspect.isclass(obj), f"{ref_mod}.{name} must be a class"
+            mskip = METHODS_NOT_MIRRORED.get((ref_mod, name), set())
+            for mname, mparams in d["methods"].items():
+                if mname in mskip or mparams is None:
+                    continue
+                if not hasattr(obj, mname):
+                    errors.append(f"{ref_mod}.{name}.{mname} is missing from the mirror")
+                    continue
+                raw = inspect.getattr_static(obj, mname)
+                fn = raw.__func__ if isinstance(raw, (staticmethod, classmethod)) else raw
+                _check_params(f"{ref_mod}.{name}.{mname}", mparams, _params_of(fn), errors)
+                checked += 1
+    assert not errors, "\n".join(errors)
+    assert checked >= 70, checked

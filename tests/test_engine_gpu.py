@@ -187,8 +187,9 @@ def test_occupancy_update_runs_and_is_deterministic(setup):
     assert not torch.equal(g0, g1)
 
 
-@pytest.mark.parametrize("enc_layout,single_pass", [("chunks", True), ("planar", True), ("rows", False)])
-def test_fast_step_matches_autograd_step(monkeypatch, enc_layout, single_pass):
+@pytest.mark.parametrize("enc_layout,single_pass,fused", [("chunks", True, True), ("chunks", True, False),
+                                                          ("planar", True, False), ("rows", False, False)])
+def test_fast_step_matches_autograd_step(monkeypatch, enc_layout, single_pass, fused):
     """the hand-chained C-ABI step (engine.step_fast) and the autograd step through the drop-in
     modules produce the same loss, gradients and parameter update (same rays, same jitter)"""
     from virus_nerf_b200 import synthetic
@@ -197,7 +198,8 @@ def test_fast_step_matches_autograd_step(monkeypatch, enc_layout, single_pass):
     args = synthetic.make_args(device=DEV, batch_size=512)
     ds = synthetic.SyntheticDataset(pool_size=1 << 13, n_images=8, device=DEV)
     e1 = TrainEngine(args, ds, DEV)
-    e2 = TrainEngine(args, ds, DEV, enc_layout=enc_layout, single_pass_march=single_pass)
+    e2 = TrainEngine(args, ds, DEV, enc_layout=enc_layout, single_pass_march=single_pass, fused_scatter=fused)
+    assert e2.fused_scatter == fused
     assert torch.equal(e1.flat_p, e2.flat_p)
     e1.step_idx = e2.step_idx = 1                       # no occupancy update (it draws random numbers)
     e1._prep_step = e2._prep_step = 1
@@ -218,7 +220,8 @@ def test_fast_step_matches_autograd_step(monkeypatch, enc_layout, single_pass):
     assert int(e1.last_samples) == int(e2.last_samples) > 0
 
 
-def test_fast_step_half_encoder_matches_autograd_step(monkeypatch):
+@pytest.mark.parametrize("fused", [True, False])
+def test_fast_step_half_encoder_matches_autograd_step(monkeypatch, fused):
     """BASELINE config 3's half-precision encoder (hash_encoder_half.py) inside the native step runner: fp16 table
     copy per step, half forward kernel, fp16 encoding gradients into the half backward kernel (zero-skip, fp32
     accumulation into the flat gradient) == the same step through the drop-in half module and torch autograd"""
@@ -228,7 +231,7 @@ def test_fast_step_half_encoder_matches_autograd_step(monkeypatch):
     args = synthetic.make_args(device=DEV, batch_size=512)
     ds = synthetic.SyntheticDataset(pool_size=1 << 13, n_images=8, device=DEV)
     e1 = TrainEngine(args, ds, DEV, half_opt=True)
-    e2 = TrainEngine(args, ds, DEV, half_opt=True)
+    e2 = TrainEngine(args, ds, DEV, half_opt=True, fused_scatter=fused)
     assert type(e2.model.pos_encoder).__module__.endswith("hash_encoder_half") and e2._table_h is not None
     # the reference initialises the half table with U(-1e-4, 1e-4): give the encoding some signal
     with torch.no_grad():

@@ -199,6 +199,86 @@ def test_fused_mlp_chunk_plane_format(S):
         close_l2(a, b, 2e-3, "dW fmt 5 vs 3")
 
 
+def _ray_points(n_rays, per_ray, seed):
+    """unit-cube points laid out like a march: consecutive samples of a ray are neighbours (exercises the warp runs)"""
+    g = torch.Generator().manual_seed(seed)
+    o = torch.rand(n_rays, 1, 3, generator=g) * 0.6 + 0.2
+    d = torch.randn(n_rays, 1, 3, generator=g)
+    d = d / d.norm(dim=2, keepdim=True)
+    t = torch.arange(per_ray).view(1, per_ray, 1) * (3 ** 0.5 / 1024)
+    return (o + d * t).clamp(0.0, 1.0).reshape(-1, 3).contiguous()
+
+
+@pytest.mark.parametrize("S,half", [(1, False), (129, False), (5000, False), (5000, True), (100000, False), (100000, True)])
+def test_fused_mlp_backward_with_hash_scatter(S, half):
+    """vn_mlp_bwd_scatter (d(enc) scattered from tensor memory) == vn_mlp_bwd + vn_hash_encode_bwd_f32 / _f16 up to the
+    order of the atomic adds, and == the oracle's hash backward fed with the d(enc) the unfused kernel wrote"""
+    import oracle
+    from virus_nerf_b200 import _lib
+    torch.manual_seed(S + 3)
+    Wg = [w.to(DEV).contiguous() for w in _weights(S)]
+    lv = _lib.hash_levels(16, 1024, 16, 2 ** 19)
+    per_ray = 64
+    xyz = _ray_points((S + per_ray - 1) // per_ray, per_ray, S)[:S].contiguous().to(DEV)
+    enc_c = _to_chunks(torch.rand(S, 32, device=DEV).half())
+    dirs = torch.randn(S, 3, device=DEV)
+    dsig = torch.randn(S, device=DEV) * 3; drgb = torch.randn(S, 3, device=DEV) * 3
+    dsig[::5] = 0; drgb[::5] = 0                           # samples behind an opaque surface: exactly zero gradient
+    F16 = 8
+    n_tab = 2 * lv.total_entries
+    # unfused: MLP backward writes d(enc), the hash backward scatters it
+    denc = torch.zeros(S * 32, device=DEV, dtype=torch.float16 if half else torch.float32)
+    dW_a = [torch.zeros_like(w) for w in Wg]
+    _lib.call("vn_mlp_bwd", enc_c, 3 | (F16 if half else 0), dirs, *Wg, S, 0, dsig, drgb, denc, *dW_a)
+    grad_a = torch.zeros(n_tab, device=DEV)
+    flags = _lib.VN_HASH_PLANAR | _lib.VN_HASH_LEVEL_GROUPS_2 | _lib.VN_HASH_SKIP_ZERO_GRADS
+    if half:
+        _lib.call("vn_hash_encode_bwd_f16", xyz, denc, grad_a, S, lv, flags | _lib.VN_HASH_F16_CHUNKS)
+    else:
+        _lib.call("vn_hash_encode_bwd_f32", xyz, denc, grad_a, S, lv, flags)
+    # fused
+    dW_b = [torch.zeros_like(w) for w in Wg]
+    grad_b = torch.zeros(n_tab, device=DEV)
+    _lib.call("vn_mlp_bwd_scatter", enc_c, 3, dirs, *Wg, S, dsig, drgb, xyz, lv, 1 if half else 0, grad_b, *dW_b)
+    for a, b in zip(dW_a, dW_b):
+        if S <= 128:
+            assert torch.equal(a, b)
+        else:
+            close_l2(a, b, 1e-5, "dW fused vs unfused")
+    scale = float(grad_a.abs().max())
+    assert scale > 0
+    assert float((grad_a - grad_b).abs().max()) <= 1e-4 * scale, float((grad_a - grad_b).abs().max()) / scale
+    # oracle: hash backward of the same d(enc) rows
+    if S <= 5000:
+        lv_o = oracle.HashLevels(16, 1024, 16, 2 ** 19)
+        if half:
+            rows = denc.view(4, S, 8).permute(1, 0, 2).reshape(S, 16, 2).cpu().numpy()
+            ref = oracle.hash_bwd_f16(xyz.cpu().numpy(), rows, lv_o)
+        else:
+            rows = denc.view(8, S, 4).permute(1, 0, 2).reshape(S, 32).cpu().numpy()
+            ref = oracle.hash_bwd_f32(xyz.cpu().numpy(), rows, lv_o)
+        np.testing.assert_allclose(grad_b.view(-1, 2).cpu().numpy(), ref.reshape(-1, 2), rtol=1e-4, atol=1e-5 * np.abs(ref).max())
+    # accumulation: a second call adds the same gradient again
+    _lib.call("vn_mlp_bwd_scatter", enc_c, 3, dirs, *Wg, S, dsig, drgb, xyz, lv, 1 if half else 0, grad_b, *dW_b)
+    assert float((grad_b - 2 * grad_a).abs().max()) <= 2e-4 * scale
+
+
+def test_fused_mlp_backward_with_hash_scatter_rejects_bad_arguments():
+    from virus_nerf_b200 import _lib
+    S = 64
+    Wg = [w.to(DEV).contiguous() for w in _weights(0)]
+    enc_c = _to_chunks(torch.rand(S, 32, device=DEV).half())
+    z = torch.zeros(S, device=DEV); z3 = torch.zeros(S, 3, device=DEV)
+    dW = [torch.zeros_like(w) for w in Wg]
+    lv = _lib.hash_levels(16, 1024, 16, 2 ** 19)
+    grad = torch.zeros(2 * lv.total_entries, device=DEV)
+    with pytest.raises(RuntimeError, match="enc_format"):
+        _lib.call("vn_mlp_bwd_scatter", enc_c, 2, z3, *Wg, S, z, z3, z3, lv, 0, grad, *dW)
+    lv8 = _lib.hash_levels(16, 512, 8, 2 ** 19)
+    with pytest.raises(RuntimeError, match="16 levels"):
+        _lib.call("vn_mlp_bwd_scatter", enc_c, 3, z3, *Wg, S, z, z3, z3, lv8, 0, grad, *dW)
+
+
 def test_fused_mlp_pipelined_backward_equals_serial_kernel(monkeypatch):
     """A/B of the two backward kernels (VN_MLP_PIPE=0 selects the serial one in a fresh process is the bench
     switch; here the density-only entry keeps the serial kernel alive): same tile math => d_enc bit-identical"""

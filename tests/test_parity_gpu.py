@@ -498,6 +498,21 @@ def test_occ_calc_pos_and_ray_prob(vn, oracle_mod, scene_rays, G):
     o_po, o_pe = oracle_mod.occ_ray_prob(meas, o_d, og.false_detection_prob_every_m, og.std_every_m)
     np.testing.assert_allclose(N(po), o_po, rtol=1e-5, atol=1e-7)
     np.testing.assert_allclose(N(pe), o_pe, rtol=1e-5, atol=1e-7)
+    # return_probs=True (occupancy_grid.py:387-388): the four factors, against the reference's own torch expressions
+    # (:361-381) written with the mirror's _sensorEmptyPDF / _sensorOccupiedPDF
+    po2, pe2, eq_emp, eq_occ, nl_emp, nl_occ = og._rayProb(T(meas), dists, return_probs=True)
+    assert torch.equal(po2, po) and torch.equal(pe2, pe)
+    m = T(meas)
+    r_eq_emp = og._sensorEmptyPDF(shape=dists.shape)
+    r_eq_occ = r_eq_emp + og._sensorOccupiedPDF(meas=m[:, None], dists=dists)
+    r_nl_emp = (1 - r_eq_emp * dists).clamp(min=og.prob_min)
+    y = torch.linspace(0, 1, og.I, device=DEV, dtype=torch.float32)[None, :] * m[:, None]
+    integral = og._sensorOccupiedPDF(meas=y[:, None, :], dists=dists[:, :, None]).sum(dim=2) * (m / og.I)[:, None]
+    r_nl_occ = (r_nl_emp - integral).clamp(min=og.prob_min)
+    for got, ref in ((eq_emp, r_eq_emp), (eq_occ, r_eq_occ), (nl_emp, r_nl_emp), (nl_occ, r_nl_occ)):
+        np.testing.assert_allclose(N(got), N(ref), rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(N(eq_emp * nl_emp), N(pe), rtol=1e-6)
+    np.testing.assert_allclose(N(eq_occ * nl_occ), N(po), rtol=1e-6)
 
 
 def test_occ_bayes_update_and_pack_bit_exact(vn, oracle_mod, scene_rays):

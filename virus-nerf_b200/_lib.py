@@ -26,6 +26,7 @@ VN_HASH_TIGHT_REGS = 1024
 VN_HASH_PAIR_LOADS = 2048
 VN_HASH_SKIP_ZERO_GRADS = 4096
 VN_HASH_F16_CHUNKS = 8192
+VN_HASH_FUSED_SCATTER = 16384
 
 
 class HashLevels(ctypes.Structure):
@@ -103,6 +104,7 @@ _SPECS = {
     "vn_packbits": "plfps",
     "vn_occ_calc_pos_prob": "pppp" "liiif" "ffff" "ppppp" "s",
     "vn_occ_ray_prob": "pp" "lii" "fff" "pp" "s",
+    "vn_occ_ray_prob_terms": "pp" "lii" "fff" "ppp" "s",
     "vn_occ_nerf_prob": "pldfppps",
     "vn_occ_bayes_update": "piplppp" "ps",
     "vn_occ_decay_pack": "pififps",
@@ -128,6 +130,7 @@ _SPECS = {
     "vn_ngp_threshold_pack": "plfppps",
     "vn_mlp_fwd": "pip" "ppppp" "li" "ppp" "s",
     "vn_mlp_bwd": "pip" "ppppp" "li" "pp" "p" "ppppp" "s",
+    "vn_mlp_bwd_scatter": "pip" "ppppp" "l" "pp" "p" "hi" "p" "ppppp" "s",
 }
 
 _CT = {"p": ctypes.c_void_p, "l": ctypes.c_int64, "i": ctypes.c_int, "f": ctypes.c_float,
@@ -187,7 +190,7 @@ def _ptr(t, name, pos):
 
 
 KERNEL_NAMES = ["hash_encode_fwd", "hash_encode_bwd", "mlp_fwd", "mlp_bwd", "march_count", "march_write",
-                "composite_fwd", "composite_bwd", "adam"]
+                "composite_fwd", "composite_bwd", "adam", "mlp_bwd_hash_scatter"]
 
 
 def profile_start(kernels=None):

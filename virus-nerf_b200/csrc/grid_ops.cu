@@ -108,7 +108,7 @@ __device__ __forceinline__ float occ_pdf(float meas, float dist, float std_every
 
 // _rayProb for one (ray, m): occupancy_grid.py:361-385
 __device__ __forceinline__ void ray_prob(float me, float dist, int I, float p_false, float std_every_m, float prob_min,
-                                         float* po, float* pe) {
+                                         float* po, float* pe, float* terms = nullptr, int64_t term_stride = 0) {
     const float eq_emp = p_false;                                         // :361-363
     const float eq_occ = vn_add(eq_emp, occ_pdf(me, dist, std_every_m));  // :364-367
     float nl_emp = vn_sub(1.0f, vn_mul(eq_emp, dist));                    // :370
@@ -121,6 +121,9 @@ __device__ __forceinline__ void ray_prob(float me, float dist, int I, float p_fa
     if (nl_occ < prob_min) nl_occ = prob_min;                             // :381
     *pe = vn_mul(eq_emp, nl_emp);                                         // :384
     *po = vn_mul(eq_occ, nl_occ);                                         // :385
+    if (terms) {                                                          // return_probs=True, :387-388
+        terms[0] = eq_emp; terms[term_stride] = eq_occ; terms[2 * term_stride] = nl_emp; terms[3 * term_stride] = nl_occ;
+    }
 }
 
 __global__ void __launch_bounds__(128) occ_calc_pos_prob_kernel(
@@ -168,10 +171,11 @@ __global__ void __launch_bounds__(128) occ_calc_pos_prob_kernel(
 __global__ void __launch_bounds__(128) occ_ray_prob_kernel(const float* __restrict__ meas, const float* __restrict__ dists,
                                                            int64_t N, int M, int I, float p_false, float std_every_m,
                                                            float prob_min, float* __restrict__ probs_occ,
-                                                           float* __restrict__ probs_emp) {
+                                                           float* __restrict__ probs_emp, float* __restrict__ terms) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= N * M) return;
-    ray_prob(__ldg(meas + t / M), __ldg(dists + t), I, p_false, std_every_m, prob_min, probs_occ + t, probs_emp + t);
+    ray_prob(__ldg(meas + t / M), __ldg(dists + t), I, p_false, std_every_m, prob_min, probs_occ + t, probs_emp + t,
+             terms ? terms + t : nullptr, N * M);
 }
 
 VN_API int vn_occ_ray_prob(const float* meas, const float* dists, int64_t N, int M, int I, float p_false,
@@ -180,7 +184,19 @@ VN_API int vn_occ_ray_prob(const float* meas, const float* dists, int64_t N, int
     if (N == 0) return VN_OK;
     VN_REQUIRE(meas && dists && probs_occ && probs_emp, "vn_occ_ray_prob: null pointer");
     occ_ray_prob_kernel<<<vn_blocks(N * M, 128), 128, 0, (cudaStream_t)stream>>>(meas, dists, N, M, I, p_false, std_every_m,
-                                                                              prob_min, probs_occ, probs_emp);
+                                                                              prob_min, probs_occ, probs_emp, nullptr);
+    VN_CHECK_LAUNCH("occ_ray_prob_kernel");
+    return VN_OK;
+}
+
+VN_API int vn_occ_ray_prob_terms(const float* meas, const float* dists, int64_t N, int M, int I, float p_false,
+                                 float std_every_m, float prob_min, float* probs_occ, float* probs_emp, float* terms,
+                                 void* stream) {
+    VN_REQUIRE(N >= 0 && M >= 1 && I >= 2, "vn_occ_ray_prob_terms: bad sizes");
+    if (N == 0) return VN_OK;
+    VN_REQUIRE(meas && dists && probs_occ && probs_emp && terms, "vn_occ_ray_prob_terms: null pointer");
+    occ_ray_prob_kernel<<<vn_blocks(N * M, 128), 128, 0, (cudaStream_t)stream>>>(meas, dists, N, M, I, p_false, std_every_m,
+                                                                              prob_min, probs_occ, probs_emp, terms);
     VN_CHECK_LAUNCH("occ_ray_prob_kernel");
     return VN_OK;
 }

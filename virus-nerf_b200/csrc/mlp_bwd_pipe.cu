@@ -33,6 +33,13 @@
 //   * epilogues work on packed halves: cvt.rn.relu.f16x2.f32 for the ReLU, a half2 compare mask
 //     + AND for the ReLU backward.
 //
+//   * SCATTER = true (vn_mlp_bwd_scatter): d(enc) never leaves the SM.  After r10 every chain thread (sample row, column
+//     half) reads its 8 levels of d(enc) back from tensor memory one level at a time and runs the hash encoder's
+//     warp-aggregated gradient scatter (hash_common.cuh: lanes of a warp are consecutive samples of a ray) straight into
+//     the table gradient.  The red traffic of one chain runs under the MMA rounds of the other two: the LSU / L2-atomic
+//     bound scatter and the latency-bound MMA chain share the SM instead of running back to back as two kernels, and
+//     the 2 x 128 B / sample round trip of d(enc) through HBM disappears.
+//
 // Main rounds per tile (TMP = the chain's TMEM accumulator, A = its TMEM operand columns):
 //   r1  TMP[0:64]  = X0(smem) W1^T      -> A = H1 = relu          ; smem HA = H1
 //   r2  TMP[0:16]  = A W2^T             -> smem IN2[:,16:32] = h, keep dsigma*exp(h0)
@@ -46,6 +53,7 @@
 //   r9  TMP[0:64]  = A W2               -> A = dH1 = TMP * (HA>0) ; smem HA = dH1     => wgrad dW1   += HA^T X0
 //   r10 TMP[0:32]  = A W1               -> d(enc) to global
 #include "mlp_common.cuh"
+#include "hash_common.cuh"
 #include <stdlib.h>
 
 namespace mlp {
@@ -146,6 +154,10 @@ __device__ __forceinline__ uint32_t gt0_mask(uint32_t act2) {
 }
 template <int N>
 __device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t* r);
+template <>
+__device__ __forceinline__ void tmem_ld<2>(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr));
+}
 template <>
 __device__ __forceinline__ void tmem_ld<8>(uint32_t taddr, uint32_t* r) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -299,7 +311,8 @@ struct Shared {
     uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(NTHR, 1) mlp_bwd_pipe_kernel(const MlpArgs a) {
+template <bool SCATTER>
+__global__ void __launch_bounds__(NTHR, 1) mlp_bwd_pipe_kernel(const MlpArgs a, const __grid_constant__ ScatterArgs hs) {
     vn_pdl_trigger();
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ Shared sh;
@@ -745,9 +758,35 @@ __global__ void __launch_bounds__(NTHR, 1) mlp_bwd_pipe_kernel(const MlpArgs a) 
             post_wg();                                                     // => dW1 += dH1^T X0
             TIM(20);
             // ---- r10: d(enc) ------------------------------------------------------------------------
+            float px = 0.0f, py = 0.0f, pz = 0.0f;
+            if (SCATTER && valid) {        // issued before the wait: the load latency hides behind the MMA
+                px = __ldg(hs.xyz + 3 * s); py = __ldg(hs.xyz + 3 * s + 1); pz = __ldg(hs.xyz + 3 * s + 2);
+            }
             wait_done();
             TIM(21);
-            {
+            if (SCATTER) {
+                // this thread: sample `row`, levels 8 * half .. 8 * half + 7 (TMEM columns 16 * half + 2 l, + 1)
+#pragma unroll 1
+                for (int l = 0; l < 8; ++l) {
+                    const int level = 8 * half + l;
+                    uint32_t r2[2];
+                    tmem_ld<2>(tm + 16 * half + 2 * l, r2);
+                    umma::tmem_ld_wait();
+                    float d0 = __uint_as_float(r2[0]), d1 = __uint_as_float(r2[1]);
+                    if (hs.round_f16) {        // half-precision encoder: d(enc) is an fp16 tensor (hash_encoder_half.py:344)
+                        const uint32_t u = pack2<false>(r2[0], r2[1]);
+                        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u));
+                        d0 = f.x; d1 = f.y;
+                    }
+                    const bool v = valid && !(d0 == 0.0f && d1 == 0.0f);           // hash_encoder_half.py:210
+                    const Cell cl = cell_of(px, py, pz, hs.P.scales[level]);
+                    float* gl = hs.grad + 2 * (size_t)hs.P.offsets[level];
+                    if (level < hs.P.begin_fast)
+                        level_scatter<float, true, true, true>(gl, cl, hs.P.res[level], hs.P.sizes[level], 0u, d0, d1, v);
+                    else
+                        level_scatter<float, false, true, true>(gl, cl, hs.P.res[level], hs.P.sizes[level], hs.P.pow2mask[level], d0, d1, v);
+                }
+            } else {
                 uint32_t r[16];
                 tmem_ld<16>(tm + 16 * half, r);
                 umma::tmem_ld_wait();
@@ -825,17 +864,23 @@ extern "C" __attribute__((visibility("default"))) int vn_mlp_debug_timing(unsign
 }
 #endif
 
-int launch_mlp_bwd_pipe(const MlpArgs& a, cudaStream_t st) {
+int launch_mlp_bwd_pipe(const MlpArgs& a, const ScatterArgs* hs, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        VN_CUDA(cudaFuncSetAttribute(mlp_bwd_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_PIPE));
+        VN_CUDA(cudaFuncSetAttribute(mlp_bwd_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_PIPE));
+        VN_CUDA(cudaFuncSetAttribute(mlp_bwd_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_PIPE));
         attr_set = true;
     }
-    VnProfScope prof(VN_K_MLP_BWD, a.S, st);
+    VnProfScope prof(hs ? VN_K_MLP_BWD_SCATTER : VN_K_MLP_BWD, a.S, st);
     const int64_t n_tiles = (a.S + TILE - 1) / TILE;
     int64_t grid = vn_sm_count();
     if (grid > n_tiles) grid = n_tiles;
-    vn_launch_pdl(mlp_bwd_pipe_kernel, dim3((unsigned)grid), dim3(NTHR), SMEM_PIPE, st, a);
+    if (hs) {
+        vn_launch_pdl(mlp_bwd_pipe_kernel<true>, dim3((unsigned)grid), dim3(NTHR), SMEM_PIPE, st, a, *hs);
+    } else {
+        static const ScatterArgs none{};
+        vn_launch_pdl(mlp_bwd_pipe_kernel<false>, dim3((unsigned)grid), dim3(NTHR), SMEM_PIPE, st, a, none);
+    }
     VN_CHECK_LAUNCH("mlp_bwd_pipe_kernel");
     return VN_OK;
 }

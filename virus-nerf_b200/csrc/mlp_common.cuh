@@ -3,6 +3,7 @@
 #pragma once
 #include "common.cuh"
 #include "umma.cuh"
+#include "hash_common.cuh"
 
 namespace mlp {
 
@@ -66,6 +67,14 @@ __device__ __forceinline__ void sh16_half(float x, float y, float z, float* e) {
 }
 
 
-int launch_mlp_bwd_pipe(const MlpArgs& a, cudaStream_t st);   // mlp_bwd_pipe.cu
+// the hash encoder's side of the fused backward (vn_mlp_bwd_scatter): d(enc) is scattered into `grad` instead of stored
+struct ScatterArgs {
+    const float* xyz;      // [S,3] unit-cube positions (the hash forward's input)
+    float* grad;           // table gradient [total_entries, 2] f32, accumulated with red.global.add
+    int round_f16;         // d(enc) rounded to fp16 before the scatter (half-precision encoder)
+    HashParams P;
+};
+
+int launch_mlp_bwd_pipe(const MlpArgs& a, const ScatterArgs* hs, cudaStream_t st);   // mlp_bwd_pipe.cu
 
 }  // namespace mlp

@@ -577,6 +577,35 @@ VN_API int vn_mlp_bwd(const void* enc, int enc_format, const float* dirs, const 
     a.denc_fmt = denc_f16 ? 3 : (base_fmt >= 2 ? 2 : 0);
     // the pipelined three-chain kernel (mlp_bwd_pipe.cu) is the backward; the serial kernel remains for the
     // density-only variant and as the A/B baseline (VN_MLP_PIPE=0)
-    if (!density_only && (g_mlp_pipe || enc_format >= 3)) return launch_mlp_bwd_pipe(a, (cudaStream_t)stream);
+    if (!density_only && (g_mlp_pipe || enc_format >= 3)) return launch_mlp_bwd_pipe(a, nullptr, (cudaStream_t)stream);
     return launch_mlp(true, a, (cudaStream_t)stream);
+}
+
+// MLP backward fused with the hash encoder's backward: d(enc) is scattered into the table gradient from inside the
+// kernel (mlp_bwd_pipe.cu, SCATTER) instead of being written out for vn_hash_encode_bwd_*.
+VN_API int vn_mlp_bwd_scatter(const void* enc, int enc_format, const float* dirs, const float* W1, const float* W2,
+                              const float* W3, const float* W4, const float* W5, int64_t S, const float* dsigmas,
+                              const float* drgbs, const float* xyz, const vn_hash_levels_t* lv, int round_f16,
+                              float* table_grad, float* dW1, float* dW2, float* dW3, float* dW4, float* dW5, void* stream) {
+    VN_REQUIRE(S >= 0, "vn_mlp_bwd_scatter: S < 0");
+    if (S == 0) return VN_OK;
+    VN_REQUIRE(enc && W1 && W2 && W3 && W4 && W5 && dsigmas && drgbs && xyz && lv && table_grad && dW1 && dW2 && dW3 && dW4 && dW5,
+               "vn_mlp_bwd_scatter: null pointer");
+    VN_REQUIRE(enc_format == 3 || enc_format == 5, "vn_mlp_bwd_scatter: enc_format must be 3 (f16 chunk planes) or 5 (+ SH planes)");
+    VN_REQUIRE(dirs || enc_format == 5, "vn_mlp_bwd_scatter: dirs is required unless enc_format is 5");
+    VN_REQUIRE(lv->levels == 16, "vn_mlp_bwd_scatter: the fused backward is built for 16 levels x 2 features (32-wide encoding)");
+    VN_REQUIRE(vn_aligned(enc, 16) && vn_aligned(table_grad, 16) && vn_aligned(xyz, 4), "vn_mlp_bwd_scatter: misaligned buffer");
+    VN_REQUIRE(vn_aligned(W1, 16) && vn_aligned(W2, 16) && vn_aligned(W3, 16) && vn_aligned(W4, 16) && vn_aligned(W5, 16),
+               "vn_mlp_bwd_scatter: weight matrices must be 16-byte aligned");
+    MlpArgs a{};
+    a.enc = (const float*)enc; a.dirs = dirs;
+    a.W[0] = W1; a.W[1] = W2; a.W[2] = W3; a.W[3] = W4; a.W[4] = W5;
+    a.dsigmas = dsigmas; a.drgbs = drgbs; a.denc = nullptr;
+    a.dW[0] = dW1; a.dW[1] = dW2; a.dW[2] = dW3; a.dW[3] = dW4; a.dW[4] = dW5;
+    a.S = S; a.enc_fmt = enc_format; a.denc_fmt = round_f16 ? 3 : 2;
+    ScatterArgs hs{};
+    hs.xyz = xyz; hs.grad = table_grad; hs.round_f16 = round_f16 ? 1 : 0;
+    int rc = make_params(lv, hs.P);
+    if (rc) return rc;
+    return launch_mlp_bwd_pipe(a, &hs, (cudaStream_t)stream);
 }

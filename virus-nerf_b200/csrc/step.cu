@@ -52,6 +52,9 @@ VN_API int vn_train_step_run(const vn_step_t* s, int64_t S, int phase, int do_op
     const int enc_fmt = chunks ? (s->ts_rows ? 5 : 3) : ((s->hash_flags & VN_HASH_PLANAR) ? 2 : 0);
     const bool half_enc = s->table_h != nullptr;       // hash_encoder_half.py inside the step
     VN_REQUIRE(!half_enc || chunks, "vn_train_step_run: the half-precision encoder needs VN_HASH_F16_CHUNKS");
+    const bool fused_scatter = (s->hash_flags & VN_HASH_FUSED_SCATTER) != 0;
+    VN_REQUIRE(!fused_scatter || (chunks && s->levels.levels == 16),
+               "vn_train_step_run: VN_HASH_FUSED_SCATTER needs VN_HASH_F16_CHUNKS and 16 levels");
     VN_REQUIRE(!(s->hash_flags & VN_HASH_F16_CHUNKS) || (s->hash_flags & VN_HASH_PLANAR),
                "vn_train_step_run: VN_HASH_F16_CHUNKS needs VN_HASH_PLANAR (d_enc planes)");
     if (phase == 0 || phase == 1) {
@@ -86,10 +89,16 @@ VN_API int vn_train_step_run(const vn_step_t* s, int64_t S, int phase, int do_op
                            s->loss_out, stream));
         VN_TRY(vn_composite_train_bwd(s->sigmas, s->rgbs, s->deltas, s->ts, s->rays_a, s->N, S, s->T_threshold, s->d_opacity,
                                       s->d_depth, s->d_rgb, nullptr, s->d_sigmas, s->d_rgbs, stream));
-        VN_TRY(vn_mlp_bwd(s->enc, half_enc ? (enc_fmt | VN_MLP_DENC_F16) : enc_fmt, s->dirs, W[0], W[1], W[2], W[3], W[4], S, 0,
-                          s->d_sigmas, s->d_rgbs, s->d_enc, dW[0], dW[1], dW[2], dW[3], dW[4], stream));
-        if (half_enc) VN_TRY(vn_hash_encode_bwd_f16(s->unit, s->d_enc, table_grad, S, &s->levels, s->hash_flags, stream));
-        else          VN_TRY(vn_hash_encode_bwd_f32(s->unit, s->d_enc, table_grad, S, &s->levels, s->hash_flags, stream));
+        if (fused_scatter) {
+            // one kernel: d(enc) goes from tensor memory straight into the table gradient
+            VN_TRY(vn_mlp_bwd_scatter(s->enc, enc_fmt, s->dirs, W[0], W[1], W[2], W[3], W[4], S, s->d_sigmas, s->d_rgbs, s->unit,
+                                      &s->levels, half_enc ? 1 : 0, table_grad, dW[0], dW[1], dW[2], dW[3], dW[4], stream));
+        } else {
+            VN_TRY(vn_mlp_bwd(s->enc, half_enc ? (enc_fmt | VN_MLP_DENC_F16) : enc_fmt, s->dirs, W[0], W[1], W[2], W[3], W[4], S, 0,
+                              s->d_sigmas, s->d_rgbs, s->d_enc, dW[0], dW[1], dW[2], dW[3], dW[4], stream));
+            if (half_enc) VN_TRY(vn_hash_encode_bwd_f16(s->unit, s->d_enc, table_grad, S, &s->levels, s->hash_flags, stream));
+            else          VN_TRY(vn_hash_encode_bwd_f32(s->unit, s->d_enc, table_grad, S, &s->levels, s->hash_flags, stream));
+        }
         if (do_optim) VN_TRY(vn_train_step_optim(s, stream));
     }
     return VN_OK;

@@ -86,7 +86,7 @@ class _Workspace:
 class TrainEngine:
     def __init__(self, args, dataset, device, world_size=1, rank=0, log2_T=19, max_res=1024, half_opt=False,
                  autocast=True, seed=21, grad_scale=2.0 ** 19, comm="auto", enc_layout="chunks",
-                 single_pass_march=True):
+                 single_pass_march=True, fused_scatter=True):
         self.args = args
         self.device = torch.device(device)
         self.world_size, self.rank = world_size, rank
@@ -97,6 +97,9 @@ class TrainEngine:
         assert enc_layout in ("chunks", "planar", "rows")
         self.enc_planar = enc_layout in ("planar", "chunks")
         self.enc_chunks = enc_layout == "chunks" and autocast
+        # MLP backward and hash backward as ONE kernel (vn_mlp_bwd_scatter): d(enc) goes from tensor memory straight into
+        # the table gradient; only with the operand-chunk layout
+        self.fused_scatter = bool(fused_scatter) and self.enc_chunks
         # single-pass march of the fast step: the count pass stores t of every sample in a [N, 1024] scratch and
         # the write pass only expands it (bit-identical to re-marching); capped at 64 Ki rays (256 MB scratch x 2)
         self.single_pass_march = single_pass_march
@@ -263,6 +266,8 @@ class TrainEngine:
             # where autocast rounds the Linear input) and the MLP kernels pull tiles in with bulk async copies
             if self.enc_chunks:
                 st.hash_flags |= _lib.VN_HASH_F16_CHUNKS
+            if self.fused_scatter:
+                st.hash_flags |= _lib.VN_HASH_FUSED_SCATTER
         t = a.training
         st.w_color, st.w_uss, st.w_tof, st.w_rgbd = t.color_loss_w, t.uss_loss_w, t.tof_loss_w, t.rgbd_loss_w
         st.lr, st.beta1, st.beta2, st.eps = self.lr, self.betas[0], self.betas[1], self.eps
@@ -361,7 +366,7 @@ class TrainEngine:
         st.set_ptrs(xyzs=ws.get("xyzs", S, 3), dirs=ws.get("dirs", S, 3), unit=ws.get("unit", S, 3),
                     deltas=ws.get("deltas", S), ts=ws.get("ts", S), enc=ws.get("enc", S, 32), sigmas=ws.get("sig", S),
                     rgbs=ws.get("rgbs", S, 3), ws=ws.get("ws", S), d_sigmas=ws.get("d_sig", S),
-                    d_rgbs=ws.get("d_rgbs", S, 3), d_enc=ws.get("d_enc", S, 32))
+                    d_rgbs=ws.get("d_rgbs", S, 3), d_enc=None if self.fused_scatter else ws.get("d_enc", S, 32))
         self.adam_step += 1
         st.adam_step = self.adam_step
         self.step_idx += 1

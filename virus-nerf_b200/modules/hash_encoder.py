@@ -40,7 +40,7 @@ class _HashEncode(torch.autograd.Function):
 
 class HashEncoder(torch.nn.Module):
 
-    def __init__(self, max_params: float = 2 ** 19, levels: int = 16, base_res: float = 16.0,
+    def __init__(self, max_params: float = 2 ** 19, levels: int = 16.0, base_res: float = 16.0,
                  max_res: float = 2048.0, feature_per_level: int = 2):
         super().__init__()
         if feature_per_level != 2:

@@ -3,7 +3,7 @@ fp16 output [N, levels*2], f32 gradient buffer ``hash_grad`` with the zero-skip 
 import torch
 
 from .. import _lib
-from .utils import scale_in_level_np
+from .utils import align_to, res_in_level_np, scale_in_level_np  # noqa: F401  (module-level names of the reference)
 
 torch_type = torch.float16
 
@@ -35,7 +35,7 @@ class _HashEncodeHalf(torch.autograd.Function):
 
 class HashEncoder(torch.nn.Module):
 
-    def __init__(self, max_params: float = 2 ** 19, levels: int = 16, base_res: float = 16.0,
+    def __init__(self, max_params: float = 2 ** 19, levels: int = 16.0, base_res: float = 16.0,
                  max_res: float = 2048.0, feature_per_level: int = 2):
         super().__init__()
         if feature_per_level != 2:

@@ -168,12 +168,16 @@ class OccupancyGrid(Grid):
     @torch.no_grad()
     def _rayProb(self, meas: torch.Tensor, dists: torch.Tensor, return_probs: bool = False):
         """:338-389 on given distances (N,M): P[meas@dist | occ], P[meas@dist | emp]"""
-        if return_probs:
-            raise NotImplementedError("return_probs=True (plot-only path) is not provided")
         N, M = dists.shape
         dev = dists.device
         probs_occ = torch.empty(N, M, dtype=torch.float32, device=dev)
         probs_emp = torch.empty(N, M, dtype=torch.float32, device=dev)
+        if return_probs:       # :387-388: + P[meas=dist|emp], P[meas=dist|occ], P[meas not< dist|emp], P[meas not< dist|occ]
+            terms = torch.empty(4, N, M, dtype=torch.float32, device=dev)
+            _lib.call("vn_occ_ray_prob_terms", meas.contiguous().float(), dists.contiguous().float(), N, M, self.I,
+                      float(self.false_detection_prob_every_m), float(self.std_every_m), float(self.prob_min),
+                      probs_occ, probs_emp, terms)
+            return probs_occ, probs_emp, terms[0], terms[1], terms[2], terms[3]
         _lib.call("vn_occ_ray_prob", meas.contiguous().float(), dists.contiguous().float(), N, M, self.I,
                   float(self.false_detection_prob_every_m), float(self.std_every_m), float(self.prob_min),
                   probs_occ, probs_emp)
@@ -202,6 +206,18 @@ class OccupancyGrid(Grid):
         tmp = torch.empty(n, dtype=torch.float32, device=cell_idxs.device)
         _lib.call("vn_occ_bayes_update", self.occ_3d_grid, self.grid_size, cell_idxs.contiguous(), n,
                   probs_occ.contiguous(), probs_emp.contiguous(), winner, tmp)
+
+    @torch.no_grad()
+    def _sensorEmptyPDF(self, shape: tuple):
+        """:433-446: P[meas=dist | cell=emp] (constant false-detection density; analysis helper -- the update path has it
+        inside vn_occ_calc_pos_prob)"""
+        return self.false_detection_prob_every_m * torch.ones(shape, device=self.args.device, dtype=torch.float32)
+
+    @torch.no_grad()
+    def _sensorOccupiedPDF(self, meas: torch.Tensor, dists: torch.Tensor):
+        """:449-465: P[meas=dist | cell=occ], any broadcastable shapes (analysis helper, see _sensorEmptyPDF)"""
+        stds = self.std_every_m * dists + 0.00001
+        return torch.exp(-0.5 * (meas - dists) ** 2 / stds ** 2)
 
     @torch.no_grad()
     def _c2idx(self, pos: torch.Tensor):

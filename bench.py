@@ -23,7 +23,12 @@ RAYS_PER_GPU = 4096
 HASH_BYTES_PER_POINT = 1164          # fwd or bwd, fp32 L16 F2 (SURVEY 8(d) / BASELINE.md section 3)
 # the two candidates for "dominant kernel of the step" (DESIGN.md section 4): both are bracketed with CUDA events
 # INSIDE the timed region and the one with the larger total there is the roofline kernel
-ROOFLINE_CANDIDATES = ("hash_encode_bwd", "mlp_bwd")
+ROOFLINE_CANDIDATES = ("hash_encode_bwd", "mlp_bwd", "mlp_bwd_hash_scatter")
+# the fused MLP-backward + hash-scatter kernel (vn_mlp_bwd_scatter): the table-gradient read-modify-write of the hash
+# backward (16 levels x 8 corners x 8 B = 1024) + xyz (12) + the MLP backward's inputs (fp16 encoding 64, SH planes 32,
+# dsigma 4, drgb 12); the 128 B/point d(enc) round trip of the unfused pair no longer exists
+FUSED_BWD_BYTES_PER_POINT = 1024 + 12 + 64 + 32 + 4 + 12
+FUSED_BWD_BYTES_PER_POINT_HALF = FUSED_BWD_BYTES_PER_POINT      # the half encoder's backward scatters fp32 too
 WORKLOAD = ("ETHZ-shaped synthetic scene, hash grid L=16 F=2 T=2^19 fp32 tables, 4096 rays/batch/GPU, RGB+USS+ToF "
             "losses, VIRUS-NeRF occupancy update every 8 steps, training from the initial (all-occupied) grid")
 
@@ -42,6 +47,7 @@ def parse():
                     help="weak: --rays per GPU; strong: --rays is ONE global batch, rank r takes its contiguous shard")
     ap.add_argument("--no-extra", action="store_true", help="skip extra_configs (configs 3 and 5)")
     ap.add_argument("--no-config3", action="store_true", help="skip the T=2^22 / 2^18-ray / half-encoder configuration")
+    ap.add_argument("--no-fused-scatter", action="store_true", help="MLP backward and hash backward as two kernels (A/B)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-autocast", action="store_true")
     ap.add_argument("--autograd-step", action="store_true", help="use the torch-autograd step instead of the fused step")
@@ -252,7 +258,8 @@ def run_ours(a):
         ds = synthetic.SyntheticDataset(scene, pool_size=1 << 18, device=str(dev), pinned=False, seed=21)
         ds.gen.manual_seed(1000 + (0 if strong else rank))    # same pool on every rank; weak: different training batches
         eng = TrainEngine(args, ds, dev, world_size=world, rank=rank, autocast=not a.no_autocast, comm=a.comm,
-                          enc_layout=a.enc_layout, single_pass_march=not a.two_pass_march)
+                          enc_layout=a.enc_layout, single_pass_march=not a.two_pass_march,
+                          fused_scatter=not a.no_fused_scatter)
         batches = make_batches(ds, W + K + 1, n, args.training.sampling_strategy, (lo, hi, n_global) if strong else None)
         noises = None
         if strong:          # the jitter of the GLOBAL batch, so that N ranks march exactly the samples one rank would
@@ -346,6 +353,7 @@ def run_ours(a):
     clk = clocks.stop()
     eng = ph["eng"]
     extra = {} if a.no_extra else extra_configs(a, eng, scene, dev, world, rank, barrier, max_over_ranks, make_batches, check_p2p)
+    eng.close()
     del eng
     ph["eng"] = None
     torch.cuda.empty_cache()
@@ -376,6 +384,9 @@ def run_ours(a):
                 if name.startswith("mlp"):
                     flop = 18816 if name == "mlp_fwd" else 56448
                     kern[name]["achieved_tflops"] = pts * flop / (t_ms * 1e-3) / 1e12
+                if name == "mlp_bwd_hash_scatter":
+                    kern[name]["achieved_gbs"] = pts * FUSED_BWD_BYTES_PER_POINT / (t_ms * 1e-3) / 1e9
+                    kern[name]["frac_of_hbm_peak"] = kern[name]["achieved_gbs"] / peak
         tflops_peak = peaks_tensor()
         # kernels timed live inside the timed windows: totals there decide which one dominates the step
         live = {}
@@ -388,9 +399,10 @@ def run_ours(a):
                                                   "share_of_timed_step": round(t_ms / (ms * R), 4)})
         dom = max(live, key=lambda k: live[k][0]) if live else None
         roof = None
-        if dom and dom.startswith("hash_encode"):
+        if dom and (dom.startswith("hash_encode") or dom == "mlp_bwd_hash_scatter"):
             t_ms, pts, nl = live[dom]
-            gbs = pts * HASH_BYTES_PER_POINT / (t_ms * 1e-3) / 1e9
+            bpp = FUSED_BWD_BYTES_PER_POINT if dom == "mlp_bwd_hash_scatter" else HASH_BYTES_PER_POINT
+            gbs = pts * bpp / (t_ms * 1e-3) / 1e9
             tr = traffic.get(dom)
             roof = {"kernel": dom, "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
                     "measured": f"CUDA events around every launch of this kernel inside the {R} timed windows ({nl} launches)",
@@ -398,8 +410,11 @@ def run_ours(a):
                     "traffic_note": (f"DRAM bytes per launch = dram__bytes_read.sum + dram__bytes_write.sum per point of this round's "
                                      f"ncu --set full capture ({tr['source']}) x mean points per launch; far below the algorithmic "
                                      f"bytes because the table and its gradient are L2 resident") if tr else "no ncu capture",
-                    "peak_source": peak_src, "algorithmic_bytes_per_launch": HASH_BYTES_PER_POINT * pts / nl,
-                    "algorithmic_bytes_per_point": HASH_BYTES_PER_POINT,
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": bpp * pts / nl,
+                    "algorithmic_bytes_per_point": bpp,
+                    "what": ("fused MLP backward + hash-gradient scatter (one kernel): table-gradient RMW 1024 B + xyz 12 B + "
+                             "MLP-backward inputs 112 B per point; also 56 448 FLOP per point on the tensor cores"
+                             if dom == "mlp_bwd_hash_scatter" else "hash-grid backward scatter"),
                     "runner_up": {k: round(v[0] / v[2], 5) for k, v in live.items() if k != dom}}
         elif dom and dom.startswith("mlp"):
             t_ms, pts, nl = live[dom]
@@ -520,7 +535,9 @@ def extra_configs(a, eng, scene, dev, world, rank, barrier, max_over_ranks, make
         args3.training.sampling_strategy = {"imgs": "all", "pixs": "random"}
         ds3 = synthetic.SyntheticDataset(scene, kind="rh2", pool_size=1 << 19, device=str(dev), seed=33)
         ds3.gen.manual_seed(77)                                              # the same global batches on every rank
-        eng3 = TrainEngine(args3, ds3, dev, world_size=world, rank=rank, log2_T=22, half_opt=True, comm=a.comm)
+        eng.close()                                                          # one owner of the peer-memory exchange at a time
+        eng3 = TrainEngine(args3, ds3, dev, world_size=world, rank=rank, log2_T=22, half_opt=True, comm=a.comm,
+                           fused_scatter=not a.no_fused_scatter)
         W3, K3 = 2, 4
         b3 = make_batches(ds3, W3 + K3 + 1, hi3 - lo3, args3.training.sampling_strategy, (lo3, hi3, n3))
         gen = torch.Generator(device=dev); gen.manual_seed(5)
@@ -529,7 +546,7 @@ def extra_configs(a, eng, scene, dev, world, rank, barrier, max_over_ranks, make
         for it in range(W3):
             losses.append(float(eng3.step_fast(b3[it], noise=noise3[it])))
         barrier()
-        _lib.profile_start(["hash_encode_fwd", "hash_encode_bwd", "mlp_fwd", "mlp_bwd"])
+        _lib.profile_start(["hash_encode_fwd", "hash_encode_bwd", "mlp_fwd", "mlp_bwd", "mlp_bwd_hash_scatter"])
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         smp = []
@@ -547,6 +564,10 @@ def extra_configs(a, eng, scene, dev, world, rank, barrier, max_over_ranks, make
             t_ms = sum(c[0] for c in calls); pts = sum(c[1] for c in calls)
             if t_ms > 0:
                 k3[name] = {"ms_per_launch": round(t_ms / len(calls), 4), "points": pts // len(calls)}
+                if name == "mlp_bwd_hash_scatter":
+                    k3[name]["achieved_gbs"] = round(pts * FUSED_BWD_BYTES_PER_POINT_HALF / (t_ms * 1e-3) / 1e9, 1)
+                    k3[name]["frac_of_hbm_peak"] = round(k3[name]["achieved_gbs"] / peak, 4)
+                    k3[name]["algorithmic_bytes_per_point"] = FUSED_BWD_BYTES_PER_POINT_HALF
                 if name.startswith("hash_encode"):
                     # algorithmic bytes per point, half encoder: fwd 588 (fp16 table reads + fp16 out),
                     # bwd 1100 (fp32 scatter); reported next to the fp32 figure of the headline
@@ -563,6 +584,7 @@ def extra_configs(a, eng, scene, dev, world, rank, barrier, max_over_ranks, make
             "losses": [round(float(x), 6) for x in losses], "kernels": k3,
             "note": "one globally seeded batch per step, rank r trains on rays [r N/n, (r+1) N/n) with the jitter of the global "
                     "batch: `losses` must agree between N = 1 and N > 1 (global loss normalisers, summed gradients)"}
+        eng3.close()
         del eng3
         torch.cuda.empty_cache()
     return out

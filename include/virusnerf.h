@@ -330,12 +330,17 @@ int vn_mlp_bwd(const void* enc, int enc_format, const float* dirs, const float* 
  * hash_encoder_half.py:164-213 (zero-skip rule, f32 red.global.add) into table_grad [total_entries,2], ACCUMULATING like
  * vn_hash_encode_bwd_f32.  xyz [S,3] = the unit-cube positions the forward encoded; round_f16 != 0 rounds d(enc) to
  * fp16 first (the half-precision encoder's gradient dtype).  Equivalent to vn_mlp_bwd(enc_format [+ VN_MLP_DENC_F16])
- * + vn_hash_encode_bwd_f32 / _f16 up to the summation order of the atomics. */
+ * + vn_hash_encode_bwd_f32 / _f16 up to the summation order of the atomics.
+ * found_inf (optional, device float[1]): set to 1.0 when any d(enc) value or weight-gradient entry of this launch is not
+ * finite -- GradScaler's inf check (training/trainer.py:140, vn_grad_check) evaluated on the contributions instead of a
+ * separate pass over the 45.7 MB gradient: |d(enc)| <= 64 * 65504^2 when finite, so a sum of fewer than 2^31 finite
+ * contributions cannot overflow and "some gradient entry is non-finite" <=> "some contribution is non-finite".  Never
+ * cleared here. */
 int vn_mlp_bwd_scatter(const void* enc, int enc_format, const float* dirs, const float* W1, const float* W2,
                        const float* W3, const float* W4, const float* W5, int64_t S, const float* dsigmas,
                        const float* drgbs, const float* xyz, const vn_hash_levels_t* lv, int round_f16,
                        float* table_grad, float* dW1, float* dW2, float* dW3, float* dW4, float* dW5,
-                       void* stream);
+                       float* found_inf, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Native step runner (caller side): the body of Trainer.train()'s loop
@@ -422,6 +427,20 @@ int vn_p2p_allreduce_small(float* data, int n, int use_max, void* stream);
 int vn_p2p_reduce_adam(int64_t n, float* m, float* v, double lr, double beta1, double beta2, double eps,
                        int step, float* found_inf, float* scale_dev, int32_t* growth_tracker,
                        void* stream);
+/*  vn_p2p_step: the same update as ONE kernel with two cross-rank barriers instead of three.  found_inf is an INPUT:
+ *               the rank's own inf check (vn_mlp_bwd_scatter's in-kernel check, or vn_grad_check) -- the start barrier
+ *               carries it through the mailboxes and every rank applies max over ranks.  Then one pass over slice r:
+ *               sum of the ranks' gradients in fixed rank order (peer loads) -> Adam (bias corrections from opt_state,
+ *               see vn_opt_state_init) with rank-local m / v -> the updated parameters stored into every replica (peer
+ *               stores; inbound and outbound NVLink traffic overlap) -> end barrier -> GradScaler update and, when the
+ *               step was applied, opt_state advanced (vn_scaler_update_dev's arithmetic).  Parameters are bit-identical
+ *               to vn_p2p_allreduce + vn_adam_step_dev on every rank.  The reduced gradient is not written back.
+ *  vn_p2p_shutdown: releases the process-wide exchange context (vn_p2p_init refuses to replace a live one).
+ *  Every cross-rank wait gives up after VN_P2P_TIMEOUT_MS (environment, default 20000): *err_dev = 1 and the step is
+ *  skipped like an overflow; the host must treat a non-zero err_dev as fatal (TrainEngine raises). */
+int vn_p2p_step(int64_t n, float* m, float* v, double lr, double beta1, double beta2, double eps,
+                float* opt_state, float* found_inf, float* scale_dev, int32_t* growth_tracker, void* stream);
+int vn_p2p_shutdown(void);
 
 /* ---------------------------------------------------------------------------------------
  * (f) row 2. Batch assembly on the device -- the gather half of DatasetBase.__call__

@@ -171,6 +171,75 @@ def test_train_steps_track_oracle(setup, monkeypatch):
     np.testing.assert_allclose(w_g, N(om.W[4]), rtol=0, atol=2e-3)
 
 
+@pytest.mark.parametrize("fused", [True, False])
+def test_fast_step_fp16_tracks_oracle_directly(fused):
+    """the path that is BENCHED -- step_fast with the fp16 tcgen05 MLP, operand-chunk layout, single-pass march, PDL and
+    (fused=True) the fused MLP-backward + hash-scatter kernel with the in-kernel inf check -- against the fp32 CPU
+    trainer of oracle/pipeline.py on the same rays, bitfield and jitter.  Stated tolerance of the fp16 MLP
+    (tests/test_mlp_gpu.py): 2e-2 relative on the loss, 5e-2 of the largest entry on gradients."""
+    import oracle
+    from oracle import pipeline
+    from virus_nerf_b200 import synthetic
+    from virus_nerf_b200.engine import TrainEngine
+    oracle.build()
+    args = synthetic.make_args(device=DEV, batch_size=256)
+    ds = synthetic.SyntheticDataset(pool_size=1 << 13, n_images=8, device=DEV)
+    eng = TrainEngine(args, ds, DEV, autocast=True, fused_scatter=fused)
+    assert eng.enc_chunks and eng.fused_scatter == fused and eng.model.fused_mlp
+    bf = synthetic.morton_pack(ds.scene.occupancy_bitfield(128))
+    eng.model.occupancy_grid.bitfield = torch.from_numpy(bf).to(DEV)
+    eng.step_idx = eng._prep_step = 1                      # no occupancy update (tested separately)
+    om = pipeline.OracleNGP(threads=4)
+    om.load_from(eng.model)
+    tr = pipeline.OracleTrainer(om, lr=args.training.lr)
+    for it in range(3):
+        data = ds(256, args.training.sampling_strategy)
+        noise = torch.rand(256, device=DEV)
+        p_before = eng.flat_p.clone()
+        loss = float(eng.step_fast(data, noise=noise))
+        o_loss, o_res = tr.step(_data_cpu(data), bf, N(noise))
+        assert int(eng.last_samples) == int(o_res["rm_samples"]) > 0          # the march is bit-exact
+        assert abs(loss - o_loss) <= 2e-2 * abs(o_loss), (it, loss, o_loss)
+        # gradients of this step: GPU flat gradient (loss-scaled) vs the oracle's autograd gradients
+        scale = float(eng.scale)
+        g_tab = N(eng.model.pos_encoder.hash_table.grad).reshape(-1) / scale
+        o_tab = N(om.hash_table.grad).reshape(-1)
+        assert np.abs(g_tab - o_tab).max() <= 5e-2 * np.abs(o_tab).max(), (it, np.abs(g_tab - o_tab).max(), np.abs(o_tab).max())
+        g_w = N(eng._mlp_g[4]) / scale
+        assert np.abs(g_w - N(om.W[4].grad)).max() <= 5e-2 * np.abs(N(om.W[4].grad)).max()
+        assert float(eng.found_inf) == 0.0 and not torch.equal(p_before, eng.flat_p)
+    assert eng.applied_steps() == 3
+    w_g = N(eng.model.rgb_net.output_layer.weight)
+    np.testing.assert_allclose(w_g, N(om.W[4]), rtol=0, atol=5e-3)
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_fast_step_skips_on_overflow(fused):
+    """GradScaler semantics through the native step runner: a step whose gradients are not finite leaves parameters and
+    Adam state untouched, halves the scale and does not advance Adam's step count -- with the separate vn_grad_check
+    pass (fused=False) and with the check evaluated inside the fused backward kernel (fused=True)"""
+    from virus_nerf_b200 import synthetic
+    from virus_nerf_b200.engine import TrainEngine
+    args = synthetic.make_args(device=DEV, batch_size=256)
+    ds = synthetic.SyntheticDataset(pool_size=1 << 13, n_images=8, device=DEV)
+    eng = TrainEngine(args, ds, DEV, fused_scatter=fused)
+    bf = synthetic.morton_pack(ds.scene.occupancy_bitfield(128))
+    eng.model.occupancy_grid.bitfield = torch.from_numpy(bf).to(DEV)
+    eng.step_idx = eng._prep_step = 1
+    good = ds(256, args.training.sampling_strategy)
+    eng.step_fast(good)
+    assert eng.applied_steps() == 1 and float(eng.scale) == 2.0 ** 19
+    p, m, v = eng.flat_p.clone(), eng.flat_m.clone(), eng.flat_v.clone()
+    bad = {k: (val.clone() if torch.is_tensor(val) else {kk: vv.clone() for kk, vv in val.items()}) for k, val in good.items()
+           if k in ("rays_o", "rays_d", "rgb", "depth")}
+    bad["rgb"][3, 1] = float("inf")                       # -> infinite colour loss gradient
+    eng.step_fast(bad)
+    assert torch.equal(p, eng.flat_p) and torch.equal(m, eng.flat_m) and torch.equal(v, eng.flat_v)
+    assert eng.applied_steps() == 1 and float(eng.scale) == 2.0 ** 18 and float(eng.found_inf) == 0.0
+    eng.step_fast(good)
+    assert eng.applied_steps() == 2 and not torch.equal(p, eng.flat_p) and torch.isfinite(eng.flat_p).all()
+
+
 def test_occupancy_update_runs_and_is_deterministic(setup):
     eng, om, ds, bf, args, pipeline = setup
     og = eng.model.occupancy_grid

@@ -223,7 +223,7 @@ def test_fused_mlp_backward_with_hash_scatter(S, half):
     enc_c = _to_chunks(torch.rand(S, 32, device=DEV).half())
     dirs = torch.randn(S, 3, device=DEV)
     dsig = torch.randn(S, device=DEV) * 3; drgb = torch.randn(S, 3, device=DEV) * 3
-    dsig[::5] = 0; drgb[::5] = 0                           # samples behind an opaque surface: exactly zero gradient
+    dsig[1::5] = 0; drgb[1::5] = 0                         # samples behind an opaque surface: exactly zero gradient
     F16 = 8
     n_tab = 2 * lv.total_entries
     # unfused: MLP backward writes d(enc), the hash backward scatters it
@@ -239,7 +239,9 @@ def test_fused_mlp_backward_with_hash_scatter(S, half):
     # fused
     dW_b = [torch.zeros_like(w) for w in Wg]
     grad_b = torch.zeros(n_tab, device=DEV)
-    _lib.call("vn_mlp_bwd_scatter", enc_c, 3, dirs, *Wg, S, dsig, drgb, xyz, lv, 1 if half else 0, grad_b, *dW_b)
+    found = torch.zeros(1, device=DEV)
+    _lib.call("vn_mlp_bwd_scatter", enc_c, 3, dirs, *Wg, S, dsig, drgb, xyz, lv, 1 if half else 0, grad_b, *dW_b, found)
+    assert float(found) == 0.0
     for a, b in zip(dW_a, dW_b):
         if S <= 128:
             assert torch.equal(a, b)
@@ -259,8 +261,23 @@ def test_fused_mlp_backward_with_hash_scatter(S, half):
             ref = oracle.hash_bwd_f32(xyz.cpu().numpy(), rows, lv_o)
         np.testing.assert_allclose(grad_b.view(-1, 2).cpu().numpy(), ref.reshape(-1, 2), rtol=1e-4, atol=1e-5 * np.abs(ref).max())
     # accumulation: a second call adds the same gradient again
-    _lib.call("vn_mlp_bwd_scatter", enc_c, 3, dirs, *Wg, S, dsig, drgb, xyz, lv, 1 if half else 0, grad_b, *dW_b)
+    _lib.call("vn_mlp_bwd_scatter", enc_c, 3, dirs, *Wg, S, dsig, drgb, xyz, lv, 1 if half else 0, grad_b, *dW_b, None)
     assert float((grad_b - 2 * grad_a).abs().max()) <= 2e-4 * scale
+    # the inf check rides in the kernel: one non-finite output gradient anywhere => found_inf, and the reference's
+    # check (vn_grad_check over the gradient buffers) agrees
+    for bad_sig in (True, False):
+        ds2, dr2 = dsig.clone(), drgb.clone()
+        if bad_sig:
+            ds2[S // 2] = float("inf")
+        else:
+            dr2[S // 3, 1] = float("nan")
+        g2 = torch.zeros(n_tab, device=DEV); dW2 = [torch.zeros_like(w) for w in Wg]
+        found.zero_()
+        _lib.call("vn_mlp_bwd_scatter", enc_c, 3, dirs, *Wg, S, ds2, dr2, xyz, lv, 1 if half else 0, g2, *dW2, found)
+        ref_found = torch.zeros(1, device=DEV)
+        for buf in [g2] + dW2:
+            _lib.call("vn_grad_check", buf.view(-1), buf.numel(), ref_found)
+        assert float(found) == 1.0 and float(ref_found) == 1.0
 
 
 def test_fused_mlp_backward_with_hash_scatter_rejects_bad_arguments():
@@ -273,10 +290,10 @@ def test_fused_mlp_backward_with_hash_scatter_rejects_bad_arguments():
     lv = _lib.hash_levels(16, 1024, 16, 2 ** 19)
     grad = torch.zeros(2 * lv.total_entries, device=DEV)
     with pytest.raises(RuntimeError, match="enc_format"):
-        _lib.call("vn_mlp_bwd_scatter", enc_c, 2, z3, *Wg, S, z, z3, z3, lv, 0, grad, *dW)
+        _lib.call("vn_mlp_bwd_scatter", enc_c, 2, z3, *Wg, S, z, z3, z3, lv, 0, grad, *dW, None)
     lv8 = _lib.hash_levels(16, 512, 8, 2 ** 19)
     with pytest.raises(RuntimeError, match="16 levels"):
-        _lib.call("vn_mlp_bwd_scatter", enc_c, 3, z3, *Wg, S, z, z3, z3, lv8, 0, grad, *dW)
+        _lib.call("vn_mlp_bwd_scatter", enc_c, 3, z3, *Wg, S, z, z3, z3, lv8, 0, grad, *dW, None)
 
 
 def test_fused_mlp_pipelined_backward_equals_serial_kernel(monkeypatch):

@@ -257,11 +257,26 @@ def test_hash_half_module(vn, oracle_mod):
     from virus_nerf_b200.modules.hash_encoder_half import HashEncoder
     enc = HashEncoder(max_params=2 ** 19, levels=16, base_res=16, max_res=1024).to(DEV)
     assert enc.hash_table.shape == (5710032, 2) and enc.hash_grad.shape == (5710032, 2)
-    xyz = torch.rand(500, 3, device=DEV)
+    lv_o = oracle_mod.HashLevels(16, 1024, 16, 2 ** 19)
+    with torch.no_grad():                                  # the reference's U(-1e-4, 1e-4) init carries no signal
+        torch.manual_seed(2)
+        enc.hash_table.copy_(torch.rand_like(enc.hash_table) * 2 - 1)
+    xyz = torch.cat([torch.rand(500, 3, device=DEV), T(ray_coherent_points(8, 64))])
+    S = xyz.shape[0]
     out = enc(xyz)
-    assert out.dtype == torch.float16 and out.shape == (500, 32)
-    out.float().sum().backward()
-    assert enc.hash_table.grad is not None and torch.isfinite(enc.hash_table.grad).all()
+    assert out.dtype == torch.float16 and out.shape == (S, 32)
+    # forward of the module == oracle's half kernel on the fp16 copy of the table (hash_encoder_half.py:367)
+    table_h = N(enc.hash_table).astype(np.float16)
+    ref = oracle_mod.hash_fwd_f16(N(xyz), table_h, lv_o)
+    np.testing.assert_allclose(N(out).astype(np.float32), ref.astype(np.float32).reshape(S, 32), rtol=2e-3, atol=1e-3)
+    # backward of the module (autograd -> hash_grad, zero-skip rule) == oracle.hash_bwd_f16 of the same fp16 gradient
+    g = torch.randn(S, 32, device=DEV).half()
+    g[::7] = 0
+    out.backward(g)
+    gref = oracle_mod.hash_bwd_f16(N(xyz), N(g).reshape(S, 16, 2), lv_o)
+    assert enc.hash_table.grad is not None and enc.hash_table.grad.dtype == torch.float32
+    np.testing.assert_allclose(N(enc.hash_table.grad), gref.reshape(-1, 2), rtol=1e-2, atol=1e-5 * np.abs(gref).max())
+    assert torch.equal(enc.hash_table.grad, enc.hash_grad)          # the reference hands out its hash_grad buffer (:352-358)
 
 
 # ------------------------------------------------------------------------------------ a5

@@ -1,6 +1,7 @@
 """2..8-rank check of the peer-memory exchange kernels (run under torchrun):
   * vn_p2p_allreduce against NCCL;
   * vn_p2p_allreduce_small (mailbox sum of the loss normalisers) against NCCL;
+  * vn_p2p_step (the same as ONE kernel, inf flag as input, step count on the device) against the same reference;
   * vn_p2p_reduce_adam (reduce-scatter + inf check + sharded Adam + parameter push + scaler
     update) against vn_p2p_allreduce + vn_grad_check + vn_adam_step + vn_scaler_update: the
     parameters must be BIT-identical on every rank, incl. a step with an injected inf.
@@ -104,6 +105,38 @@ for step in range(1, 5):
     say(f"world {world}: fused optimiser step {step}: params == reference {eq_p}, own m/v slice {eq_m}, scaler {eq_s} "
         f"(scale {float(scale_f):.0f}), replicas identical {same}")
 
+# ---- 3b. the single-kernel step (vn_p2p_step) vs allreduce + vn_grad_check + vn_adam_step_dev + vn_scaler_update_dev ----
+m_s, v_s = torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+m_q, v_q = torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+p_ref = params.clone()
+found_s, found_q = torch.zeros(1, device=dev), torch.zeros(1, device=dev)
+scale_s, scale_q = torch.tensor([2.0 ** 19], device=dev), torch.tensor([2.0 ** 19], device=dev)
+tr_s, tr_q = torch.zeros(1, dtype=torch.int32, device=dev), torch.zeros(1, dtype=torch.int32, device=dev)
+st_s, st_q = torch.zeros(4, device=dev), torch.zeros(4, device=dev)
+_lib.call("vn_opt_state_init", st_s, 0, lr, b1, b2); _lib.call("vn_opt_state_init", st_q, 0, lr, b1, b2)
+for step in range(1, 6):
+    g0 = torch.randn(n, device=dev, generator=gen) * 2.0 ** 19
+    if step == 2 and rank == world - 1:
+        g0[777] = float("nan")                        # one rank overflows: every rank must skip, Adam's count must not advance
+    grad.copy_(g0)
+    _lib.call("vn_p2p_allreduce", n)
+    _lib.call("vn_grad_check", grad, n, found_q)
+    _lib.call("vn_adam_step_dev", p_ref, grad, m_q, v_q, n, lr, b1, b2, eps, st_q, found_q, scale_q)
+    _lib.call("vn_scaler_update_dev", scale_q, tr_q, found_q, 2.0, 0.5, 2000, st_q, lr, b1, b2)
+    grad.copy_(g0)
+    torch.cuda.synchronize(); dist.barrier()
+    _lib.call("vn_grad_check", grad, n, found_s)       # the rank's OWN check is the input of vn_p2p_step
+    _lib.call("vn_p2p_step", n, m_s, v_s, lr, b1, b2, eps, st_s, found_s, scale_s, tr_s)
+    torch.cuda.synchronize()
+    eq_p = bool(torch.equal(params, p_ref))
+    eq_m = bool(torch.equal(m_s[lo:hi], m_q[lo:hi]) and torch.equal(v_s[lo:hi], v_q[lo:hi]))
+    eq_s = float(scale_s) == float(scale_q) and int(tr_s) == int(tr_q) and bool(torch.equal(st_s[:3], st_q[:3])) \
+        and float(found_s) == 0.0
+    same = identical_everywhere(params)
+    ok &= eq_p and eq_m and eq_s and same and int(err) == 0
+    say(f"world {world}: one-kernel step {step}: params == reference {eq_p}, own m/v slice {eq_m}, scaler + step count {eq_s} "
+        f"(scale {float(scale_s):.0f}, applied {int(st_s[2:3].view(torch.int32))}), replicas identical {same}")
+
 # ---- 4. timings --------------------------------------------------------------------------------
 grad.normal_()
 t_p2p = timeit(lambda: _lib.call("vn_p2p_allreduce", n))
@@ -127,15 +160,17 @@ def nccl_unfused():
 t_unf = timeit(unfused)
 t_nccl_unf = timeit(nccl_unfused)
 t_fused = timeit(lambda: _lib.call("vn_p2p_reduce_adam", n, m_f, v_f, lr, b1, b2, eps, 5, found_f, scale_f, tr_f))
+t_step = timeit(lambda: _lib.call("vn_p2p_step", n, m_s, v_s, lr, b1, b2, eps, st_s, found_s, scale_s, tr_s))
 small = torch.ones(4, device=dev)
 t_small = timeit(lambda: _lib.call("vn_p2p_allreduce_small", small, 4, 0))
 small2 = torch.ones(4, device=dev)
 t_small_nccl = timeit(lambda: dist.all_reduce(small2))
 ok &= int(err) == 0
 say(f"world {world}: allreduce p2p {t_p2p:.4f} ms, nccl {t_nccl:.4f} ms | exchange + optimiser: nccl+dense {t_nccl_unf:.4f} ms, "
-    f"p2p+dense {t_unf:.4f} ms, FUSED sharded {t_fused:.4f} ms | 4-float allreduce: mailbox {t_small:.4f} ms, nccl {t_small_nccl:.4f} ms")
+    f"p2p+dense {t_unf:.4f} ms, FUSED sharded {t_fused:.4f} ms, ONE-KERNEL sharded {t_step:.4f} ms | 4-float allreduce: mailbox {t_small:.4f} ms, nccl {t_small_nccl:.4f} ms")
 flag = torch.tensor([1.0 if ok else 0.0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+_lib.p2p_shutdown()
 dist.destroy_process_group()
 if float(flag) != 1.0:
     raise SystemExit("p2p_test: MISMATCH")

@@ -123,6 +123,7 @@ _SPECS = {
     "vn_p2p_allreduce": "ls",
     "vn_p2p_allreduce_small": "piis",
     "vn_p2p_reduce_adam": "lpp" "dddd" "i" "ppp" "s",
+    "vn_p2p_step": "lpp" "dddd" "pppp" "s",
     "vn_batch_assemble": "ppl" "ppl" "pil" "pi" "pppp" "pp" "ppp" "pppp" "pp" "p" "s",
     "vn_ngp_sample_occupied": "plfplpps",
     "vn_ngp_cell_positions": "ppliffps",
@@ -130,7 +131,7 @@ _SPECS = {
     "vn_ngp_threshold_pack": "plfppps",
     "vn_mlp_fwd": "pip" "ppppp" "li" "ppp" "s",
     "vn_mlp_bwd": "pip" "ppppp" "li" "pp" "p" "ppppp" "s",
-    "vn_mlp_bwd_scatter": "pip" "ppppp" "l" "pp" "p" "hi" "p" "ppppp" "s",
+    "vn_mlp_bwd_scatter": "pip" "ppppp" "l" "pp" "p" "hi" "p" "ppppp" "p" "s",
 }
 
 _CT = {"p": ctypes.c_void_p, "l": ctypes.c_int64, "i": ctypes.c_int, "f": ctypes.c_float,
@@ -311,7 +312,7 @@ def hash_levels(base_res, max_res, levels, max_params):
 
 def exported_symbols():
     """names declared in include/virusnerf.h (used by the CPU-side ABI test)"""
-    return ["vn_last_error", "vn_abi_version", "vn_launch_count", "vn_ipc_get_handle", "vn_ipc_open", "vn_p2p_init", "vn_p2p_attach", "vn_profile_enable", "vn_profile_enable_mask", "vn_set_pdl", "vn_profile_count", "vn_profile_get", "vn_device_info", "vn_march_scan_tmp_ints", "vn_adam_config",
+    return ["vn_last_error", "vn_abi_version", "vn_launch_count", "vn_ipc_get_handle", "vn_ipc_open", "vn_p2p_init", "vn_p2p_attach", "vn_p2p_shutdown", "vn_profile_enable", "vn_profile_enable_mask", "vn_set_pdl", "vn_profile_count", "vn_profile_get", "vn_device_info", "vn_march_scan_tmp_ints", "vn_adam_config",
             "vn_ngp_select_tmp_ints", "vn_ngp_threshold_tmp_bytes"] + list(_SPECS)
 
 
@@ -323,6 +324,11 @@ def p2p_slice(n, rank, world):
     chunk4 = (n4 + world - 1) // world
     lo = min(rank * chunk4, n4)
     return 4 * lo, 4 * min(lo + chunk4, n4)
+
+
+def p2p_shutdown():
+    """release the process-wide peer-memory exchange context (the next p2p_setup may then take it)"""
+    lib().vn_p2p_shutdown()
 
 
 _ipc_opened = {}   # 64-byte IPC handle -> mapped base pointer (a handle may be opened once per process)

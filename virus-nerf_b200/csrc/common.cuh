@@ -165,3 +165,14 @@ __device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, con
     const float denom = __fadd_rn(__fdiv_rn(sqrtf(v), c.bc2_sqrt), c.eps);   // (sqrt / bias_correction2_sqrt).add_(eps)
     p = __fsub_rn(p, __fmul_rn(c.step_size, __fdiv_rn(m, denom)));   // param.addcdiv_(exp_avg, denom, -step_size)
 }
+
+// Adam's step count on the device (optim.cu "optimiser step count on the device"): opt_state = {lr / (1 - beta1^t),
+// sqrt(1 - beta2^t) for the NEXT step t, bit pattern of the int32 count of applied steps, unused}
+#ifdef __CUDACC__
+__device__ __forceinline__ void vn_opt_state_set(float* opt_state, int applied, double lr, double beta1, double beta2) {
+    const double t = (double)(applied + 1);
+    opt_state[0] = (float)(lr / (1.0 - pow(beta1, t)));
+    opt_state[1] = (float)sqrt(1.0 - pow(beta2, t));
+    opt_state[2] = __int_as_float(applied);
+}
+#endif

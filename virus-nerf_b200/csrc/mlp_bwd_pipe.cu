@@ -778,6 +778,9 @@ __global__ void __launch_bounds__(NTHR, 1) mlp_bwd_pipe_kernel(const MlpArgs a, 
                         const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u));
                         d0 = f.x; d1 = f.y;
                     }
+                    // GradScaler's inf check (trainer.py:140) rides here: a table-gradient entry is non-finite iff one of
+                    // its contributions is (|d(enc)| <= 64 * 65504^2 otherwise, so no sum of < 2^31 finite terms overflows)
+                    if (hs.found_inf && valid && !(fabsf(d0) + fabsf(d1) < INFINITY)) *hs.found_inf = 1.0f;
                     const bool v = valid && !(d0 == 0.0f && d1 == 0.0f);           // hash_encoder_half.py:210
                     const Cell cl = cell_of(px, py, pz, hs.P.scales[level]);
                     float* gl = hs.grad + 2 * (size_t)hs.P.offsets[level];
@@ -831,6 +834,8 @@ __global__ void __launch_bounds__(NTHR, 1) mlp_bwd_pipe_kernel(const MlpArgs a, 
         const int wrow = 16 * q + lane;
         const uint32_t tl = tmem0 + ((uint32_t)(32 * q) << 16);
         uint32_t v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;
         if (grp == 0) {                       // dW1 [64 out x 32 in]
             tmem_ld<32>(tl + T_DW1, v); umma::tmem_ld_wait();
             if (lane < 16) for (int j = 0; j < 32; ++j) atomicAdd(a.dW[0] + wrow * 32 + j, __uint_as_float(v[j]));
@@ -847,6 +852,12 @@ __global__ void __launch_bounds__(NTHR, 1) mlp_bwd_pipe_kernel(const MlpArgs a, 
         } else {                              // dW5^T [64 in x 16] -> dW5 [3 x 64]
             tmem_ld<8>(tl + T_DW5T, v); umma::tmem_ld_wait();
             if (lane < 16) for (int j = 0; j < 3; ++j) atomicAdd(a.dW[4] + j * 64 + wrow, __uint_as_float(v[j]));
+        }
+        if (SCATTER && hs.found_inf && lane < 16) {   // the weight gradients' share of the inf check (lanes 16..31 hold no rows)
+            float m = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) m += fabsf(__uint_as_float(v[j]));
+            if (!(m < INFINITY)) *hs.found_inf = 1.0f;
         }
     }
     umma::fence_before_sync();

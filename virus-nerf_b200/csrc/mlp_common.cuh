@@ -72,6 +72,7 @@ struct ScatterArgs {
     const float* xyz;      // [S,3] unit-cube positions (the hash forward's input)
     float* grad;           // table gradient [total_entries, 2] f32, accumulated with red.global.add
     int round_f16;         // d(enc) rounded to fp16 before the scatter (half-precision encoder)
+    float* found_inf;      // optional: set to 1 when a gradient contribution (table or weights) is not finite
     HashParams P;
 };
 

@@ -586,7 +586,8 @@ VN_API int vn_mlp_bwd(const void* enc, int enc_format, const float* dirs, const 
 VN_API int vn_mlp_bwd_scatter(const void* enc, int enc_format, const float* dirs, const float* W1, const float* W2,
                               const float* W3, const float* W4, const float* W5, int64_t S, const float* dsigmas,
                               const float* drgbs, const float* xyz, const vn_hash_levels_t* lv, int round_f16,
-                              float* table_grad, float* dW1, float* dW2, float* dW3, float* dW4, float* dW5, void* stream) {
+                              float* table_grad, float* dW1, float* dW2, float* dW3, float* dW4, float* dW5, float* found_inf,
+                              void* stream) {
     VN_REQUIRE(S >= 0, "vn_mlp_bwd_scatter: S < 0");
     if (S == 0) return VN_OK;
     VN_REQUIRE(enc && W1 && W2 && W3 && W4 && W5 && dsigmas && drgbs && xyz && lv && table_grad && dW1 && dW2 && dW3 && dW4 && dW5,
@@ -604,7 +605,7 @@ VN_API int vn_mlp_bwd_scatter(const void* enc, int enc_format, const float* dirs
     a.dW[0] = dW1; a.dW[1] = dW2; a.dW[2] = dW3; a.dW[3] = dW4; a.dW[4] = dW5;
     a.S = S; a.enc_fmt = enc_format; a.denc_fmt = round_f16 ? 3 : 2;
     ScatterArgs hs{};
-    hs.xyz = xyz; hs.grad = table_grad; hs.round_f16 = round_f16 ? 1 : 0;
+    hs.xyz = xyz; hs.grad = table_grad; hs.round_f16 = round_f16 ? 1 : 0; hs.found_inf = found_inf;
     int rc = make_params(lv, hs.P);
     if (rc) return rc;
     return launch_mlp_bwd_pipe(a, &hs, (cudaStream_t)stream);

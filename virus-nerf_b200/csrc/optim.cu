@@ -79,14 +79,8 @@ VN_API int vn_adam_step(float* p, const float* g, float* m, float* v, int64_t n,
 // sync; opt_state = {step_size = lr / (1 - beta1^t), sqrt(1 - beta2^t), bit pattern of the int32 number of APPLIED
 // steps, unused} lives on the device: the scaler update advances the count when found_inf == 0 and derives the two
 // constants of the NEXT step in double precision (the arithmetic of vn_make_adam_cfg), one thread.
-__device__ __forceinline__ void opt_state_set(float* opt_state, int applied, double lr, double beta1, double beta2) {
-    const double t = (double)(applied + 1);
-    opt_state[0] = (float)(lr / (1.0 - pow(beta1, t)));
-    opt_state[1] = (float)sqrt(1.0 - pow(beta2, t));
-    opt_state[2] = __int_as_float(applied);
-}
 __global__ void opt_state_init_kernel(float* opt_state, int applied, double lr, double beta1, double beta2) {
-    opt_state_set(opt_state, applied, lr, beta1, beta2);
+    vn_opt_state_set(opt_state, applied, lr, beta1, beta2);
     opt_state[3] = 0.0f;
 }
 VN_API int vn_opt_state_init(float* opt_state, int applied_steps, double lr, double beta1, double beta2, void* stream) {
@@ -116,7 +110,7 @@ __global__ void scaler_update_kernel(float* scale, int32_t* tracker, float* foun
     vn_pdl_trigger(); vn_pdl_wait();          // PDL: see common.cuh
     if (*found_inf != 0.0f) { *scale = *scale * backoff; *tracker = 0; }
     else {
-        if (opt_state) opt_state_set(opt_state, __float_as_int(opt_state[2]) + 1, lr, beta1, beta2);   // the step was applied
+        if (opt_state) vn_opt_state_set(opt_state, __float_as_int(opt_state[2]) + 1, lr, beta1, beta2);   // the step was applied
         const int t = *tracker + 1;
         if (t == interval) { const float grown = *scale * growth; if (isfinite(grown)) *scale = grown; *tracker = 0; }   // torch _amp_update_scale_
         else *tracker = t;

@@ -11,6 +11,7 @@
 // scope fences); every spin has a clock64() timeout that sets an error word instead of hanging.
 #include "common.cuh"
 #include <string.h>
+#include <stdlib.h>
 
 #define VN_P2P_MAX_RANKS 8
 #define VN_P2P_MBOX 8                  // floats per rank and mailbox slot
@@ -28,7 +29,20 @@ struct P2PCtx {
 static P2PCtx g_ctx;
 static bool g_ctx_ready = false;
 
-__global__ void p2p_barrier_kernel(P2PCtx c, int value) {
+// spin budget of every cross-rank wait, in SM clocks (VN_P2P_TIMEOUT_MS in the environment, default 20 s at ~2 GHz).
+// A time-out sets *err (the engine reads it back on the step's host sync and raises) and makes the step a no-op
+// (treated like an overflow: nothing is applied to incomplete data).
+static long long timeout_from_env() {
+    const char* e = getenv("VN_P2P_TIMEOUT_MS");
+    double ms = e ? atof(e) : 20000.0;
+    if (!(ms > 0.0)) ms = 20000.0;
+    return (long long)(ms * 2.0e6);
+}
+static long long g_timeout_clocks = timeout_from_env();
+// per-context device scratch of vn_p2p_step: {go epoch, done-CTA counter, global found_inf, unused}
+static int* g_step_sync = nullptr;
+
+__global__ void p2p_barrier_kernel(P2PCtx c, int value, long long timeout) {
     vn_pdl_trigger(); vn_pdl_wait();          // PDL: may be pre-launched behind the kernel that produces the data
     const int p = threadIdx.x;
     if (p < c.world) {
@@ -38,7 +52,7 @@ __global__ void p2p_barrier_kernel(P2PCtx c, int value) {
         volatile int* src = c.flags[c.rank] + p;           // peer p's arrival, in my array
         const long long t0 = clock64();
         while (*src < value) {
-            if (clock64() - t0 > (long long)4e9) { *c.err = 1; break; }    // ~2 s: never hang the GPU
+            if (clock64() - t0 > timeout) { *c.err = 1; break; }    // never hang the GPU; the engine raises on *err
         }
         __threadfence_system();
     }
@@ -78,7 +92,7 @@ __global__ void __launch_bounds__(512) p2p_all_gather_kernel(P2PCtx c, int64_t n
 // the `world` slots of its own mailbox in rank order (sum, or max when `use_max`), so every
 // rank obtains the bit-identical result.  Two mailbox parities: a slot can only be overwritten
 // two exchanges later, i.e. after its reader has passed another barrier.
-__global__ void p2p_exchange_kernel(P2PCtx c, int value, int parity, float* data, int n, int use_max) {
+__global__ void p2p_exchange_kernel(P2PCtx c, int value, int parity, float* data, int n, int use_max, long long timeout) {
     vn_pdl_trigger(); vn_pdl_wait();          // PDL: `data` comes from the preceding kernel
     const int p = threadIdx.x;
     if (p < c.world) {
@@ -90,7 +104,7 @@ __global__ void p2p_exchange_kernel(P2PCtx c, int value, int parity, float* data
         volatile int* src = c.flags[c.rank] + p;
         const long long t0 = clock64();
         while (*src < value) {
-            if (clock64() - t0 > (long long)4e9) { *c.err = 1; break; }
+            if (clock64() - t0 > timeout) { *c.err = 1; break; }
         }
         __threadfence_system();
     }
@@ -200,6 +214,8 @@ VN_API int vn_ipc_open(const void* h_handle64, int64_t offset_bytes, void** h_pt
 VN_API int vn_p2p_init(int rank, int world, void* const* h_bufs, void* const* h_flags, int* err_dev) {
     VN_REQUIRE(world >= 1 && world <= VN_P2P_MAX_RANKS && rank >= 0 && rank < world, "vn_p2p_init: bad rank/world");
     VN_REQUIRE(h_bufs && h_flags && err_dev, "vn_p2p_init: null argument");
+    // ONE exchange context per process: a second initialisation would silently re-route the first owner's kernels
+    VN_REQUIRE(!g_ctx_ready, "vn_p2p_init: the peer-memory exchange is already owned (vn_p2p_shutdown releases it)");
     memset(&g_ctx, 0, sizeof(g_ctx));
     g_ctx.rank = rank; g_ctx.world = world; g_ctx.err = err_dev; g_ctx.epoch = 0; g_ctx.small_ops = 0;
     for (int p = 0; p < world; ++p) {
@@ -208,7 +224,15 @@ VN_API int vn_p2p_init(int rank, int world, void* const* h_bufs, void* const* h_
         g_ctx.bufs[p] = (float*)h_bufs[p];
         g_ctx.flags[p] = (int*)h_flags[p];
     }
+    if (!g_step_sync) VN_CUDA(cudaMalloc(&g_step_sync, 4 * sizeof(int)));
+    VN_CUDA(cudaMemset(g_step_sync, 0, 4 * sizeof(int)));
     g_ctx_ready = true;
+    return VN_OK;
+}
+
+VN_API int vn_p2p_shutdown(void) {
+    g_ctx_ready = false;
+    memset(&g_ctx, 0, sizeof(g_ctx));
     return VN_OK;
 }
 
@@ -222,16 +246,16 @@ VN_API int vn_p2p_allreduce(int64_t n, void* stream) {
     const int sms = vn_sm_count();
     const int e = g_ctx.epoch;
     g_ctx.epoch += 3;
-    p2p_barrier_kernel<<<1, 32, 0, st>>>(g_ctx, e + 1);                      // every rank's gradients are complete
+    p2p_barrier_kernel<<<1, 32, 0, st>>>(g_ctx, e + 1, g_timeout_clocks);                      // every rank's gradients are complete
     VN_CHECK_LAUNCH("p2p_barrier_kernel");
     p2p_reduce_scatter_kernel<<<sms, 512, 0, st>>>(g_ctx, n4, chunk4);
     VN_CHECK_LAUNCH("p2p_reduce_scatter_kernel");
-    p2p_barrier_kernel<<<1, 32, 0, st>>>(g_ctx, e + 2);                      // every slice is reduced
+    p2p_barrier_kernel<<<1, 32, 0, st>>>(g_ctx, e + 2, g_timeout_clocks);                      // every slice is reduced
     VN_CHECK_LAUNCH("p2p_barrier_kernel");
     dim3 grid((unsigned)((sms + g_ctx.world - 2) / (g_ctx.world - 1)), (unsigned)(g_ctx.world - 1));
     p2p_all_gather_kernel<<<grid, 512, 0, st>>>(g_ctx, n4, chunk4);
     VN_CHECK_LAUNCH("p2p_all_gather_kernel");
-    p2p_barrier_kernel<<<1, 32, 0, st>>>(g_ctx, e + 3);                      // nobody reads my buffer any more
+    p2p_barrier_kernel<<<1, 32, 0, st>>>(g_ctx, e + 3, g_timeout_clocks);                      // nobody reads my buffer any more
     VN_CHECK_LAUNCH("p2p_barrier_kernel");
     return VN_OK;
 }
@@ -256,7 +280,7 @@ VN_API int vn_p2p_allreduce_small(float* data, int n, int use_max, void* stream)
     if (g_ctx.world == 1) return VN_OK;
     const int e = ++g_ctx.epoch;
     const int parity = (g_ctx.small_ops++) & 1;
-    vn_launch_pdl(p2p_exchange_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, g_ctx, e, parity, data, n, use_max);
+    vn_launch_pdl(p2p_exchange_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, g_ctx, e, parity, data, n, use_max, g_timeout_clocks);
     VN_CHECK_LAUNCH("p2p_exchange_kernel");
     return VN_OK;
 }
@@ -277,18 +301,162 @@ VN_API int vn_p2p_reduce_adam(int64_t n, float* m, float* v, double lr, double b
     const int e = g_ctx.epoch;
     g_ctx.epoch += 3;
     const int parity = (g_ctx.small_ops++) & 1;
-    vn_launch_pdl(p2p_barrier_kernel, dim3(1), dim3(32), 0, st, g_ctx, e + 1);                      // every rank's gradients are complete
+    vn_launch_pdl(p2p_barrier_kernel, dim3(1), dim3(32), 0, st, g_ctx, e + 1, g_timeout_clocks);                      // every rank's gradients are complete
     VN_CHECK_LAUNCH("p2p_barrier_kernel");
     p2p_reduce_check_kernel<<<sms, 512, 0, st>>>(g_ctx, n4, chunk4, found_inf);
     VN_CHECK_LAUNCH("p2p_reduce_check_kernel");
     // every slice is reduced (nobody reads a peer's gradient after this) + global OR of the inf flags
-    p2p_exchange_kernel<<<1, 32, 0, st>>>(g_ctx, e + 2, parity, found_inf, 1, 1);
+    p2p_exchange_kernel<<<1, 32, 0, st>>>(g_ctx, e + 2, parity, found_inf, 1, 1, g_timeout_clocks);
     VN_CHECK_LAUNCH("p2p_exchange_kernel");
     p2p_adam_push_kernel<<<sms, 512, 0, st>>>(g_ctx, n4, chunk4, m, v, c, found_inf, scale_dev);
     VN_CHECK_LAUNCH("p2p_adam_push_kernel");
-    p2p_barrier_kernel<<<1, 32, 0, st>>>(g_ctx, e + 3);                      // every replica holds every updated slice
+    p2p_barrier_kernel<<<1, 32, 0, st>>>(g_ctx, e + 3, g_timeout_clocks);                      // every replica holds every updated slice
     VN_CHECK_LAUNCH("p2p_barrier_kernel");
     p2p_scaler_update_kernel<<<1, 1, 0, st>>>(scale_dev, growth_tracker, found_inf, 2.0f, 0.5f, 2000);
     VN_CHECK_LAUNCH("p2p_scaler_update_kernel");
+    return VN_OK;
+}
+
+
+// ---- the sharded optimiser as ONE kernel -----------------------------------------------------------------------------
+// vn_p2p_reduce_adam above is six launches with three cross-rank barriers, its inbound reduce and its outbound parameter
+// push never overlap, and its inf check needs a second exchange in the middle.  Here the inf flag is an INPUT (the fused
+// backward kernel -- or vn_grad_check -- has evaluated it on the rank's own gradient: every contribution is bounded, so a
+// sum over <= 8 ranks of finite gradients is finite) and rides in the start barrier's mailbox, which leaves one pass:
+//   start barrier (+ max of the inf flags) -> for every float4 of this rank's slice: sum over the ranks' gradients
+//   (fixed rank order, peer loads) -> Adam with rank-local m / v -> store the new parameters into EVERY replica (peer
+//   stores) -> end barrier -> GradScaler / step-count update.
+// Loads of later elements are in flight while the stores of earlier ones drain, so both NVLink directions are busy for
+// the whole pass.  CTA 0 runs the start barrier and releases the others through a device-scope flag; the LAST CTA to
+// finish (atomic counter) runs the end barrier and the scalar update, so the kernel's completion == "every replica
+// holds every updated slice and nobody reads my gradient buffer any more".
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(512) p2p_step_kernel(P2PCtx c, int64_t n4, int64_t chunk4, float* __restrict__ m,
+                                                       float* __restrict__ v, AdamCfg cfg, float* found_inf, float* scale_dev,
+                                                       int32_t* tracker, float* opt_state, double lr, double beta1, double beta2,
+                                                       int epoch, int parity, int* sync, long long timeout) {
+    vn_pdl_trigger(); vn_pdl_wait();          // this rank's gradients (and its inf flag) are complete
+    __shared__ float s_found;
+    int* go = sync; int* done = sync + 1; float* gfound = reinterpret_cast<float*>(sync + 2);
+    if (blockIdx.x == 0) {
+        // ---- start barrier + max of the inf flags (mailbox slot [parity][rank] of every peer)
+        const int p = threadIdx.x;
+        if (p < c.world) {
+            float* slot = c.mbox[p] + ((size_t)parity * c.world + c.rank) * VN_P2P_MBOX;
+            *reinterpret_cast<volatile float*>(slot) = *found_inf;
+            __threadfence_system();
+            *reinterpret_cast<volatile int*>(c.flags[p] + c.rank) = epoch + 1;
+            volatile int* src = c.flags[c.rank] + p;
+            const long long t0 = clock64();
+            while (*src < epoch + 1) {
+                if (clock64() - t0 > timeout) { *c.err = 1; break; }
+            }
+            __threadfence_system();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float f = 0.0f;
+            const volatile float* mine = c.mbox[c.rank] + (size_t)parity * c.world * VN_P2P_MBOX;
+            for (int q = 0; q < c.world; ++q) f = fmaxf(f, mine[(size_t)q * VN_P2P_MBOX]);
+            if (*reinterpret_cast<volatile int*>(c.err) != 0) f = 1.0f;        // timed out: apply nothing to incomplete data
+            *gfound = f;
+            __threadfence();
+            st_release_gpu(go, epoch + 1);
+        }
+    }
+    if (threadIdx.x == 0) {
+        const long long t0 = clock64();
+        while (ld_acquire_gpu(go) < epoch + 1) {
+            if (clock64() - t0 > 2 * timeout) break;                            // CTA 0 has set *err already
+        }
+        s_found = *reinterpret_cast<volatile float*>(gfound);
+    }
+    __syncthreads();
+    const bool skip = s_found != 0.0f;
+    if (!skip) {
+        cfg.inv_scale = 1.0f / *scale_dev;
+        if (opt_state) { cfg.step_size = opt_state[0]; cfg.bc2_sqrt = opt_state[1]; }
+        const int64_t lo = (int64_t)c.rank * chunk4;
+        const int64_t hi = min(lo + chunk4, n4);
+        float4* m4 = reinterpret_cast<float4*>(m);
+        float4* v4 = reinterpret_cast<float4*>(v);
+        for (int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (int64_t)gridDim.x * blockDim.x) {
+            float4 G = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int p = 0; p < VN_P2P_MAX_RANKS; ++p) {
+                if (p < c.world) {
+                    const float4 g = __ldcv(reinterpret_cast<const float4*>(c.bufs[p]) + i);
+                    G.x += g.x; G.y += g.y; G.z += g.z; G.w += g.w;
+                }
+            }
+            float4 P = reinterpret_cast<const float4*>(c.pbufs[c.rank])[i], M = m4[i], V = v4[i];
+            adam1(P.x, G.x, M.x, V.x, cfg); adam1(P.y, G.y, M.y, V.y, cfg);
+            adam1(P.z, G.z, M.z, V.z, cfg); adam1(P.w, G.w, M.w, V.w, cfg);
+            m4[i] = M; v4[i] = V;
+#pragma unroll
+            for (int q = 0; q < VN_P2P_MAX_RANKS; ++q)
+                if (q < c.world) reinterpret_cast<float4*>(c.pbufs[q])[i] = P;
+        }
+    }
+    // ---- the last CTA to get here closes the step
+    __threadfence_system();
+    __syncthreads();
+    __shared__ int s_last;
+    if (threadIdx.x == 0) s_last = (atomicAdd(done, 1) == (int)gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int p = threadIdx.x;
+    if (p < c.world) {
+        __threadfence_system();
+        *reinterpret_cast<volatile int*>(c.flags[p] + c.rank) = epoch + 2;
+        volatile int* src = c.flags[c.rank] + p;
+        const long long t0 = clock64();
+        while (*src < epoch + 2) {
+            if (clock64() - t0 > timeout) { *c.err = 1; break; }
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *done = 0;
+        // GradScaler.update + Adam's step count (vn_scaler_update_dev)
+        if (skip) { *scale_dev = *scale_dev * 0.5f; *tracker = 0; }
+        else {
+            if (opt_state) vn_opt_state_set(opt_state, __float_as_int(opt_state[2]) + 1, lr, beta1, beta2);
+            const int t = *tracker + 1;
+            if (t == 2000) { const float grown = *scale_dev * 2.0f; if (isfinite(grown)) *scale_dev = grown; *tracker = 0; }
+            else *tracker = t;
+        }
+        *found_inf = 0.0f;
+    }
+}
+
+VN_API int vn_p2p_step(int64_t n, float* m, float* v, double lr, double beta1, double beta2, double eps, float* opt_state,
+                       float* found_inf, float* scale_dev, int32_t* growth_tracker, void* stream) {
+    VN_REQUIRE(g_ctx_ready && g_ctx.mbox[0] && g_ctx.pbufs[0],
+               "vn_p2p_step: vn_p2p_init / vn_p2p_attach (with parameter buffers) have not been called");
+    VN_REQUIRE(n >= 0 && n % 4 == 0, "vn_p2p_step: n must be a multiple of 4 floats");
+    VN_REQUIRE(m && v && opt_state && found_inf && scale_dev && growth_tracker, "vn_p2p_step: null pointer");
+    VN_REQUIRE(vn_aligned(m, 16) && vn_aligned(v, 16), "vn_p2p_step: m / v must be 16-byte aligned");
+    if (n == 0) return VN_OK;
+    const int64_t n4 = n / 4;
+    const int64_t chunk4 = (n4 + g_ctx.world - 1) / g_ctx.world;
+    const AdamCfg c = vn_make_adam_cfg(lr, beta1, beta2, eps, 1, 1.0f);      // step-dependent fields come from opt_state
+    const int e = g_ctx.epoch;
+    g_ctx.epoch += 2;
+    const int parity = (g_ctx.small_ops++) & 1;
+    // all CTAs must be co-resident (grid-wide flags): one per SM
+    vn_launch_pdl(p2p_step_kernel, dim3((unsigned)vn_sm_count()), dim3(512), 0, (cudaStream_t)stream, g_ctx, n4, chunk4, m, v, c,
+                  found_inf, scale_dev, growth_tracker, opt_state, lr, beta1, beta2, e, parity, g_step_sync, g_timeout_clocks);
+    VN_CHECK_LAUNCH("p2p_step_kernel");
     return VN_OK;
 }

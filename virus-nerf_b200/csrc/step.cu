@@ -20,7 +20,8 @@ VN_API int vn_train_step_prepare(const vn_step_t* s, void* stream) {
 
 VN_API int vn_train_step_optim(const vn_step_t* s, void* stream) {
     VN_REQUIRE(s != nullptr, "vn_train_step_optim: null step");
-    VN_TRY(vn_grad_check(s->flat_g, s->n_params, s->found_inf, stream));
+    // VN_HASH_FUSED_SCATTER: the fused backward kernel has already evaluated the inf check on the contributions
+    if (!(s->hash_flags & VN_HASH_FUSED_SCATTER)) VN_TRY(vn_grad_check(s->flat_g, s->n_params, s->found_inf, stream));
     if (s->step_dev) {       // step count on the device: skipped steps do not advance Adam's bias corrections
         VN_TRY(vn_adam_step_dev(s->flat_p, s->flat_g, s->flat_m, s->flat_v, s->n_params, s->lr, s->beta1, s->beta2, s->eps,
                                 (const float*)s->step_dev, s->found_inf, s->scale_dev, stream));
@@ -92,7 +93,8 @@ VN_API int vn_train_step_run(const vn_step_t* s, int64_t S, int phase, int do_op
         if (fused_scatter) {
             // one kernel: d(enc) goes from tensor memory straight into the table gradient
             VN_TRY(vn_mlp_bwd_scatter(s->enc, enc_fmt, s->dirs, W[0], W[1], W[2], W[3], W[4], S, s->d_sigmas, s->d_rgbs, s->unit,
-                                      &s->levels, half_enc ? 1 : 0, table_grad, dW[0], dW[1], dW[2], dW[3], dW[4], stream));
+                                      &s->levels, half_enc ? 1 : 0, table_grad, dW[0], dW[1], dW[2], dW[3], dW[4], s->found_inf,
+                                      stream));
         } else {
             VN_TRY(vn_mlp_bwd(s->enc, half_enc ? (enc_fmt | VN_MLP_DENC_F16) : enc_fmt, s->dirs, W[0], W[1], W[2], W[3], W[4], S, 0,
                               s->d_sigmas, s->d_rgbs, s->d_enc, dW[0], dW[1], dW[2], dW[3], dW[4], stream));

@@ -200,6 +200,7 @@ class TrainEngine:
                 if self.comm == "nccl":
                     self._p2p = None
         self._p2p_fused = self.comm == "p2p_fused"
+        self._err_host = torch.zeros(1, dtype=torch.int32).pin_memory() if (self._p2p is not None) else None
         self._hash_slice_idx = [i for i, p in enumerate(params) if p is enc.hash_table][0]
         self._structs = [self._new_step_struct(), self._new_step_struct()] if self.device.type == "cuda" else None
 
@@ -326,6 +327,8 @@ class TrainEngine:
                         d_opacity=ws.get("d_op", N))
             _lib.call("vn_train_step_prepare", st)
             self._counter_hosts[par].copy_(self._counters[par], non_blocking=True)
+            if self._err_host is not None:       # time-out word of the peer-memory exchange rides on the same host sync
+                self._err_host.copy_(self._p2p_err, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record()
             return ev, nz
@@ -362,6 +365,9 @@ class TrainEngine:
         if tk["side"]:
             torch.cuda.current_stream().wait_event(tk["event"])           # main stream: front half done
         S = int(self._counter_hosts[tk["par"]][0])
+        if self._err_host is not None and int(self._err_host[0]) != 0:
+            raise RuntimeError("TrainEngine: a cross-rank wait of the peer-memory exchange timed out (VN_P2P_TIMEOUT_MS): "
+                               "the replicas are no longer synchronised -- restart from the last checkpoint")
         self.last_samples = S
         st.set_ptrs(xyzs=ws.get("xyzs", S, 3), dirs=ws.get("dirs", S, 3), unit=ws.get("unit", S, 3),
                     deltas=ws.get("deltas", S), ts=ws.get("ts", S), enc=ws.get("enc", S, 32), sigmas=ws.get("sig", S),
@@ -386,8 +392,12 @@ class TrainEngine:
         if self._p2p_fused:
             # reduce-scatter + inf check + sharded Adam + parameter push + scaler update, on the main stream: the next
             # step's main-stream work needs its result anyway, only the front half of the next step (side stream) overlaps
-            _lib.call("vn_p2p_reduce_adam", self.n_params, self.flat_m, self.flat_v, self.lr, self.betas[0],
-                      self.betas[1], self.eps, self.adam_step, self.found_inf, self.scale, self.growth_tracker)
+            # ONE kernel (csrc/p2p_allreduce.cu, vn_p2p_step); its inf flag is this rank's own check: evaluated inside the
+            # fused backward kernel, else by a pass over the local gradient
+            if not self.fused_scatter:
+                _lib.call("vn_grad_check", self.flat_g, self.n_params, self.found_inf)
+            _lib.call("vn_p2p_step", self.n_params, self.flat_m, self.flat_v, self.lr, self.betas[0], self.betas[1],
+                      self.eps, self.opt_state, self.found_inf, self.scale, self.growth_tracker)
             if next_data is not None and not update_due:
                 self._ticket = self.prepare(next_data, elapse_time, noise=next_noise, ready=ready_next)
         else:
@@ -441,6 +451,19 @@ class TrainEngine:
                   self.lr, self.betas[0], self.betas[1], self.eps, self.opt_state, self.found_inf, self.scale)
         _lib.call("vn_scaler_update_dev", self.scale, self.growth_tracker, self.found_inf, 2.0, 0.5, 2000,
                   self.opt_state, self.lr, self.betas[0], self.betas[1])
+
+    def close(self):
+        """release the process-wide peer-memory exchange (one engine may own it at a time)"""
+        if getattr(self, "_p2p", None) is not None:
+            torch.cuda.synchronize(self.device)
+            _lib.p2p_shutdown()
+            self._p2p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def applied_steps(self):
         """number of optimiser steps that were applied (torch Adam's state['step']); synchronises"""

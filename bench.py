@@ -232,6 +232,13 @@ def run_ours(a):
             return float(t)
         return ms
 
+    def global_loss(loss):
+        """a rank's loss_out is ITS share sum_k w_k sums_k(local) / counts_k(global): the shares add up to the loss"""
+        t = loss.detach().clone().reshape(1).float()
+        if world > 1:
+            dist.all_reduce(t)
+        return float(t)
+
     def check_p2p(eng):
         if world > 1 and eng._p2p is not None and int(eng._p2p_err) != 0:
             raise SystemExit("bench.py: peer-memory exchange barrier timed out")
@@ -345,14 +352,14 @@ def run_ours(a):
             dist.all_reduce(clo, op=dist.ReduceOp.MIN); dist.all_reduce(chi, op=dist.ReduceOp.MAX)
             same = bool((clo == chi).all())
         return {"window_ms": window_ms, "launches": launches, "samples": [int(x) for x in samples], "prof": prof, "h2d": h2d,
-                "d2h": d2h, "loss": float(loss), "same": same, "eng": eng, "comm": eng.comm}
+                "d2h": d2h, "loss": global_loss(loss), "same": same, "eng": eng, "comm": eng.comm}
 
     clocks = ClockSampler(local)
     clocks.start()
     ph = run_phase(pinned=False)
     clk = clocks.stop()
     eng = ph["eng"]
-    extra = {} if a.no_extra else extra_configs(a, eng, scene, dev, world, rank, barrier, max_over_ranks, make_batches, check_p2p)
+    extra = {} if a.no_extra else extra_configs(a, eng, scene, dev, world, rank, barrier, max_over_ranks, make_batches, check_p2p, global_loss)
     eng.close()
     del eng
     ph["eng"] = None
@@ -469,7 +476,7 @@ def ncu_traffic():
         return {}
 
 
-def extra_configs(a, eng, scene, dev, world, rank, barrier, max_over_ranks, make_batches, check_p2p):
+def extra_configs(a, eng, scene, dev, world, rank, barrier, max_over_ranks, make_batches, check_p2p, global_loss):
     """BASELINE.json configs[2] and [4], untimed by the headline (after its timed windows, before the end-to-end phase):
     config 5 = 1080p test-time frame (rays sharded, no collective) + occupancy-update sweep; config 3 = Robot@Home2-shaped
     scene, T = 2^22, 2^18 rays per step split over the ranks (strong scaling), half-precision encoder."""
@@ -544,7 +551,7 @@ def extra_configs(a, eng, scene, dev, world, rank, barrier, max_over_ranks, make
         noise3 = [torch.rand(n3, device=dev, generator=gen)[lo3:hi3].contiguous() for _ in b3]   # same jitter as the 1-GPU run
         losses = []
         for it in range(W3):
-            losses.append(float(eng3.step_fast(b3[it], noise=noise3[it])))
+            losses.append(eng3.step_fast(b3[it], noise=noise3[it]).clone())
         barrier()
         _lib.profile_start(["hash_encode_fwd", "hash_encode_bwd", "mlp_fwd", "mlp_bwd", "mlp_bwd_hash_scatter"])
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -581,7 +588,7 @@ def extra_configs(a, eng, scene, dev, world, rank, barrier, max_over_ranks, make
             "samples_per_step_per_gpu": int(statistics.mean(smp)), "steps": K3, "warmup": W3,
             "encoder": "half (fp16 table copy per step, fp16 encoding and encoding gradient, fp32 scatter)", "log2_T": 22,
             "table_mb_fp32": round(eng3.model.pos_encoder.hash_table.numel() * 4 / 2 ** 20, 1), "grad_exchange": eng3.comm,
-            "losses": [round(float(x), 6) for x in losses], "kernels": k3,
+            "losses": [round(global_loss(x), 6) for x in losses], "kernels": k3,
             "note": "one globally seeded batch per step, rank r trains on rays [r N/n, (r+1) N/n) with the jitter of the global "
                     "batch: `losses` must agree between N = 1 and N > 1 (global loss normalisers, summed gradients)"}
         eng3.close()

@@ -327,7 +327,9 @@ VN_API int vn_p2p_reduce_adam(int64_t n, float* m, float* v, double lr, double b
 //   (fixed rank order, peer loads) -> Adam with rank-local m / v -> store the new parameters into EVERY replica (peer
 //   stores) -> end barrier -> GradScaler / step-count update.
 // Loads of later elements are in flight while the stores of earlier ones drain, so both NVLink directions are busy for
-// the whole pass.  CTA 0 runs the start barrier and releases the others through a device-scope flag; the LAST CTA to
+// the whole pass (a rank also serves its peers' loads while it loads, so either direction carries 2 (n-1)/n of the buffer
+// per step: 80 MB at 8 ranks, i.e. >= 0.09 ms at the 900 GB/s of NVLink 5; measured 0.172 ms, NCCL's allreduce of the same
+// buffer alone 0.209 ms).  CTA 0 runs the start barrier and releases the others through a device-scope flag; the LAST CTA to
 // finish (atomic counter) runs the end barrier and the scalar update, so the kernel's completion == "every replica
 // holds every updated slice and nobody reads my gradient buffer any more".
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
@@ -345,6 +347,7 @@ __global__ void __launch_bounds__(512) p2p_step_kernel(P2PCtx c, int64_t n4, int
                                                        int epoch, int parity, int* sync, long long timeout) {
     vn_pdl_trigger(); vn_pdl_wait();          // this rank's gradients (and its inf flag) are complete
     __shared__ float s_found;
+    __shared__ int s_last;
     int* go = sync; int* done = sync + 1; float* gfound = reinterpret_cast<float*>(sync + 2);
     if (blockIdx.x == 0) {
         // ---- start barrier + max of the inf flags (mailbox slot [parity][rank] of every peer)
@@ -409,7 +412,6 @@ __global__ void __launch_bounds__(512) p2p_step_kernel(P2PCtx c, int64_t n4, int
     // ---- the last CTA to get here closes the step
     __threadfence_system();
     __syncthreads();
-    __shared__ int s_last;
     if (threadIdx.x == 0) s_last = (atomicAdd(done, 1) == (int)gridDim.x - 1) ? 1 : 0;
     __syncthreads();
     if (!s_last) return;
@@ -454,7 +456,11 @@ VN_API int vn_p2p_step(int64_t n, float* m, float* v, double lr, double beta1, d
     const int e = g_ctx.epoch;
     g_ctx.epoch += 2;
     const int parity = (g_ctx.small_ops++) & 1;
-    // all CTAs must be co-resident (grid-wide flags): one per SM
+    // all CTAs must be co-resident (grid-wide flags): one per SM; half of them reduce, half push (VN_P2P_STEP_SPLIT=0: every
+    // thread does both)
+    // all CTAs must be co-resident (grid-wide flags): one per SM.  (Measured at 2 and 8 ranks, profiles/r2_dp.md: splitting
+    // the CTAs into reducers and pushers, or running "all loads, grid barrier, all stores", is not faster -- both NVLink
+    // directions are busy in either phase, because a rank serves its peers' loads while it loads.)
     vn_launch_pdl(p2p_step_kernel, dim3((unsigned)vn_sm_count()), dim3(512), 0, (cudaStream_t)stream, g_ctx, n4, chunk4, m, v, c,
                   found_inf, scale_dev, growth_tracker, opt_state, lr, beta1, beta2, e, parity, g_step_sync, g_timeout_clocks);
     VN_CHECK_LAUNCH("p2p_step_kernel");

@@ -248,6 +248,23 @@ int vn_occ_bayes_update(float* grid, int grid_size, const int32_t* cell_idxs, in
                         float* new_probs_tmp, void* stream);
 int vn_occ_decay_pack(float* grid, int grid_size, float decay, int apply_decay, float threshold,
                       uint8_t* bitfield, void* stream);
+/* OccupancyGrid.update (:65-105) after its two batches have been sampled, as ONE host call: depth-sensor update of
+ * N_ray rays (r_rays_o / r_rays_d [N_ray,3], r_meas [N_ray], no NaN), NeRF update of N_nerf rays (n_noise [N_nerf,M,3]
+ * uniform [0,1): the torch.rand of :326) with NGP.density (networks.py:134-148) evaluated as (x - xyz_min) /
+ * (xyz_max - xyz_min) -> hash forward (f32 table, or -- when table_h != NULL -- the half-precision encoder on a fresh
+ * fp16 copy of the table, hash_encoder_half.py:367) -> density-only fused MLP (W1 [64,32], W2 [16,64]); then the warm-up
+ * decay (apply_decay) and the bitfield repack.  The same kernels in the same order as vn_occ_calc_pos_prob /
+ * vn_occ_bayes_update / vn_hash_encode_fwd_* / vn_mlp_fwd / vn_occ_nerf_prob / vn_occ_decay_pack called one by one:
+ * the grid is bit-identical.  winner: i32 [grid_size^3] filled with -1 (restored on return); ws: caller-owned scratch of
+ * at least vn_occ_update_ws_floats(N_ray, N_nerf, M) floats, 16-byte aligned. */
+int64_t vn_occ_update_ws_floats(int64_t N_ray, int64_t N_nerf, int M);
+int vn_occ_update(float* grid, int grid_size, uint8_t* bitfield, int32_t* winner, const float* r_rays_o,
+                  const float* r_rays_d, const float* r_meas, int64_t N_ray, const float* n_rays_o,
+                  const float* n_rays_d, const float* n_noise, int64_t N_nerf, int M, int I, float scale,
+                  float noise_every_m, float p_false, float std_every_m, float prob_min, double nerf_thr_max,
+                  float nerf_slope, float decay, int apply_decay, float threshold, const float* table,
+                  void* table_h, const vn_hash_levels_t* lv, int hash_flags, const float* W1, const float* W2,
+                  float xyz_min, float xyz_max, float* ws, int64_t ws_floats, void* stream);
 
 /* f2 (caller side). training/loss.py:34-198 as two kernels around the (optional) allreduce of
  * the valid counts.  Per-ray inputs: rgb [N,3] (composite output, before background), opacity,
@@ -389,7 +406,13 @@ typedef struct vn_step {
 } vn_step_t;
 
 int vn_train_step_prepare(const vn_step_t* h_step, void* stream);
-/* phase: 0 = whole forward+backward, 1 = up to and including loss fwd, 2 = from loss bwd on */
+/* phase: 0 = whole forward+backward, 1 = up to and including loss fwd, 2 = from loss bwd on; + VN_STEP_SKIP_EXPAND when
+ * the caller has already enqueued vn_train_step_expand for this step.
+ * vn_train_step_expand: the sample-expansion stage alone (march write, or the expansion of the single-pass march's
+ * ts_rows, incl. the per-ray SH planes): it depends on _prepare's outputs only -- not on the parameters -- so a caller
+ * with double-buffered sample arrays can run it on another stream under the previous step's backward / optimiser. */
+#define VN_STEP_SKIP_EXPAND 8
+int vn_train_step_expand(const vn_step_t* h_step, int64_t S, void* stream);
 int vn_train_step_run(const vn_step_t* h_step, int64_t S, int phase, int do_optim, void* stream);
 int vn_train_step_optim(const vn_step_t* h_step, void* stream);
 
@@ -459,6 +482,17 @@ int vn_batch_assemble(const int32_t* img_idxs, const int32_t* pix_idxs, int64_t 
                       const int32_t* sensor_ids, const float* times, float* rays_o, float* rays_d,
                       float* rgb, float* out_depth0, float* out_depth1, float* out_depth2,
                       float* out_depth3, int32_t* ids_out, float* time_out, int32_t* err, void* stream);
+
+/* (f) row 2, resident ray pool: batch n = pool[sel[draw[n]]] (sel == NULL: pool[draw[n]]) for rays that are already
+ * assembled on the device (the real-time mode's seen-so-far rays; the synthetic dataset of the benchmark): rays_o /
+ * rays_d / rgb [pool,3] and up to three per-ray depth sensors [pool]; draw [B] i64 uniform integers (torch.randint),
+ * sel [n_sel] i64 = the rays that carry a measurement of the sensor being sampled (datasets/dataset_base.py:216-222's
+ * valid-depth filter, precomputed).  ONE launch for all outputs; an out-of-range index leaves NaN and sets err[0]. */
+int vn_pool_gather(const int64_t* draw, const int64_t* sel, int64_t n_sel, int64_t pool, int64_t B,
+                   const float* rays_o, const float* rays_d, const float* rgb, const float* depth0,
+                   const float* depth1, const float* depth2, float* out_rays_o, float* out_rays_d,
+                   float* out_rgb, float* out_depth0, float* out_depth1, float* out_depth2, int32_t* err,
+                   void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * (f) row 3. NGPGrid, modules/ngp_grid.py:37-152 (the Instant-NGP baseline grid of the ablation).

@@ -256,6 +256,37 @@ def test_occupancy_update_runs_and_is_deterministic(setup):
     assert not torch.equal(g0, g1)
 
 
+@pytest.mark.parametrize("half_opt", [False, True])
+def test_occupancy_update_single_call_is_bit_identical(half_opt):
+    """vn_occ_update (the whole OccupancyGrid.update after sampling as one C call, caller-owned workspace) produces the
+    same grid and bitfield, bit for bit, as the reference-shaped sequence _rayUpdate / _nerfUpdate / decay + repack"""
+    from virus_nerf_b200 import synthetic
+    from virus_nerf_b200.engine import TrainEngine
+    args = synthetic.make_args(device=DEV, batch_size=256)
+    ds = synthetic.SyntheticDataset(pool_size=1 << 13, n_images=8, device=DEV)
+    eng = TrainEngine(args, ds, DEV, half_opt=half_opt)
+    og = eng.model.occupancy_grid
+    if half_opt:
+        with torch.no_grad():
+            torch.manual_seed(4)
+            eng.model.pos_encoder.hash_table.copy_(torch.rand_like(eng.model.pos_encoder.hash_table) * 0.2 - 0.1)
+    assert og._native_model(torch.device(DEV)) is eng.model
+    results = []
+    g0, step0 = og.occ_3d_grid.clone(), og.update_step
+    for native in (True, False, True):
+        og.native_update = native
+        og.occ_3d_grid.copy_(g0); og.update_step = step0
+        torch.manual_seed(5); og.dataset.gen.manual_seed(5)
+        with torch.autocast(device_type="cuda", dtype=torch.float16):
+            for _ in range(3):                                      # three updates: decay steps and re-marked cells
+                og.update(elapse_time=0.0)
+        results.append((og.occ_3d_grid.clone(), og.getBitfield().clone()))
+    assert not torch.equal(results[0][0], g0)
+    for k in (1, 2):
+        assert torch.equal(results[0][0], results[k][0]) and torch.equal(results[0][1], results[k][1])
+    assert (og._winner == -1).all()
+
+
 @pytest.mark.parametrize("enc_layout,single_pass,fused", [("chunks", True, True), ("chunks", True, False),
                                                           ("planar", True, False), ("rows", False, False)])
 def test_fast_step_matches_autograd_step(monkeypatch, enc_layout, single_pass, fused):

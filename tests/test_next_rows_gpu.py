@@ -190,3 +190,25 @@ def test_engine_trains_with_the_ngp_grid():
     g = eng.model.occupancy_grid
     assert g.getBitfield().numel() == 128 ** 3 // 8 and 0 < int(g.getBitfield().count_nonzero())
     assert np.isfinite(g.threshold) and g.threshold <= float(np.float32(0.01 * 1024 / 3 ** 0.5))
+
+
+@pytest.mark.parametrize("kind", ["ethz", "rh2"])
+def test_pool_gather_equals_advanced_indexing(kind):
+    """vn_pool_gather (one launch per batch segment) returns exactly the batches of the torch advanced-indexing path, for
+    the training strategy (three segments) and the occupancy-update strategies (valid-sensor subsets)"""
+    from virus_nerf_b200 import synthetic
+    ds = synthetic.SyntheticDataset(kind=kind, pool_size=1 << 13, n_images=8, device=DEV, seed=3)
+    strategies = [{"imgs": "all", "pixs": {"valid_uss": 0.4, "valid_tof": 0.4}}, {"imgs": "all", "pixs": "valid_uss"},
+                  {"imgs": "all", "pixs": "valid_tof"}, {"imgs": "all", "pixs": "random"}, None]
+    for strat in strategies:
+        for B in (1, 257, 4096):
+            ds.fast_gather = True; ds.gen.manual_seed(11)
+            fast = ds(B, strat)
+            ds.fast_gather = False; ds.gen.manual_seed(11)
+            slow = ds(B, strat)
+            for k in ("rays_o", "rays_d", "rgb"):
+                assert fast[k].is_contiguous() and fast[k].shape == slow[k].shape and torch.equal(fast[k], slow[k]), (strat, B, k)
+            assert set(fast["depth"]) == set(slow["depth"]) == set(ds.sensors)
+            for k in ds.sensors:
+                assert torch.equal(torch.nan_to_num(fast["depth"][k], nan=-1.0), torch.nan_to_num(slow["depth"][k], nan=-1.0))
+            assert fast["depth_valid_by_construction"] == slow["depth_valid_by_construction"]

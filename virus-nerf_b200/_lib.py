@@ -27,6 +27,7 @@ VN_HASH_PAIR_LOADS = 2048
 VN_HASH_SKIP_ZERO_GRADS = 4096
 VN_HASH_F16_CHUNKS = 8192
 VN_HASH_FUSED_SCATTER = 16384
+VN_STEP_SKIP_EXPAND = 8
 
 
 class HashLevels(ctypes.Structure):
@@ -108,6 +109,7 @@ _SPECS = {
     "vn_occ_nerf_prob": "pldfppps",
     "vn_occ_bayes_update": "piplppp" "ps",
     "vn_occ_decay_pack": "pififps",
+    "vn_occ_update": "pipp" "pppl" "pppl" "ii" "fffff" "df" "fif" "pp" "hi" "pp" "ff" "pl" "s",
     "vn_loss_fwd": "ppppppp" "lff" "pp" "s",
     "vn_loss_bwd": "ppppppp" "lff" "pp" "ffff" "p" "pppp" "s",
     "vn_grad_check": "plps",
@@ -119,12 +121,14 @@ _SPECS = {
     "vn_umma_selftest": "iiippps",
     "vn_train_step_prepare": "hs",
     "vn_train_step_run": "hliis",
+    "vn_train_step_expand": "hls",
     "vn_train_step_optim": "hs",
     "vn_p2p_allreduce": "ls",
     "vn_p2p_allreduce_small": "piis",
     "vn_p2p_reduce_adam": "lpp" "dddd" "i" "ppp" "s",
     "vn_p2p_step": "lpp" "dddd" "pppp" "s",
     "vn_batch_assemble": "ppl" "ppl" "pil" "pi" "pppp" "pp" "ppp" "pppp" "pp" "p" "s",
+    "vn_pool_gather": "pplll" "pppppp" "pppppp" "p" "s",
     "vn_ngp_sample_occupied": "plfplpps",
     "vn_ngp_cell_positions": "ppliffps",
     "vn_ngp_grid_update": "ppplpplfps",
@@ -163,6 +167,8 @@ def lib():
         L.vn_ngp_threshold_tmp_bytes.restype = ctypes.c_int64
         L.vn_march_scan_tmp_ints.argtypes = [ctypes.c_int64]
         L.vn_launch_count.restype = ctypes.c_int64
+        L.vn_occ_update_ws_floats.restype = ctypes.c_int64
+        L.vn_occ_update_ws_floats.argtypes = [ctypes.c_int64, ctypes.c_int64, ctypes.c_int]
         for name, spec in _SPECS.items():
             fn = getattr(L, name)
             fn.restype = ctypes.c_int
@@ -313,7 +319,7 @@ def hash_levels(base_res, max_res, levels, max_params):
 def exported_symbols():
     """names declared in include/virusnerf.h (used by the CPU-side ABI test)"""
     return ["vn_last_error", "vn_abi_version", "vn_launch_count", "vn_ipc_get_handle", "vn_ipc_open", "vn_p2p_init", "vn_p2p_attach", "vn_p2p_shutdown", "vn_profile_enable", "vn_profile_enable_mask", "vn_set_pdl", "vn_profile_count", "vn_profile_get", "vn_device_info", "vn_march_scan_tmp_ints", "vn_adam_config",
-            "vn_ngp_select_tmp_ints", "vn_ngp_threshold_tmp_bytes"] + list(_SPECS)
+            "vn_ngp_select_tmp_ints", "vn_ngp_threshold_tmp_bytes", "vn_occ_update_ws_floats"] + list(_SPECS)
 
 
 def p2p_slice(n, rank, world):

@@ -83,3 +83,54 @@ VN_API int vn_batch_assemble(const int32_t* img_idxs, const int32_t* pix_idxs, i
     VN_CHECK_LAUNCH("batch_assemble_kernel");
     return VN_OK;
 }
+
+// ---- gather from a pre-assembled RAY POOL (rays_o / rays_d / rgb / up to three depth sensors already per ray) -----------
+// The reference's real-time mode keeps the rays of the images seen so far resident on the device; a batch is
+// pool[sel[draw[n]]] (sel = the subset of rays that carry a measurement of the sensor being sampled, or NULL for the
+// whole pool).  One launch writes all six outputs instead of one advanced-indexing launch per tensor.
+__global__ void __launch_bounds__(256) pool_gather_kernel(const int64_t* __restrict__ draw, const int64_t* __restrict__ sel,
+                                                          int64_t n_sel, int64_t pool, int64_t B,
+                                                          const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                          const float* __restrict__ rgb, const float* __restrict__ d0,
+                                                          const float* __restrict__ d1, const float* __restrict__ d2,
+                                                          float* __restrict__ o_rays_o, float* __restrict__ o_rays_d,
+                                                          float* __restrict__ o_rgb, float* __restrict__ o_d0,
+                                                          float* __restrict__ o_d1, float* __restrict__ o_d2, int32_t* err) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= B) return;
+    int64_t i = draw[n];
+    bool ok = i >= 0 && i < (sel ? n_sel : pool);
+    if (ok && sel) { i = sel[i]; ok = i >= 0 && i < pool; }
+    if (!ok) {
+        if (err) *err = 1;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { o_rays_o[3 * n + k] = NAN; o_rays_d[3 * n + k] = NAN; if (o_rgb) o_rgb[3 * n + k] = NAN; }
+        if (o_d0) o_d0[n] = NAN; if (o_d1) o_d1[n] = NAN; if (o_d2) o_d2[n] = NAN;
+        return;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        o_rays_o[3 * n + k] = __ldg(rays_o + 3 * i + k);
+        o_rays_d[3 * n + k] = __ldg(rays_d + 3 * i + k);
+        if (o_rgb) o_rgb[3 * n + k] = __ldg(rgb + 3 * i + k);
+    }
+    if (o_d0) o_d0[n] = __ldg(d0 + i);
+    if (o_d1) o_d1[n] = __ldg(d1 + i);
+    if (o_d2) o_d2[n] = __ldg(d2 + i);
+}
+
+VN_API int vn_pool_gather(const int64_t* draw, const int64_t* sel, int64_t n_sel, int64_t pool, int64_t B,
+                          const float* rays_o, const float* rays_d, const float* rgb, const float* depth0,
+                          const float* depth1, const float* depth2, float* out_rays_o, float* out_rays_d, float* out_rgb,
+                          float* out_depth0, float* out_depth1, float* out_depth2, int32_t* err, void* stream) {
+    VN_REQUIRE(B >= 0 && pool >= 1 && (!sel || n_sel >= 1), "vn_pool_gather: bad sizes");
+    if (B == 0) return VN_OK;
+    VN_REQUIRE(draw && rays_o && rays_d && out_rays_o && out_rays_d, "vn_pool_gather: null pointer");
+    VN_REQUIRE((!out_rgb || rgb) && (!out_depth0 || depth0) && (!out_depth1 || depth1) && (!out_depth2 || depth2),
+               "vn_pool_gather: output without a source");
+    pool_gather_kernel<<<vn_blocks(B, 256), 256, 0, (cudaStream_t)stream>>>(draw, sel, n_sel, pool, B, rays_o, rays_d, rgb, depth0,
+                                                                           depth1, depth2, out_rays_o, out_rays_d, out_rgb,
+                                                                           out_depth0, out_depth1, out_depth2, err);
+    VN_CHECK_LAUNCH("pool_gather_kernel");
+    return VN_OK;
+}

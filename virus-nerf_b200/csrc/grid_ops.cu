@@ -130,7 +130,8 @@ __global__ void __launch_bounds__(128) occ_calc_pos_prob_kernel(
     const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ noise,
     const float* __restrict__ meas, int64_t N, int M, int I, int G, float scale, float noise_every_m, float p_false,
     float std_every_m, float prob_min, float* __restrict__ cell_dists, float* __restrict__ cell_pos,
-    int32_t* __restrict__ cell_idxs, float* __restrict__ probs_occ, float* __restrict__ probs_emp) {
+    int32_t* __restrict__ cell_idxs, float* __restrict__ probs_occ, float* __restrict__ probs_emp,
+    float* __restrict__ unit_pos = nullptr, float xyz_min = 0.0f, float xyz_max = 1.0f) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= N * M) return;
     const int64_t n = t / M;
@@ -158,6 +159,7 @@ __global__ void __launch_bounds__(128) occ_calc_pos_prob_kernel(
             p = vn_add(p, vn_mul(vn_mul(noise_every_m, dist), nz));                  // :327
         }
         if (cell_pos) cell_pos[3 * t + k] = p;
+        if (unit_pos) unit_pos[3 * t + k] = vn_div(vn_sub(p, xyz_min), vn_sub(xyz_max, xyz_min));   // networks.py:141
         if (cell_idxs) {
             const float mi = vn_div(vn_mul((float)(G - 1), vn_add(p, scale)), vn_mul(2.0f, scale));   // :479
             int ii = (int)rintf(mi);                     // torch.round = half to even
@@ -344,4 +346,76 @@ VN_API int vn_occ_decay_pack(float* grid, int grid_size, float decay, int apply_
     decay_pack_kernel<<<vn_blocks(nb, 256), 256, 0, (cudaStream_t)stream>>>(grid, grid_size, decay, apply_decay, threshold, nb, bitfield);
     VN_CHECK_LAUNCH("decay_pack_kernel");
     return VN_OK;
+}
+
+// ---- a14, the whole update as ONE host call ------------------------------------------------------------------------
+// OccupancyGrid.update (occupancy_grid.py:65-105) after the two batches have been sampled: depth-sensor update
+// (_rayUpdate :225-258), NeRF update (_nerfUpdate :261-290 with NGP.density, networks.py:134-148, as hash forward +
+// density-only fused MLP), warm-up decay and bitfield repack.  The same kernels in the same order as the module-level
+// calls (bit-identical grid), enqueued from C with a caller-owned workspace: no allocation, no Python between launches.
+static inline int64_t align4(int64_t n) { return (n + 3) / 4 * 4; }
+
+VN_API int64_t vn_occ_update_ws_floats(int64_t N_ray, int64_t N_nerf, int M) {
+    if (N_ray < 0 || N_nerf < 0 || M < 1) return -1;
+    const int64_t r = N_ray * M, n = N_nerf * M;
+    // ray: idx 3r | po r | pe r | tmp r          nerf: pos 3n | unit 3n | idx 3n | enc 32n | sigma n | po n | pe n | tmp n
+    return align4(3 * r) + 3 * align4(r) + 3 * align4(3 * n) + align4(32 * n) + 4 * align4(n) + 1024;
+}
+
+VN_API int vn_occ_update(float* grid, int grid_size, uint8_t* bitfield, int32_t* winner, const float* r_rays_o,
+                         const float* r_rays_d, const float* r_meas, int64_t N_ray, const float* n_rays_o,
+                         const float* n_rays_d, const float* n_noise, int64_t N_nerf, int M, int I, float scale,
+                         float noise_every_m, float p_false, float std_every_m, float prob_min, double nerf_thr_max,
+                         float nerf_slope, float decay, int apply_decay, float threshold, const float* table,
+                         void* table_h, const vn_hash_levels_t* lv, int hash_flags, const float* W1, const float* W2,
+                         float xyz_min, float xyz_max, float* ws, int64_t ws_floats, void* stream) {
+    VN_REQUIRE(grid && bitfield && winner && ws, "vn_occ_update: null pointer");
+    VN_REQUIRE(N_ray >= 0 && N_nerf >= 0 && M >= 2 && I >= 2, "vn_occ_update: bad sizes");
+    VN_REQUIRE(N_ray == 0 || (r_rays_o && r_rays_d && r_meas), "vn_occ_update: null ray-update batch");
+    VN_REQUIRE(N_nerf == 0 || (n_rays_o && n_rays_d && n_noise && table && lv && W1 && W2), "vn_occ_update: null NeRF-update input");
+    VN_REQUIRE(ws_floats >= vn_occ_update_ws_floats(N_ray, N_nerf, M), "vn_occ_update: workspace too small (vn_occ_update_ws_floats)");
+    VN_REQUIRE(vn_aligned(ws, 16), "vn_occ_update: workspace must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t r = N_ray * M, n = N_nerf * M;
+    float* p = ws;
+    int32_t* r_idx = (int32_t*)p; p += align4(3 * r);
+    float* r_po = p; p += align4(r);
+    float* r_pe = p; p += align4(r);
+    float* r_tmp = p; p += align4(r);
+    float* n_pos = p; p += align4(3 * n);
+    float* n_unit = p; p += align4(3 * n);
+    int32_t* n_idx = (int32_t*)p; p += align4(3 * n);
+    float* n_enc = p; p += align4(32 * n);
+    float* n_sig = p; p += align4(n);
+    float* n_po = p; p += align4(n);
+    float* n_pe = p; p += align4(n);
+    float* n_tmp = p; p += align4(n);
+    float* scratch = p;                                    // 1024 floats: vn_occ_nerf_prob's partial sums
+    if (N_ray > 0) {       // _rayUpdate: _calcPos (no noise) + _rayProb in one kernel, then _updateGrid
+        occ_calc_pos_prob_kernel<<<vn_blocks(r, 128), 128, 0, st>>>(r_rays_o, r_rays_d, nullptr, r_meas, N_ray, M, I, grid_size,
+                                                                   scale, noise_every_m, p_false, std_every_m, prob_min, nullptr,
+                                                                   nullptr, r_idx, r_po, r_pe);
+        VN_CHECK_LAUNCH("occ_calc_pos_prob_kernel");
+        int rc = vn_occ_bayes_update(grid, grid_size, r_idx, r, r_po, r_pe, winner, r_tmp, stream);
+        if (rc) return rc;
+    }
+    if (N_nerf > 0) {      // _nerfUpdate: _calcPos with position noise -> NGP.density -> _nerfProb -> _updateGrid
+        occ_calc_pos_prob_kernel<<<vn_blocks(n, 128), 128, 0, st>>>(n_rays_o, n_rays_d, n_noise, nullptr, N_nerf, M, I, grid_size,
+                                                                   scale, noise_every_m, p_false, std_every_m, prob_min, nullptr,
+                                                                   n_pos, n_idx, nullptr, nullptr, n_unit, xyz_min, xyz_max);
+        VN_CHECK_LAUNCH("occ_calc_pos_prob_kernel");
+        int rc;
+        if (table_h) {     // half-precision encoder: fp16 copy of the table per call (hash_encoder_half.py:367), fp16 rows
+            rc = vn_f32_to_f16(table, table_h, 2 * lv->total_entries, stream); if (rc) return rc;
+            rc = vn_hash_encode_fwd_f16(n_unit, table_h, n_enc, n, lv, hash_flags, stream); if (rc) return rc;
+            rc = vn_mlp_fwd(n_enc, 1, nullptr, W1, W2, nullptr, nullptr, nullptr, n, 1, n_sig, nullptr, nullptr, stream);
+        } else {
+            rc = vn_hash_encode_fwd_f32(n_unit, table, n_enc, n, lv, hash_flags, stream); if (rc) return rc;
+            rc = vn_mlp_fwd(n_enc, 0, nullptr, W1, W2, nullptr, nullptr, nullptr, n, 1, n_sig, nullptr, nullptr, stream);
+        }
+        if (rc) return rc;
+        rc = vn_occ_nerf_prob(n_sig, n, nerf_thr_max, nerf_slope, scratch, n_po, n_pe, stream); if (rc) return rc;
+        rc = vn_occ_bayes_update(grid, grid_size, n_idx, n, n_po, n_pe, winner, n_tmp, stream); if (rc) return rc;
+    }
+    return vn_occ_decay_pack(grid, grid_size, decay, apply_decay, threshold, bitfield, stream);
 }

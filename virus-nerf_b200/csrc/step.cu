@@ -35,7 +35,29 @@ VN_API int vn_train_step_optim(const vn_step_t* s, void* stream) {
     return VN_OK;
 }
 
+// the sample-expansion stage of a step (march write / expand): depends only on the front half, not on the parameters, so
+// the caller may enqueue it early on another stream (into buffers the previous step does not use) and pass
+// VN_STEP_SKIP_EXPAND to vn_train_step_run
+VN_API int vn_train_step_expand(const vn_step_t* s, int64_t S, void* stream) {
+    VN_REQUIRE(s != nullptr && S >= 0, "vn_train_step_expand: bad arguments");
+    const bool chunks = (s->hash_flags & VN_HASH_F16_CHUNKS) != 0;
+    if (s->ts_rows && chunks)      // enc = [4 hash planes | 2 SH planes][S] x 16 B
+        VN_TRY(vn_march_train_expand_sh(s->rays_o, s->rays_d, s->rays_a, s->ts_rows, s->N, s->max_samples, s->grid_size,
+                                        s->scale, s->exp_step_factor, S, s->xyzs, s->dirs, s->deltas, s->ts, s->unit,
+                                        (char*)s->enc + (size_t)S * 64, S, stream));
+    else if (s->ts_rows)
+        VN_TRY(vn_march_train_expand(s->rays_o, s->rays_d, s->rays_a, s->ts_rows, s->N, s->max_samples, s->grid_size,
+                                     s->scale, s->exp_step_factor, S, s->xyzs, s->dirs, s->deltas, s->ts, s->unit, stream));
+    else
+        VN_TRY(vn_march_train_write(s->rays_o, s->rays_d, s->hits_t, s->bitfield, s->noise, s->N, s->cascades,
+                                    s->grid_size, s->scale, s->exp_step_factor, s->rays_a, S, s->xyzs, s->dirs, s->deltas,
+                                    s->ts, s->unit, stream));
+    return VN_OK;
+}
+
 VN_API int vn_train_step_run(const vn_step_t* s, int64_t S, int phase, int do_optim, void* stream) {
+    const bool skip_expand = (phase & VN_STEP_SKIP_EXPAND) != 0;
+    phase &= ~VN_STEP_SKIP_EXPAND;
     VN_REQUIRE(s != nullptr && S >= 0 && phase >= 0 && phase <= 2, "vn_train_step_run: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     const float* W[5];
@@ -61,17 +83,7 @@ VN_API int vn_train_step_run(const vn_step_t* s, int64_t S, int phase, int do_op
     if (phase == 0 || phase == 1) {
         VN_CUDA(cudaMemsetAsync(s->flat_g, 0, sizeof(float) * (size_t)s->n_params, st));
         VN_CUDA(cudaMemsetAsync(s->loss_acc, 0, sizeof(float) * 8, st));
-        if (s->ts_rows && chunks)      // enc = [4 hash planes | 2 SH planes][S] x 16 B
-            VN_TRY(vn_march_train_expand_sh(s->rays_o, s->rays_d, s->rays_a, s->ts_rows, s->N, s->max_samples, s->grid_size,
-                                            s->scale, s->exp_step_factor, S, s->xyzs, s->dirs, s->deltas, s->ts, s->unit,
-                                            (char*)s->enc + (size_t)S * 64, S, stream));
-        else if (s->ts_rows)
-            VN_TRY(vn_march_train_expand(s->rays_o, s->rays_d, s->rays_a, s->ts_rows, s->N, s->max_samples, s->grid_size,
-                                         s->scale, s->exp_step_factor, S, s->xyzs, s->dirs, s->deltas, s->ts, s->unit, stream));
-        else
-            VN_TRY(vn_march_train_write(s->rays_o, s->rays_d, s->hits_t, s->bitfield, s->noise, s->N, s->cascades,
-                                        s->grid_size, s->scale, s->exp_step_factor, s->rays_a, S, s->xyzs, s->dirs, s->deltas,
-                                        s->ts, s->unit, stream));
+        if (!skip_expand) VN_TRY(vn_train_step_expand(s, S, stream));
         if (half_enc) {
             VN_TRY(vn_f32_to_f16(table, s->table_h, 2 * s->levels.total_entries, stream));       // hash_encoder_half.py:367
             VN_TRY(vn_hash_encode_fwd_f16(s->unit, s->table_h, s->enc, S, &s->levels, s->hash_flags, stream));

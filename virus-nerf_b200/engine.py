@@ -71,6 +71,7 @@ class _Workspace:
     def __init__(self, device):
         self.device = device
         self.bufs = {}
+        self.retired = []     # outgrown buffers stay alive for a while: kernels of another stream may still use them
 
     def get(self, name, rows, cols=None, dtype=torch.float32):
         key = (name, cols, dtype)
@@ -78,6 +79,9 @@ class _Workspace:
         if t is None or t.shape[0] < rows:
             cap = max(int(rows * 1.25) + 1024, 4096)
             shape = (cap,) if cols is None else (cap, cols)
+            if t is not None:
+                self.retired.append(t)
+                del self.retired[:-16]
             t = torch.empty(shape, dtype=dtype, device=self.device)
             self.bufs[key] = t
         return t[:rows]
@@ -86,7 +90,7 @@ class _Workspace:
 class TrainEngine:
     def __init__(self, args, dataset, device, world_size=1, rank=0, log2_T=19, max_res=1024, half_opt=False,
                  autocast=True, seed=21, grad_scale=2.0 ** 19, comm="auto", enc_layout="chunks",
-                 single_pass_march=True, fused_scatter=True):
+                 single_pass_march=True, fused_scatter=True, early_expand=True):
         self.args = args
         self.device = torch.device(device)
         self.world_size, self.rank = world_size, rank
@@ -100,6 +104,9 @@ class TrainEngine:
         # MLP backward and hash backward as ONE kernel (vn_mlp_bwd_scatter): d(enc) goes from tensor memory straight into
         # the table gradient; only with the operand-chunk layout
         self.fused_scatter = bool(fused_scatter) and self.enc_chunks
+        # the sample expansion of step k+1 (no dependence on the parameters) runs on the side stream under step k's
+        # backward / optimiser / gradient exchange; the per-sample arrays it writes are double-buffered
+        self.early_expand = bool(early_expand)
         # single-pass march of the fast step: the count pass stores t of every sample in a [N, 1024] scratch and
         # the write pass only expands it (bit-identical to re-marching); capped at 64 Ki rays (256 MB scratch x 2)
         self.single_pass_march = single_pass_march
@@ -369,21 +376,32 @@ class TrainEngine:
             raise RuntimeError("TrainEngine: a cross-rank wait of the peer-memory exchange timed out (VN_P2P_TIMEOUT_MS): "
                                "the replicas are no longer synchronised -- restart from the last checkpoint")
         self.last_samples = S
-        st.set_ptrs(xyzs=ws.get("xyzs", S, 3), dirs=ws.get("dirs", S, 3), unit=ws.get("unit", S, 3),
-                    deltas=ws.get("deltas", S), ts=ws.get("ts", S), enc=ws.get("enc", S, 32), sigmas=ws.get("sig", S),
-                    rgbs=ws.get("rgbs", S, 3), ws=ws.get("ws", S), d_sigmas=ws.get("d_sig", S),
+        par = tk["par"]
+        enc_cols = 24 if self.enc_chunks else 32          # operand chunks: [4 hash + 2 SH planes][S] x 16 B
+        st.set_ptrs(xyzs=ws.get(f"xyzs{par}", S, 3), dirs=ws.get(f"dirs{par}", S, 3), unit=ws.get(f"unit{par}", S, 3),
+                    deltas=ws.get(f"deltas{par}", S), ts=ws.get(f"ts{par}", S), enc=ws.get(f"enc{par}", S, enc_cols),
+                    sigmas=ws.get("sig", S), rgbs=ws.get("rgbs", S, 3), ws=ws.get("ws", S), d_sigmas=ws.get("d_sig", S),
                     d_rgbs=ws.get("d_rgbs", S, 3), d_enc=None if self.fused_scatter else ws.get("d_enc", S, 32))
+        skip_expand = 0
+        if self.early_expand and tk["side"]:
+            # front half on the side stream => no occupancy update in between: the expansion can follow it there, under
+            # the previous step's tail (its buffers have the other parity); the main stream picks it up before the encoder
+            with torch.cuda.stream(self._prep_stream):
+                _lib.call("vn_train_step_expand", st, S)
+                expanded = torch.cuda.Event(); expanded.record()
+            torch.cuda.current_stream().wait_event(expanded)
+            skip_expand = _lib.VN_STEP_SKIP_EXPAND
         self.adam_step += 1
         st.adam_step = self.adam_step
         self.step_idx += 1
         update_due = self._prep_step % self.grid_update_interval == 0     # next front half needs the new weights
         if self.world_size == 1:
-            _lib.call("vn_train_step_run", st, S, 0, 1)
+            _lib.call("vn_train_step_run", st, S, 0 | skip_expand, 1)
             if next_data is not None:
                 self._ticket = self.prepare(next_data, elapse_time, noise=next_noise, ready=None if update_due else ready_next)
             return self._loss_out[0]
         # ---- data parallel ----------------------------------------------------------------
-        _lib.call("vn_train_step_run", st, S, 1, 0)
+        _lib.call("vn_train_step_run", st, S, 1 | skip_expand, 0)
         if self._p2p_fused:                                               # global normalisers
             _lib.call("vn_p2p_allreduce_small", self._loss_acc[4:], 4, 0)
         else:

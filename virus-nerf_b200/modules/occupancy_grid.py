@@ -51,6 +51,9 @@ class OccupancyGrid(Grid):
         # kernel scratch (caller-owned, see include/virusnerf.h a14)
         self._winner = None
         self._scratch = None
+        self._ws = None              # workspace of vn_occ_update
+        self._table_h = None
+        self.native_update = True    # False: always the step-by-step path (one C-ABI call per reference method)
 
     def _buffers(self, device):
         if self._winner is None or self._winner.device != device:
@@ -58,10 +61,65 @@ class OccupancyGrid(Grid):
             self._scratch = torch.zeros(1024, dtype=torch.float32, device=device)
         return self._winner, self._scratch
 
+    def _native_model(self, device):
+        """the NGP whose density this grid queries, when NGP.density runs as hash forward + fused density MLP (then the
+        whole update can be enqueued by ONE C call, vn_occ_update); None -> the step-by-step path below"""
+        if not self.native_update or device.type != "cuda":
+            return None
+        m = getattr(self.fct_density, "__self__", None)
+        if m is None or not hasattr(m, "pos_encoder") or not getattr(m, "fused_mlp", False):
+            return None
+        if m.pos_encoder.out_dim != 32 or not m.pos_encoder.hash_table.is_cuda:
+            return None
+        return m
+
+    @torch.no_grad()
+    def _updateNative(self, m, ray_update: dict, nerf_update: dict, apply_decay: bool):
+        """:65-105 from the sampled batches on: _rayUpdate, _nerfUpdate, decay and repack through vn_occ_update"""
+        grid = self.occ_3d_grid
+        dev = grid.device
+        f = lambda t: t.contiguous().float()
+        n_ray, n_nerf = int(ray_update["batch_size"]), int(nerf_update["batch_size"])
+        n_ray = ray_update["rays_o"].shape[0] if n_ray > 0 else 0
+        n_nerf = nerf_update["rays_o"].shape[0] if n_nerf > 0 else 0
+        need = _lib.lib().vn_occ_update_ws_floats(n_ray, n_nerf, self.M)
+        if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
+            self._ws = torch.empty(int(need * 1.25) + 1024, dtype=torch.float32, device=dev)
+        winner, _ = self._buffers(dev)
+        bf = self.bitfield
+        if bf.numel() != self.grid_size ** 3 // 8 or bf.device != dev:
+            bf = torch.zeros(self.grid_size ** 3 // 8, dtype=torch.uint8, device=dev)   # grid.py:205
+        noise = torch.rand(size=(n_nerf, self.M, 3), device=dev, dtype=torch.float32) if n_nerf > 0 else None   # :326
+        enc = m.pos_encoder
+        table_h = None
+        if enc.hash_table.dim() == 2:          # hash_encoder_half: fp16 copy of the table per forward (:367)
+            if self._table_h is None or self._table_h.numel() != enc.hash_table.numel():
+                self._table_h = torch.empty(enc.hash_table.numel(), dtype=torch.float16, device=dev)
+            table_h = self._table_h
+        og = self.args.occ_grid
+        _lib.call("vn_occ_update", grid, self.grid_size, bf, winner,
+                  f(ray_update["rays_o"]) if n_ray else None, f(ray_update["rays_d"]) if n_ray else None,
+                  f(ray_update["depth_meas"]) if n_ray else None, n_ray,
+                  f(nerf_update["rays_o"]) if n_nerf else None, f(nerf_update["rays_d"]) if n_nerf else None, noise, n_nerf,
+                  self.M, self.I, float(self.args.model.scale), float(self.nerf_pos_noise_every_m),
+                  float(self.false_detection_prob_every_m), float(self.std_every_m), float(self.prob_min),
+                  float(og.nerf_threshold_max), float(og.nerf_threshold_slope), float(self.grid_decay),
+                  1 if apply_decay else 0, float(self.threshold), enc.hash_table.detach(), table_h, enc._levels,
+                  enc.kernel_flags, m.xyz_encoder.hidden_layers[0].weight.detach(), m.xyz_encoder.output_layer.weight.detach(),
+                  -float(m.scale), float(m.scale), self._ws, self._ws.numel())
+        self.bitfield = bf
+
     @torch.no_grad()
     def update(self, elapse_time: float):
         """:65-105"""
         ray_update, nerf_update = self._sample(elapse_time=elapse_time)
+
+        m = self._native_model(self.occ_3d_grid.device)
+        if m is not None:
+            self.update_step += 1
+            self._updateNative(m, ray_update, nerf_update,
+                               apply_decay=self.update_step <= self.args.occ_grid.decay_warmup_steps)
+            return
 
         if ray_update["batch_size"] > 0:
             self._rayUpdate(rays_o=ray_update["rays_o"], rays_d=ray_update["rays_d"], meas=ray_update["depth_meas"])

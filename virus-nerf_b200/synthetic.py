@@ -206,6 +206,7 @@ class SyntheticDataset:
         self.gen = torch.Generator(device="cpu" if pinned else self.device)
         self.gen.manual_seed(seed)
         self.sensors = ("RGBD", "USS", "ToF") if kind == "rh2" else ("USS", "ToF")
+        self.fast_gather = True      # device pool: vn_pool_gather instead of torch advanced indexing (same batches)
 
     def __len__(self):
         return self.n_images
@@ -245,9 +246,43 @@ class SyntheticDataset:
         return {"rays_o": out["rays_o"], "rays_d": out["rays_d"], "rgb": out["rgb"],
                 "depth": {s: out[s] for s in self.sensors}}
 
+    def _fast_call(self, batch_size, sampling_strategy):
+        """device-resident pool: the same random draws as sample_indices(), but ONE vn_pool_gather launch per segment
+        writes all outputs (instead of index + six advanced-indexing gathers); bit-identical batches"""
+        from . import _lib
+        pixs = sampling_strategy.get("pixs", "random") if sampling_strategy else "random"
+        dev = self.device
+        if isinstance(pixs, dict):
+            n_u = int(batch_size * pixs.get("valid_uss", 0.0))
+            n_t = int(batch_size * pixs.get("valid_tof", 0.0))
+            segs = [(self.idx_uss, n_u), (self.idx_tof, n_t), (None, batch_size - n_u - n_t)]
+        else:
+            segs = [({"valid_uss": self.idx_uss, "valid_tof": self.idx_tof}.get(pixs), batch_size)]
+        B = batch_size
+        ns = len(self.sensors)
+        out = torch.empty((9 + ns) * B, dtype=torch.float32, device=dev)
+        ro, rd, rgb = out[0:3 * B].view(B, 3), out[3 * B:6 * B].view(B, 3), out[6 * B:9 * B].view(B, 3)
+        dep = [out[(9 + k) * B:(10 + k) * B] for k in range(ns)]
+        src = [self.pool[s_] for s_ in self.sensors] + [None] * (3 - ns)
+        off = 0
+        for sel, n in segs:
+            if n == 0:
+                continue
+            hi = len(sel) if sel is not None else self.pool_size
+            draw = torch.randint(0, hi, (n,), generator=self.gen, device=self.gen.device)
+            _lib.call("vn_pool_gather", draw, sel, hi if sel is not None else 0, self.pool_size, n, self.pool["rays_o"],
+                      self.pool["rays_d"], self.pool["rgb"], src[0], src[1], src[2], ro[off:off + n], rd[off:off + n],
+                      rgb[off:off + n], dep[0][off:off + n] if ns > 0 else None, dep[1][off:off + n] if ns > 1 else None,
+                      dep[2][off:off + n] if ns > 2 else None, None)
+            off += n
+        return {"rays_o": ro, "rays_d": rd, "rgb": rgb, "depth": {s_: dep[k] for k, s_ in enumerate(self.sensors)}}
+
     def __call__(self, batch_size, sampling_strategy=None, elapse_time=None):
         """datasets/dataset_base.py:23-76 shape: dict(rays_o, rays_d, rgb, depth{sensor: (N,)})"""
-        batch = self.gather(self.sample_indices(batch_size, sampling_strategy))
+        if self.fast_gather and not self.pinned and self.device.type == "cuda":
+            batch = self._fast_call(batch_size, sampling_strategy)
+        else:
+            batch = self.gather(self.sample_indices(batch_size, sampling_strategy))
         pixs = sampling_strategy.get("pixs", "random") if sampling_strategy else "random"
         # every ray drawn from the valid-<sensor> subset carries a measurement of that sensor
         batch["depth_valid_by_construction"] = {"valid_uss": ("USS",), "valid_tof": ("ToF",)}.get(pixs, ()) \

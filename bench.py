@@ -267,7 +267,7 @@ def run_ours(a):
         ds.gen.manual_seed(1000 + (0 if strong else rank))    # same pool on every rank; weak: different training batches
         eng = TrainEngine(args, ds, dev, world_size=world, rank=rank, autocast=not a.no_autocast, comm=a.comm,
                           enc_layout=a.enc_layout, single_pass_march=not a.two_pass_march,
-                          fused_scatter=not a.no_fused_scatter, early_expand=not a.no_early_expand)
+                          fused_scatter=False if a.no_fused_scatter else "auto", early_expand=not a.no_early_expand)
         batches = make_batches(ds, W + K + 1, n, args.training.sampling_strategy, (lo, hi, n_global) if strong else None)
         noises = None
         if strong:          # the jitter of the GLOBAL batch, so that N ranks march exactly the samples one rank would
@@ -545,7 +545,7 @@ def extra_configs(a, eng, scene, dev, world, rank, barrier, max_over_ranks, make
         ds3.gen.manual_seed(77)                                              # the same global batches on every rank
         eng.close()                                                          # one owner of the peer-memory exchange at a time
         eng3 = TrainEngine(args3, ds3, dev, world_size=world, rank=rank, log2_T=22, half_opt=True, comm=a.comm,
-                           fused_scatter=not a.no_fused_scatter, early_expand=not a.no_early_expand)
+                           fused_scatter=False if a.no_fused_scatter else "auto", early_expand=not a.no_early_expand)
         W3, K3 = 2, 4
         b3 = make_batches(ds3, W3 + K3 + 1, hi3 - lo3, args3.training.sampling_strategy, (lo3, hi3, n3))
         gen = torch.Generator(device=dev); gen.manual_seed(5)

@@ -11,7 +11,8 @@ import subprocess
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libvirusnerf_sm100.so")
+# VN_LIB_PATH: development switch for A/B runs of an experimental build (make BUILD=build_exp OUT=... EXTRA=-D...)
+LIB_PATH = os.environ.get("VN_LIB_PATH") or os.path.join(_PKG, "lib", "libvirusnerf_sm100.so")
 CSRC = os.path.join(_PKG, "csrc")
 
 VN_MAX_LEVELS = 32

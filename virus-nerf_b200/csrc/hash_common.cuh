@@ -118,26 +118,114 @@ __device__ __forceinline__ void warp_reduce8_distribute(float* v0, float* v1, in
 }
 
 constexpr int kScanMaxHeads = 24;
+// (Measured dead end, profiles/r2_kbench.md: NOT looking for runs at the finest levels -- where nearly every lane is its
+// own run -- is slower, 0.526 -> 0.531 / 0.535 ms for the fused kernel with the cut at level 14 / 13: the warps of rays
+// that run along a grid axis still merge there, and a red lane costs more than the 12 instructions of the test.)
+
+// run detection shared by the scatter variants: bit l of the result = lane l starts a new run (its cell differs from the
+// previous lane's, or one of the two lanes carries no gradient).  Two shuffles: (x | y << 16) and (z | invalid << 31).
+__device__ __forceinline__ unsigned run_heads(const Cell& c, bool valid, int lane) {
+    const unsigned full = 0xffffffffu;
+    const uint32_t k1 = c.g[0] | (c.g[1] << 16), k2 = c.g[2] | (valid ? 0u : 0x80000000u);
+    const uint32_t p1 = __shfl_up_sync(full, k1, 1), p2 = __shfl_up_sync(full, k2, 1);
+    const bool head = (lane == 0) || !valid || p1 != k1 || p2 != k2;
+    return __ballot_sync(full, head);
+}
+
+// segmented inclusive scan of the 8 float2 corner values over the runs given by `heads`; returns true in the last lane
+// of every run (which then holds the run's sums)
+__device__ __forceinline__ bool run_scan(float* v0, float* v1, unsigned heads, int lane) {
+    const unsigned full = 0xffffffffu;
+    const int seg_start = 31 - __clz(heads & (full >> (31 - lane)));
+    const int max_run = __reduce_max_sync(full, lane - seg_start + 1);     // bounds the number of useful scan steps
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        if (off >= max_run) break;
+        const bool take = (lane - off) >= seg_start;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float a = __shfl_up_sync(full, v0[k], off), b = __shfl_up_sync(full, v1[k], off);
+            if (take) { v0[k] += a; v1[k] += b; }
+        }
+    }
+    return (lane == 31) || ((heads >> (lane + 1)) & 1u);
+}
+
+// Hashed level whose table size is a power of two (every hashed level of the shipped configurations).
+// index(x, y, z) = (x ^ y P1 ^ z P2) & mask with odd primes: for an EVEN cell x the two x-corners of a (y, z) pair are
+// the entries i and i ^ 1 -- one aligned 16-byte red.v4 -- and WHICH of them sits at the even address is the parity
+// q ^ ky ^ kz with q = (y ^ z) & 1.  Instead of ordering the four values of a pair with selects when the atomic is
+// issued, the pair is STORED in address order from the start: slot 2j of pair j = (ky, kz) holds x-offset xs_j (0 or 1),
+// slot 2j + 1 the other one; that costs two selects on the x-weights.  All lanes of a run share the cell, hence the
+// order, so the run sums need no reordering either.  The same products in the same order as corner_weight().
+template <bool AGG>
+__device__ __forceinline__ void level_scatter_hashed_pow2(float* __restrict__ grad_level, const Cell& c, uint32_t mask, float d0,
+                                                          float d1, bool valid) {
+    const int lane = threadIdx.x & 31;
+    d0 = valid ? d0 : 0.0f;
+    d1 = valid ? d1 : 0.0f;
+    const bool pair = (c.g[0] & 1u) == 0u;                      // all four pairs of the cell alike
+    const bool q = ((c.g[1] ^ c.g[2]) & 1u) != 0u;
+    const bool swap_e = pair && q, swap_o = pair && !q;         // pairs (0,0), (1,1)  /  pairs (1,0), (0,1)
+    const float wx0 = vn_sub(1.0f, c.f[0]), wx1 = c.f[0];
+    const float e_first = swap_e ? wx1 : wx0, e_second = swap_e ? wx0 : wx1;
+    const float o_first = swap_o ? wx1 : wx0, o_second = swap_o ? wx0 : wx1;
+    const float wy0 = vn_sub(1.0f, c.f[1]), wy1 = c.f[1], wz0 = vn_sub(1.0f, c.f[2]), wz1 = c.f[2];
+    float v0[8], v1[8];
+    {
+        // pair j = ky + 2 kz: j = 0 (0,0) E, 1 (1,0) O, 2 (0,1) O, 3 (1,1) E
+        const float w[8] = {vn_mul(vn_mul(e_first, wy0), wz0), vn_mul(vn_mul(e_second, wy0), wz0),
+                            vn_mul(vn_mul(o_first, wy1), wz0), vn_mul(vn_mul(o_second, wy1), wz0),
+                            vn_mul(vn_mul(o_first, wy0), wz1), vn_mul(vn_mul(o_second, wy0), wz1),
+                            vn_mul(vn_mul(e_first, wy1), wz1), vn_mul(vn_mul(e_second, wy1), wz1)};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { v0[k] = vn_mul(w[k], d0); v1[k] = vn_mul(w[k], d1); }
+    }
+    bool leader = valid;
+    if (AGG) {
+        const unsigned heads = run_heads(c, valid, lane);
+        // (a whole warp inside one cell of a hashed level does not occur with marched samples: no special case)
+        if (__popc(heads) <= kScanMaxHeads) leader = run_scan(v0, v1, heads, lane) && valid;
+    }
+    if (!leader) return;
+    const uint32_t y0 = c.g[1] * 2654435761u, y1 = y0 + 2654435761u, z0 = c.g[2] * 805459861u, z1 = z0 + 805459861u;
+    const uint32_t A[4] = {y0 ^ z0, y1 ^ z0, y0 ^ z1, y1 ^ z1};
+    const uint32_t xe = c.g[0] + (swap_e ? 1u : 0u), xo = c.g[0] + (swap_o ? 1u : 0u), x1 = c.g[0] + 1u;
+    if (pair) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t i_first = (((j == 0 || j == 3) ? xe : xo) ^ A[j]) & mask;     // even by construction
+            vn_red_add_v4(grad_level + 2 * (size_t)i_first, v0[2 * j], v1[2 * j], v0[2 * j + 1], v1[2 * j + 1]);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            vn_red_add_v2(grad_level + 2 * (size_t)((c.g[0] ^ A[j]) & mask), v0[2 * j], v1[2 * j]);
+            vn_red_add_v2(grad_level + 2 * (size_t)((x1 ^ A[j]) & mask), v0[2 * j + 1], v1[2 * j + 1]);
+        }
+    }
+}
 
 template <typename DT, bool DENSE, bool AGG, bool ZERO_SKIP>
 __device__ __forceinline__ void level_scatter(float* __restrict__ grad_level, const Cell& c, uint32_t res,
                                               uint32_t size, uint32_t mask, float d0, float d1, bool valid) {
-    const unsigned full = 0xffffffffu;
+    if (!DENSE && mask > 2u) {       // warp-uniform (a property of the level)
+        level_scatter_hashed_pow2<AGG>(grad_level, c, mask, d0, d1, valid);
+        return;
+    }
     const int lane = threadIdx.x & 31;
+    d0 = valid ? d0 : 0.0f;
+    d1 = valid ? d1 : 0.0f;
     float v0[8], v1[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        float w = corner_weight(c, k);
-        v0[k] = valid ? vn_mul(w, d0) : 0.0f;
-        v1[k] = valid ? vn_mul(w, d1) : 0.0f;
+        const float w = corner_weight(c, k);
+        v0[k] = vn_mul(w, d0);
+        v1[k] = vn_mul(w, d1);
     }
     bool leader = valid;
     if (AGG) {
-        uint32_t p0 = __shfl_up_sync(full, c.g[0], 1), p1 = __shfl_up_sync(full, c.g[1], 1),
-                 p2 = __shfl_up_sync(full, c.g[2], 1);
-        int pv = __shfl_up_sync(full, (int)valid, 1);
-        bool head = (lane == 0) || !valid || !pv || p0 != c.g[0] || p1 != c.g[1] || p2 != c.g[2];
-        unsigned heads = __ballot_sync(full, head);
+        const unsigned heads = run_heads(c, valid, lane);
         if (heads == 1u) {          // the whole warp sits in one cell (coarse levels)
             float r0, r1;
             warp_reduce8_distribute(v0, v1, lane, &r0, &r1);
@@ -148,43 +236,29 @@ __device__ __forceinline__ void level_scatter(float* __restrict__ grad_level, co
             }
             return;
         }
-        if (__popc(heads) <= kScanMaxHeads) {  // warp-uniform: enough sharing to pay for the scan
-            int seg_start = 31 - __clz(heads & (full >> (31 - lane)));
-            // longest run in the warp bounds the number of scan steps that can do anything
-            const int max_run = __reduce_max_sync(full, lane - seg_start + 1);
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                if (off >= max_run) break;
-                bool take = (lane - off) >= seg_start;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    float a = __shfl_up_sync(full, v0[k], off), b = __shfl_up_sync(full, v1[k], off);
-                    if (take) { v0[k] += a; v1[k] += b; }
-                }
-            }
-            bool tail = (lane == 31) || ((heads >> (lane + 1)) & 1u);
-            leader = valid && tail;
-        }
+        if (__popc(heads) <= kScanMaxHeads) leader = run_scan(v0, v1, heads, lane) && valid;   // enough sharing to pay for the scan
     }
     if (leader) {
-        // the x / x+1 corners of a cell are neighbouring table entries whenever their indices
-        // differ only in bit 0 (dense levels: x + ... with an even index; hashed levels: the x
-        // prime is 1, so an even x gives h and h^1): one 16-byte red.v4 instead of two red.v2
+        // the x / x+1 corners of a cell are neighbouring table entries whenever their indices differ only in bit 0: one
+        // 16-byte red.v4 instead of two red.v2.  Dense levels: index x + y res + z res^2 -- i1 = i0 + 1, so the pair is
+        // adjacent exactly when i0 is even (a wrap-around at the end of the slab never yields i0 ^ i1 == 1) and needs no
+        // reordering.  (An exactly-zero corner value is added like any other: x + 0 = x, hash_encoder_half.py:212.)
 #pragma unroll
         for (int k = 0; k < 8; k += 2) {
             const uint32_t i0 = corner_index<DENSE>(c, k, res, size, mask);
             const uint32_t i1 = corner_index<DENSE>(c, k + 1, res, size, mask);
             if ((i0 ^ i1) == 1u) {
-                const bool lo0 = (i0 & 1u) == 0u;
-                vn_red_add_v4(grad_level + 2 * (size_t)(i0 & ~1u), lo0 ? v0[k] : v0[k + 1], lo0 ? v1[k] : v1[k + 1],
-                              lo0 ? v0[k + 1] : v0[k], lo0 ? v1[k + 1] : v1[k]);
+                if (DENSE) {
+                    vn_red_add_v4(grad_level + 2 * (size_t)i0, v0[k], v1[k], v0[k + 1], v1[k + 1]);
+                } else {
+                    const bool lo0 = (i0 & 1u) == 0u;
+                    vn_red_add_v4(grad_level + 2 * (size_t)(i0 & ~1u), lo0 ? v0[k] : v0[k + 1], lo0 ? v1[k] : v1[k + 1],
+                                  lo0 ? v0[k + 1] : v0[k], lo0 ? v1[k + 1] : v1[k]);
+                }
             } else {
-                if (!(ZERO_SKIP && v0[k] == 0.0f && v1[k] == 0.0f))       // hash_encoder_half.py:212
-                    vn_red_add_v2(grad_level + 2 * (size_t)i0, v0[k], v1[k]);
-                if (!(ZERO_SKIP && v0[k + 1] == 0.0f && v1[k + 1] == 0.0f))
-                    vn_red_add_v2(grad_level + 2 * (size_t)i1, v0[k + 1], v1[k + 1]);
+                vn_red_add_v2(grad_level + 2 * (size_t)i0, v0[k], v1[k]);
+                vn_red_add_v2(grad_level + 2 * (size_t)i1, v0[k + 1], v1[k + 1]);
             }
         }
     }
 }
-

@@ -765,12 +765,14 @@ __global__ void __launch_bounds__(NTHR, 1) mlp_bwd_pipe_kernel(const MlpArgs a, 
             wait_done();
             TIM(21);
             if (SCATTER) {
-                // this thread: sample `row`, levels 8 * half .. 8 * half + 7 (TMEM columns 16 * half + 2 l, + 1)
+                // this thread: sample `row`, levels half, half + 2, .. (TMEM columns 2 * level, + 1).  The two column halves
+                // take the even / the odd levels so that both get the same mix of coarse (few atomics per warp) and fine
+                // (one run per lane) levels: the chain waits for the slower of its warps.
 #pragma unroll 1
                 for (int l = 0; l < 8; ++l) {
-                    const int level = 8 * half + l;
+                    const int level = 2 * l + half;
                     uint32_t r2[2];
-                    tmem_ld<2>(tm + 16 * half + 2 * l, r2);
+                    tmem_ld<2>(tm + 2 * level, r2);
                     umma::tmem_ld_wait();
                     float d0 = __uint_as_float(r2[0]), d1 = __uint_as_float(r2[1]);
                     if (hs.round_f16) {        // half-precision encoder: d(enc) is an fp16 tensor (hash_encoder_half.py:344)
@@ -782,8 +784,8 @@ __global__ void __launch_bounds__(NTHR, 1) mlp_bwd_pipe_kernel(const MlpArgs a, 
                     // its contributions is (|d(enc)| <= 64 * 65504^2 otherwise, so no sum of < 2^31 finite terms overflows)
                     if (hs.found_inf && valid && !(fabsf(d0) + fabsf(d1) < INFINITY)) *hs.found_inf = 1.0f;
                     const bool v = valid && !(d0 == 0.0f && d1 == 0.0f);           // hash_encoder_half.py:210
-                    const Cell cl = cell_of(px, py, pz, hs.P.scales[level]);
                     float* gl = hs.grad + 2 * (size_t)hs.P.offsets[level];
+                    const Cell cl = cell_of(px, py, pz, hs.P.scales[level]);
                     if (level < hs.P.begin_fast)
                         level_scatter<float, true, true, true>(gl, cl, hs.P.res[level], hs.P.sizes[level], 0u, d0, d1, v);
                     else

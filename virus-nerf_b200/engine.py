@@ -90,7 +90,7 @@ class _Workspace:
 class TrainEngine:
     def __init__(self, args, dataset, device, world_size=1, rank=0, log2_T=19, max_res=1024, half_opt=False,
                  autocast=True, seed=21, grad_scale=2.0 ** 19, comm="auto", enc_layout="chunks",
-                 single_pass_march=True, fused_scatter=True, early_expand=True):
+                 single_pass_march=True, fused_scatter="auto", early_expand=True):
         self.args = args
         self.device = torch.device(device)
         self.world_size, self.rank = world_size, rank
@@ -103,6 +103,10 @@ class TrainEngine:
         self.enc_chunks = enc_layout == "chunks" and autocast
         # MLP backward and hash backward as ONE kernel (vn_mlp_bwd_scatter): d(enc) goes from tensor memory straight into
         # the table gradient; only with the operand-chunk layout
+        # (measured, profiles/r2_kbench.md: faster than the two kernels while the table is L2 resident -- 0.539 vs 0.565 ms
+        # at 1.3 M samples, T = 2^19 -- and slower when it is not -- T = 2^22: 0.68 vs 0.63 ms: "auto" decides on the size)
+        if fused_scatter == "auto":
+            fused_scatter = (2 ** log2_T) * 2 * 4 * 16 <= (96 << 20)
         self.fused_scatter = bool(fused_scatter) and self.enc_chunks
         # the sample expansion of step k+1 (no dependence on the parameters) runs on the side stream under step k's
         # backward / optimiser / gradient exchange; the per-sample arrays it writes are double-buffered

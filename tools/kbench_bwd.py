@@ -43,6 +43,12 @@ def main():
 
     for log2_T in (19, 22):
         lv = _lib.hash_levels(16, 1024, 16, 2 ** log2_T)
+        table = torch.rand(2 * lv.total_entries, device=DEV)
+        enc_o = torch.empty(S * 32, device=DEV)
+        ffl = _lib.VN_HASH_PLANAR | _lib.VN_HASH_LEVEL_GROUPS_2 | _lib.VN_HASH_PAIR_LOADS | _lib.VN_HASH_F16_CHUNKS
+        ms = timeit(lambda: _lib.call("vn_hash_encode_fwd_f32", x, table, enc_o, S, lv, ffl), reps=7)
+        rec("hash_fwd_f32_chunks", ms, log2_T=log2_T, frac=round(S * 1164 / ms / 1e6 / 6454.9, 4))
+        del table
         grad = torch.zeros(2 * lv.total_entries, device=DEV)
         dout = torch.randn(8, S, 4, device=DEV)
         ms = timeit(lambda: _lib.call("vn_hash_encode_bwd_f32", x, dout, grad, S, lv, FAST), reps=7)

@@ -48,7 +48,11 @@ VN_API int vn_hash_levels_init(double base_res, double max_res, int levels, int6
 }
 
 // ---- table element access ---------------------------------------------------------------
+// (Measured dead end, profiles/r2_kbench.md: ld.global.nc.L1::no_allocate for the gathers -- the idea being that random
+// 8-byte gathers have no reuse -- is 28 % SLOWER, 0.190 -> 0.243 ms at 1.3 M samples: the coarse levels and the
+// neighbouring samples of a ray do reuse lines in L1.)
 __device__ __forceinline__ float2 load_entry(const float2* t, uint32_t i) { return __ldg(t + i); }
+__device__ __forceinline__ float4 load_pair(const float4* t, uint32_t i) { return __ldg(t + i); }
 __device__ __forceinline__ float2 load_entry(const __half2* t, uint32_t i) {
     return __half22float2(__ldg(t + i));
 }
@@ -67,7 +71,7 @@ __device__ __forceinline__ void level_gather(const TT* __restrict__ tbl, const C
             const uint32_t i0 = corner_index<DENSE>(c, k, res, size, mask);
             const uint32_t i1 = corner_index<DENSE>(c, k + 1, res, size, mask);
             if ((i0 ^ i1) == 1u) {
-                const float4 q = __ldg(reinterpret_cast<const float4*>(tbl) + (i0 >> 1));
+                const float4 q = load_pair(reinterpret_cast<const float4*>(tbl), i0 >> 1);
                 const bool lo0 = (i0 & 1u) == 0u;
                 v[k] = lo0 ? make_float2(q.x, q.y) : make_float2(q.z, q.w);
                 v[k + 1] = lo0 ? make_float2(q.z, q.w) : make_float2(q.x, q.y);

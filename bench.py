@@ -48,7 +48,6 @@ def parse():
     ap.add_argument("--no-extra", action="store_true", help="skip extra_configs (configs 3 and 5)")
     ap.add_argument("--no-config3", action="store_true", help="skip the T=2^22 / 2^18-ray / half-encoder configuration")
     ap.add_argument("--no-fused-scatter", action="store_true", help="MLP backward and hash backward as two kernels (A/B)")
-    ap.add_argument("--no-fused-gather", action="store_true", help="hash forward and MLP forward as two kernels (A/B)")
     ap.add_argument("--no-early-expand", action="store_true", help="sample expansion inside the step instead of ahead of it (A/B)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-autocast", action="store_true")
@@ -268,8 +267,7 @@ def run_ours(a):
         ds.gen.manual_seed(1000 + (0 if strong else rank))    # same pool on every rank; weak: different training batches
         eng = TrainEngine(args, ds, dev, world_size=world, rank=rank, autocast=not a.no_autocast, comm=a.comm,
                           enc_layout=a.enc_layout, single_pass_march=not a.two_pass_march,
-                          fused_scatter=False if a.no_fused_scatter else "auto", early_expand=not a.no_early_expand,
-                          fused_gather=not a.no_fused_gather)
+                          fused_scatter=False if a.no_fused_scatter else "auto", early_expand=not a.no_early_expand)
         batches = make_batches(ds, W + K + 1, n, args.training.sampling_strategy, (lo, hi, n_global) if strong else None)
         noises = None
         if strong:          # the jitter of the GLOBAL batch, so that N ranks march exactly the samples one rank would
@@ -397,10 +395,6 @@ def run_ours(a):
                 if name == "mlp_bwd_hash_scatter":
                     kern[name]["achieved_gbs"] = pts * FUSED_BWD_BYTES_PER_POINT / (t_ms * 1e-3) / 1e9
                     kern[name]["frac_of_hbm_peak"] = kern[name]["achieved_gbs"] / peak
-                if name == "hash_mlp_fwd":      # table gathers 1024 + xyz 12 + encoding planes written 64 + SH planes 32 + sigma, rgb 16
-                    kern[name]["achieved_gbs"] = pts * 1148 / (t_ms * 1e-3) / 1e9
-                    kern[name]["frac_of_hbm_peak"] = kern[name]["achieved_gbs"] / peak
-                    kern[name]["achieved_tflops"] = pts * 18816 / (t_ms * 1e-3) / 1e12
         tflops_peak = peaks_tensor()
         # kernels timed live inside the timed windows: totals there decide which one dominates the step
         live = {}
@@ -551,8 +545,7 @@ def extra_configs(a, eng, scene, dev, world, rank, barrier, max_over_ranks, make
         ds3.gen.manual_seed(77)                                              # the same global batches on every rank
         eng.close()                                                          # one owner of the peer-memory exchange at a time
         eng3 = TrainEngine(args3, ds3, dev, world_size=world, rank=rank, log2_T=22, half_opt=True, comm=a.comm,
-                           fused_scatter=False if a.no_fused_scatter else "auto", early_expand=not a.no_early_expand,
-                           fused_gather=not a.no_fused_gather)
+                           fused_scatter=False if a.no_fused_scatter else "auto", early_expand=not a.no_early_expand)
         W3, K3 = 2, 4
         b3 = make_batches(ds3, W3 + K3 + 1, hi3 - lo3, args3.training.sampling_strategy, (lo3, hi3, n3))
         gen = torch.Generator(device=dev); gen.manual_seed(5)
@@ -561,7 +554,7 @@ def extra_configs(a, eng, scene, dev, world, rank, barrier, max_over_ranks, make
         for it in range(W3):
             losses.append(eng3.step_fast(b3[it], noise=noise3[it]).clone())
         barrier()
-        _lib.profile_start(["hash_encode_fwd", "hash_encode_bwd", "mlp_fwd", "mlp_bwd", "mlp_bwd_hash_scatter", "hash_mlp_fwd"])
+        _lib.profile_start(["hash_encode_fwd", "hash_encode_bwd", "mlp_fwd", "mlp_bwd", "mlp_bwd_hash_scatter"])
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         smp = []

@@ -49,8 +49,6 @@ extern "C" {
 #define VN_HASH_PAIR_LOADS 2048 /* planar fwd: 16-byte loads for x / x+1 corner pairs that are neighbours */
 #define VN_HASH_FUSED_SCATTER 16384 /* native step runner: MLP backward and hash backward run as one kernel
                                        (vn_mlp_bwd_scatter); needs VN_HASH_F16_CHUNKS */
-#define VN_HASH_FUSED_GATHER 32768 /* native step runner: hash forward and MLP forward run as one kernel
-                                      (vn_hash_mlp_fwd); needs VN_HASH_F16_CHUNKS */
 #define VN_HASH_F16_CHUNKS 8192 /* fwd (f32 or f16 table): out is [levels/4][S] x 16 B "chunk planes": plane c holds
                                   levels 4c..4c+3 of every point as 8 fp16 values = one row of one column chunk of the
                                   fused MLP's tensor-core operand (vn_mlp_fwd enc_format 3, vn_mlp_bwd 3 / 4); bwd
@@ -343,16 +341,6 @@ int vn_mlp_bwd(const void* enc, int enc_format, const float* dirs, const float* 
                const float* W3, const float* W4, const float* W5, int64_t S, int density_only,
                const float* dsigmas, const float* drgbs, float* denc, float* dW1, float* dW2,
                float* dW3, float* dW4, float* dW5, void* stream);
-/* a2 / a4 + a12 fused: vn_hash_encode_fwd_f32 (VN_HASH_F16_CHUNKS | VN_HASH_PAIR_LOADS) -- or, with table_f16 != 0,
- * vn_hash_encode_fwd_f16 on the fp16 table -- followed by vn_mlp_fwd(enc_format 3 or 5) as ONE kernel (16 levels x 2
- * features): every thread of the MLP kernel gathers 8 levels of its sample (hash_encoder.py:89-143 /
- * hash_encoder_half.py:112-160: the same loads, summation order and fp16 rounding point as the stand-alone kernel) straight
- * into the tensor-core operand tile, so the gathers of one tile run under the layer chain of the SM's other tiles.  enc
- * [4 (+2 SH)][S] x 16 B: planes 0..3 are WRITTEN (the chunk planes vn_mlp_bwd / vn_mlp_bwd_scatter read), planes 4, 5 are
- * read when enc_format is 5.  Bit-identical to the two calls. */
-int vn_hash_mlp_fwd(const float* xyz, const void* table, int table_f16, const vn_hash_levels_t* lv, void* enc,
-                    int enc_format, const float* dirs, const float* W1, const float* W2, const float* W3,
-                    const float* W4, const float* W5, int64_t S, float* sigmas, float* rgbs, void* stream);
 /* a12 + a3 / a4 fused: vn_mlp_bwd followed by vn_hash_encode_bwd_* as ONE kernel (enc_format 3 or 5, 16 levels x 2
  * features).  The gradient w.r.t. the encoding never leaves the SM: every thread of the MLP epilogue reads its levels of
  * d(enc) back from tensor memory and runs the warp-aggregated scatter of hash_encoder.py:264-277 /

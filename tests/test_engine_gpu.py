@@ -184,8 +184,8 @@ def test_fast_step_fp16_tracks_oracle_directly(fused):
     oracle.build()
     args = synthetic.make_args(device=DEV, batch_size=256)
     ds = synthetic.SyntheticDataset(pool_size=1 << 13, n_images=8, device=DEV)
-    eng = TrainEngine(args, ds, DEV, autocast=True, fused_scatter=fused, fused_gather=fused)
-    assert eng.enc_chunks and eng.fused_scatter == fused and eng.fused_gather == fused and eng.model.fused_mlp
+    eng = TrainEngine(args, ds, DEV, autocast=True, fused_scatter=fused)
+    assert eng.enc_chunks and eng.fused_scatter == fused and eng.model.fused_mlp
     bf = synthetic.morton_pack(ds.scene.occupancy_bitfield(128))
     eng.model.occupancy_grid.bitfield = torch.from_numpy(bf).to(DEV)
     eng.step_idx = eng._prep_step = 1                      # no occupancy update (tested separately)
@@ -288,8 +288,7 @@ def test_occupancy_update_single_call_is_bit_identical(half_opt):
 
 
 @pytest.mark.parametrize("enc_layout,single_pass,fused", [("chunks", True, True), ("chunks", True, False),
-                                                          ("chunks", True, "bwd_only"), ("planar", True, False),
-                                                          ("rows", False, False)])
+                                                          ("planar", True, False), ("rows", False, False)])
 def test_fast_step_matches_autograd_step(monkeypatch, enc_layout, single_pass, fused):
     """the hand-chained C-ABI step (engine.step_fast) and the autograd step through the drop-in
     modules produce the same loss, gradients and parameter update (same rays, same jitter)"""
@@ -299,9 +298,8 @@ def test_fast_step_matches_autograd_step(monkeypatch, enc_layout, single_pass, f
     args = synthetic.make_args(device=DEV, batch_size=512)
     ds = synthetic.SyntheticDataset(pool_size=1 << 13, n_images=8, device=DEV)
     e1 = TrainEngine(args, ds, DEV)
-    e2 = TrainEngine(args, ds, DEV, enc_layout=enc_layout, single_pass_march=single_pass, fused_scatter=bool(fused),
-                     fused_gather=fused is True)
-    assert e2.fused_scatter == bool(fused) and e2.fused_gather == (fused is True)
+    e2 = TrainEngine(args, ds, DEV, enc_layout=enc_layout, single_pass_march=single_pass, fused_scatter=fused)
+    assert e2.fused_scatter == fused
     assert torch.equal(e1.flat_p, e2.flat_p)
     e1.step_idx = e2.step_idx = 1                       # no occupancy update (it draws random numbers)
     e1._prep_step = e2._prep_step = 1
@@ -333,7 +331,7 @@ def test_fast_step_half_encoder_matches_autograd_step(monkeypatch, fused):
     args = synthetic.make_args(device=DEV, batch_size=512)
     ds = synthetic.SyntheticDataset(pool_size=1 << 13, n_images=8, device=DEV)
     e1 = TrainEngine(args, ds, DEV, half_opt=True)
-    e2 = TrainEngine(args, ds, DEV, half_opt=True, fused_scatter=fused, fused_gather=fused)
+    e2 = TrainEngine(args, ds, DEV, half_opt=True, fused_scatter=fused)
     assert type(e2.model.pos_encoder).__module__.endswith("hash_encoder_half") and e2._table_h is not None
     # the reference initialises the half table with U(-1e-4, 1e-4): give the encoding some signal
     with torch.no_grad():

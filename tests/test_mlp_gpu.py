@@ -280,57 +280,6 @@ def test_fused_mlp_backward_with_hash_scatter(S, half):
         assert float(found) == 1.0 and float(ref_found) == 1.0
 
 
-@pytest.mark.parametrize("S,half,fmt", [(1, False, 3), (129, False, 3), (5000, False, 5), (5000, True, 3), (100000, False, 5),
-                                        (100000, True, 5)])
-def test_fused_hash_gather_mlp_forward(S, half, fmt):
-    """vn_hash_mlp_fwd (the encoding gathered from the table inside the MLP kernel) == vn_hash_encode_fwd_* into chunk
-    planes + vn_mlp_fwd, bit for bit: the encoding planes it leaves for the backward, sigma and rgb"""
-    import oracle
-    from virus_nerf_b200 import _lib
-    torch.manual_seed(S + 5)
-    Wg = [w.to(DEV).contiguous() for w in _weights(S + 1)]
-    lv = _lib.hash_levels(16, 1024, 16, 2 ** 19)
-    xyz = _ray_points((S + 63) // 64, 64, S + 2)[:S].contiguous().to(DEV)
-    table = (torch.rand(2 * lv.total_entries, device=DEV) * 2 - 1)
-    dirs = torch.randn(S, 3, device=DEV)
-    d = dirs / dirs.norm(dim=1, keepdim=True)
-    sh16 = torch.from_numpy(oracle.sh_encode(((d + 1) / 2).cpu().numpy())).to(DEV).half()
-    planes = 6 if fmt == 5 else 4
-    flags = _lib.VN_HASH_PLANAR | _lib.VN_HASH_LEVEL_GROUPS_2 | _lib.VN_HASH_PAIR_LOADS | _lib.VN_HASH_F16_CHUNKS
-
-    def fresh_enc():
-        e = torch.zeros(planes, S, 8, device=DEV, dtype=torch.float16)
-        if fmt == 5:
-            e[4:] = sh16.view(S, 2, 8).permute(1, 0, 2)
-        return e
-
-    tab = table
-    if half:
-        tab = torch.empty(2 * lv.total_entries, device=DEV, dtype=torch.float16)
-        _lib.call("vn_f32_to_f16", table, tab, table.numel())
-    # two kernels
-    enc_a = fresh_enc()
-    if half:
-        _lib.call("vn_hash_encode_fwd_f16", xyz, tab, enc_a, S, lv, flags)
-    else:
-        _lib.call("vn_hash_encode_fwd_f32", xyz, table, enc_a, S, lv, flags)
-    sig_a = torch.empty(S, device=DEV); rgb_a = torch.empty(S, 3, device=DEV)
-    _lib.call("vn_mlp_fwd", enc_a, fmt, None if fmt == 5 else dirs, *Wg, S, 0, sig_a, rgb_a, None)
-    # one kernel
-    enc_b = fresh_enc()
-    sig_b = torch.empty(S, device=DEV); rgb_b = torch.empty(S, 3, device=DEV)
-    _lib.call("vn_hash_mlp_fwd", xyz, tab, 1 if half else 0, lv, enc_b, fmt, None if fmt == 5 else dirs, *Wg, S, sig_b, rgb_b)
-    assert torch.equal(enc_a.view(torch.int16), enc_b.view(torch.int16))
-    assert torch.equal(sig_a, sig_b) and torch.equal(rgb_a, rgb_b)
-    assert float(enc_b[:4].float().abs().max()) > 0
-    # and the oracle's encoding (fp32 table path), rounded to fp16
-    if not half and S <= 5000:
-        lv_o = oracle.HashLevels(16, 1024, 16, 2 ** 19)
-        ref = oracle.hash_fwd_f32(xyz.cpu().numpy(), table.cpu().numpy(), lv_o)
-        got = enc_b[:4].permute(1, 0, 2).reshape(S, 32).float().cpu().numpy()
-        np.testing.assert_allclose(got, ref, rtol=2e-3, atol=1e-3)
-
-
 def test_fused_mlp_backward_with_hash_scatter_rejects_bad_arguments():
     from virus_nerf_b200 import _lib
     S = 64

@@ -48,11 +48,6 @@ def main():
         ffl = _lib.VN_HASH_PLANAR | _lib.VN_HASH_LEVEL_GROUPS_2 | _lib.VN_HASH_PAIR_LOADS | _lib.VN_HASH_F16_CHUNKS
         ms = timeit(lambda: _lib.call("vn_hash_encode_fwd_f32", x, table, enc_o, S, lv, ffl), reps=7)
         rec("hash_fwd_f32_chunks", ms, log2_T=log2_T, frac=round(S * 1164 / ms / 1e6 / 6454.9, 4))
-        sig = torch.empty(S, device=DEV); rgbo = torch.empty(S, 3, device=DEV)
-        ms = timeit(lambda: _lib.call("vn_mlp_fwd", enc_o, 3, dirs, *W, S, 0, sig, rgbo, None), reps=7)
-        rec("mlp_fwd_chunks", ms, log2_T=log2_T)
-        ms = timeit(lambda: _lib.call("vn_hash_mlp_fwd", x, table, 0, lv, enc_o, 3, dirs, *W, S, sig, rgbo), reps=7)
-        rec("hash_mlp_fwd", ms, log2_T=log2_T, frac=round(S * 1164 / ms / 1e6 / 6454.9, 4))
         del table
         grad = torch.zeros(2 * lv.total_entries, device=DEV)
         dout = torch.randn(8, S, 4, device=DEV)

@@ -28,7 +28,6 @@ VN_HASH_PAIR_LOADS = 2048
 VN_HASH_SKIP_ZERO_GRADS = 4096
 VN_HASH_F16_CHUNKS = 8192
 VN_HASH_FUSED_SCATTER = 16384
-VN_HASH_FUSED_GATHER = 32768
 VN_STEP_SKIP_EXPAND = 8
 
 
@@ -137,7 +136,6 @@ _SPECS = {
     "vn_ngp_threshold_pack": "plfppps",
     "vn_mlp_fwd": "pip" "ppppp" "li" "ppp" "s",
     "vn_mlp_bwd": "pip" "ppppp" "li" "pp" "p" "ppppp" "s",
-    "vn_hash_mlp_fwd": "ppi" "h" "pi" "p" "ppppp" "l" "pp" "s",
     "vn_mlp_bwd_scatter": "pip" "ppppp" "l" "pp" "p" "hi" "p" "ppppp" "p" "s",
 }
 
@@ -200,7 +198,7 @@ def _ptr(t, name, pos):
 
 
 KERNEL_NAMES = ["hash_encode_fwd", "hash_encode_bwd", "mlp_fwd", "mlp_bwd", "march_count", "march_write",
-                "composite_fwd", "composite_bwd", "adam", "mlp_bwd_hash_scatter", "hash_mlp_fwd"]
+                "composite_fwd", "composite_bwd", "adam", "mlp_bwd_hash_scatter"]
 
 
 def profile_start(kernels=None):

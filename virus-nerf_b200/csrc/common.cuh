@@ -43,7 +43,7 @@ extern unsigned long long g_vn_launches;   // kernels launched by this library (
 
 // ---- optional in-stream kernel timing (CUDA events around a launch; see vn_profile_*) ----
 enum { VN_K_HASH_FWD = 0, VN_K_HASH_BWD, VN_K_MLP_FWD, VN_K_MLP_BWD, VN_K_MARCH_COUNT, VN_K_MARCH_WRITE, VN_K_COMP_FWD,
-       VN_K_COMP_BWD, VN_K_ADAM, VN_K_MLP_BWD_SCATTER, VN_K_HASH_MLP_FWD, VN_K_COUNT };
+       VN_K_COMP_BWD, VN_K_ADAM, VN_K_MLP_BWD_SCATTER, VN_K_COUNT };
 extern unsigned g_vn_profiling;           // bit k set: kernel id k is timed
 void vn_prof_begin(int kernel_id, int64_t size, cudaStream_t st);
 void vn_prof_end(cudaStream_t st);

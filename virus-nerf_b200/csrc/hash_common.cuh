@@ -78,64 +78,6 @@ __device__ __forceinline__ float corner_weight(const Cell& c, int k) {
     return w;
 }
 
-// ---- table element access ---------------------------------------------------------------
-// (Measured dead end, profiles/r2_kbench.md: ld.global.nc.L1::no_allocate for the gathers -- the idea being that random
-// 8-byte gathers have no reuse -- is 28 % SLOWER, 0.190 -> 0.243 ms at 1.3 M samples: the coarse levels and the
-// neighbouring samples of a ray do reuse lines in L1.)
-__device__ __forceinline__ float2 load_entry(const float2* t, uint32_t i) { return __ldg(t + i); }
-__device__ __forceinline__ float4 load_pair(const float4* t, uint32_t i) { return __ldg(t + i); }
-__device__ __forceinline__ float2 load_entry(const __half2* t, uint32_t i) {
-    return __half22float2(__ldg(t + i));
-}
-
-// PAIR (fp32 tables): the x / x+1 corners of a cell are neighbouring entries whenever their
-// indices differ only in bit 0 (see level_scatter) -- one 16-byte load instead of two 8-byte
-// loads, i.e. half the L1 wavefronts for those lanes.  Values and summation order unchanged.
-template <typename TT, bool DENSE, bool PAIR>
-__device__ __forceinline__ void level_gather(const TT* __restrict__ tbl, const Cell& c, uint32_t res, uint32_t size,
-                                             uint32_t mask, float& a0, float& a1) {
-    float2 v[8];
-    float w[8];
-    if (PAIR && sizeof(TT) == sizeof(float2)) {
-#pragma unroll
-        for (int k = 0; k < 8; k += 2) {
-            const uint32_t i0 = corner_index<DENSE>(c, k, res, size, mask);
-            const uint32_t i1 = corner_index<DENSE>(c, k + 1, res, size, mask);
-            if ((i0 ^ i1) == 1u) {
-                const float4 q = load_pair(reinterpret_cast<const float4*>(tbl), i0 >> 1);
-                const bool lo0 = (i0 & 1u) == 0u;
-                v[k] = lo0 ? make_float2(q.x, q.y) : make_float2(q.z, q.w);
-                v[k + 1] = lo0 ? make_float2(q.z, q.w) : make_float2(q.x, q.y);
-            } else {
-                v[k] = load_entry(tbl, i0);
-                v[k + 1] = load_entry(tbl, i1);
-            }
-            w[k] = corner_weight(c, k);
-            w[k + 1] = corner_weight(c, k + 1);
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            v[k] = load_entry(tbl, corner_index<DENSE>(c, k, res, size, mask));
-            w[k] = corner_weight(c, k);
-        }
-    }
-    if (sizeof(TT) == sizeof(float2)) {
-        a0 = 0.0f; a1 = 0.0f;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { a0 = fmaf(w[k], v[k].x, a0); a1 = fmaf(w[k], v[k].y, a1); }
-    } else {
-        // hash_encoder_half.py:159: local_features(f16) += f16(w * table)
-        __half h0 = __float2half_rn(0.0f), h1 = __float2half_rn(0.0f);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            h0 = __hadd(h0, __float2half_rn(vn_mul(w[k], v[k].x)));
-            h1 = __hadd(h1, __float2half_rn(vn_mul(w[k], v[k].y)));
-        }
-        a0 = __half2float(h0); a1 = __half2float(h1);
-    }
-}
-
 // ---- backward ---------------------------------------------------------------------------
 // Warp pre-reduction: lanes are consecutive samples of a ray, so lanes in the same grid cell
 // form contiguous runs.  Head flags come from cell equality with the previous lane; a

@@ -4,7 +4,6 @@
 #include "common.cuh"
 #include "umma.cuh"
 #include "mlp_common.cuh"
-#include <type_traits>
 #include <stdlib.h>
 
 // ---- UMMA self-test: one 128 x N x K product in each operand mode the fused kernels use ----
@@ -232,20 +231,8 @@ __device__ __forceinline__ void mask_store_half(uint8_t* smem, int off_dst, int 
     }
 }
 
-// GATHER (forward only; vn_hash_mlp_fwd): 1 = the encoding is not read from a.enc but gathered from the fp32 hash table by
-// this kernel (2 = from the fp16 table of the half-precision encoder): every thread (sample row, column half) evaluates
-// 8 of the 16 levels of its sample with the hash forward's own level_gather() (same loads, same summation order, same
-// fp16 rounding point), writes them straight into the X0 operand tile and -- for the backward -- copies the finished
-// tile to the chunk planes of a.enc.  The L1-bound gathers of one CTA run under the latency-bound MMA chain of the other
-// CTAs of the SM, and the 64 B / sample round trip of the encoding through HBM becomes a write only.
-struct GatherArgs {
-    const float* xyz;      // [S,3] unit-cube positions
-    const void* table;     // float2 [total] (GATHER 1) or __half2 [total] (GATHER 2)
-    HashParams P;
-};
-
-template <bool BWD, int GATHER = 0>
-__global__ void __launch_bounds__(NTHREADS, BWD ? 2 : 3) mlp_kernel(const MlpArgs a, const __grid_constant__ GatherArgs ga) {
+template <bool BWD>
+__global__ void __launch_bounds__(NTHREADS, BWD ? 2 : 3) mlp_kernel(const MlpArgs a) {
     vn_pdl_trigger();                         // PDL: the wait follows the prologue
     using L = Lay<BWD>;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -274,10 +261,7 @@ __global__ void __launch_bounds__(NTHREADS, BWD ? 2 : 3) mlp_kernel(const MlpArg
     auto fetch = [&](int64_t tile, Staged& st) {
         const int64_t s = tile * TILE + row;
         const bool valid = tile < n_tiles && s < a.S;
-        if (GATHER) {                  // only the position travels ahead: e[0] = (x, y, z, -)
-            st.e[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (valid) st.e[0] = make_float4(__ldg(ga.xyz + 3 * s), __ldg(ga.xyz + 3 * s + 1), __ldg(ga.xyz + 3 * s + 2), 0.f);
-        } else if (valid) {
+        if (valid) {
             if (a.enc_fmt == 3 || a.enc_fmt == 5) {
                 // f16 chunk planes [4][S] x 16 B: chunks 2*half, 2*half+1 of this row
                 const uint4* src = reinterpret_cast<const uint4*>(a.enc) + (int64_t)(2 * half) * a.S + s;
@@ -335,33 +319,11 @@ __global__ void __launch_bounds__(NTHREADS, BWD ? 2 : 3) mlp_kernel(const MlpArg
         const bool valid = s < a.S;
         // ---- stage inputs: half enc row -> X0, half of SH(dir) -> IN2[:, 0:16] ------------------
         {
-            if (GATHER) {
-                // levels half, half + 2, .. (both column halves get the same mix of coarse and fine levels); level l is the
-                // half2 number (l & 3) of chunk l >> 2 of this row
-                using TT = typename std::conditional<GATHER == 2, __half2, float2>::type;
-                const float px = cur.e[0].x, py = cur.e[0].y, pz = cur.e[0].z;
-#pragma unroll 2
-                for (int l = 0; l < 8; ++l) {
-                    const int level = 2 * l + half;
-                    float a0 = 0.0f, a1 = 0.0f;
-                    if (valid) {
-                        const Cell c = cell_of(px, py, pz, ga.P.scales[level]);
-                        const TT* tbl = reinterpret_cast<const TT*>(ga.table) + ga.P.offsets[level];
-                        if (level < ga.P.begin_fast)
-                            level_gather<TT, true, true>(tbl, c, ga.P.res[level], ga.P.sizes[level], 0u, a0, a1);
-                        else
-                            level_gather<TT, false, true>(tbl, c, ga.P.res[level], ga.P.sizes[level], ga.P.pow2mask[level], a0, a1);
-                    }
-                    *reinterpret_cast<__half2*>(smem + L::X0 + (level >> 2) * (TILE * 16) + row * 16 + (level & 3) * 4) =
-                        __floats2half2_rn(a0, a1);
-                }
-            } else {
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const float v[8] = {cur.e[2 * c].x, cur.e[2 * c].y, cur.e[2 * c].z, cur.e[2 * c].w,
-                                        cur.e[2 * c + 1].x, cur.e[2 * c + 1].y, cur.e[2 * c + 1].z, cur.e[2 * c + 1].w};
-                    st_row8(smem, L::X0, row, 2 * half + c, v);
-                }
+            for (int c = 0; c < 2; ++c) {
+                const float v[8] = {cur.e[2 * c].x, cur.e[2 * c].y, cur.e[2 * c].z, cur.e[2 * c].w,
+                                    cur.e[2 * c + 1].x, cur.e[2 * c + 1].y, cur.e[2 * c + 1].z, cur.e[2 * c + 1].w};
+                st_row8(smem, L::X0, row, 2 * half + c, v);
             }
             if (!a.density_only && a.enc_fmt == 5) {
                 *reinterpret_cast<uint4*>(smem + L::IN2 + half * (TILE * 16) + row * 16) = cur.sh;
@@ -382,13 +344,6 @@ __global__ void __launch_bounds__(NTHREADS, BWD ? 2 : 3) mlp_kernel(const MlpArg
         publish();
         // ---- L1: 32 -> 64, ReLU -----------------------------------------------------------
         if (tid == 0) { umma::fence_after_sync(); mma_fwd(sbase, L::X0, L::W1, 64, 32, tmp); umma::commit(&bar); }
-        if (GATHER && valid) {
-            // the finished operand tile is the encoding the backward needs: chunk planes [4][S] x 16 B of a.enc (in the shadow
-            // of the first MMA; X0 is not written again before the next tile)
-            uint4* dst = reinterpret_cast<uint4*>(const_cast<float*>(a.enc)) + (int64_t)(2 * half) * a.S + s;
-            dst[0] = ld_chunk(smem, L::X0, row, 2 * half);
-            dst[a.S] = ld_chunk(smem, L::X0, row, 2 * half + 1);
-        }
         wait_mma(p);
         float acc[32];
         read_acc<32>(p, TC_TMP + 32 * half, acc);
@@ -552,26 +507,20 @@ __global__ void __launch_bounds__(NTHREADS, BWD ? 2 : 3) mlp_kernel(const MlpArg
     if (warp == 0) umma::tmem_dealloc(p.tm, BWD ? TMEM_BWD : TMEM_FWD);
 }
 
-// gather: null, or the hash-table side of vn_hash_mlp_fwd (table_f16: the half-precision encoder's fp16 table)
-int launch_mlp(bool bwd, const MlpArgs& a, cudaStream_t st, const GatherArgs* gather = nullptr, bool table_f16 = false) {
+int launch_mlp(bool bwd, const MlpArgs& a, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
         VN_CUDA(cudaFuncSetAttribute(mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD));
-        VN_CUDA(cudaFuncSetAttribute(mlp_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD));
-        VN_CUDA(cudaFuncSetAttribute(mlp_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD));
         VN_CUDA(cudaFuncSetAttribute(mlp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD));
         attr_set = true;
     }
-    VnProfScope prof(bwd ? VN_K_MLP_BWD : (gather ? VN_K_HASH_MLP_FWD : VN_K_MLP_FWD), a.S, st);
+    VnProfScope prof(bwd ? VN_K_MLP_BWD : VN_K_MLP_FWD, a.S, st);
     const int64_t n_tiles = (a.S + TILE - 1) / TILE;
     const int per_sm = bwd ? 2 : 3;
     int64_t grid = (int64_t)vn_sm_count() * per_sm;
     if (grid > n_tiles) grid = n_tiles;
-    static const GatherArgs none{};
-    if (bwd)                 vn_launch_pdl(mlp_kernel<true>, dim3((unsigned)grid), dim3(NTHREADS), SMEM_BWD, st, a, none);
-    else if (!gather)        vn_launch_pdl(mlp_kernel<false>, dim3((unsigned)grid), dim3(NTHREADS), SMEM_FWD, st, a, none);
-    else if (!table_f16)     vn_launch_pdl(mlp_kernel<false, 1>, dim3((unsigned)grid), dim3(NTHREADS), SMEM_FWD, st, a, *gather);
-    else                     vn_launch_pdl(mlp_kernel<false, 2>, dim3((unsigned)grid), dim3(NTHREADS), SMEM_FWD, st, a, *gather);
+    if (bwd) vn_launch_pdl(mlp_kernel<true>, dim3((unsigned)grid), dim3(NTHREADS), SMEM_BWD, st, a);
+    else     vn_launch_pdl(mlp_kernel<false>, dim3((unsigned)grid), dim3(NTHREADS), SMEM_FWD, st, a);
     VN_CHECK_LAUNCH(bwd ? "mlp_kernel<bwd>" : "mlp_kernel<fwd>");
     return VN_OK;
 }
@@ -660,28 +609,4 @@ VN_API int vn_mlp_bwd_scatter(const void* enc, int enc_format, const float* dirs
     int rc = make_params(lv, hs.P);
     if (rc) return rc;
     return launch_mlp_bwd_pipe(a, &hs, (cudaStream_t)stream);
-}
-
-// hash forward fused into the MLP forward (GATHER): see mlp_kernel
-VN_API int vn_hash_mlp_fwd(const float* xyz, const void* table, int table_f16, const vn_hash_levels_t* lv, void* enc,
-                           int enc_format, const float* dirs, const float* W1, const float* W2, const float* W3,
-                           const float* W4, const float* W5, int64_t S, float* sigmas, float* rgbs, void* stream) {
-    VN_REQUIRE(S >= 0, "vn_hash_mlp_fwd: S < 0");
-    if (S == 0) return VN_OK;
-    VN_REQUIRE(xyz && table && lv && enc && W1 && W2 && W3 && W4 && W5 && sigmas && rgbs, "vn_hash_mlp_fwd: null pointer");
-    VN_REQUIRE(enc_format == 3 || enc_format == 5, "vn_hash_mlp_fwd: enc_format must be 3 (f16 chunk planes) or 5 (+ SH planes)");
-    VN_REQUIRE(dirs || enc_format == 5, "vn_hash_mlp_fwd: dirs is required unless enc_format is 5");
-    VN_REQUIRE(lv->levels == 16, "vn_hash_mlp_fwd: the fused forward is built for 16 levels x 2 features (32-wide encoding)");
-    VN_REQUIRE(vn_aligned(enc, 16) && vn_aligned(table, 16) && vn_aligned(xyz, 4), "vn_hash_mlp_fwd: misaligned buffer");
-    VN_REQUIRE(vn_aligned(W1, 16) && vn_aligned(W2, 16) && vn_aligned(W3, 16) && vn_aligned(W4, 16) && vn_aligned(W5, 16),
-               "vn_hash_mlp_fwd: weight matrices must be 16-byte aligned");
-    MlpArgs a{};
-    a.enc = (const float*)enc; a.enc_fmt = enc_format; a.dirs = dirs;
-    a.W[0] = W1; a.W[1] = W2; a.W[2] = W3; a.W[3] = W4; a.W[4] = W5;
-    a.sigmas = sigmas; a.rgbs = rgbs; a.S = S;
-    GatherArgs g{};
-    g.xyz = xyz; g.table = table;
-    int rc = make_params(lv, g.P);
-    if (rc) return rc;
-    return launch_mlp(false, a, (cudaStream_t)stream, &g, table_f16 != 0);
 }

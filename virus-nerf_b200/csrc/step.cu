@@ -76,9 +76,6 @@ VN_API int vn_train_step_run(const vn_step_t* s, int64_t S, int phase, int do_op
     const bool half_enc = s->table_h != nullptr;       // hash_encoder_half.py inside the step
     VN_REQUIRE(!half_enc || chunks, "vn_train_step_run: the half-precision encoder needs VN_HASH_F16_CHUNKS");
     const bool fused_scatter = (s->hash_flags & VN_HASH_FUSED_SCATTER) != 0;
-    const bool fused_gather = (s->hash_flags & VN_HASH_FUSED_GATHER) != 0;
-    VN_REQUIRE(!fused_gather || (chunks && s->levels.levels == 16),
-               "vn_train_step_run: VN_HASH_FUSED_GATHER needs VN_HASH_F16_CHUNKS and 16 levels");
     VN_REQUIRE(!fused_scatter || (chunks && s->levels.levels == 16),
                "vn_train_step_run: VN_HASH_FUSED_SCATTER needs VN_HASH_F16_CHUNKS and 16 levels");
     VN_REQUIRE(!(s->hash_flags & VN_HASH_F16_CHUNKS) || (s->hash_flags & VN_HASH_PLANAR),
@@ -87,16 +84,13 @@ VN_API int vn_train_step_run(const vn_step_t* s, int64_t S, int phase, int do_op
         VN_CUDA(cudaMemsetAsync(s->flat_g, 0, sizeof(float) * (size_t)s->n_params, st));
         VN_CUDA(cudaMemsetAsync(s->loss_acc, 0, sizeof(float) * 8, st));
         if (!skip_expand) VN_TRY(vn_train_step_expand(s, S, stream));
-        if (half_enc) VN_TRY(vn_f32_to_f16(table, s->table_h, 2 * s->levels.total_entries, stream));   // hash_encoder_half.py:367
-        if (fused_gather) {
-            // one kernel: the encoding goes from the table straight into the tensor-core operand tile
-            VN_TRY(vn_hash_mlp_fwd(s->unit, half_enc ? (const void*)s->table_h : (const void*)table, half_enc ? 1 : 0, &s->levels,
-                                   s->enc, enc_fmt, s->dirs, W[0], W[1], W[2], W[3], W[4], S, s->sigmas, s->rgbs, stream));
+        if (half_enc) {
+            VN_TRY(vn_f32_to_f16(table, s->table_h, 2 * s->levels.total_entries, stream));       // hash_encoder_half.py:367
+            VN_TRY(vn_hash_encode_fwd_f16(s->unit, s->table_h, s->enc, S, &s->levels, s->hash_flags, stream));
         } else {
-            if (half_enc) VN_TRY(vn_hash_encode_fwd_f16(s->unit, s->table_h, s->enc, S, &s->levels, s->hash_flags, stream));
-            else          VN_TRY(vn_hash_encode_fwd_f32(s->unit, table, s->enc, S, &s->levels, s->hash_flags, stream));
-            VN_TRY(vn_mlp_fwd(s->enc, enc_fmt, s->dirs, W[0], W[1], W[2], W[3], W[4], S, 0, s->sigmas, s->rgbs, nullptr, stream));
+            VN_TRY(vn_hash_encode_fwd_f32(s->unit, table, s->enc, S, &s->levels, s->hash_flags, stream));
         }
+        VN_TRY(vn_mlp_fwd(s->enc, enc_fmt, s->dirs, W[0], W[1], W[2], W[3], W[4], S, 0, s->sigmas, s->rgbs, nullptr, stream));
         VN_TRY(vn_composite_train_fwd(s->sigmas, s->rgbs, s->deltas, s->ts, s->rays_a, s->N, S, s->T_threshold, s->vr_samples,
                                       s->opacity, s->depth, s->rgb, s->ws, stream));
         VN_TRY(vn_loss_fwd(s->rgb, s->opacity, s->depth, s->gt_rgb, s->uss, s->tof, s->rgbd, s->N, s->bg, s->uss_tol, sums,

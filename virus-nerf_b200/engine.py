@@ -90,7 +90,7 @@ class _Workspace:
 class TrainEngine:
     def __init__(self, args, dataset, device, world_size=1, rank=0, log2_T=19, max_res=1024, half_opt=False,
                  autocast=True, seed=21, grad_scale=2.0 ** 19, comm="auto", enc_layout="chunks",
-                 single_pass_march=True, fused_scatter="auto", early_expand=True, fused_gather=True):
+                 single_pass_march=True, fused_scatter="auto", early_expand=True):
         self.args = args
         self.device = torch.device(device)
         self.world_size, self.rank = world_size, rank
@@ -108,8 +108,6 @@ class TrainEngine:
         if fused_scatter == "auto":
             fused_scatter = (2 ** log2_T) * 2 * 4 * 16 <= (96 << 20)
         self.fused_scatter = bool(fused_scatter) and self.enc_chunks
-        # hash forward and MLP forward as ONE kernel (vn_hash_mlp_fwd); only with the operand-chunk layout
-        self.fused_gather = bool(fused_gather) and self.enc_chunks
         # the sample expansion of step k+1 (no dependence on the parameters) runs on the side stream under step k's
         # backward / optimiser / gradient exchange; the per-sample arrays it writes are double-buffered
         self.early_expand = bool(early_expand)
@@ -282,8 +280,6 @@ class TrainEngine:
                 st.hash_flags |= _lib.VN_HASH_F16_CHUNKS
             if self.fused_scatter:
                 st.hash_flags |= _lib.VN_HASH_FUSED_SCATTER
-            if self.fused_gather:
-                st.hash_flags |= _lib.VN_HASH_FUSED_GATHER
         t = a.training
         st.w_color, st.w_uss, st.w_tof, st.w_rgbd = t.color_loss_w, t.uss_loss_w, t.tof_loss_w, t.rgbd_loss_w
         st.lr, st.beta1, st.beta2, st.eps = self.lr, self.betas[0], self.betas[1], self.eps

@@ -283,6 +283,22 @@ int vn_loss_bwd(const float* rgb, const float* opacity, const float* depth, cons
                 float uss_tol, const float* sums, const float* counts, float w_color, float w_uss,
                 float w_tof, float w_rgbd, const float* scale_dev, float* dL_drgb, float* dL_ddepth,
                 float* dL_dopacity, float* loss_out, void* stream);
+/* a8 + f2 / a9 + f2 fused (what the native step runner enqueues): vn_composite_train_fwd that also accumulates sums[4] /
+ * counts[4] of its rays' loss terms (one block-level reduction, then atomics -- vn_loss_fwd without a launch of its own),
+ * and vn_composite_train_bwd that forms the per-ray gradient seeds itself from rgb / opacity / depth [N,*] (the forward's
+ * outputs), the targets and the (global) counts -- vn_loss_bwd's arithmetic -- and writes loss_out[0].  Same outputs as
+ * the separate calls (the sums differ in the order of their floating-point additions). */
+int vn_composite_loss_fwd(const float* sigmas, const float* rgbs, const float* deltas, const float* ts,
+                          const int32_t* rays_a, int64_t N, int64_t S, float T_threshold,
+                          int32_t* total_samples, float* opacity, float* depth, float* rgb, float* ws,
+                          const float* gt_rgb, const float* uss, const float* tof, const float* rgbd, float bg,
+                          float uss_tol, float* sums, float* counts, void* stream);
+int vn_composite_loss_bwd(const float* sigmas, const float* rgbs, const float* deltas, const float* ts,
+                          const int32_t* rays_a, int64_t N, int64_t S, float T_threshold, const float* rgb,
+                          const float* opacity, const float* depth, const float* gt_rgb, const float* uss,
+                          const float* tof, const float* rgbd, float bg, float uss_tol, const float* sums,
+                          const float* counts, float w_color, float w_uss, float w_tof, float w_rgbd,
+                          const float* scale_dev, float* dsigmas, float* drgbs, float* loss_out, void* stream);
 
 /* f1 (caller side). GradScaler.unscale_ + inf check + torch.optim.Adam(eps=1e-15) step,
  * training/trainer.py:49-57,138-141, as one pass.  found_inf [1] f32 (device): set to 1 by

@@ -256,6 +256,28 @@ def test_occupancy_update_runs_and_is_deterministic(setup):
     assert not torch.equal(g0, g1)
 
 
+def test_engine_converts_world_lengths_with_the_scene():
+    """loss.py:28-30 and occupancy_grid.py:50-62: the 3 cm USS tolerance and the sensor-model parameters are world
+    lengths; with a scene they reach the kernels in cube units (scene.w2c(only_scale=True))"""
+    from types import SimpleNamespace
+    from virus_nerf_b200 import synthetic
+    from virus_nerf_b200.engine import TrainEngine
+    k = 0.25
+    scene = SimpleNamespace(w2c=lambda pos, only_scale=False, copy=True: pos * k)
+    args = synthetic.make_args(device=DEV, batch_size=256)
+    ds = synthetic.SyntheticDataset(pool_size=1 << 13, n_images=8, device=DEV)
+    eng = TrainEngine(args, ds, DEV, scene=scene)
+    og = eng.model.occupancy_grid
+    assert abs(eng.loss_fn.uss_depth_tol - 0.03 * k) < 1e-12
+    assert abs(eng._structs[0].uss_tol - 0.03 * k) < 1e-9
+    assert abs(og.std_every_m - args.occ_grid.std_every_m * k) < 1e-12
+    assert abs(og.false_detection_prob_every_m - args.occ_grid.false_detection_prob_every_m / k) < 1e-12
+    plain = TrainEngine(args, ds, DEV)
+    assert plain.loss_fn.uss_depth_tol == 0.03
+    loss = float(eng.step_fast(ds(256, args.training.sampling_strategy)))
+    assert np.isfinite(loss)
+
+
 @pytest.mark.parametrize("half_opt", [False, True])
 def test_occupancy_update_single_call_is_bit_identical(half_opt):
     """vn_occ_update (the whole OccupancyGrid.update after sampling as one C call, caller-owned workspace) produces the

@@ -432,6 +432,51 @@ def test_composite_train_fwd_bwd(vn, oracle_mod, scene_rays, sigma_scale):
     np.testing.assert_allclose(N(cg.grad), r_dc, rtol=1e-4, atol=1e-6 * np.abs(r_dc).max())
 
 
+@pytest.mark.parametrize("sigma_scale", [30.0, 3000.0])
+def test_composite_with_fused_loss_equals_separate_kernels(vn, oracle_mod, scene_rays, sigma_scale):
+    """vn_composite_loss_fwd / _bwd (what the native step runner enqueues) == vn_composite_train_fwd + vn_loss_fwd and
+    vn_loss_bwd + vn_composite_train_bwd: per-ray outputs, valid counts and sample gradients bit-identical, loss sums equal
+    up to the order of the additions"""
+    rays_a, sigmas, rgbs, deltas, ts = _composite_inputs(oracle_mod, scene_rays, sigma_scale=sigma_scale)
+    n, S = rays_a.shape[0], sigmas.shape[0]
+    rng = np.random.default_rng(3)
+    gt = T(rng.random((n, 3)).astype(np.float32))
+    uss = rng.random(n).astype(np.float32) * 2; uss[::3] = np.nan
+    tof = rng.random(n).astype(np.float32); tof[1::2] = np.nan
+    uss, tof = T(uss), T(tof)
+    sg, cg, de, tt, ra = T(sigmas), T(rgbs), T(deltas), T(ts), T(rays_a)
+    scale = torch.tensor([2.0 ** 12], device=DEV)
+    w = (1.0, 0.7, 0.3, 0.0)
+    res = []
+    for fused in (False, True):
+        vr = torch.zeros(n, dtype=torch.int32, device=DEV)
+        op = torch.zeros(n, device=DEV); dp = torch.zeros(n, device=DEV); rgb = torch.zeros(n, 3, device=DEV)
+        ws = torch.zeros(S, device=DEV)
+        acc = torch.zeros(8, device=DEV); loss = torch.zeros(1, device=DEV)
+        ds = torch.zeros(S, device=DEV); dc = torch.zeros(S, 3, device=DEV)
+        if fused:
+            vn.call("vn_composite_loss_fwd", sg, cg, de, tt, ra, n, S, 1e-4, vr, op, dp, rgb, ws, gt, uss, tof, None, 1.0, 0.03,
+                    acc[:4], acc[4:])
+            vn.call("vn_composite_loss_bwd", sg, cg, de, tt, ra, n, S, 1e-4, rgb, op, dp, gt, uss, tof, None, 1.0, 0.03,
+                    acc[:4], acc[4:], *w, scale, ds, dc, loss)
+        else:
+            vn.call("vn_composite_train_fwd", sg, cg, de, tt, ra, n, S, 1e-4, vr, op, dp, rgb, ws)
+            vn.call("vn_loss_fwd", rgb, op, dp, gt, uss, tof, None, n, 1.0, 0.03, acc[:4], acc[4:])
+            d_rgb = torch.zeros(n, 3, device=DEV); d_dp = torch.zeros(n, device=DEV); d_op = torch.zeros(n, device=DEV)
+            vn.call("vn_loss_bwd", rgb, op, dp, gt, uss, tof, None, n, 1.0, 0.03, acc[:4], acc[4:], *w, scale, d_rgb, d_dp, d_op, loss)
+            vn.call("vn_composite_train_bwd", sg, cg, de, tt, ra, n, S, 1e-4, d_op, d_dp, d_rgb, None, ds, dc)
+        res.append((vr, op, dp, rgb, ws, acc.clone(), loss.clone(), ds, dc))
+    a, b = res
+    for k in range(5):
+        assert torch.equal(a[k], b[k]), k
+    assert torch.equal(a[5][4:], b[5][4:]) and float(a[5][5]) > 0 and float(a[5][6]) > 0        # counts are exact
+    np.testing.assert_allclose(N(a[5][:4]), N(b[5][:4]), rtol=1e-5)
+    np.testing.assert_allclose(N(a[6]), N(b[6]), rtol=1e-5)
+    np.testing.assert_allclose(N(a[7]), N(b[7]), rtol=1e-6, atol=1e-6 * float(a[7].abs().max()))
+    np.testing.assert_allclose(N(a[8]), N(b[8]), rtol=1e-6, atol=1e-6 * float(a[8].abs().max()))
+    assert float(a[7].abs().max()) > 0
+
+
 def test_composite_closed_form(vn):
     """constant-sigma slab: opacity = 1 - exp(-sigma L); zero-sample rays give zeros"""
     from virus_nerf_b200.modules.volume_train import VolumeRenderer

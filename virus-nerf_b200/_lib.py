@@ -112,6 +112,8 @@ _SPECS = {
     "vn_occ_decay_pack": "pififps",
     "vn_occ_update": "pipp" "pppl" "pppl" "ii" "fffff" "df" "fif" "pp" "hi" "pp" "ff" "pl" "s",
     "vn_loss_fwd": "ppppppp" "lff" "pp" "s",
+    "vn_composite_loss_fwd": "ppppp" "llf" "ppppp" "pppp" "ff" "pp" "s",
+    "vn_composite_loss_bwd": "ppppp" "llf" "ppp" "pppp" "ff" "pp" "ffff" "p" "ppp" "s",
     "vn_loss_bwd": "ppppppp" "lff" "pp" "ffff" "p" "pppp" "s",
     "vn_grad_check": "plps",
     "vn_adam_step": "ppppl" "f" "dddd" "ipps",

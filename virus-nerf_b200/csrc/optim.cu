@@ -2,6 +2,7 @@
 // inf check + torch.optim.Adam(eps=1e-15) step over the dense hash table and the MLP
 // weights as ONE streaming pass each (training/trainer.py:49-57, 138-141).
 #include "common.cuh"
+#include "loss_common.cuh"
 
 __global__ void __launch_bounds__(256) grad_check_kernel(const float4* __restrict__ g4, const float* __restrict__ g, int64_t n,
                                                          float* __restrict__ found_inf) {
@@ -138,24 +139,6 @@ VN_API int vn_scaler_update_dev(float* scale, int32_t* growth_tracker, float* fo
 }
 
 // ---- f2: training/loss.py as two kernels --------------------------------------------------
-struct RayLoss { float dc[3]; float e_uss, e_tof, e_rgbd; bool v_uss, v_tof, v_rgbd; };
-
-__device__ __forceinline__ RayLoss ray_loss(const float* __restrict__ rgb, const float* __restrict__ opacity,
-                                            const float* __restrict__ depth, const float* __restrict__ gt_rgb,
-                                            const float* __restrict__ uss, const float* __restrict__ tof,
-                                            const float* __restrict__ rgbd, int64_t n, float bg, float uss_tol) {
-    RayLoss r;
-    const float op = __ldg(opacity + n), d = __ldg(depth + n);
-#pragma unroll
-    for (int c = 0; c < 3; ++c) r.dc[c] = (__ldg(rgb + 3 * n + c) + bg * (1.0f - op)) - __ldg(gt_rgb + 3 * n + c);   // rendering.py:225
-    r.v_uss = r.v_tof = r.v_rgbd = false;
-    r.e_uss = r.e_tof = r.e_rgbd = 0.0f;
-    if (uss) { const float m = __ldg(uss + n); r.v_uss = !isnan(m) && (d < m - uss_tol); if (r.v_uss) r.e_uss = d - m; }   // loss.py:186-194
-    if (tof) { const float m = __ldg(tof + n); r.v_tof = !isnan(m); if (r.v_tof) r.e_tof = d - m; }                        // loss.py:140-141
-    if (rgbd) { const float m = __ldg(rgbd + n); r.v_rgbd = !isnan(m); if (r.v_rgbd) r.e_rgbd = d - m; }                   // loss.py:118-119
-    return r;
-}
-
 __global__ void __launch_bounds__(256) loss_fwd_kernel(const float* __restrict__ rgb, const float* __restrict__ opacity,
                                                        const float* __restrict__ depth, const float* __restrict__ gt_rgb,
                                                        const float* __restrict__ uss, const float* __restrict__ tof,

@@ -91,17 +91,16 @@ VN_API int vn_train_step_run(const vn_step_t* s, int64_t S, int phase, int do_op
             VN_TRY(vn_hash_encode_fwd_f32(s->unit, table, s->enc, S, &s->levels, s->hash_flags, stream));
         }
         VN_TRY(vn_mlp_fwd(s->enc, enc_fmt, s->dirs, W[0], W[1], W[2], W[3], W[4], S, 0, s->sigmas, s->rgbs, nullptr, stream));
-        VN_TRY(vn_composite_train_fwd(s->sigmas, s->rgbs, s->deltas, s->ts, s->rays_a, s->N, S, s->T_threshold, s->vr_samples,
-                                      s->opacity, s->depth, s->rgb, s->ws, stream));
-        VN_TRY(vn_loss_fwd(s->rgb, s->opacity, s->depth, s->gt_rgb, s->uss, s->tof, s->rgbd, s->N, s->bg, s->uss_tol, sums,
-                           cnts, stream));
+        // compositing forward + the loss terms of its rays in one kernel (vn_composite_train_fwd + vn_loss_fwd)
+        VN_TRY(vn_composite_loss_fwd(s->sigmas, s->rgbs, s->deltas, s->ts, s->rays_a, s->N, S, s->T_threshold, s->vr_samples,
+                                     s->opacity, s->depth, s->rgb, s->ws, s->gt_rgb, s->uss, s->tof, s->rgbd, s->bg, s->uss_tol,
+                                     sums, cnts, stream));
     }
     if (phase == 0 || phase == 2) {
-        VN_TRY(vn_loss_bwd(s->rgb, s->opacity, s->depth, s->gt_rgb, s->uss, s->tof, s->rgbd, s->N, s->bg, s->uss_tol, sums,
-                           cnts, s->w_color, s->w_uss, s->w_tof, s->w_rgbd, s->scale_dev, s->d_rgb, s->d_depth, s->d_opacity,
-                           s->loss_out, stream));
-        VN_TRY(vn_composite_train_bwd(s->sigmas, s->rgbs, s->deltas, s->ts, s->rays_a, s->N, S, s->T_threshold, s->d_opacity,
-                                      s->d_depth, s->d_rgb, nullptr, s->d_sigmas, s->d_rgbs, stream));
+        // loss backward (gradient seeds from the global counts) + compositing backward in one kernel
+        VN_TRY(vn_composite_loss_bwd(s->sigmas, s->rgbs, s->deltas, s->ts, s->rays_a, s->N, S, s->T_threshold, s->rgb, s->opacity,
+                                     s->depth, s->gt_rgb, s->uss, s->tof, s->rgbd, s->bg, s->uss_tol, sums, cnts, s->w_color,
+                                     s->w_uss, s->w_tof, s->w_rgbd, s->scale_dev, s->d_sigmas, s->d_rgbs, s->loss_out, stream));
         if (fused_scatter) {
             // one kernel: d(enc) goes from tensor memory straight into the table gradient
             VN_TRY(vn_mlp_bwd_scatter(s->enc, enc_fmt, s->dirs, W[0], W[1], W[2], W[3], W[4], S, s->d_sigmas, s->d_rgbs, s->unit,

@@ -90,7 +90,7 @@ class _Workspace:
 class TrainEngine:
     def __init__(self, args, dataset, device, world_size=1, rank=0, log2_T=19, max_res=1024, half_opt=False,
                  autocast=True, seed=21, grad_scale=2.0 ** 19, comm="auto", enc_layout="chunks",
-                 single_pass_march=True, fused_scatter="auto", early_expand=True):
+                 single_pass_march=True, fused_scatter="auto", early_expand=True, scene=None):
         self.args = args
         self.device = torch.device(device)
         self.world_size, self.rank = world_size, rank
@@ -116,7 +116,7 @@ class TrainEngine:
         self.single_pass_march = single_pass_march
         torch.manual_seed(seed)          # identical replicas on every rank
         self.model = NGP(scale=args.model.scale, pos_encoder_type='hash', levels=args.model.hash_levels,
-                         max_res=max_res, log2_T=log2_T, half_opt=half_opt, args=args, dataset=dataset)
+                         max_res=max_res, log2_T=log2_T, half_opt=half_opt, args=args, dataset=dataset, scene=scene)
         self.model.to(self.device)
         # the occupancy update is REPLICATED: every rank runs the same update from the same
         # ray pool with an identically seeded sampler, so the grids stay bit-identical without
@@ -124,7 +124,10 @@ class TrainEngine:
         if hasattr(dataset, "clone_with_seed"):
             self.model.occupancy_grid.dataset = dataset.clone_with_seed(seed)
         self.model.fused_mlp = self.model.fused_mlp and autocast   # fp32 mode (tests): torch.nn.Linear fp32
-        self.loss_fn = Loss(args)
+        # loss.py:28-30: the 3 cm USS tolerance is a WORLD length; with a scene it is converted to cube units like the
+        # occupancy grid's sensor-model parameters (occupancy_grid.py:50-62); without one the numbers are taken as cube units
+        uss_tol = 0.03 if scene is None else float(scene.w2c(pos=0.03, only_scale=True, copy=True))
+        self.loss_fn = Loss(args, uss_depth_tol=uss_tol)
         self.step_idx = 0
         self.grid_type = getattr(args.model, "grid_type", "occ")
         # trainer_base.py:85-88

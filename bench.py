@@ -353,7 +353,8 @@ def run_ours(a):
             dist.all_reduce(clo, op=dist.ReduceOp.MIN); dist.all_reduce(chi, op=dist.ReduceOp.MAX)
             same = bool((clo == chi).all())
         return {"window_ms": window_ms, "launches": launches, "samples": [int(x) for x in samples], "prof": prof, "h2d": h2d,
-                "d2h": d2h, "loss": global_loss(loss), "same": same, "eng": eng, "comm": eng.comm}
+                "d2h": d2h, "loss": global_loss(loss), "same": same, "eng": eng,
+                "comm": eng.comm + ("+nvls" if getattr(eng, "nvls", False) else "")}
 
     clocks = ClockSampler(local)
     clocks.start()
@@ -421,7 +422,10 @@ def run_ours(a):
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": bpp * pts / nl,
                     "algorithmic_bytes_per_point": bpp,
                     "what": ("fused MLP backward + hash-gradient scatter (one kernel): table-gradient RMW 1024 B + xyz 12 B + "
-                             "MLP-backward inputs 112 B per point; also 56 448 FLOP per point on the tensor cores"
+                             "MLP-backward inputs 112 B per point; also 56 448 FLOP per point on the tensor cores.  Round 1's "
+                             "roofline kernel was the hash backward ALONE; it now runs inside this kernel together with the "
+                             "whole MLP backward (extra_configs.backward_as_two_kernels has the two-kernel figures of the same "
+                             "build: hash backward alone >= 0.62 of the HBM peak)"
                              if dom == "mlp_bwd_hash_scatter" else "hash-grid backward scatter"),
                     "runner_up": {k: round(v[0] / v[2], 5) for k, v in live.items() if k != dom}}
         elif dom and dom.startswith("mlp"):
@@ -545,6 +549,41 @@ def extra_configs(a, eng, scene, dev, world, rank, barrier, max_over_ranks, make
             del grid
     out["occupancy_update_sweep"] = sweep
 
+    # ---- the backward as TWO kernels (MLP backward, hash backward), for comparison with round 1's roofline kernel: the
+    # headline runs them fused (mlp_bwd_hash_scatter) when the table is L2 resident.  Rank 0 only, single engine, untimed.
+    if world == 1 and eng.fused_scatter:
+        args_u = synthetic.make_args(device=str(dev), batch_size=a.rays)
+        ds_u = synthetic.SyntheticDataset(scene, pool_size=1 << 18, device=str(dev), pinned=False, seed=21)
+        ds_u.gen.manual_seed(1000)
+        eng_u = TrainEngine(args_u, ds_u, dev, fused_scatter=False)
+        bu = [ds_u(a.rays, args_u.training.sampling_strategy) for _ in range(a.warmup + a.steps + 1)]
+        for it in range(a.warmup):
+            eng_u.step_fast(bu[it], next_data=bu[it + 1])
+        torch.cuda.synchronize()
+        _lib.profile_start(["hash_encode_bwd", "mlp_bwd"])
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for it in range(a.warmup, a.warmup + a.steps):
+            eng_u.step_fast(bu[it], next_data=bu[it + 1])
+        e1.record(); torch.cuda.synchronize()
+        pu = _lib.profile_stop()
+        peak, _ = peaks()
+        hb, mb = pu.get("hash_encode_bwd", []), pu.get("mlp_bwd", [])
+        if hb and mb:
+            t_h, p_h = sum(c[0] for c in hb), sum(c[1] for c in hb)
+            t_m, p_m = sum(c[0] for c in mb), sum(c[1] for c in mb)
+            out["backward_as_two_kernels"] = {
+                "ms_per_step": e0.elapsed_time(e1) / a.steps,
+                "hash_encode_bwd": {"ms_per_launch": round(t_h / len(hb), 5), "points_per_launch": p_h // len(hb),
+                                    "achieved_gbs": round(p_h * HASH_BYTES_PER_POINT / (t_h * 1e-3) / 1e9, 1),
+                                    "frac_of_hbm_peak": round(p_h * HASH_BYTES_PER_POINT / (t_h * 1e-3) / 1e9 / peak, 4),
+                                    "algorithmic_bytes_per_point": HASH_BYTES_PER_POINT},
+                "mlp_bwd": {"ms_per_launch": round(t_m / len(mb), 5), "achieved_tflops": round(p_m * 56448 / (t_m * 1e-3) / 1e12, 1)},
+                "note": "the same steps with fused_scatter=False (round 1's structure, this round's kernels): the hash backward "
+                        "alone is the kernel round 1 quoted its roofline fraction on"}
+        del eng_u
+        torch.cuda.empty_cache()
+
     # ---- config 3: RH2-shaped (RGBD + USS + ToF), T = 2^22, 2^18 rays per step over all ranks, half-precision encoder
     if not a.no_config3:
         n3 = 1 << 18
@@ -598,7 +637,7 @@ def extra_configs(a, eng, scene, dev, world, rank, barrier, max_over_ranks, make
             "n_gpus": world, "scaling": "strong", "global_rays_per_step": n3, "rays_per_step_per_gpu": hi3 - lo3,
             "samples_per_step_per_gpu": int(statistics.mean(smp)), "steps": K3, "warmup": W3,
             "encoder": "half (fp16 table copy per step, fp16 encoding and encoding gradient, fp32 scatter)", "log2_T": 22,
-            "table_mb_fp32": round(eng3.model.pos_encoder.hash_table.numel() * 4 / 2 ** 20, 1), "grad_exchange": eng3.comm,
+            "table_mb_fp32": round(eng3.model.pos_encoder.hash_table.numel() * 4 / 2 ** 20, 1), "grad_exchange": eng3.comm + ("+nvls" if getattr(eng3, "nvls", False) else ""),
             "losses": [round(global_loss(x), 6) for x in losses], "kernels": k3,
             "note": "one globally seeded batch per step, rank r trains on rays [r N/n, (r+1) N/n) with the jitter of the global "
                     "batch: `losses` must agree between N = 1 and N > 1 (global loss normalisers, summed gradients)"}

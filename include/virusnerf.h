@@ -480,6 +480,14 @@ int vn_p2p_reduce_adam(int64_t n, float* m, float* v, double lr, double beta1, d
 int vn_p2p_step(int64_t n, float* m, float* v, double lr, double beta1, double beta2, double eps,
                 float* opt_state, float* found_inf, float* scale_dev, int32_t* growth_tracker, void* stream);
 int vn_p2p_shutdown(void);
+/*  vn_p2p_set_multicast: NVLink-multicast (NVLS) addresses of the gradient and the parameter buffers -- one address that
+ *               stands for the same offset in every rank's buffer (cuMulticast*; torch's symmetric memory hands them out
+ *               as multicast_ptr).  vn_p2p_step then sums slice r with one multimem.ld_reduce per 16 bytes (the NVSwitch
+ *               adds the replicas) and distributes the new parameters with one multimem.st (the switch replicates): the
+ *               bytes on a GPU's links drop from 2 (n-1)/n to about 2/n of the buffer per direction.  The order of the
+ *               additions inside the switch is unspecified: replicas stay bit-identical to each other, the result agrees
+ *               with the fixed-order path to rounding.  (NULL, NULL) switches back to peer loads / stores. */
+int vn_p2p_set_multicast(void* mc_grad, void* mc_params);
 
 /* ---------------------------------------------------------------------------------------
  * (f) row 2. Batch assembly on the device -- the gather half of DatasetBase.__call__

@@ -171,8 +171,64 @@ t_small_nccl = timeit(lambda: dist.all_reduce(small2))
 ok &= int(err) == 0
 say(f"world {world}: allreduce p2p {t_p2p:.4f} ms, nccl {t_nccl:.4f} ms | exchange + optimiser: nccl+dense {t_nccl_unf:.4f} ms, "
     f"p2p+dense {t_unf:.4f} ms, FUSED sharded {t_fused:.4f} ms, ONE-KERNEL sharded {t_step:.4f} ms | 4-float allreduce: mailbox {t_small:.4f} ms, nccl {t_small_nccl:.4f} ms")
+# ---- 5. the same step through NVLink multicast (NVLS): symmetric-memory buffers, multimem.ld_reduce / multimem.st ----------
+try:
+    _lib.p2p_shutdown()
+    g2, g_ptrs, mc_g, hg = _lib.symmetric_empty(n, dev)
+    p2, p_ptrs, mc_p, hp = _lib.symmetric_empty(n, dev)
+    have_nvls = bool(mc_g and mc_p)
+except Exception as e:      # no symmetric memory here
+    have_nvls = False
+    say(f"world {world}: symmetric memory unavailable ({e!r}); NVLS step not tested")
+if have_nvls:
+    flags2 = torch.zeros(world, dtype=torch.int32, device=dev); err2 = torch.zeros(1, dtype=torch.int32, device=dev)
+    mbox2 = torch.zeros(2, world, 8, device=dev)
+    keep2 = _lib.p2p_setup_symmetric(g_ptrs, p_ptrs, mc_g, mc_p, flags2, err2, mbox2, rank, world)
+    p2.copy_(params)
+    p_ref = params.clone()
+    m_s, v_s, m_q, v_q = (torch.zeros(n, device=dev) for _ in range(4))
+    found_s.zero_(); found_q.zero_(); scale_s.fill_(2.0 ** 19); scale_q.fill_(2.0 ** 19); tr_s.zero_(); tr_q.zero_()
+    _lib.call("vn_opt_state_init", st_s, 0, lr, b1, b2); _lib.call("vn_opt_state_init", st_q, 0, lr, b1, b2)
+    for step in range(1, 5):
+        g0 = torch.randn(n, device=dev, generator=gen) * 2.0 ** 19
+        if step == 2 and rank == 0:
+            g0[4321] = float("inf")
+        ref_g = g0.clone(); dist.all_reduce(ref_g)               # NCCL sum: the reference up to the order of the additions
+        _lib.call("vn_grad_check", ref_g, n, found_q)
+        _lib.call("vn_adam_step_dev", p_ref, ref_g, m_q, v_q, n, lr, b1, b2, eps, st_q, found_q, scale_q)
+        _lib.call("vn_scaler_update_dev", scale_q, tr_q, found_q, 2.0, 0.5, 2000, st_q, lr, b1, b2)
+        g2.copy_(g0)
+        torch.cuda.synchronize(); dist.barrier()
+        _lib.call("vn_grad_check", g2, n, found_s)
+        _lib.call("vn_p2p_step", n, m_s, v_s, lr, b1, b2, eps, st_s, found_s, scale_s, tr_s)
+        torch.cuda.synchronize()
+        # Adam's update is lr * m / (sqrt(v) + eps): a last-bit difference of the gradient sum moves a parameter by
+        # far less than lr; compare at 1e-3 * lr absolute
+        dmax = float((p2 - p_ref).abs().max())
+        eq_s = float(scale_s) == float(scale_q) and bool(torch.equal(st_s[:3], st_q[:3]))
+        same = identical_everywhere(p2)
+        good = dmax <= 1e-3 * lr and eq_s and same and int(err2) == 0
+        ok &= good
+        say(f"world {world}: NVLS step {step}: max |params - (nccl allreduce + dense Adam)| = {dmax:.3e}, scaler + step count {eq_s} "
+            f"(scale {float(scale_s):.0f}, applied {int(st_s[2:3].view(torch.int32))}), replicas identical {same}")
+
+    def nvls_step():
+        _lib.call("vn_p2p_step", n, m_s, v_s, lr, b1, b2, eps, st_s, found_s, scale_s, tr_s)
+
+    g2.normal_().mul_(1e-30)
+    for _ in range(3):
+        nvls_step()
+    dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        nvls_step()
+    e1.record(); torch.cuda.synchronize()
+    ok &= int(err2) == 0
+    say(f"world {world}: ONE-KERNEL sharded step through NVLS {e0.elapsed_time(e1) / 20:.4f} ms (peer loads / stores: {t_step:.4f} ms)")
 flag = torch.tensor([1.0 if ok else 0.0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+torch.cuda.synchronize()
 _lib.p2p_shutdown()
 dist.destroy_process_group()
 if float(flag) != 1.0:

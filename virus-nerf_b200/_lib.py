@@ -321,7 +321,7 @@ def hash_levels(base_res, max_res, levels, max_params):
 
 def exported_symbols():
     """names declared in include/virusnerf.h (used by the CPU-side ABI test)"""
-    return ["vn_last_error", "vn_abi_version", "vn_launch_count", "vn_ipc_get_handle", "vn_ipc_open", "vn_p2p_init", "vn_p2p_attach", "vn_p2p_shutdown", "vn_profile_enable", "vn_profile_enable_mask", "vn_set_pdl", "vn_profile_count", "vn_profile_get", "vn_device_info", "vn_march_scan_tmp_ints", "vn_adam_config",
+    return ["vn_last_error", "vn_abi_version", "vn_launch_count", "vn_ipc_get_handle", "vn_ipc_open", "vn_p2p_init", "vn_p2p_attach", "vn_p2p_shutdown", "vn_p2p_set_multicast", "vn_profile_enable", "vn_profile_enable_mask", "vn_set_pdl", "vn_profile_count", "vn_profile_get", "vn_device_info", "vn_march_scan_tmp_ints", "vn_adam_config",
             "vn_ngp_select_tmp_ints", "vn_ngp_threshold_tmp_bytes", "vn_occ_update_ws_floats"] + list(_SPECS)
 
 
@@ -333,6 +333,60 @@ def p2p_slice(n, rank, world):
     chunk4 = (n4 + world - 1) // world
     lo = min(rank * chunk4, n4)
     return 4 * lo, 4 * min(lo + chunk4, n4)
+
+
+def symmetric_empty(numel, device, group=None):
+    """flat fp32 buffer in torch's symmetric memory (CUDA VMM allocation mapped into every rank, + an NVLink-multicast
+    address when the fabric supports it).  Collective.  -> (tensor, peer pointers [world], multicast pointer or 0, handle)"""
+    import torch.distributed as dist
+    import torch.distributed._symmetric_memory as symm_mem
+    t = symm_mem.empty(int(numel), dtype=torch.float32, device=device)
+    t.zero_()
+    hdl = symm_mem.rendezvous(t, group if group is not None else dist.group.WORLD)
+    mc = int(hdl.multicast_ptr) if hdl.multicast_ptr else 0
+    return t, [int(x) for x in hdl.buffer_ptrs], mc, hdl
+
+
+def p2p_setup_symmetric(grad_ptrs, param_ptrs, mc_grad, mc_params, flags, err, mbox, rank, world, group=None):
+    """the peer-memory exchange over SYMMETRIC-MEMORY buffers: gradient / parameter peer pointers (and their multicast
+    addresses) come from symmetric_empty(); the small flag / mailbox arrays are exchanged through CUDA IPC as in p2p_setup"""
+    import torch.distributed as dist
+    L = lib()
+
+    def share(t):
+        handle = ctypes.create_string_buffer(64)
+        off = ctypes.c_int64(0)
+        if L.vn_ipc_get_handle(ctypes.c_void_p(t.data_ptr()), handle, ctypes.byref(off)) != 0:
+            raise RuntimeError(f"vn_ipc_get_handle failed: {last_error()}")
+        return handle.raw, int(off.value)
+
+    def open_peer(handle, off):
+        base = _ipc_opened.get(handle)
+        if base is None:
+            out = ctypes.c_void_p()
+            if L.vn_ipc_open(ctypes.c_char_p(handle), ctypes.c_int64(0), ctypes.byref(out)) != 0:
+                raise RuntimeError(f"vn_ipc_open failed: {last_error()}")
+            base = _ipc_opened[handle] = out.value
+        return base + off
+
+    mine = (share(flags), share(mbox))
+    everyone = [None] * world
+    dist.all_gather_object(everyone, mine, group=group)
+    arrs = [(ctypes.c_void_p * world)() for _ in range(4)]
+    for p in range(world):
+        arrs[0][p] = grad_ptrs[p]
+        arrs[1][p] = flags.data_ptr() if p == rank else open_peer(*everyone[p][0])
+        arrs[2][p] = param_ptrs[p]
+        arrs[3][p] = mbox.data_ptr() if p == rank else open_peer(*everyone[p][1])
+    if L.vn_p2p_init(ctypes.c_int(rank), ctypes.c_int(world), arrs[0], arrs[1], ctypes.c_void_p(err.data_ptr())) != 0:
+        raise RuntimeError(f"vn_p2p_init failed: {last_error()}")
+    if L.vn_p2p_attach(arrs[2], arrs[3]) != 0:
+        raise RuntimeError(f"vn_p2p_attach failed: {last_error()}")
+    if mc_grad and mc_params:
+        if L.vn_p2p_set_multicast(ctypes.c_void_p(mc_grad), ctypes.c_void_p(mc_params)) != 0:
+            raise RuntimeError(f"vn_p2p_set_multicast failed: {last_error()}")
+    dist.barrier(group=group)
+    return arrs
 
 
 def p2p_shutdown():

@@ -22,6 +22,8 @@ struct P2PCtx {
     int* flags[VN_P2P_MAX_RANKS];      // peer-mapped flag arrays, [world] ints each
     float* pbufs[VN_P2P_MAX_RANKS];    // peer-mapped parameter buffers (fused optimiser), or null
     float* mbox[VN_P2P_MAX_RANKS];     // peer-mapped mailboxes, [2][world][VN_P2P_MBOX] floats each, or null
+    float* mc_grad;                    // NVLink-multicast (NVLS) address of the gradient buffers of all ranks, or null
+    float* mc_params;                  // ... of the parameter buffers
     int* err;                          // local device int
     int epoch;
     int small_ops;                     // number of mailbox exchanges so far (mailbox parity)
@@ -230,6 +232,17 @@ VN_API int vn_p2p_init(int rank, int world, void* const* h_bufs, void* const* h_
     return VN_OK;
 }
 
+// NVLink-multicast addresses of the gradient / parameter buffers (one address that stands for the same offset in every
+// rank's buffer; e.g. torch.distributed._symmetric_memory's multicast_ptr): vn_p2p_step then reduces and broadcasts
+// through the switch.  NULL switches back to peer loads / stores.
+VN_API int vn_p2p_set_multicast(void* mc_grad, void* mc_params) {
+    VN_REQUIRE(g_ctx_ready, "vn_p2p_set_multicast: vn_p2p_init has not been called");
+    VN_REQUIRE((mc_grad == nullptr) == (mc_params == nullptr), "vn_p2p_set_multicast: both addresses or none");
+    VN_REQUIRE(vn_aligned(mc_grad, 16) && vn_aligned(mc_params, 16), "vn_p2p_set_multicast: addresses must be 16-byte aligned");
+    g_ctx.mc_grad = (float*)mc_grad; g_ctx.mc_params = (float*)mc_params;
+    return VN_OK;
+}
+
 VN_API int vn_p2p_shutdown(void) {
     g_ctx_ready = false;
     memset(&g_ctx, 0, sizeof(g_ctx));
@@ -341,6 +354,24 @@ __device__ __forceinline__ void st_release_gpu(int* p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// NVLS: the sum over the ranks is ONE multimem.ld_reduce per float4 -- the NVSwitch adds the replicas' values and returns
+// the result, so 16 bytes cross this GPU's link instead of 16 (n - 1) -- and the new parameters reach every replica with
+// ONE multimem.st that the switch replicates.  Per step and direction a GPU then moves ~2 x 45.7 MB / n instead of
+// 2 x 45.7 MB (n - 1) / n.  The order of the additions inside the switch is not the fixed rank order of the peer-load
+// path: the replicas stay bit-identical to EACH OTHER (every slice is reduced once, by its owner), but agree with
+// allreduce + dense Adam only to rounding.
+__device__ __forceinline__ float4 multimem_ld_reduce_add(const float4* mc) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+    return v;
+}
+__device__ __forceinline__ void multimem_st(float4* mc, const float4& v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
+template <bool NVLS>
 __global__ void __launch_bounds__(512) p2p_step_kernel(P2PCtx c, int64_t n4, int64_t chunk4, float* __restrict__ m,
                                                        float* __restrict__ v, AdamCfg cfg, float* found_inf, float* scale_dev,
                                                        int32_t* tracker, float* opt_state, double lr, double beta1, double beta2,
@@ -391,22 +422,32 @@ __global__ void __launch_bounds__(512) p2p_step_kernel(P2PCtx c, int64_t n4, int
         const int64_t hi = min(lo + chunk4, n4);
         float4* m4 = reinterpret_cast<float4*>(m);
         float4* v4 = reinterpret_cast<float4*>(v);
+        // (Measured dead end, profiles/r2_dp.md: four elements per thread with all loads / switch reductions issued before
+        // the first use -- 0.141 -> 0.164 ms through NVLS at 8 ranks, 0.102 -> 0.106 ms with peer loads at 2.)
         for (int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (int64_t)gridDim.x * blockDim.x) {
             float4 G = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (NVLS) {
+                G = multimem_ld_reduce_add(reinterpret_cast<const float4*>(c.mc_grad) + i);
+            } else {
 #pragma unroll
-            for (int p = 0; p < VN_P2P_MAX_RANKS; ++p) {
-                if (p < c.world) {
-                    const float4 g = __ldcv(reinterpret_cast<const float4*>(c.bufs[p]) + i);
-                    G.x += g.x; G.y += g.y; G.z += g.z; G.w += g.w;
+                for (int p = 0; p < VN_P2P_MAX_RANKS; ++p) {
+                    if (p < c.world) {
+                        const float4 g = __ldcv(reinterpret_cast<const float4*>(c.bufs[p]) + i);
+                        G.x += g.x; G.y += g.y; G.z += g.z; G.w += g.w;
+                    }
                 }
             }
             float4 P = reinterpret_cast<const float4*>(c.pbufs[c.rank])[i], M = m4[i], V = v4[i];
             adam1(P.x, G.x, M.x, V.x, cfg); adam1(P.y, G.y, M.y, V.y, cfg);
             adam1(P.z, G.z, M.z, V.z, cfg); adam1(P.w, G.w, M.w, V.w, cfg);
             m4[i] = M; v4[i] = V;
+            if (NVLS) {
+                multimem_st(reinterpret_cast<float4*>(c.mc_params) + i, P);
+            } else {
 #pragma unroll
-            for (int q = 0; q < VN_P2P_MAX_RANKS; ++q)
-                if (q < c.world) reinterpret_cast<float4*>(c.pbufs[q])[i] = P;
+                for (int q = 0; q < VN_P2P_MAX_RANKS; ++q)
+                    if (q < c.world) reinterpret_cast<float4*>(c.pbufs[q])[i] = P;
+            }
         }
     }
     // ---- the last CTA to get here closes the step
@@ -461,8 +502,12 @@ VN_API int vn_p2p_step(int64_t n, float* m, float* v, double lr, double beta1, d
     // all CTAs must be co-resident (grid-wide flags): one per SM.  (Measured at 2 and 8 ranks, profiles/r2_dp.md: splitting
     // the CTAs into reducers and pushers, or running "all loads, grid barrier, all stores", is not faster -- both NVLink
     // directions are busy in either phase, because a rank serves its peers' loads while it loads.)
-    vn_launch_pdl(p2p_step_kernel, dim3((unsigned)vn_sm_count()), dim3(512), 0, (cudaStream_t)stream, g_ctx, n4, chunk4, m, v, c,
-                  found_inf, scale_dev, growth_tracker, opt_state, lr, beta1, beta2, e, parity, g_step_sync, g_timeout_clocks);
+    if (g_ctx.mc_grad && g_ctx.mc_params)
+        vn_launch_pdl(p2p_step_kernel<true>, dim3((unsigned)vn_sm_count()), dim3(512), 0, (cudaStream_t)stream, g_ctx, n4, chunk4, m, v,
+                      c, found_inf, scale_dev, growth_tracker, opt_state, lr, beta1, beta2, e, parity, g_step_sync, g_timeout_clocks);
+    else
+        vn_launch_pdl(p2p_step_kernel<false>, dim3((unsigned)vn_sm_count()), dim3(512), 0, (cudaStream_t)stream, g_ctx, n4, chunk4, m, v,
+                      c, found_inf, scale_dev, growth_tracker, opt_state, lr, beta1, beta2, e, parity, g_step_sync, g_timeout_clocks);
     VN_CHECK_LAUNCH("p2p_step_kernel");
     return VN_OK;
 }

@@ -283,9 +283,18 @@ def run_ours(a):
             loss_host = torch.zeros(1).pin_memory()
         h2d = d2h = 0
 
+        copy_stream = torch.cuda.Stream(device=dev) if pinned else None
+
         def get_batch(it):
             if pinned:
-                buf = host_batches[it].to(dev, non_blocking=True)
+                # the H2D copy of a batch goes through its own stream, so that it runs under the tail of the step that is
+                # executing instead of in front of the next one; the compute stream waits for it (still inside the timed
+                # region) before anything that reads the batch is enqueued
+                with torch.cuda.stream(copy_stream):
+                    buf = host_batches[it].to(dev, non_blocking=True)
+                    landed = torch.cuda.Event(); landed.record()
+                torch.cuda.current_stream().wait_event(landed)
+                buf.record_stream(torch.cuda.current_stream())
                 ro, rd, rgb_t = buf[0:3 * n].view(n, 3), buf[3 * n:6 * n].view(n, 3), buf[6 * n:9 * n].view(n, 3)
                 return {"rays_o": ro, "rays_d": rd, "rgb": rgb_t, "depth": {"USS": buf[9 * n:10 * n], "ToF": buf[10 * n:11 * n]}}
             return batches[it]

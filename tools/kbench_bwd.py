@@ -48,6 +48,9 @@ def main():
         ffl = _lib.VN_HASH_PLANAR | _lib.VN_HASH_LEVEL_GROUPS_2 | _lib.VN_HASH_PAIR_LOADS | _lib.VN_HASH_F16_CHUNKS
         ms = timeit(lambda: _lib.call("vn_hash_encode_fwd_f32", x, table, enc_o, S, lv, ffl), reps=7)
         rec("hash_fwd_f32_chunks", ms, log2_T=log2_T, frac=round(S * 1164 / ms / 1e6 / 6454.9, 4))
+        for extra, lpt_tag in ((_lib.VN_HASH_LEVEL_GROUPS_8, "lpt8"), (_lib.VN_HASH_LEVEL_GROUPS_16, "lpt16")):
+            ms = timeit(lambda: _lib.call("vn_hash_encode_fwd_f32", x, table, enc_o, S, lv, (ffl & ~_lib.VN_HASH_LEVEL_GROUPS_2) | extra), reps=7)
+            rec("hash_fwd_f32_chunks_" + lpt_tag, ms, log2_T=log2_T, frac=round(S * 1164 / ms / 1e6 / 6454.9, 4))
         del table
         grad = torch.zeros(2 * lv.total_entries, device=DEV)
         dout = torch.randn(8, S, 4, device=DEV)

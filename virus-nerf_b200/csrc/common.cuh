@@ -58,6 +58,10 @@ struct VnProfScope {
 // (index math, weight staging, TMEM allocation) overlap the tail of kernel k.  Every such kernel
 // executes vn_pdl_wait() before it touches memory a predecessor may still be writing (or reading)
 // and vn_pdl_trigger() as early as possible.  VN_PDL=0 in the environment turns the attribute off.
+// RULE: data that a predecessor kernel of the stream produces is read with ld.global.cg (__ldcg) or plain loads, never
+// with the non-coherent ld.global.nc (__ldg): an invariant load is not ordered by the asm memory clobber of
+// griddepcontrol.wait and may be scheduled above it (observed in round 2: profiles/r2_kbench.md).  __ldg stays for data
+// that is older than the previous kernel (tables after the optimiser step, rays, positions, measurement targets).
 extern bool g_vn_pdl;
 template <typename... KArgs, typename... Args>
 static inline void vn_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,

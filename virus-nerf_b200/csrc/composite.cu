@@ -71,8 +71,8 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(const float* __restr
         const int64_t s = start + k;
         float a = 0.0f, c0 = 0.f, c1 = 0.f, c2 = 0.f, tm = 0.f;
         if (in) {
-            a = alpha_of(__ldg(sigmas + s), __ldg(deltas + s));     // :37
-            c0 = __ldg(rgbs + 3 * s); c1 = __ldg(rgbs + 3 * s + 1); c2 = __ldg(rgbs + 3 * s + 2);
+            a = alpha_of(__ldcg(sigmas + s), __ldg(deltas + s));     // :37
+            c0 = __ldcg(rgbs + 3 * s); c1 = __ldcg(rgbs + 3 * s + 1); c2 = __ldcg(rgbs + 3 * s + 2);
             tm = __ldg(ts + s);
         }
         float chunk_prod;
@@ -200,8 +200,8 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(const float* __restr
         go -= la.bg * g0; go -= la.bg * g1; go -= la.bg * g2;
         gd = k_uss * r.e_uss + k_tof * r.e_tof + k_rgbd * r.e_rgbd;
     } else {
-        g0 = __ldg(dL_drgb + 3 * ray); g1 = __ldg(dL_drgb + 3 * ray + 1); g2 = __ldg(dL_drgb + 3 * ray + 2);
-        gd = __ldg(dL_ddepth + ray); go = __ldg(dL_dopacity + ray);
+        g0 = __ldcg(dL_drgb + 3 * ray); g1 = __ldcg(dL_drgb + 3 * ray + 1); g2 = __ldcg(dL_drgb + 3 * ray + 2);
+        gd = __ldcg(dL_ddepth + ray); go = __ldcg(dL_dopacity + ray);
     }
     // ---- sweep 1: R = sum G_j w_j over the used prefix
     double Rl = 0.0;
@@ -213,9 +213,9 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(const float* __restr
         const int64_t s = start + k;
         float a = 0.0f, G = 0.0f;
         if (in) {
-            a = alpha_of(__ldg(sigmas + s), __ldg(deltas + s));
-            G = g0 * __ldg(rgbs + 3 * s) + g1 * __ldg(rgbs + 3 * s + 1) + g2 * __ldg(rgbs + 3 * s + 2) + gd * __ldg(ts + s) + go;
-            if (dL_dws) G += __ldg(dL_dws + s);
+            a = alpha_of(__ldcg(sigmas + s), __ldg(deltas + s));
+            G = g0 * __ldcg(rgbs + 3 * s) + g1 * __ldcg(rgbs + 3 * s + 1) + g2 * __ldcg(rgbs + 3 * s + 2) + gd * __ldg(ts + s) + go;
+            if (dL_dws) G += __ldcg(dL_dws + s);
         }
         float chunk_prod;
         const float Tj = T * warp_excl_prod(1.0f - a, lane, &chunk_prod);
@@ -240,9 +240,9 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(const float* __restr
         float a = 0.0f, G = 0.0f, delta = 0.0f;
         if (in) {
             delta = __ldg(deltas + s);
-            a = alpha_of(__ldg(sigmas + s), delta);
-            G = g0 * __ldg(rgbs + 3 * s) + g1 * __ldg(rgbs + 3 * s + 1) + g2 * __ldg(rgbs + 3 * s + 2) + gd * __ldg(ts + s) + go;
-            if (dL_dws) G += __ldg(dL_dws + s);
+            a = alpha_of(__ldcg(sigmas + s), delta);
+            G = g0 * __ldcg(rgbs + 3 * s) + g1 * __ldcg(rgbs + 3 * s + 1) + g2 * __ldcg(rgbs + 3 * s + 2) + gd * __ldg(ts + s) + go;
+            if (dL_dws) G += __ldcg(dL_dws + s);
         }
         float chunk_prod;
         const float Tj = T * warp_excl_prod(1.0f - a, lane, &chunk_prod);

@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(256) hash_fwd_kernel(const float* __restrict__
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= S) return;
     const int level0 = blockIdx.y * LPT;
-    const float x = __ldg(xyz + 3 * i), y = __ldg(xyz + 3 * i + 1), z = __ldg(xyz + 3 * i + 2);
+    const float x = __ldcg(xyz + 3 * i), y = __ldcg(xyz + 3 * i + 1), z = __ldcg(xyz + 3 * i + 2);
     float acc[2 * LPT];
 #pragma unroll
     for (int l = 0; l < LPT; ++l) {
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(256, MINB) hash_bwd_kernel(const float* __rest
 #pragma unroll
     for (int l = 0; l < 2 * LPT; ++l) d[l] = 0.0f;
     if (valid) {
-        x = __ldg(xyz + 3 * i); y = __ldg(xyz + 3 * i + 1); z = __ldg(xyz + 3 * i + 2);
+        x = __ldcg(xyz + 3 * i); y = __ldcg(xyz + 3 * i + 1); z = __ldcg(xyz + 3 * i + 2);
         const int W = 2 * P.levels;
         if (PLANAR) {
             // level0 is even (level_begin and LPT even): plane level0/2 + q at index i
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(256, MINB) hash_bwd_kernel(const float* __rest
 #pragma unroll
             for (int q = 0; q < LPT / 2; ++q)
                 if (level0 + 2 * q < P.level_end) {
-                    float4 t = __ldg(dp + (int64_t)q * S);
+                    float4 t = __ldcg(dp + (int64_t)q * S);
                     d[4 * q] = t.x; d[4 * q + 1] = t.y; d[4 * q + 2] = t.z; d[4 * q + 3] = t.w;
                 }
         } else if (sizeof(DT) == 4) {
@@ -205,23 +205,23 @@ __global__ void __launch_bounds__(256, MINB) hash_bwd_kernel(const float* __rest
             if (LPT % 2 == 0 && (W % 4) == 0 && level0 + LPT <= P.level_end) {
 #pragma unroll
                 for (int q = 0; q < LPT / 2; ++q) {
-                    float4 t = __ldg((const float4*)dp + q);
+                    float4 t = __ldcg((const float4*)dp + q);
                     d[4 * q] = t.x; d[4 * q + 1] = t.y; d[4 * q + 2] = t.z; d[4 * q + 3] = t.w;
                 }
             } else {
 #pragma unroll
                 for (int l = 0; l < LPT; ++l)
-                    if (level0 + l < P.level_end) { float2 t = __ldg((const float2*)dp + l); d[2 * l] = t.x; d[2 * l + 1] = t.y; }
+                    if (level0 + l < P.level_end) { float2 t = __ldcg((const float2*)dp + l); d[2 * l] = t.x; d[2 * l + 1] = t.y; }
             }
         } else if (CHUNK) {
             // level l of point i: half2 number (l & 3) of the 16-byte element i of plane l >> 2
             if (LPT == 4 && (level0 & 3) == 0 && level0 + 4 <= P.level_end) {
-                const uint4 u = __ldg((const uint4*)dout + (int64_t)(level0 >> 2) * S + i);
+                const uint4 u = __ldcg((const uint4*)dout + (int64_t)(level0 >> 2) * S + i);
                 const __half2* h = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
                 for (int l = 0; l < 4; ++l) { const float2 t = __half22float2(h[l]); d[2 * l] = t.x; d[2 * l + 1] = t.y; }
             } else if (LPT == 2 && (level0 & 1) == 0 && level0 + 2 <= P.level_end) {
-                const uint2 u = __ldg((const uint2*)dout + ((int64_t)(level0 >> 2) * S + i) * 2 + ((level0 >> 1) & 1));
+                const uint2 u = __ldcg((const uint2*)dout + ((int64_t)(level0 >> 2) * S + i) * 2 + ((level0 >> 1) & 1));
                 const __half2* h = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
                 for (int l = 0; l < 2; ++l) { const float2 t = __half22float2(h[l]); d[2 * l] = t.x; d[2 * l + 1] = t.y; }
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(256, MINB) hash_bwd_kernel(const float* __rest
                 for (int l = 0; l < LPT; ++l) {
                     const int level = level0 + l;
                     if (level < P.level_end) {
-                        const float2 t = __half22float2(__ldg((const __half2*)dout + ((int64_t)(level >> 2) * S + i) * 4 + (level & 3)));
+                        const float2 t = __half22float2(__ldcg((const __half2*)dout + ((int64_t)(level >> 2) * S + i) * 4 + (level & 3)));
                         d[2 * l] = t.x; d[2 * l + 1] = t.y;
                     }
                 }
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(256, MINB) hash_bwd_kernel(const float* __rest
             const __half2* dp = (const __half2*)dout + i * P.levels + level0;
 #pragma unroll
             for (int l = 0; l < LPT; ++l)
-                if (level0 + l < P.level_end) { float2 t = __half22float2(__ldg(dp + l)); d[2 * l] = t.x; d[2 * l + 1] = t.y; }
+                if (level0 + l < P.level_end) { float2 t = __half22float2(__ldcg(dp + l)); d[2 * l] = t.x; d[2 * l + 1] = t.y; }
         }
     }
 #pragma unroll

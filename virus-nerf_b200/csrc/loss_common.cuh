@@ -10,9 +10,9 @@ __device__ __forceinline__ RayLoss ray_loss(const float* __restrict__ rgb, const
                                             const float* __restrict__ uss, const float* __restrict__ tof,
                                             const float* __restrict__ rgbd, int64_t n, float bg, float uss_tol) {
     RayLoss r;
-    const float op = __ldg(opacity + n), d = __ldg(depth + n);
+    const float op = __ldcg(opacity + n), d = __ldcg(depth + n);   // predecessor's outputs: coherent loads (common.cuh, PDL)
 #pragma unroll
-    for (int c = 0; c < 3; ++c) r.dc[c] = (__ldg(rgb + 3 * n + c) + bg * (1.0f - op)) - __ldg(gt_rgb + 3 * n + c);   // rendering.py:225
+    for (int c = 0; c < 3; ++c) r.dc[c] = (__ldcg(rgb + 3 * n + c) + bg * (1.0f - op)) - __ldg(gt_rgb + 3 * n + c);   // rendering.py:225
     r.v_uss = r.v_tof = r.v_rgbd = false;
     r.e_uss = r.e_tof = r.e_rgbd = 0.0f;
     if (uss) { const float m = __ldg(uss + n); r.v_uss = !isnan(m) && (d < m - uss_tol); if (r.v_uss) r.e_uss = d - m; }   // loss.py:186-194

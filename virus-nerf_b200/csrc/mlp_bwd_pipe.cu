@@ -523,7 +523,7 @@ __global__ void __launch_bounds__(NTHR, 1) mlp_bwd_pipe_kernel(const MlpArgs a, 
                         const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(a.enc) + s * 32 + 16 * half);
 #pragma unroll
                         for (int k = 0; k < 2; ++k) {
-                            const uint4 u = __ldg(src + k);
+                            const uint4 u = __ldcg(src + k);
                             const __half2* h = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
                             for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); e[8 * k + 2 * j] = f.x; e[8 * k + 2 * j + 1] = f.y; }
@@ -534,7 +534,7 @@ __global__ void __launch_bounds__(NTHR, 1) mlp_bwd_pipe_kernel(const MlpArgs a, 
                         const int64_t step = a.enc_fmt == 2 ? a.S : 1;
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            const float4 f = __ldg(src + k * step);
+                            const float4 f = __ldcg(src + k * step);
                             e[4 * k] = f.x; e[4 * k + 1] = f.y; e[4 * k + 2] = f.z; e[4 * k + 3] = f.w;
                         }
                     }
@@ -589,7 +589,7 @@ __global__ void __launch_bounds__(NTHR, 1) mlp_bwd_pipe_kernel(const MlpArgs a, 
                 u.x = pack2<false>(r[0], r[1]); u.y = pack2<false>(r[2], r[3]); u.z = pack2<false>(r[4], r[5]); u.w = pack2<false>(r[6], r[7]);
                 *reinterpret_cast<uint4*>(cs + C_IN2 + (2 + half) * (TILE * 16) + row * 16) = u;
                 if (half == 0 && valid) {
-                    const float dsig = small ? reinterpret_cast<const float*>(aux + AUX_DSIG)[row] : __ldg(a.dsigmas + s);
+                    const float dsig = small ? reinterpret_cast<const float*>(aux + AUX_DSIG)[row] : __ldcg(a.dsigmas + s);
                     dh_sigma = dsig * expf(fminf(fmaxf(__uint_as_float(r[0]), -15.0f), 15.0f));          // TruncExp bwd, networks.py:28
                 }
             }
@@ -636,7 +636,7 @@ __global__ void __launch_bounds__(NTHR, 1) mlp_bwd_pipe_kernel(const MlpArgs a, 
                 if (valid) {
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
-                        const float g = small ? reinterpret_cast<const float*>(aux + AUX_DRGB)[3 * row + k] : __ldg(a.drgbs + 3 * s + k);
+                        const float g = small ? reinterpret_cast<const float*>(aux + AUX_DRGB)[3 * row + k] : __ldcg(a.drgbs + 3 * s + k);
                         const float rgb = __fdividef(1.0f, 1.0f + __expf(-__uint_as_float(r[k])));
                         d5[k] = g * rgb * (1.0f - rgb);
                     }

@@ -231,8 +231,11 @@ __device__ __forceinline__ void mask_store_half(uint8_t* smem, int off_dst, int 
     }
 }
 
-template <bool BWD>
-__global__ void __launch_bounds__(NTHREADS, BWD ? 2 : 3) mlp_kernel(const MlpArgs a) {
+// CHUNKS (forward only): the encoding arrives as fp16 operand chunk planes (enc_fmt 3 / 5) and nothing else has to be
+// supported: the prefetched tile is kept as the raw 16-byte chunks (8 registers instead of 16 + conversions), which
+// brings the kernel under 64 registers -> 4 CTAs per SM instead of 3 for the latency-bound layer chain.
+template <bool BWD, bool CHUNKS = false>
+__global__ void __launch_bounds__(NTHREADS, BWD ? 2 : (CHUNKS ? 4 : 3)) mlp_kernel(const MlpArgs a) {
     vn_pdl_trigger();                         // PDL: the wait follows the prologue
     using L = Lay<BWD>;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -257,17 +260,29 @@ __global__ void __launch_bounds__(NTHREADS, BWD ? 2 : 3) mlp_kernel(const MlpArg
     const int64_t n_tiles = (a.S + TILE - 1) / TILE;
     // software prefetch: the NEXT tile's half enc row / direction (and, for the backward, its
     // output gradients) are loaded into registers while the current tile runs the layer chain
-    struct Staged { float4 e[4]; float d[3]; float dsig; float drgb[3]; uint4 sh; };
+    // NOTE on the loads below: everything a PREDECESSOR KERNEL of the stream produces (enc, dsigmas, drgbs) is read with
+    // ld.global.cg (__ldcg), never with the non-coherent ld.global.nc (__ldg).  An "invariant" load may be scheduled above
+    // griddepcontrol.wait -- the asm memory clobber does not order it -- and then reads the buffer while the predecessor is
+    // still writing it.  That happened to the 64-register instantiation of this kernel (intermittent wrong losses inside
+    // the PDL-chained step, none with VN_PDL=0; profiles/r2_kbench.md).
+    struct Staged { float4 e[CHUNKS ? 2 : 4]; float d[3]; float dsig; float drgb[3]; uint4 sh; };
     auto fetch = [&](int64_t tile, Staged& st) {
         const int64_t s = tile * TILE + row;
         const bool valid = tile < n_tiles && s < a.S;
-        if (valid) {
+        if (CHUNKS) {
+            // raw chunks 2*half, 2*half+1 of this row (bit patterns travel in the float4 registers)
+            st.e[0] = make_float4(0.f, 0.f, 0.f, 0.f); st.e[1] = st.e[0];
+            if (valid) {
+                const float4* src = reinterpret_cast<const float4*>(a.enc) + (int64_t)(2 * half) * a.S + s;
+                st.e[0] = __ldcg(src); st.e[1] = __ldcg(src + a.S);
+            }
+        } else if (valid) {
             if (a.enc_fmt == 3 || a.enc_fmt == 5) {
                 // f16 chunk planes [4][S] x 16 B: chunks 2*half, 2*half+1 of this row
                 const uint4* src = reinterpret_cast<const uint4*>(a.enc) + (int64_t)(2 * half) * a.S + s;
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
-                    const uint4 u = __ldg(src + (int64_t)q * a.S);
+                    const uint4 u = __ldcg(src + (int64_t)q * a.S);
                     const __half2* h = reinterpret_cast<const __half2*>(&u);
                     const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]), f2 = __half22float2(h[2]), f3 = __half22float2(h[3]);
                     st.e[2 * q] = make_float4(f0.x, f0.y, f1.x, f1.y);
@@ -277,7 +292,7 @@ __global__ void __launch_bounds__(NTHREADS, BWD ? 2 : 3) mlp_kernel(const MlpArg
                 const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(a.enc) + s * 32 + 16 * half);
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
-                    const uint4 u = __ldg(src + q);
+                    const uint4 u = __ldcg(src + q);
                     const __half2* h = reinterpret_cast<const __half2*>(&u);
                     const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]), f2 = __half22float2(h[2]), f3 = __half22float2(h[3]);
                     st.e[2 * q] = make_float4(f0.x, f0.y, f1.x, f1.y);
@@ -287,25 +302,25 @@ __global__ void __launch_bounds__(NTHREADS, BWD ? 2 : 3) mlp_kernel(const MlpArg
                 // planes 4*half .. 4*half+3 at index s: consecutive rows = consecutive float4
                 const float4* src = reinterpret_cast<const float4*>(a.enc) + (int64_t)(4 * half) * a.S + s;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) st.e[q] = __ldg(src + (int64_t)q * a.S);
+                for (int q = 0; q < 4; ++q) st.e[q] = __ldcg(src + (int64_t)q * a.S);
             } else {
                 const float4* src = reinterpret_cast<const float4*>(a.enc + s * 32 + 16 * half);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) st.e[q] = __ldg(src + q);
+                for (int q = 0; q < 4; ++q) st.e[q] = __ldcg(src + q);
             }
         } else {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) st.e[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int q = 0; q < (CHUNKS ? 2 : 4); ++q) st.e[q] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         st.d[0] = 1.0f; st.d[1] = 0.0f; st.d[2] = 0.0f;
         st.sh = make_uint4(0u, 0u, 0u, 0u);
         if (a.enc_fmt == 5) {          // planes 4, 5: the direction encoding, already an operand chunk (vn_march_train_expand_sh)
-            if (valid && !a.density_only) st.sh = __ldg(reinterpret_cast<const uint4*>(a.enc) + (int64_t)(4 + half) * a.S + s);
+            if (valid && !a.density_only) st.sh = __ldcg(reinterpret_cast<const uint4*>(a.enc) + (int64_t)(4 + half) * a.S + s);
         } else if (valid && !a.density_only) { st.d[0] = __ldg(a.dirs + 3 * s); st.d[1] = __ldg(a.dirs + 3 * s + 1); st.d[2] = __ldg(a.dirs + 3 * s + 2); }
         st.dsig = 0.0f; st.drgb[0] = st.drgb[1] = st.drgb[2] = 0.0f;
         if (BWD && valid && half == 0) {
-            st.dsig = __ldg(a.dsigmas + s);
-            if (!a.density_only) { st.drgb[0] = __ldg(a.drgbs + 3 * s); st.drgb[1] = __ldg(a.drgbs + 3 * s + 1); st.drgb[2] = __ldg(a.drgbs + 3 * s + 2); }
+            st.dsig = __ldcg(a.dsigmas + s);
+            if (!a.density_only) { st.drgb[0] = __ldcg(a.drgbs + 3 * s); st.drgb[1] = __ldcg(a.drgbs + 3 * s + 1); st.drgb[2] = __ldcg(a.drgbs + 3 * s + 2); }
         }
     };
     Staged cur;
@@ -319,11 +334,18 @@ __global__ void __launch_bounds__(NTHREADS, BWD ? 2 : 3) mlp_kernel(const MlpArg
         const bool valid = s < a.S;
         // ---- stage inputs: half enc row -> X0, half of SH(dir) -> IN2[:, 0:16] ------------------
         {
+            if (CHUNKS) {
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const float v[8] = {cur.e[2 * c].x, cur.e[2 * c].y, cur.e[2 * c].z, cur.e[2 * c].w,
-                                    cur.e[2 * c + 1].x, cur.e[2 * c + 1].y, cur.e[2 * c + 1].z, cur.e[2 * c + 1].w};
-                st_row8(smem, L::X0, row, 2 * half + c, v);
+                for (int c = 0; c < 2; ++c)
+                    *reinterpret_cast<float4*>(smem + L::X0 + (2 * half + c) * (TILE * 16) + row * 16) = cur.e[c];
+            } else {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const float v[8] = {cur.e[2 * c].x, cur.e[2 * c].y, cur.e[2 * c].z, cur.e[2 * c].w,
+                                        cur.e[2 * (CHUNKS ? 0 : c) + 1].x, cur.e[2 * (CHUNKS ? 0 : c) + 1].y,
+                                        cur.e[2 * (CHUNKS ? 0 : c) + 1].z, cur.e[2 * (CHUNKS ? 0 : c) + 1].w};
+                    st_row8(smem, L::X0, row, 2 * half + c, v);
+                }
             }
             if (!a.density_only && a.enc_fmt == 5) {
                 *reinterpret_cast<uint4*>(smem + L::IN2 + half * (TILE * 16) + row * 16) = cur.sh;
@@ -507,10 +529,14 @@ __global__ void __launch_bounds__(NTHREADS, BWD ? 2 : 3) mlp_kernel(const MlpArg
     if (warp == 0) umma::tmem_dealloc(p.tm, BWD ? TMEM_BWD : TMEM_FWD);
 }
 
+// VN_MLP_FWD4 = CTAs per SM of the slim chunk-format forward (0: use the generic 3-CTA kernel)
+static const int g_mlp_fwd4 = []() { const char* e = getenv("VN_MLP_FWD4"); return e ? atoi(e) : 4; }();
+
 int launch_mlp(bool bwd, const MlpArgs& a, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
         VN_CUDA(cudaFuncSetAttribute(mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD));
+        VN_CUDA(cudaFuncSetAttribute(mlp_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD));
         VN_CUDA(cudaFuncSetAttribute(mlp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD));
         attr_set = true;
     }
@@ -519,8 +545,14 @@ int launch_mlp(bool bwd, const MlpArgs& a, cudaStream_t st) {
     const int per_sm = bwd ? 2 : 3;
     int64_t grid = (int64_t)vn_sm_count() * per_sm;
     if (grid > n_tiles) grid = n_tiles;
-    if (bwd) vn_launch_pdl(mlp_kernel<true>, dim3((unsigned)grid), dim3(NTHREADS), SMEM_BWD, st, a);
-    else     vn_launch_pdl(mlp_kernel<false>, dim3((unsigned)grid), dim3(NTHREADS), SMEM_FWD, st, a);
+    const bool chunks = !bwd && !a.density_only && (a.enc_fmt == 3 || a.enc_fmt == 5) && g_mlp_fwd4 > 0;
+    if (chunks) {
+        grid = (int64_t)vn_sm_count() * g_mlp_fwd4;
+        if (grid > n_tiles) grid = n_tiles;
+    }
+    if (bwd)         vn_launch_pdl(mlp_kernel<true>, dim3((unsigned)grid), dim3(NTHREADS), SMEM_BWD, st, a);
+    else if (chunks) vn_launch_pdl(mlp_kernel<false, true>, dim3((unsigned)grid), dim3(NTHREADS), SMEM_FWD, st, a);
+    else             vn_launch_pdl(mlp_kernel<false>, dim3((unsigned)grid), dim3(NTHREADS), SMEM_FWD, st, a);
     VN_CHECK_LAUNCH(bwd ? "mlp_kernel<bwd>" : "mlp_kernel<fwd>");
     return VN_OK;
 }

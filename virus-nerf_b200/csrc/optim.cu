@@ -10,7 +10,7 @@ __global__ void __launch_bounds__(256) grad_check_kernel(const float4* __restric
     const int64_t n4 = n / 4;
     bool bad = false;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-        const float4 v = __ldg(g4 + i);
+        const float4 v = __ldcg(g4 + i);
         bad |= !(isfinite(v.x) && isfinite(v.y) && isfinite(v.z) && isfinite(v.w));
     }
     if (blockIdx.x == 0 && threadIdx.x < (n & 3)) bad |= !isfinite(g[n4 * 4 + threadIdx.x]);
@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i + 3 < n) {
         float4 P = *(float4*)(p + i), M = *(float4*)(m + i), V = *(float4*)(v + i);
-        const float4 Gd = __ldg((const float4*)(g + i));
+        const float4 Gd = __ldcg((const float4*)(g + i));
         adam1(P.x, Gd.x, M.x, V.x, c); adam1(P.y, Gd.y, M.y, V.y, c);
         adam1(P.z, Gd.z, M.z, V.z, c); adam1(P.w, Gd.w, M.w, V.w, c);
         *(float4*)(p + i) = P; *(float4*)(m + i) = M; *(float4*)(v + i) = V;

@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
                                                    const float* __restrict__ scale_dev,
                                                    const float* __restrict__ opt_state) {
     vn_pdl_trigger(); vn_pdl_wait();          // PDL: see common.cuh
-    if (found_inf && *found_inf != 0.0f) return;          // GradScaler.step skips the optimizer step
+    if (found_inf && __ldcg(found_inf) != 0.0f) return;   // GradScaler.step skips the optimizer step (flag set by the predecessor: coherent load)
     if (scale_dev) c.inv_scale = 1.0f / *scale_dev;
     if (opt_state) { c.step_size = opt_state[0]; c.bc2_sqrt = opt_state[1]; }   // bias corrections of the device-side step count
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;

@@ -274,3 +274,27 @@ def test_mirrors_match_the_reference_signatures():
                 checked += 1
     assert not errors, "\n".join(errors)
     assert checked >= 70, checked
+
+
+def test_pdl_rule_no_noncoherent_loads_of_predecessor_data():
+    """csrc/common.cuh, RULE at vn_launch_pdl: arrays that the previous kernels of the stream produce (encoding and its
+    gradient, MLP outputs and their gradients, the compositor's per-ray outputs, the flat gradient read by the optimiser)
+    must not be read with __ldg (ld.global.nc): an invariant load may be scheduled above griddepcontrol.wait.  A static
+    check of the kernels' sources (found as a real failure in round 2: profiles/r2_kbench.md)."""
+    csrc = os.path.join(ROOT, "virus-nerf_b200", "csrc")
+    banned = re.compile(r"__ldg\(\s*(?:\([^()]*\)\s*)?\(?\s*(a\.enc|a\.dsigmas|a\.drgbs|sigmas\b|rgbs\b|dout\b|dp\b|dL_d\w+|g4\b|g \+|"
+                        r"opacity\b|depth\b|rgb \+|src \+ \(int64_t\)q|src \+ q|src\b\))")
+    offenders = []
+    for name in ("mlp_fused.cu", "mlp_bwd_pipe.cu", "hash_encoder.cu", "optim.cu", "loss_common.cuh"):
+        for i, line in enumerate(open(os.path.join(csrc, name)), 1):
+            if banned.search(line):
+                offenders.append(f"{name}:{i}: {line.strip()[:100]}")
+    # composite.cu: the training kernels (everything above the test-time compositor, which is not PDL-launched)
+    comp = open(os.path.join(csrc, "composite.cu")).read()
+    train = comp[:comp.index("// ---- a10 ----")]
+    for i, line in enumerate(train.split("\n"), 1):
+        if banned.search(line):
+            offenders.append(f"composite.cu:{i}: {line.strip()[:100]}")
+    assert not offenders, "\n".join(offenders)
+    # and the rule is written down where the launches are defined
+    assert "RULE" in open(os.path.join(csrc, "common.cuh")).read()

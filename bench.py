@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--rays", type=int, default=RAYS_PER_GPU)
     ap.add_argument("--cpu-rays", type=int, default=RAYS_PER_GPU,
                     help="rays per step of the CPU arm (default: the full 4096-ray batch of the GPU arm's config)")
-    ap.add_argument("--windows", type=int, default=5, help="repetitions of the K-step timed window (median reported)")
+    ap.add_argument("--windows", type=int, default=7, help="repetitions of the K-step timed window (median reported)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --rays per GPU; strong: --rays is ONE global batch, rank r takes its contiguous shard")
     ap.add_argument("--no-extra", action="store_true", help="skip extra_configs (configs 3 and 5)")

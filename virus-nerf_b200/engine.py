@@ -13,6 +13,7 @@ What is deliberately different from the reference's loop (DESIGN.md "engine"):
     reproduce the single-process gradient of the concatenated batch.
 """
 import math
+import os
 
 import torch
 import torch.distributed as dist
@@ -147,7 +148,6 @@ class TrainEngine:
         # available (peer pointers without CUDA IPC and, on an NVSwitch fabric, NVLink-multicast addresses: vn_p2p_step
         # then reduces and broadcasts through the switch).  VN_P2P_NVLS=0 keeps plain allocations + CUDA IPC.
         self._symm = None
-        import os
         # (measured: at 2 ranks the multicast path is slower than peer loads / stores -- one peer, no traffic to save:
         # 0.150 vs 0.102 ms -- so "auto" takes it from 4 ranks on; VN_P2P_NVLS=1 / 0 forces it on / off)
         nvls_env = os.environ.get("VN_P2P_NVLS", "auto")

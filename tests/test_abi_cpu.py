@@ -298,3 +298,21 @@ def test_pdl_rule_no_noncoherent_loads_of_predecessor_data():
     assert not offenders, "\n".join(offenders)
     # and the rule is written down where the launches are defined
     assert "RULE" in open(os.path.join(csrc, "common.cuh")).read()
+
+
+def test_roofline_traffic_comes_from_the_committed_ncu_capture(tmp_path):
+    """bench.py's roofline.traffic = DRAM bytes per point of this round's `ncu --set full` capture x points per launch:
+    profiles/r2_ncu_traffic.json must be what tools/ncu_traffic.py derives from the committed raw CSVs"""
+    import json
+    import subprocess
+    import sys
+    out = tmp_path / "t.json"
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "ncu_traffic.py"),
+                           os.path.join(ROOT, "profiles", "r2_ncu_step_raw.csv"), "--json", str(out), "--points", "853812"],
+                          stdout=subprocess.DEVNULL)
+    fresh = json.load(open(out))
+    committed = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")))
+    for k in ("mlp_bwd_hash_scatter", "hash_encode_fwd", "mlp_fwd", "adam"):
+        assert abs(fresh[k]["dram_bytes_per_point"] - committed[k]["dram_bytes_per_point"]) < 1e-6, k
+    # the fused backward moves far fewer DRAM bytes than its 1148 algorithmic bytes per point (table gradient in L2)
+    assert 100 < committed["mlp_bwd_hash_scatter"]["dram_bytes_per_point"] < 400
